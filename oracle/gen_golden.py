@@ -1,0 +1,102 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules
+(imported from /root/reference through oracle/refshim.py) on seeded synthetic
+weights and inputs (wan2gp_b200/synth.py).  Run in the build container only:
+
+    python oracle/gen_golden.py [tiny] [tiny_i2v] [p13b] [vae_tiny] [vae_p]
+
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.refshim import Pipe, load_reference  # noqa: E402
+from wan2gp_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+WAN_CASES = {
+    # name: (config, latent (T,H,W), seed)
+    "tiny": ("tiny", (3, 8, 12), 0),
+    "tiny_i2v": ("tiny_i2v", (2, 8, 8), 1),
+    "small": ("small", (5, 16, 24), 2),
+    "p13b": ("t2v_1.3B", (9, 30, 52), 0),     # BASELINE config 1 (shared/mps/test_mps_forward.py:75-110)
+}
+VAE_CASES = {
+    "vae_tiny": (synth.VAE_CFG_TINY, (16, 3, 6, 8), 0),
+    "vae_small": (synth.VAE_CFG, (16, 5, 8, 10), 1),
+    "vae_p": (synth.VAE_CFG, (16, 3, 30, 52), 0),  # BASELINE.md section 2 decode probe shape
+}
+
+
+def build_reference_wan(cfg_name, seed):
+    ref = load_reference()
+    cfg = synth.WAN_CONFIGS[cfg_name]
+    model = ref.WanModel(**cfg).eval().requires_grad_(False)
+    sd = synth.make_wan_state_dict(cfg, seed)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not missing, missing
+    model.apply_post_init_changes()        # required before forward (model.py:1291-1303)
+    return ref, model, cfg, sd
+
+
+def run_wan(name):
+    cfg_name, thw, seed = WAN_CASES[name]
+    ref, model, cfg, sd = build_reference_wan(cfg_name, seed)
+    x, t, ctx, y = synth.make_wan_inputs(cfg, thw, seed)
+    freqs = ref.get_rotary_pos_embed(thw)
+    t0 = time.time()
+    with torch.no_grad():
+        out = model([x.clone()], t, [ctx], y=y, freqs=freqs, pipeline=Pipe())[0]
+    dt = time.time() - t0
+    print(f"{name}: reference fp32 forward {dt:.2f}s out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    # float64 run: WanRMSNorm's `y = x.float()` (model.py:165) only COPIES when x is not fp32, so this
+    # run has the production (bf16/GPU) RMSNorm semantics without the fp32 aliasing artefact.
+    model.double()
+    with torch.no_grad():
+        out64 = model([x.double()], t.double(), [ctx.double()], y=None if y is None else y.double(),
+                      freqs=freqs, pipeline=Pipe())[0]
+    print(f"{name}: reference fp64 forward absmean {out64.abs().mean():.6f} "
+          f"fp32-vs-fp64 rel {((out - out64).norm() / out64.norm()).item():.3e}")
+    np.savez_compressed(os.path.join(GOLDEN, f"wan_{name}.npz"),
+                        out=out.numpy().astype(np.float32), out64=out64.numpy().astype(np.float32),
+                        cos=freqs[0][:64].numpy(), sin=freqs[1][:64].numpy(),
+                        seconds=np.float32(dt), threads=np.int32(torch.get_num_threads()))
+
+
+def run_vae(name):
+    ref = load_reference()
+    cfg, zshape, seed = VAE_CASES[name]
+    vae = ref.WanVAE_(dim=cfg["dim"], z_dim=cfg["z_dim"], dim_mult=cfg["dim_mult"],
+                      num_res_blocks=cfg["num_res_blocks"], attn_scales=[],
+                      temperal_downsample=[False, True, True], dropout=0.0).eval().requires_grad_(False)
+    sd = synth.make_vae_state_dict(cfg, seed)
+    full = vae.state_dict()
+    for k in full:
+        if k in sd:
+            full[k] = sd[k]
+    vae.load_state_dict(full)
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    scale = [torch.tensor(synth.VAE_MEAN), 1.0 / torch.tensor(synth.VAE_STD)]
+    t0 = time.time()
+    with torch.no_grad():
+        out = vae.decode(z, scale)
+    dt = time.time() - t0
+    print(f"{name}: reference decode {dt:.2f}s out {tuple(out.shape)} absmean {out.abs().mean():.6f} "
+          f"min {out.min():.3f} max {out.max():.3f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float16 if out.numel() > 2_000_000 else np.float32),
+                        seconds=np.float32(dt), threads=np.int32(torch.get_num_threads()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    os.makedirs(GOLDEN, exist_ok=True)
+    names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
+    for n in names:
+        (run_wan if n in WAN_CASES else run_vae)(n)

@@ -1,0 +1,120 @@
+"""Import shims that let the UNMODIFIED reference modules under /root/reference
+run on CPU in this container (test infrastructure only -- see oracle/README.md).
+
+The reference (deepbeepmeep/Wan2GP) needs third-party packages that are not
+installed here (mmgp, diffusers) and imports its whole model zoo from
+models/wan/__init__.py.  SURVEY.md section 8c lists the blockers; this module
+clears them with stub modules so that
+
+    models/wan/modules/model.py      (WanModel, reference hot path W1-W11)
+    models/wan/modules/vae.py        (WanVAE_,  reference hot path V1-V7)
+    models/wan/modules/posemb_layers (RoPE tables, W0)
+
+import and execute exactly as written.  Nothing here is arithmetic: every
+number that comes out of `load_reference()` is produced by reference code.
+
+/root/reference does not exist on the GPU box, so only oracle/gen_golden.py
+(run here, output committed under tests/golden/) and the CPU-only validation
+tests that are skipped when the tree is absent may call this.
+"""
+import functools
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("WAN2GP_REFERENCE", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models/wan/modules/model.py"))
+
+
+class _Stub(types.ModuleType):
+    """Module whose every attribute is an empty class (sibling conditioning
+    modules imported at model.py:18-27 and never touched on the t2v/i2v2_2 path)."""
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return type(k, (), {})
+
+
+_loaded = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's WanModel, WanVAE_, get_rotary_pos_embed."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import torch
+
+    sys.path.insert(0, REFERENCE_ROOT)
+    # ---- mmgp (requirements.txt:2, not installed): no arithmetic on this path ----
+    mmgp = types.ModuleType("mmgp")
+    offload = types.ModuleType("mmgp.offload")
+    offload.shared_state = {"_attention": "sdpa"}
+    _caches = {}
+    offload.get_cache = lambda name: _caches.setdefault(name, {})
+    offload.clear_caches = _caches.clear
+    mmgp.offload = offload
+    st2 = types.ModuleType("mmgp.safetensors2")
+    mmgp.safetensors2 = st2
+    sys.modules.update({"mmgp": mmgp, "mmgp.offload": offload, "mmgp.safetensors2": st2})
+
+    # ---- diffusers (only base classes / decorator are used at model.py:10-11) ----
+    class ConfigMixin:
+        pass
+
+    class ModelMixin(torch.nn.Module):
+        pass
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def w(self, *a, **k):
+            return init(self, *a, **k)
+        return w
+
+    d = types.ModuleType("diffusers")
+    dc = types.ModuleType("diffusers.configuration_utils")
+    dm = types.ModuleType("diffusers.models")
+    dmu = types.ModuleType("diffusers.models.modeling_utils")
+    dc.ConfigMixin = ConfigMixin
+    dc.register_to_config = register_to_config
+    dmu.ModelMixin = ModelMixin
+    dm.ModelMixin = ModelMixin
+    sys.modules.update({"diffusers": d, "diffusers.configuration_utils": dc,
+                        "diffusers.models": dm, "diffusers.models.modeling_utils": dmu})
+
+    # shared/attention.py:14 probes the CUDA device at import time
+    torch.cuda.get_device_capability = lambda *a, **k: (0, 0)
+
+    # bypass models/wan/__init__.py (imports the whole pipeline zoo)
+    for name, rel in [("models", "models"), ("models.wan", "models/wan"),
+                      ("models.wan.modules", "models/wan/modules")]:
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+        sys.modules[name] = m
+    for name in ["multitalk", "multitalk.multitalk_utils", "animate", "animate.motion_encoder",
+                 "animate.face_blocks", "animate.model_animate", "scail", "scail.model_scail",
+                 "scail2", "steadydancer", "steadydancer.small_archs",
+                 "steadydancer.mobilenetv2_dcd", "shotplan", "animate2"]:
+        sys.modules["models.wan." + name] = _Stub("models.wan." + name)
+
+    from models.wan.modules.model import WanModel, sinusoidal_embedding_1d
+    from models.wan.modules.posemb_layers import get_rotary_pos_embed
+    from models.wan.modules.vae import WanVAE_
+
+    ns = types.SimpleNamespace(WanModel=WanModel, WanVAE_=WanVAE_,
+                               get_rotary_pos_embed=get_rotary_pos_embed,
+                               sinusoidal_embedding_1d=sinusoidal_embedding_1d,
+                               offload=offload)
+    _loaded = ns
+    return ns
+
+
+class Pipe:
+    """Stand-in for the pipeline object polled at model.py:1997."""
+    _interrupt = False

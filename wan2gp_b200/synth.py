@@ -1,0 +1,212 @@
+"""Seeded synthetic weights and inputs (there are no checkpoints offline).
+
+State-dict names and shapes follow the reference modules exactly (SURVEY.md
+Appendix B; models/wan/modules/model.py:1131-1143, 530-551, 847-850 and
+models/wan/modules/vae.py:430-484) so the same dict loads into the reference
+`WanModel` / `WanVAE_` (oracle side) and into this package's modules.
+
+Initialisation is the reference's `init_weights` (model.py:2128-2150) with the
+"tempered" overrides of SURVEY.md section 7/H1: with the stock init the QK logits
+have std ~ sqrt(128) and softmax is near-argmax, which makes any bf16-vs-fp32
+comparison chaotic; `norm_q/k.weight ~ 0.3` keeps attention in a realistic regime.
+Every tensor has its own generator seeded from (seed, crc32(name)) so a single
+tensor can be regenerated anywhere (CPU values are bit-reproducible across hosts).
+"""
+import math
+import zlib
+
+import torch
+
+WAN_CONFIGS = {
+    # models/wan/configs/t2v_1.3B.json
+    "t2v_1.3B": dict(model_type="t2v", dim=1536, ffn_dim=8960, freq_dim=256, in_dim=16, out_dim=16,
+                     num_heads=12, num_layers=30, text_len=512, text_dim=4096, eps=1e-6),
+    # models/wan/configs/t2v_2_2.json (Wan2.2 14B, high- and low-noise experts share it)
+    "t2v_2_2": dict(model_type="t2v", dim=5120, ffn_dim=13824, freq_dim=256, in_dim=16, out_dim=16,
+                    num_heads=40, num_layers=40, text_len=512, text_dim=4096, eps=1e-6),
+    # models/wan/configs/i2v_2_2.json
+    "i2v_2_2": dict(model_type="i2v2_2", dim=5120, ffn_dim=13824, freq_dim=256, in_dim=36, out_dim=16,
+                    num_heads=40, num_layers=40, text_len=512, text_dim=4096, eps=1e-6),
+    # reduced configs for fast parity tests (head_dim stays 128 as in every Wan model)
+    "tiny": dict(model_type="t2v", dim=256, ffn_dim=768, freq_dim=256, in_dim=16, out_dim=16,
+                 num_heads=2, num_layers=2, text_len=64, text_dim=128, eps=1e-6),
+    "tiny_i2v": dict(model_type="i2v2_2", dim=256, ffn_dim=768, freq_dim=256, in_dim=36, out_dim=16,
+                     num_heads=2, num_layers=2, text_len=64, text_dim=128, eps=1e-6),
+    "small": dict(model_type="t2v", dim=512, ffn_dim=1536, freq_dim=256, in_dim=16, out_dim=16,
+                  num_heads=4, num_layers=3, text_len=512, text_dim=512, eps=1e-6),
+}
+
+
+def _gen(seed, name, device):
+    g = torch.Generator(device=device)
+    g.manual_seed((int(seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
+    return g
+
+
+def _normal(shape, std, seed, name, device, mean=0.0):
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    t.normal_(mean, std, generator=_gen(seed, name, device))
+    return t
+
+
+def _xavier(shape, seed, name, device):
+    fan_out, fan_in = shape[0], math.prod(shape[1:])
+    a = math.sqrt(6.0 / (fan_in + fan_out))
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    t.uniform_(-a, a, generator=_gen(seed, name, device))
+    return t
+
+
+def wan_param_shapes(cfg):
+    """name -> shape for the t2v / i2v2_2 WanModel."""
+    D, F, Cin, Td, Fd = cfg["dim"], cfg["ffn_dim"], cfg["in_dim"], cfg["text_dim"], cfg["freq_dim"]
+    s = {
+        "patch_embedding.weight": (D, Cin, 1, 2, 2), "patch_embedding.bias": (D,),
+        "text_embedding.0.weight": (D, Td), "text_embedding.0.bias": (D,),
+        "text_embedding.2.weight": (D, D), "text_embedding.2.bias": (D,),
+        "time_embedding.0.weight": (D, Fd), "time_embedding.0.bias": (D,),
+        "time_embedding.2.weight": (D, D), "time_embedding.2.bias": (D,),
+        "time_projection.1.weight": (6 * D, D), "time_projection.1.bias": (6 * D,),
+        "head.modulation": (1, 2, D),
+        "head.head.weight": (4 * cfg["out_dim"], D), "head.head.bias": (4 * cfg["out_dim"],),
+    }
+    for i in range(cfg["num_layers"]):
+        p = f"blocks.{i}."
+        s[p + "modulation"] = (1, 6, D)
+        for a in ("self_attn", "cross_attn"):
+            for l in "qkvo":
+                s[p + f"{a}.{l}.weight"] = (D, D)
+                s[p + f"{a}.{l}.bias"] = (D,)
+            s[p + f"{a}.norm_q.weight"] = (D,)
+            s[p + f"{a}.norm_k.weight"] = (D,)
+        s[p + "norm3.weight"] = (D,)
+        s[p + "norm3.bias"] = (D,)
+        s[p + "ffn.0.weight"] = (F, D)
+        s[p + "ffn.0.bias"] = (F,)
+        s[p + "ffn.2.weight"] = (D, F)
+        s[p + "ffn.2.bias"] = (D,)
+    return s
+
+
+def make_wan_tensor(name, shape, cfg, seed=0, device="cpu"):
+    D = cfg["dim"]
+    if name.endswith("modulation"):
+        return _normal(shape, 1.0 / math.sqrt(D), seed, name, device)
+    if "norm_q" in name or "norm_k" in name:
+        return 0.3 * (1.0 + _normal(shape, 0.1, seed, name, device))
+    if name.endswith("norm3.weight"):
+        return 1.0 + _normal(shape, 0.1, seed, name, device)
+    if name.endswith("bias"):
+        return _normal(shape, 0.02, seed, name, device)
+    if name.startswith(("text_embedding", "time_embedding")) or name == "head.head.weight":
+        return _normal(shape, 0.02, seed, name, device)
+    return _xavier(shape, seed, name, device)  # Linear / patch-embed weights
+
+
+def make_wan_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    return {n: make_wan_tensor(n, s, cfg, seed, device).to(dtype) for n, s in wan_param_shapes(cfg).items()}
+
+
+# --------------------------------------------------------------------------- VAE
+
+VAE_CFG = dict(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2)  # vae.py:911-918
+VAE_CFG_TINY = dict(dim=32, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2)
+
+VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+            0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]  # vae.py:948-951
+VAE_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+           3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]       # vae.py:952-955
+
+
+def vae_decoder_layout(cfg=VAE_CFG):
+    """Structural description of Decoder3d (vae.py:430-484): list of
+    ("res", cin, cout) | ("attn", c) | ("up3d", c) | ("up2d", c) for `upsamples`,
+    plus the channel count of conv1/middle and of the head."""
+    dim, mult = cfg["dim"], cfg["dim_mult"]
+    dims = [dim * u for u in [mult[-1]] + mult[::-1]]
+    temporal = [False, True, True][::-1]  # temperal_downsample reversed (vae.py:573)
+    ups = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        if i in (1, 2, 3):
+            cin = cin // 2
+        for _ in range(cfg["num_res_blocks"] + 1):
+            ups.append(("res", cin, cout))
+            cin = cout
+        if i != len(mult) - 1:
+            ups.append(("up3d" if temporal[i] else "up2d", cout))
+    return dims[0], ups, dims[-1]
+
+
+def vae_param_shapes(cfg=VAE_CFG):
+    z = cfg["z_dim"]
+    c0, ups, c_out = vae_decoder_layout(cfg)
+    s = {"conv2.weight": (z, z, 1, 1, 1), "conv2.bias": (z,),
+         "decoder.conv1.weight": (c0, z, 3, 3, 3), "decoder.conv1.bias": (c0,)}
+
+    def res(p, ci, co):
+        s[p + "residual.0.gamma"] = (ci, 1, 1, 1)
+        s[p + "residual.2.weight"] = (co, ci, 3, 3, 3)
+        s[p + "residual.2.bias"] = (co,)
+        s[p + "residual.3.gamma"] = (co, 1, 1, 1)
+        s[p + "residual.6.weight"] = (co, co, 3, 3, 3)
+        s[p + "residual.6.bias"] = (co,)
+        if ci != co:
+            s[p + "shortcut.weight"] = (co, ci, 1, 1, 1)
+            s[p + "shortcut.bias"] = (co,)
+
+    res("decoder.middle.0.", c0, c0)
+    s["decoder.middle.1.norm.gamma"] = (c0, 1, 1)
+    s["decoder.middle.1.to_qkv.weight"] = (3 * c0, c0, 1, 1)
+    s["decoder.middle.1.to_qkv.bias"] = (3 * c0,)
+    s["decoder.middle.1.proj.weight"] = (c0, c0, 1, 1)
+    s["decoder.middle.1.proj.bias"] = (c0,)
+    res("decoder.middle.2.", c0, c0)
+    for j, u in enumerate(ups):
+        p = f"decoder.upsamples.{j}."
+        if u[0] == "res":
+            res(p, u[1], u[2])
+        else:
+            c = u[1]
+            s[p + "resample.1.weight"] = (c // 2, c, 3, 3)
+            s[p + "resample.1.bias"] = (c // 2,)
+            if u[0] == "up3d":
+                s[p + "time_conv.weight"] = (2 * c, c, 3, 1, 1)
+                s[p + "time_conv.bias"] = (2 * c,)
+    s["decoder.head.0.gamma"] = (c_out, 1, 1, 1)
+    s["decoder.head.2.weight"] = (3, c_out, 3, 3, 3)
+    s["decoder.head.2.bias"] = (3,)
+    return s
+
+
+def make_vae_tensor(name, shape, seed=0, device="cpu"):
+    if name.endswith("gamma"):
+        return 1.0 + _normal(shape, 0.1, seed, name, device)
+    if name.endswith("bias"):
+        return _normal(shape, 0.02, seed, name, device)
+    # PyTorch default conv init (kaiming_uniform a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)),
+    # scaled x1.7 so activations keep O(1) magnitude through 30 conv layers of random weights
+    fan_in = math.prod(shape[1:])
+    a = 1.7 / math.sqrt(fan_in)
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    t.uniform_(-a, a, generator=_gen(seed, name, device))
+    return t
+
+
+def make_vae_state_dict(cfg=VAE_CFG, seed=0, device="cpu", dtype=torch.float32):
+    return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in vae_param_shapes(cfg).items()}
+
+
+# ------------------------------------------------------------------------ inputs
+
+def make_wan_inputs(cfg, latent_shape, seed=0, batch=1):
+    """latent x~N(0,1) [B,16,T,H,W]; context ~N(0,1) [1,text_len,text_dim]; t=500;
+    i2v: y [20,T,H,W] with first 4 channels in {0,1}."""
+    T, H, W = latent_shape
+    x = _normal((batch, 16, T, H, W), 1.0, seed, "input.x", "cpu")
+    ctx = _normal((1, cfg["text_len"], cfg["text_dim"]), 1.0, seed, "input.context", "cpu")
+    t = torch.tensor([500.0])
+    y = None
+    if cfg["in_dim"] > 16:
+        y = _normal((cfg["in_dim"] - 16, T, H, W), 1.0, seed, "input.y", "cpu")
+        y[:4] = (y[:4] > 0).float()
+    return x, t, ctx, y
