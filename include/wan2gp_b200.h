@@ -1,0 +1,120 @@
+/* wan2gp_b200 -- C ABI of the B200 (sm_100a) kernels behind the Wan DiT denoise / WanVAE decode hot path.
+ *
+ * The reference (deepbeepmeep/Wan2GP) has no FFI on this path: its "operator API" is Python duck typing
+ * (SURVEY.md section 8b).  This header is the boundary BELOW the Python modules that mirror
+ * models/wan/modules/model.py::WanModel and models/wan/modules/vae.py::WanVAE; each entry point names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding the reference side would add.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); kernels never
+ * allocate, never synchronise, and run on `stream` (a cudaStream_t passed as void*).  bf16 = raw 16-bit
+ * brain-float.  Return value 0 = ok, < 0 = error (text from b200_last_error(), thread-local).  No
+ * exceptions cross the ABI.  One host thread drives one device (the reference's single "generation"
+ * worker thread, shared/utils/thread_utils.py:9-52).
+ */
+#ifndef WAN2GP_B200_H
+#define WAN2GP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_DRIVER (-3)
+
+#define B200_ACT_NONE 0
+#define B200_ACT_GELU_TANH 1
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of kernels this library has launched in the calling process (bench.py reports it as gpu_launches) */
+long long b200_launch_count(void);
+
+/* D[M,N] = act(A[M,K] * B^T + bias) [* gate] ; A bf16 row-major (lda), B bf16 [N,K] row-major (ldb)
+ * (nn.Linear weight layout) or, with b_mn_major=1, B bf16 [K,N] row-major.
+ * out: bf16 (out_fp32=0) or fp32 (out_fp32=1); accumulate=1 (fp32 only): out += value (residual stream).
+ * bias/gate: fp32 [N] or NULL; residual_bf16: bf16 [M,N] with row stride ldc, added after the gate, or NULL.
+ * N % 8 == 0, K % 8 == 0, lda/ldb/ldc % 8 == 0 (partial tiles are handled by TMA zero fill + masked stores).
+ * Replaces nn.Linear on the hot path: model.py:322/337 (q,k,v), :405 (o), :551-553/:694-710 (ffn),
+ * :1133-1135 (text_embedding), :659/:710 (gated residual addcmul_), :668 (cross-attn residual). */
+int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                   long long ldc, const float* bias, const float* gate, const void* residual_bf16, int act,
+                   int out_fp32, int accumulate, int b_mn_major, void* stream);
+
+/* y[L,D] bf16 = LN(x[L,D] fp32) * (1 + scale[D]) + shift[D]   (affine=0: WanLayerNorm + modulation, model.py:634-638,
+ * 686-691, 857-861)  or  LN(x) * scale + shift (affine=1: norm3, model.py:664).  D % 4 == 0, D <= 8192. */
+int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, void* y_bf16, int L, int D,
+                     float eps, void* stream);
+
+/* in place on bf16 rows x[L, D] (row stride ld): RoPE(x * rsqrt(mean(x^2)+eps) * w); cos/sin fp32 [L,128] or NULL.
+ * WanRMSNorm over the full dim (model.py:152-175) + apply_rotary_emb (posemb_layers.py:251-269). D % 128 == 0. */
+int b200_rmsnorm_rope(void* x_bf16, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
+                      const float* sin_t, void* stream);
+
+/* out[Lq, H*128] = softmax(q k^T / sqrt(128)) v per head; q/k/v/out bf16 with row strides ldq/ldk/ldv/ldo
+ * (elements), head h at columns [128h, 128h+128).  Non-causal, no mask.
+ * Replaces pay_attention -> sdpa_wrapper (shared/attention.py:208-225) at model.py:385 (self) and :265 (cross). */
+int b200_attention_d128(const void* q, const void* k, const void* v, void* out, int Lq, int Lk, int H, long long ldq,
+                        long long ldk, long long ldv, long long ldo, float scale, void* stream);
+
+/* x fp32 -> bf16, n % 4 == 0 */
+int b200_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
+
+/* Patch embedding Conv3d k=s=(1,2,2) (model.py:1131-1132, 1631, 1731) over cat(x0[C0], x1[C1]) [C,T,H,W] fp32
+ * (x1 = i2v `y`, model.py:1597-1600; NULL/0 for t2v) -> out [L=T*H/2*W/2, D] fp32.  w fp32 [D, (C0+C1)*4]. */
+int b200_patch_embed(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out,
+                     int T, int H, int W, int D, void* stream);
+
+/* unpatchify (model.py:2100-2126): y [L, 4*C] fp32, feature order (ph,pw,c) -> out [C,T,H,W] fp32 */
+int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, void* stream);
+
+/* out[N] = act_out(sum_k act_in(x[k]) W[N,K] + b) fp32 GEMV (time_embedding / time_projection, model.py:1815-1818) */
+int b200_gemv_f32(const float* x, const float* w, const float* b, float* out, int N, int K, int silu_in, int silu_out,
+                  void* stream);
+/* sinusoidal_embedding_1d (model.py:32-42) */
+int b200_sinusoid(float t, float* out, int dim, void* stream);
+/* out[i] = a[i] + b[i % bmod] */
+int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, void* stream);
+
+/* lat -= dt * (u + g (c - u)); uncond may be NULL (no CFG); pred_out optional.  any2video.py:1701-1722 +
+ * euler_scheduler.py:67-86.  n % 4 == 0. */
+int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt, float* pred_out,
+                        long long n, void* stream);
+
+/* ---- WanVAE decode (channels-last bf16 activations [T,H,W,C]) ---- */
+
+/* Causal 3-D / 2-D convolution as implicit GEMM (vae.py:43-63 CausalConv3d, :127-133 Conv2d):
+ * x bf16 [T,H,W,Cin], w bf16 [Cout, kt*kh*kw, Cin] (tap order t,h,w), bias fp32 [Cout] -> out.
+ * Zero padding kh/2, kw/2 in space, (kt-1) frames in FRONT in time.  residual (bf16, same layout as out) is
+ * added when non-NULL (ResidualBlock skip, vae.py:273).
+ * out_mode 0: bf16 [T,H,W,Cout];  1: time-interleave (vae.py:186-189): Cout = 2C, channel s*C+c of frame t goes to
+ * out[(t_off + 2t + s), h, w, c] of a [*,H,W,C] bf16 tensor;  2: planar fp32 [Cout, T, H, W] (decoder head). */
+int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
+                   int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream);
+
+/* y = silu(x / max(||x||_2 over C, 1e-12) * sqrt(C) * gamma) per pixel (vae.py:85-103 RMS_norm + nn.SiLU),
+ * bf16 [P, C] -> bf16 [P, C]; silu=0 skips the activation (AttentionBlock norm, vae.py:293). */
+int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream);
+
+/* nearest-exact 2x spatial upsample (vae.py:105-111, 124-127), bf16 [T,H,W,C] -> [T,2H,2W,C] */
+int b200_upsample2x_cl(const void* x, void* y, int T, int H, int W, int C, void* stream);
+
+/* latent z fp32 [16,T,H,W] -> (z*std+mean) through conv2 1x1x1 (vae.py:631-637) -> bf16 [T,H,W,16] */
+int b200_vae_prologue(const float* z, const float* mean, const float* std, const float* w, const float* b, void* out,
+                      int T, int H, int W, void* stream);
+
+/* single-head attention, head dim C <= 512 (C % 64 == 0), per frame over N tokens: qkv bf16 [F, N, 3C];
+ * out bf16 [F, N, C] (vae.py:276-315 AttentionBlock core, F.scaled_dot_product_attention).
+ * workspace: caller-owned, >= N * roundup(N,64) * 6 bytes (fp32 scores + bf16 probabilities of one frame). */
+int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
+                         float scale, void* stream);
+
+/* frames fp32 planar [3,T,H,W] -> uint8 [3,T,H,W]: round(clamp((clamp(x,-1,1)+1)*127.5,0,255)) (vae.py:18-20) */
+int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,299 @@
+// C ABI (include/wan2gp_b200.h) -> kernel launches.  Host-side work here is only: argument checks,
+// TMA descriptor encoding (cuTensorMapEncodeTiled via the runtime's driver entry point, so the library
+// has no link-time dependency on libcuda and loads on a CPU-only box), grid sizing, launch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/wan2gp_b200.h"
+#include "attn_sm100.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+#include "host_util.h"
+
+using namespace b200;
+
+// ------------------------------------------------------------------ error / bookkeeping
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int b200_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" int b200_version(void) { return 100; }
+extern "C" long long b200_launch_count(void) { return g_launches.load(); }
+
+int b200_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ------------------------------------------------------------------ tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor, dims[0] is the contiguous dimension; strides (bytes) for dims 1..rank-1; 128B swizzle.
+int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box) {
+    auto enc = get_encode();
+    if (!enc) return b200_set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return b200_set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,..] box=[%u,%u,..]", (int)r,
+                              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+                              rank > 1 ? box[1] : 0);
+    return B200_OK;
+}
+
+#define CHECK_LAUNCH(name)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                                \
+        if (e__ != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+        b200_count_launch();                                                                                 \
+    } while (0)
+
+// ------------------------------------------------------------------ GEMM
+template <int BN, bool MN>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_tcgen05_kernel<BN, MN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
+    kern<<<grid, 256, GemmSmem<BN>::kBytes, st>>>(ta, tb, p);
+    CHECK_LAUNCH("gemm_tcgen05");
+    return B200_OK;
+}
+
+int b200_launch_gemm(int BN, bool mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    if (mn) {
+        switch (BN) {
+            case 256: return launch_gemm_inst<256, true>(ta, tb, p, st);
+            case 128: return launch_gemm_inst<128, true>(ta, tb, p, st);
+            case 64: return launch_gemm_inst<64, true>(ta, tb, p, st);
+        }
+    } else {
+        switch (BN) {
+            case 256: return launch_gemm_inst<256, false>(ta, tb, p, st);
+            case 192: return launch_gemm_inst<192, false>(ta, tb, p, st);
+            case 128: return launch_gemm_inst<128, false>(ta, tb, p, st);
+            case 96: return launch_gemm_inst<96, false>(ta, tb, p, st);
+            case 64: return launch_gemm_inst<64, false>(ta, tb, p, st);
+            case 32: return launch_gemm_inst<32, false>(ta, tb, p, st);
+            case 16: return launch_gemm_inst<16, false>(ta, tb, p, st);
+        }
+    }
+    return b200_set_error(B200_ERR_ARG, "no GEMM instance for BN=%d mn=%d", BN, (int)mn);
+}
+
+// N tile: minimise padded columns, with a mild preference for wide tiles (fewer A re-reads, better MMA shape)
+int b200_pick_bn(int N, bool mn) {
+    const int cands_k[] = {256, 192, 128, 96, 64, 32, 16};
+    const int cands_mn[] = {256, 128, 64};
+    const int* c = mn ? cands_mn : cands_k;
+    const int n = mn ? 3 : 7;
+    int best = c[0];
+    double best_cost = 1e30;
+    for (int i = 0; i < n; ++i) {
+        const double padded = (double)((N + c[i] - 1) / c[i]) * c[i];
+        const double cost = padded * (1.0 + 32.0 / c[i]);
+        if (cost < best_cost) { best_cost = cost; best = c[i]; }
+    }
+    return best;
+}
+
+extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                              long long ldc, const float* bias, const float* gate, const void* residual_bf16, int act,
+                              int out_fp32, int accumulate, int b_mn_major, void* stream) {
+    if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return b200_set_error(B200_ERR_ARG, "gemm: null/empty argument");
+    if (N % 8 || K % 8 || lda % 8 || ldb % 8 || ldc % 8) return b200_set_error(B200_ERR_ARG, "gemm: N%%8, K%%8, ld%%8 required (N=%d K=%d)", N, K);
+    if (accumulate && !out_fp32) return b200_set_error(B200_ERR_ARG, "gemm: accumulate needs fp32 out");
+    if (b_mn_major && N % 64) return b200_set_error(B200_ERR_ARG, "gemm: MN-major B needs N%%64==0");
+    const bool mn = b_mn_major != 0;
+    const int BN = b200_pick_bn(N, mn);
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)lda * 2};
+        uint32_t box[2] = {GEMM_BK, GEMM_BM};
+        int r = b200_make_tmap_bf16(&ta, A, 2, dims, str, box);
+        if (r) return r;
+    }
+    if (!mn) {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldb * 2};
+        uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (r) return r;
+    } else {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+        uint64_t str[1] = {(uint64_t)ldb * 2};
+        uint32_t box[2] = {64, GEMM_BK};
+        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (r) return r;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.mode = MODE_LINEAR;
+    p.num_k_iters = (K + GEMM_BK - 1) / GEMM_BK;
+    p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    p.n_tiles = (N + BN - 1) / BN;
+    p.n_group = 16;
+    p.out = out; p.out_fp32 = out_fp32; p.accumulate = accumulate; p.ldc = ldc;
+    p.bias = bias; p.gate = gate; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16); p.act = act;
+    return b200_launch_gemm(BN, mn, ta, tb, p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ attention
+extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, void* out, int Lq, int Lk, int H,
+                                   long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+    if (!q || !k || !v || !out || Lq <= 0 || Lk <= 0 || H <= 0) return b200_set_error(B200_ERR_ARG, "attention: null/empty argument");
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return b200_set_error(B200_ERR_ARG, "attention: row strides must be multiples of 8");
+    CUtensorMap tq, tk, tv;
+    uint32_t box[2] = {64, 128};
+    {
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lq}; uint64_t str[1] = {(uint64_t)ldq * 2};
+        int r = b200_make_tmap_bf16(&tq, q, 2, dims, str, box); if (r) return r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldk * 2};
+        int r = b200_make_tmap_bf16(&tk, k, 2, dims, str, box); if (r) return r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldv * 2};
+        int r = b200_make_tmap_bf16(&tv, v, 2, dims, str, box); if (r) return r;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    AttnParams p;
+    p.Lq = Lq; p.Lk = Lk; p.H = H;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H);
+    attn_fwd_d128_kernel<<<grid, 256, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    CHECK_LAUNCH("attn_fwd_d128");
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ row / elementwise kernels
+extern "C" int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, void* y, int L, int D,
+                                float eps, void* stream) {
+    if (!x || !shift || !scale || !y || L <= 0) return b200_set_error(B200_ERR_ARG, "ln_modulate: null/empty argument");
+    if (D % 4 || D > 256 * 4 * LN_MAXV) return b200_set_error(B200_ERR_ARG, "ln_modulate: D=%d unsupported", D);
+    ln_modulate_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, affine, reinterpret_cast<__nv_bfloat16*>(y), D, eps);
+    CHECK_LAUNCH("ln_modulate");
+    return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_rope(void* x, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
+                                 const float* sin_t, void* stream) {
+    if (!x || !w || L <= 0) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: null/empty argument");
+    if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
+    if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: cos/sin must both be given");
+    rmsnorm_rope_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
+    CHECK_LAUNCH("rmsnorm_rope");
+    return B200_OK;
+}
+
+extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+    if (!x || !y || n <= 0 || n % 4) return b200_set_error(B200_ERR_ARG, "cast: bad argument");
+    const long long n4 = n / 4;
+    cast_f32_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n4);
+    CHECK_LAUNCH("cast_f32_bf16");
+    return B200_OK;
+}
+
+extern "C" int b200_patch_embed(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias,
+                                float* out, int T, int H, int W, int D, void* stream) {
+    if (!x0 || !w || !bias || !out || (C1 > 0 && !x1)) return b200_set_error(B200_ERR_ARG, "patch_embed: null argument");
+    if (H % 2 || W % 2) return b200_set_error(B200_ERR_ARG, "patch_embed: H, W must be even");
+    const int L = T * (H / 2) * (W / 2);
+    dim3 grid((L + PE_TOK - 1) / PE_TOK, (D + PE_CH - 1) / PE_CH);
+    patch_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, w, bias, out, T, H, W, D);
+    CHECK_LAUNCH("patch_embed");
+    return B200_OK;
+}
+
+extern "C" int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, void* stream) {
+    if (!y || !out) return b200_set_error(B200_ERR_ARG, "unpatchify: null argument");
+    const long long n = (long long)C * T * H * W;
+    unpatchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, out, C, T, H, W);
+    CHECK_LAUNCH("unpatchify");
+    return B200_OK;
+}
+
+extern "C" int b200_gemv_f32(const float* x, const float* w, const float* b, float* out, int N, int K, int silu_in,
+                             int silu_out, void* stream) {
+    if (!x || !w || !b || !out || K % 4) return b200_set_error(B200_ERR_ARG, "gemv: bad argument");
+    gemv_f32_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, N, K, silu_in, silu_out);
+    CHECK_LAUNCH("gemv_f32");
+    return B200_OK;
+}
+
+extern "C" int b200_sinusoid(float t, float* out, int dim, void* stream) {
+    if (!out || dim % 2) return b200_set_error(B200_ERR_ARG, "sinusoid: bad argument");
+    sinusoid_kernel<<<(dim / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, dim);
+    CHECK_LAUNCH("sinusoid");
+    return B200_OK;
+}
+
+extern "C" int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, void* stream) {
+    if (!a || !b || !out || n <= 0 || bmod <= 0) return b200_set_error(B200_ERR_ARG, "add_vec: bad argument");
+    add_vec_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, out, n, bmod);
+    CHECK_LAUNCH("add_vec");
+    return B200_OK;
+}
+
+extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt,
+                                   float* pred_out, long long n, void* stream) {
+    if (!lat || !cond || n <= 0 || n % 4) return b200_set_error(B200_ERR_ARG, "cfg_euler_step: bad argument");
+    const long long n4 = n / 4;
+    cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, pred_out, n4);
+    CHECK_LAUNCH("cfg_euler_step");
+    return B200_OK;
+}

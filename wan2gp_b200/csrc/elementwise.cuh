@@ -1,0 +1,259 @@
+// HBM-bound row kernels of the Wan DiT block: LayerNorm+modulation, full-width QK RMSNorm + RoPE,
+// patch embed, head unpatchify, conditioning GEMVs, CFG + scheduler step.  One CTA per token row,
+// 128-bit loads/stores, fp32 statistics, row kept in registers so every tensor is read once.
+#pragma once
+#include "sm100.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// y = LN(x) * (1 + scale) + shift            (WanLayerNorm no-affine + modulation, model.py:634-638, 686-691)
+// y = LN(x) * w + b                          (norm3, model.py:664)         -> bf16
+// x fp32 [L, D] (row stride D), mean/var two-pass in registers (matches torch layer_norm numerics).
+constexpr int LN_MAXV = 8;    // float4 per thread, D <= 256*4*8 = 8192
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+                   int scale_is_affine, __nv_bfloat16* __restrict__ y, int D, float eps) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const int nv = D >> 2;
+    float4 v[LN_MAXV];
+    float s = 0.f;
+    #pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        if (idx < nv) { v[i] = __ldg(xr + idx); s += v[i].x + v[i].y + v[i].z + v[i].w; }
+    }
+    const float mean = block_sum_256(s, red) / D;
+    float q = 0.f;
+    #pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        if (idx < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = rsqrtf(block_sum_256(q, red) / D + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+    #pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        if (idx < nv) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + idx);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + idx);
+            const float add = scale_is_affine ? 0.f : 1.f;
+            const float a = (v[i].x - mean) * rstd * (add + sc.x) + sh.x;
+            const float b = (v[i].y - mean) * rstd * (add + sc.y) + sh.y;
+            const float c = (v[i].z - mean) * rstd * (add + sc.z) + sh.z;
+            const float d = (v[i].w - mean) * rstd * (add + sc.w) + sh.w;
+            yr[idx] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-place on a bf16 row of width D (all heads): x <- RoPE( x * rsqrt(mean(x^2)+eps) * w )
+// WanRMSNorm over the FULL dim (model.py:152-175, production semantics) then the interleaved-pair rotation
+// of posemb_layers.py:251-259 in fp32 with the [L,128] cos/sin tables; cos == nullptr skips RoPE
+// (cross-attention q/k, model.py:255-258).
+constexpr int RN_MAXV = 4;    // uint4 (8 bf16) per thread, D <= 256*8*4 = 8192
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __restrict__ w, int D, float eps,
+                    const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    uint4* xr = reinterpret_cast<uint4*>(x + row * ld);
+    const int nv = D >> 3;
+    uint4 v[RN_MAXV];
+    float s = 0.f;
+    #pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        if (idx < nv) {
+            v[i] = xr[idx];
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
+                s += a * a + b * b;
+            }
+        }
+    }
+    const float r = rsqrtf(block_sum_256(s, red) / D + eps);
+    #pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        if (idx < nv) {
+            const int col = idx << 3;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col + 4));
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            float f[8];
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[2 * k] = __uint_as_float(u[k] << 16) * r * wv[2 * k];
+                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * r * wv[2 * k + 1];
+            }
+            if (cos_t) {
+                const int d = col & 127;        // position inside the 128-wide head
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d));
+                const float4 c1 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d + 4));
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d + 4));
+                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float x0 = f[2 * k], x1 = f[2 * k + 1];
+                    f[2 * k] = x0 * cv[2 * k] - x1 * sv[2 * k];
+                    f[2 * k + 1] = x1 * cv[2 * k + 1] + x0 * sv[2 * k + 1];
+                }
+            }
+            xr[idx] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (context / misc), n % 4 == 0
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding (Conv3d k=s=(1,2,2) == per-token GEMM, model.py:1131-1132, 1631, 1731) in fp32 (the
+// reference locks this layer to fp32, model.py:1330-1371).  x = cat(latent[C0], y[C1]) channel-wise
+// (model.py:1597-1600), [C,T,H,W] fp32; out [L, D] fp32, token order (t, h', w'), K order (c, ph, pw).
+// Tile: 32 tokens x 128 channels per CTA of 256 threads; K walked in chunks of 32 through smem.
+constexpr int PE_TOK = 32, PE_CH = 128, PE_KC = 32;
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ out, int T, int H, int W, int D) {
+    __shared__ float sx[PE_TOK][PE_KC + 1];
+    __shared__ float sw[PE_CH][PE_KC + 1];
+    const int K = (C0 + C1) * 4;
+    const int Hp = H >> 1, Wp = W >> 1;
+    const int L = T * Hp * Wp;
+    const int tok0 = blockIdx.x * PE_TOK, ch0 = blockIdx.y * PE_CH;
+    // thread -> 4 tokens x 4 channels
+    const int tc = threadIdx.x & 31, tt = threadIdx.x >> 5;      // channel lane (x4 strided by 32), token group (4 tokens)
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += PE_KC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < PE_TOK * PE_KC; i += 256) {
+            const int tl = i / PE_KC, k = k0 + (i % PE_KC);
+            const int l = tok0 + tl;
+            float val = 0.f;
+            if (l < L && k < K) {
+                const int t = l / (Hp * Wp), r = l - t * (Hp * Wp), hp = r / Wp, wp = r - hp * Wp;
+                const int c = k >> 2, ph = (k >> 1) & 1, pw = k & 1;
+                const float* src = c < C0 ? x0 + (long long)c * T * H * W : x1 + (long long)(c - C0) * T * H * W;
+                val = __ldg(src + ((long long)t * H + (2 * hp + ph)) * W + 2 * wp + pw);
+            }
+            sx[tl][i % PE_KC] = val;
+        }
+        for (int i = threadIdx.x; i < PE_CH * PE_KC; i += 256) {
+            const int cl = i / PE_KC, k = k0 + (i % PE_KC);
+            sw[cl][i % PE_KC] = (ch0 + cl < D && k < K) ? __ldg(w + (long long)(ch0 + cl) * K + k) : 0.f;
+        }
+        __syncthreads();
+        #pragma unroll 8
+        for (int k = 0; k < PE_KC; ++k) {
+            float a[4], b[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sx[tt * 4 + i][k]; b[i] = sw[tc + 32 * i][k]; }
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int l = tok0 + tt * 4 + i;
+        if (l >= L) continue;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = ch0 + tc + 32 * j;
+            if (ch < D) out[(long long)l * D + ch] = acc[i][j] + __ldg(bias + ch);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unpatchify (model.py:2100-2126): y [L, 4*C] fp32 with feature order (ph, pw, c) -> out [C, T, H, W] fp32
+__global__ void unpatchify_kernel(const float* __restrict__ y, float* __restrict__ out, int C, int T, int H, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)C * T * H * W;
+    if (i >= n) return;
+    const int w = i % W; long long r = i / W;
+    const int h = r % H; r /= H;
+    const int t = r % T; const int c = r / T;
+    const int Hp = H >> 1, Wp = W >> 1;
+    const long long l = ((long long)t * Hp + (h >> 1)) * Wp + (w >> 1);
+    out[i] = __ldg(y + l * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[n] = act_out( sum_k act_in(x[k]) * W[n,k] + b[n] )   fp32 GEMV, one warp per output (time embedding MLP,
+// model.py:1141-1143, 1815-1818: Linear(256,D) SiLU Linear(D,D); time_projection = SiLU Linear(D,6D))
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__global__ void gemv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ out, int N, int K, int silu_in, int silu_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    const float4* wr = reinterpret_cast<const float4*>(w + (long long)n * K);
+    const float4* xr = reinterpret_cast<const float4*>(x);
+    for (int k = lane; k < (K >> 2); k += 32) {
+        float4 xv = __ldg(xr + k);
+        if (silu_in) { xv.x = silu(xv.x); xv.y = silu(xv.y); xv.z = silu(xv.z); xv.w = silu(xv.w); }
+        const float4 wv = __ldg(wr + k);
+        acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        acc += b[n];
+        out[n] = silu_out ? silu(acc) : acc;
+    }
+}
+// sinusoidal_embedding_1d (model.py:32-42): out[0:half] = cos(t * 10000^(-i/half)), out[half:] = sin(...)
+__global__ void sinusoid_kernel(float t, float* __restrict__ out, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim >> 1;
+    if (i >= half) return;
+    const float a = t * powf(10000.f, -(float)i / (float)half);
+    out[i] = cosf(a);
+    out[half + i] = sinf(a);
+}
+// out[j] = a[j] + b[j]   (modulation tables: blocks.i.modulation + e0, head.modulation + e)
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n, int bmod) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i % bmod];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG combine + flow-matching Euler update (any2video.py:1701-1722 plain CFG; euler_scheduler.py:67-86):
+// lat <- lat - dt * (u + g (c - u)); also writes the combined prediction (optional)
+__global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond,
+                                 float g, float dt, float* __restrict__ pred_out, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
+    float4 u = uncond ? __ldg(reinterpret_cast<const float4*>(uncond) + i) : c;
+    float4 p = make_float4(u.x + g * (c.x - u.x), u.y + g * (c.y - u.y), u.z + g * (c.z - u.z), u.w + g * (c.w - u.w));
+    float4 x = reinterpret_cast<float4*>(lat)[i];
+    x.x -= dt * p.x; x.y -= dt * p.y; x.z -= dt * p.z; x.w -= dt * p.w;
+    reinterpret_cast<float4*>(lat)[i] = x;
+    if (pred_out) reinterpret_cast<float4*>(pred_out)[i] = p;
+}
+
+}  // namespace b200

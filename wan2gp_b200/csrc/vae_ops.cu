@@ -1,0 +1,282 @@
+// WanVAE decode kernels (channels-last bf16 activations) and their C ABI entry points.
+// The convolutions reuse the tcgen05 GEMM main loop in MODE_CONV (gemm_sm100.cuh); everything else here is
+// HBM-bound row work with 128-bit accesses.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "../../include/wan2gp_b200.h"
+#include "gemm_sm100.cuh"
+#include "host_util.h"
+
+using namespace b200;
+
+#define CHECK_LAUNCH(name)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                                \
+        if (e__ != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+        b200_count_launch();                                                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// RMS_norm over channels (vae.py:85-103: F.normalize(x, dim=C) * sqrt(C) * gamma) + SiLU, per pixel.
+// LPP lanes cooperate on one pixel, each holding up to two 16-byte chunks (C <= 16 * LPP).
+template <int LPP>
+__global__ void __launch_bounds__(256)
+rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ y,
+                   long long P, int C, int do_silu) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pix = gt / LPP;
+    const int sub = (int)(gt % LPP);
+    const int nchunk = C >> 3;
+    const bool active = pix < P;
+    uint4 v[2];
+    float ss = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int ch = sub + i * LPP;
+        if (active && ch < nchunk) {
+            v[i] = __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch);
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
+                ss += a * a + b * b;
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
+    #pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int ch = sub + i * LPP;
+        if (active && ch < nchunk) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            float f[8];
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[2 * k] = __uint_as_float(u[k] << 16) * inv * g[2 * k];
+                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * inv * g[2 * k + 1];
+            }
+            if (do_silu) {
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
+            }
+            reinterpret_cast<uint4*>(y + pix * C)[ch] =
+                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+    }
+}
+
+template <int LPP>
+static int launch_rms(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st) {
+    const long long threads = P * LPP;
+    rms_silu_cl_kernel<LPP><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), P, C, silu);
+    CHECK_LAUNCH("rms_silu_cl");
+    return B200_OK;
+}
+
+extern "C" int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream) {
+    if (!x || !gamma || !y || P <= 0 || C % 8 || C > 512) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: bad argument (C=%d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunk = C / 8;
+    if (nchunk <= 4) return launch_rms<2>(x, gamma, y, P, C, silu, st);
+    if (nchunk <= 8) return launch_rms<4>(x, gamma, y, P, C, silu, st);
+    if (nchunk <= 16) return launch_rms<8>(x, gamma, y, P, C, silu, st);
+    if (nchunk <= 32) return launch_rms<16>(x, gamma, y, P, C, silu, st);
+    return launch_rms<32>(x, gamma, y, P, C, silu, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest-exact 2x upsample in space, channels-last (vae.py:105-111, 124-127)
+__global__ void upsample2x_cl_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int C8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)T * 2 * H * 2 * W * C8;
+    if (i >= n) return;
+    const int c = i % C8; long long r = i / C8;
+    const int wo = r % (2 * W); r /= (2 * W);
+    const int ho = r % (2 * H); const int t = r / (2 * H);
+    y[i] = __ldg(x + (((long long)t * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+}
+extern "C" int b200_upsample2x_cl(const void* x, void* y, int T, int H, int W, int C, void* stream) {
+    if (!x || !y || C % 8) return b200_set_error(B200_ERR_ARG, "upsample2x_cl: bad argument");
+    const long long n = (long long)T * 4 * H * W * (C / 8);
+    upsample2x_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), T, H, W, C / 8);
+    CHECK_LAUNCH("upsample2x_cl");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// z -> z*std + mean -> conv2 (1x1x1, 16x16, fp32) -> bf16 channels-last [T,H,W,16]   (vae.py:631-637)
+__global__ void vae_prologue_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                    const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                    long long npix) {
+    __shared__ float sw[16 * 16], sb[16], sm[16], ss[16];
+    if (threadIdx.x < 256) sw[threadIdx.x] = w[threadIdx.x];
+    if (threadIdx.x < 16) { sb[threadIdx.x] = b[threadIdx.x]; sm[threadIdx.x] = mean[threadIdx.x]; ss[threadIdx.x] = stdv[threadIdx.x]; }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float x[16];
+    #pragma unroll
+    for (int c = 0; c < 16; ++c) x[c] = __ldg(z + c * npix + i) * ss[c] + sm[c];
+    uint32_t o[8];
+    #pragma unroll
+    for (int co = 0; co < 16; co += 2) {
+        float a0 = sb[co], a1 = sb[co + 1];
+        #pragma unroll
+        for (int c = 0; c < 16; ++c) { a0 = fmaf(sw[co * 16 + c], x[c], a0); a1 = fmaf(sw[(co + 1) * 16 + c], x[c], a1); }
+        o[co >> 1] = pack_bf16x2(a0, a1);
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + i * 16);
+    op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+extern "C" int b200_vae_prologue(const float* z, const float* mean, const float* stdv, const float* w, const float* b, void* out,
+                                 int T, int H, int W, void* stream) {
+    if (!z || !mean || !stdv || !w || !b || !out) return b200_set_error(B200_ERR_ARG, "vae_prologue: null argument");
+    const long long npix = (long long)T * H * W;
+    vae_prologue_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        z, mean, stdv, w, b, reinterpret_cast<__nv_bfloat16*>(out), npix);
+    CHECK_LAUNCH("vae_prologue");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frames -> uint8 (vae.py:18-20)
+__global__ void frames_to_u8_kernel(const float4* __restrict__ x, uchar4* __restrict__ out, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(x + i);
+    auto cvt = [](float f) -> unsigned char {
+        f = fminf(fmaxf(f, -1.f), 1.f);
+        f = rintf((f + 1.f) * 127.5f);              // torch.round == round-half-to-even
+        return (unsigned char)fminf(fmaxf(f, 0.f), 255.f);
+    };
+    out[i] = make_uchar4(cvt(v.x), cvt(v.y), cvt(v.z), cvt(v.w));
+}
+extern "C" int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void* stream) {
+    if (!x || !out || n <= 0 || n % 4) return b200_set_error(B200_ERR_ARG, "frames_to_u8: bad argument");
+    const long long n4 = n / 4;
+    frames_to_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<uchar4*>(out), n4);
+    CHECK_LAUNCH("frames_to_u8");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// causal conv as implicit GEMM
+extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
+                              int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
+    if (!x || !w || !out || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
+    if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
+    if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
+    if (out_mode == 1 && (Cout % 64 || residual)) return b200_set_error(B200_ERR_ARG, "conv3d_cl: bad interleave arguments");
+    const int taps = kt * kh * kw;
+    const int BN = b200_pick_bn(out_mode == 2 ? 16 : Cout, false);
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
+        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, CONV_BW, CONV_BH, 1};
+        int r = b200_make_tmap_bf16(&ta, x, 4, dims, str, box);
+        if (r) return r;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
+        uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2};
+        uint32_t box[3] = {64, 1, (uint32_t)BN};
+        int r = b200_make_tmap_bf16(&tb, w, 3, dims, str, box);
+        if (r) return r;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = MODE_CONV;
+    p.N = Cout;
+    p.T = T; p.H = H; p.W = W; p.kt = kt; p.kh = kh; p.kw = kw;
+    p.cin_chunks = (Cin + 63) / 64;
+    p.num_k_iters = taps * p.cin_chunks;
+    p.tiles_h = (H + CONV_BH - 1) / CONV_BH;
+    p.tiles_w = (W + CONV_BW - 1) / CONV_BW;
+    p.m_tiles = T * p.tiles_h * p.tiles_w;
+    p.M = p.m_tiles * GEMM_BM;
+    p.n_tiles = (Cout + BN - 1) / BN;
+    p.n_group = p.n_tiles;            // weights are small: all N tiles of one pixel tile run back to back
+    p.bias = bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    if (out_mode == 0) {
+        p.out = out;
+        p.st_w = Cout; p.st_h = (long long)W * Cout; p.st_t = (long long)H * W * Cout;
+    } else if (out_mode == 1) {
+        const int C = Cout / 2;
+        p.out = reinterpret_cast<__nv_bfloat16*>(out) + (long long)t_off * H * W * C;
+        p.st_w = C; p.st_h = (long long)W * C; p.st_t = 2LL * H * W * C;
+        p.csplit = C; p.st_split = (long long)H * W * C;
+    } else if (out_mode == 2) {
+        p.out = out; p.out_fp32 = 1; p.planar = 1;
+        p.st_w = 1; p.st_h = W; p.st_t = (long long)H * W; p.st_split = (long long)T * H * W;
+    } else {
+        return b200_set_error(B200_ERR_ARG, "conv3d_cl: out_mode %d", out_mode);
+    }
+    return b200_launch_gemm(BN, false, ta, tb, p, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-head attention for the VAE middle block (1% of decode FLOPs): S = q k^T (tcgen05 GEMM, fp32),
+// row softmax (this kernel), O = P v (tcgen05 GEMM with v as an MN-major B operand).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int N, long long lds, long long ldp, float scale_log2) {
+    extern __shared__ float row[];
+    __shared__ float red[8];
+    const float* sr = s + (long long)blockIdx.x * lds;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += 256) { const float v = sr[i] * scale_log2; row[i] = v; mx = fmaxf(mx, v); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    #pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) { const float e = exp2f(row[i] - mx); row[i] = e; sum += e; }
+    const float inv = 1.f / block_sum_256(sum, red);
+    __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
+    for (int i = threadIdx.x; i < N; i += 256) pr[i] = __float2bfloat16_rn(row[i] * inv);
+}
+
+extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
+                                    float scale, void* stream) {
+    if (!qkv || !out || !workspace) return b200_set_error(B200_ERR_ARG, "attention_1head: null argument");
+    if (C % 64 || N % 8) return b200_set_error(B200_ERR_ARG, "attention_1head: C %% 64 or N %% 8 != 0");
+    const long long Np = (N + 63) / 64 * 64;          // padded row pitch so P is a legal GEMM operand
+    const long long need = (long long)N * Np * 4 + (long long)N * Np * 2;
+    if (workspace_bytes < need) return b200_set_error(B200_ERR_ARG, "attention_1head: workspace %lld < %lld bytes", workspace_bytes, need);
+    float* S = reinterpret_cast<float*>(workspace);
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + (long long)N * Np);
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    if ((long long)N * 4 > 200 * 1024) return b200_set_error(B200_ERR_ARG, "attention_1head: N=%d too large", N);
+    for (int f = 0; f < F; ++f) {
+        const __nv_bfloat16* q = base + (long long)f * N * 3 * C;
+        int r = b200_gemm_bf16(q, q + C, S, N, N, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
+        if (r) return r;
+        softmax_rows_kernel<<<N, 256, N * sizeof(float), st>>>(S, P, N, Np, Np, scale * 1.4426950408889634f);
+        CHECK_LAUNCH("softmax_rows");
+        r = b200_gemm_bf16(P, q + 2 * C, reinterpret_cast<__nv_bfloat16*>(out) + (long long)f * N * C, N, C, N, Np, 3LL * C, C,
+                           nullptr, nullptr, nullptr, 0, 0, 0, 1, stream);
+        if (r) return r;
+    }
+    return B200_OK;
+}

@@ -1,0 +1,143 @@
+"""Thin torch-tensor wrappers over the C ABI.  PyTorch is only the allocator / stream provider here:
+every function checks dtype/layout, passes raw device pointers + the current CUDA stream, and raises
+B200Error on failure (no eager fallback)."""
+import math
+
+import torch
+
+from . import _lib
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t.device.type != "cuda":
+        raise _lib.B200Error(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.B200Error(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def gemm(a, b, out=None, bias=None, gate=None, residual=None, act=0, out_dtype=bf16, accumulate=False, b_mn_major=False):
+    """out[M,N] = act(a[M,K] @ b[N,K]^T + bias) * gate   (b_mn_major: b is [K,N])."""
+    _chk(a, bf16, "a"), _chk(b, bf16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[1] if b_mn_major else b.shape[0]
+    assert (b.shape[0] if b_mn_major else b.shape[1]) == K
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (bf16, f32)
+    for v, n in ((bias, "bias"), (gate, "gate")):
+        if v is not None:
+            _chk(v, f32, n)
+            assert v.numel() == N and v.is_contiguous()
+    if residual is not None:
+        _chk(residual, bf16, "residual")
+        assert residual.shape == (M, N) and residual.stride() == out.stride() and out.dtype == bf16
+    _lib.call("b200_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+              out.stride(0), _p(bias), _p(gate), _p(residual), int(act), int(out.dtype == f32), int(accumulate), int(b_mn_major), _stream())
+    return out
+
+
+def ln_modulate(x, shift, scale, affine=False, eps=1e-6, out=None):
+    _chk(x, f32, "x"), _chk(shift, f32, "shift"), _chk(scale, f32, "scale")
+    L, D = x.shape
+    assert x.is_contiguous() and shift.numel() == D and scale.numel() == D
+    if out is None:
+        out = torch.empty(L, D, device=x.device, dtype=bf16)
+    _lib.call("b200_ln_modulate", x.data_ptr(), shift.data_ptr(), scale.data_ptr(), int(affine), out.data_ptr(), L, D,
+              float(eps), _stream())
+    return out
+
+
+def rmsnorm_rope_(x, w, eps=1e-6, cos=None, sin=None):
+    """In place on bf16 x[L, D] (last dim contiguous, arbitrary row stride)."""
+    _chk(x, bf16, "x"), _chk(w, f32, "w")
+    L, D = x.shape
+    assert x.stride(1) == 1 and w.numel() == D
+    if cos is not None:
+        _chk(cos, f32, "cos"), _chk(sin, f32, "sin")
+        assert cos.shape == (L, 128) and sin.shape == (L, 128) and cos.is_contiguous() and sin.is_contiguous()
+    _lib.call("b200_rmsnorm_rope", x.data_ptr(), x.stride(0), w.data_ptr(), L, D, float(eps), _p(cos), _p(sin), _stream())
+    return x
+
+
+def attention(q, k, v, num_heads, out=None, scale=None):
+    """q [Lq, H*128], k/v [Lk, H*128] bf16 (row-strided views allowed) -> [Lq, H*128] bf16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, bf16, n)
+        assert t.dim() == 2 and t.stride(1) == 1 and t.shape[1] == num_heads * 128
+    Lq, Lk = q.shape[0], k.shape[0]
+    if out is None:
+        out = torch.empty(Lq, num_heads * 128, device=q.device, dtype=bf16)
+    scale = 1.0 / math.sqrt(128) if scale is None else scale
+    _lib.call("b200_attention_d128", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Lq, Lk, num_heads,
+              q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream())
+    return out
+
+
+def cast_bf16(x):
+    _chk(x, f32, "x")
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=bf16)
+    _lib.call("b200_cast_f32_bf16", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def patch_embed(x, y, w, bias, D):
+    """x [C0,T,H,W] fp32, y [C1,T,H,W] fp32 or None, w [D, (C0+C1)*4] fp32 -> [L, D] fp32."""
+    _chk(x, f32, "x"), _chk(w, f32, "w"), _chk(bias, f32, "bias")
+    C0, T, H, W = x.shape
+    C1 = 0 if y is None else y.shape[0]
+    assert x.is_contiguous() and (y is None or y.is_contiguous()) and w.is_contiguous()
+    out = torch.empty(T * (H // 2) * (W // 2), D, device=x.device, dtype=f32)
+    _lib.call("b200_patch_embed", x.data_ptr(), C0, _p(y), C1, w.data_ptr(), bias.data_ptr(), out.data_ptr(), T, H, W, D,
+              _stream())
+    return out
+
+
+def unpatchify(y, C, T, H, W):
+    _chk(y, f32, "y")
+    assert y.is_contiguous() and y.shape == (T * (H // 2) * (W // 2), 4 * C)
+    out = torch.empty(C, T, H, W, device=y.device, dtype=f32)
+    _lib.call("b200_unpatchify", y.data_ptr(), out.data_ptr(), C, T, H, W, _stream())
+    return out
+
+
+def gemv(x, w, b, silu_in=False, silu_out=False):
+    _chk(x, f32, "x"), _chk(w, f32, "w"), _chk(b, f32, "b")
+    N, K = w.shape
+    assert x.numel() == K and w.is_contiguous()
+    out = torch.empty(N, device=x.device, dtype=f32)
+    _lib.call("b200_gemv_f32", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, K, int(silu_in), int(silu_out),
+              _stream())
+    return out
+
+
+def sinusoid(t, dim, device):
+    out = torch.empty(dim, device=device, dtype=f32)
+    _lib.call("b200_sinusoid", float(t), out.data_ptr(), dim, _stream())
+    return out
+
+
+def add_vec(a, b):
+    _chk(a, f32, "a"), _chk(b, f32, "b")
+    out = torch.empty_like(a)
+    _lib.call("b200_add_vec", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), b.numel(), _stream())
+    return out
+
+
+def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None):
+    _chk(lat, f32, "lat"), _chk(cond, f32, "cond")
+    assert lat.is_contiguous() and cond.is_contiguous() and (uncond is None or uncond.is_contiguous())
+    _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
+              lat.numel(), _stream())
+    return lat

@@ -1,0 +1,3 @@
+from .model import WanModel  # noqa: F401
+from .rope import get_rotary_pos_embed  # noqa: F401
+from .vae import WanVAE  # noqa: F401

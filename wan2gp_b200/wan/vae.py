@@ -1,0 +1,217 @@
+"""B200-native Wan2.1 VAE decode with the reference `models/wan/modules/vae.py::WanVAE` API
+(SURVEY.md section 8b level 3): .decode(zs, tile_size), .decode_to_cpu_uint8(zs, tile_size, ...), .mean/.std/.scale,
+.model.z_dim, get_VAE_tile_size.
+
+The reference decodes one latent frame per Python-loop iteration through per-conv feature caches
+(vae.py:639-655).  Here the WHOLE clip is decoded in one pass (180 GB of HBM holds every level of a
+720p x 81-frame decode), using the exact whole-sequence equivalent of the chunked semantics
+(restated and pinned in oracle/vae_oracle.py):
+  * CausalConv3d  = causal conv with two leading zero frames  -> TMA out-of-bounds zero fill, no padded copies
+  * upsample3d    = frame 0 bypasses time_conv; time_conv runs causally over frames 1.. with zero history and
+                    its 2C channels are interleaved in time by the GEMM epilogue's store mapping
+Activations are channels-last bf16 [T,H,W,C]; every conv is a tcgen05 implicit GEMM (csrc/gemm_sm100.cuh).
+"""
+import torch
+
+from .. import _lib, ops, synth
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Conv:
+    """Repacked conv weights: bf16 [Cout, taps, Cin] (tap order t,h,w), fp32 bias."""
+
+    def __init__(self, w, b, device):
+        if w.dim() == 4:                                  # Conv2d [Co,Ci,kh,kw] -> kt = 1
+            w = w.unsqueeze(2)
+        co, ci, kt, kh, kw = w.shape
+        self.cout, self.cin, self.k = co, ci, (kt, kh, kw)
+        self.w = w.detach().to(device, f32).permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw, ci).to(bf16).contiguous()
+        bias = b.detach().to(device, f32)
+        if co % 4:                                        # planar head (Cout=3): pad for safety of vector loads
+            bias = torch.cat([bias, bias.new_zeros(16 - co)])
+        self.b = bias.contiguous()
+
+    def __call__(self, x, residual=None, out=None, out_mode=0, t_off=0):
+        T, H, W, C = x.shape
+        assert C == self.cin and x.is_contiguous() and x.dtype == bf16
+        kt, kh, kw = self.k
+        if out is None:
+            out = (torch.empty(self.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
+                   else torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16))
+        _lib.call("b200_conv3d_cl", x.data_ptr(), self.w.data_ptr(), self.b.data_ptr(),
+                  0 if residual is None else residual.data_ptr(), out.data_ptr(), T, H, W, self.cin, self.cout,
+                  kt, kh, kw, out_mode, t_off, _s())
+        return out
+
+
+def rms_silu(x, gamma, silu=True):
+    y = torch.empty_like(x)
+    C = x.shape[-1]
+    _lib.call("b200_rms_silu_cl", x.data_ptr(), gamma.data_ptr(), y.data_ptr(), x.numel() // C, C, int(silu), _s())
+    return y
+
+
+def upsample2x(x):
+    T, H, W, C = x.shape
+    y = torch.empty(T, 2 * H, 2 * W, C, device=x.device, dtype=bf16)
+    _lib.call("b200_upsample2x_cl", x.data_ptr(), y.data_ptr(), T, H, W, C, _s())
+    return y
+
+
+class WanVAEDecoder(torch.nn.Module):
+    """Decoder half of WanVAE_ (vae.py:549-662); `decode(z, scale)` mirrors WanVAE_.decode."""
+
+    def __init__(self, cfg=None, device="cuda"):
+        super().__init__()
+        self.cfg = dict(cfg or synth.VAE_CFG)
+        self.z_dim = self.cfg["z_dim"]
+        self.upsampler_factor = 1
+        self.device = torch.device(device)
+        self._ready = False
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        dev = self.device
+        g = lambda k: sd[k].detach().to(dev, f32).contiguous()  # noqa: E731
+        self.conv2_w, self.conv2_b = g("conv2.weight").reshape(self.z_dim, self.z_dim), g("conv2.bias")
+        self.conv1 = _Conv(sd["decoder.conv1.weight"], sd["decoder.conv1.bias"], dev)
+
+        def res(p):
+            d = {"g0": g(p + "residual.0.gamma").reshape(-1), "c0": _Conv(sd[p + "residual.2.weight"], sd[p + "residual.2.bias"], dev),
+                 "g1": g(p + "residual.3.gamma").reshape(-1), "c1": _Conv(sd[p + "residual.6.weight"], sd[p + "residual.6.bias"], dev)}
+            if p + "shortcut.weight" in sd:
+                d["sc"] = _Conv(sd[p + "shortcut.weight"], sd[p + "shortcut.bias"], dev)
+            return d
+
+        self.mid0, self.mid2 = res("decoder.middle.0."), res("decoder.middle.2.")
+        a = "decoder.middle.1."
+        c0 = sd[a + "proj.weight"].shape[0]
+        self.attn = {"g": g(a + "norm.gamma").reshape(-1), "wqkv": sd[a + "to_qkv.weight"].detach().to(dev, bf16).reshape(3 * c0, c0).contiguous(),
+                     "bqkv": g(a + "to_qkv.bias"), "wproj": sd[a + "proj.weight"].detach().to(dev, bf16).reshape(c0, c0).contiguous(),
+                     "bproj": g(a + "proj.bias")}
+        _, ups, _ = synth.vae_decoder_layout(self.cfg)
+        self.ups = []
+        for j, u in enumerate(ups):
+            p = f"decoder.upsamples.{j}."
+            if u[0] == "res":
+                self.ups.append(("res", res(p)))
+            else:
+                d = {"conv": _Conv(sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], dev)}
+                if u[0] == "up3d":
+                    d["time"] = _Conv(sd[p + "time_conv.weight"], sd[p + "time_conv.bias"], dev)
+                self.ups.append((u[0], d))
+        self.head_g = g("decoder.head.0.gamma").reshape(-1)
+        self.head = _Conv(sd["decoder.head.2.weight"], sd["decoder.head.2.bias"], dev)
+        self._ready = True
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    # ---- blocks
+    @staticmethod
+    def _res(d, x):
+        h = d["sc"](x) if "sc" in d else x                                   # vae.py:255 shortcut
+        y = d["c0"](rms_silu(x, d["g0"]))
+        return d["c1"](rms_silu(y, d["g1"]), residual=h)                     # vae.py:273 x + h fused in the epilogue
+
+    def _attn(self, x):
+        T, H, W, C = x.shape
+        a = self.attn
+        xn = rms_silu(x, a["g"], silu=False).reshape(T * H * W, C)
+        qkv = ops.gemm(xn, a["wqkv"], bias=a["bqkv"])                        # 1x1 conv == GEMM over pixels
+        N = H * W
+        npad = (N + 63) // 64 * 64
+        ws = torch.empty(N * npad * 6, device=x.device, dtype=torch.uint8)
+        o = torch.empty(T * N, C, device=x.device, dtype=bf16)
+        _lib.call("b200_attention_1head", qkv.data_ptr(), o.data_ptr(), ws.data_ptr(), ws.numel(), T, N, C, float(C) ** -0.5, _s())
+        return ops.gemm(o, a["wproj"], bias=a["bproj"], residual=x.reshape(T * N, C)).reshape(T, H, W, C)
+
+    @staticmethod
+    def _up(kind, d, x):
+        T, H, W, C = x.shape
+        if kind == "up3d" and T > 1:
+            y = torch.empty(2 * T - 1, H, W, C, device=x.device, dtype=bf16)
+            y[0].copy_(x[0])                                                 # frame 0 bypasses time_conv (vae.py:155-158)
+            d["time"](x[1:], out=y, out_mode=1, t_off=1)                     # causal over frames 1.., interleaved store
+            x = y
+        return d["conv"](upsample2x(x))
+
+    @torch.no_grad()
+    def decode_frames(self, z, mean, std):
+        """z [16,Tl,h,w] fp32 on device -> fp32 planar frames [3, 4(Tl-1)+1, 8h, 8w] (un-clamped)."""
+        if not self._ready:
+            raise RuntimeError("WanVAE: load_state_dict() must be called before decode")
+        C, T, H, W = z.shape
+        z = z.to(self.device, f32).contiguous()
+        x = torch.empty(T, H, W, 16, device=self.device, dtype=bf16)
+        _lib.call("b200_vae_prologue", z.data_ptr(), mean.data_ptr(), std.data_ptr(), self.conv2_w.data_ptr(),
+                  self.conv2_b.data_ptr(), x.data_ptr(), T, H, W, _s())
+        x = self.conv1(x)
+        x = self._res(self.mid0, x)
+        x = self._attn(x)
+        x = self._res(self.mid2, x)
+        for kind, d in self.ups:
+            x = self._res(d, x) if kind == "res" else self._up(kind, d, x)
+        return self.head(rms_silu(x, self.head_g), out_mode=2)
+
+    def decode(self, z, scale=None, any_end_frame=False):
+        """WanVAE_.decode contract (vae.py:628-662): z [1,16,T,h,w]; scale = [mean, 1/std] -> [1,3,F,H,W] fp32."""
+        if any_end_frame:
+            raise NotImplementedError("any_end_frame decode is outside the t2v/i2v2_2 hot path")
+        mean, inv_std = scale
+        mean = torch.as_tensor(mean, dtype=f32, device=self.device).contiguous()
+        std = (1.0 / torch.as_tensor(inv_std, dtype=f32, device=self.device)).contiguous()
+        return torch.stack([self.decode_frames(zi, mean, std) for zi in z], 0)
+
+
+class WanVAE:
+    """Mirror of models/wan/modules/vae.py::WanVAE (:935-1027)."""
+
+    def __init__(self, z_dim=16, vae_pth=None, dtype=torch.float, upsampler_factor=1, device="cuda", preprocess_sd=None,
+                 state_dict=None, cfg=None):
+        if upsampler_factor != 1:
+            raise NotImplementedError("upsampler VAE variants are outside the hot path")
+        self.dtype, self.device, self.z_dim = dtype, device, z_dim
+        self.mean = torch.tensor(synth.VAE_MEAN, dtype=f32, device=device)          # vae.py:948-951
+        self.std = torch.tensor(synth.VAE_STD, dtype=f32, device=device)            # vae.py:952-955
+        self.scale = [self.mean, 1.0 / self.std]
+        self.model = WanVAEDecoder(cfg, device)
+        if state_dict is None and vae_pth is not None:
+            state_dict = torch.load(vae_pth, map_location="cpu")
+            if preprocess_sd is not None:
+                state_dict = preprocess_sd(state_dict)
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict)
+
+    @staticmethod
+    def get_VAE_tile_size(vae_config, device_mem_capacity, mixed_precision, output_height=None, output_width=None):
+        """vae.py:968-1000 picks a tile size from free VRAM; on a 180 GB B200 the whole clip is decoded untiled."""
+        return 0
+
+    def decode(self, zs, tile_size=0, any_end_frame=False):
+        """list of [16,Tl,h,w] -> list of fp32 [3,F,H,W] clamped to [-1,1] (vae.py:1012-1017)."""
+        if tile_size and tile_size > 0:
+            raise NotImplementedError("tiled decode is a 'next' row (SURVEY.md 8f.3); B200 decodes untiled")
+        return [self.model.decode(u.unsqueeze(0), self.scale, any_end_frame)[0].clamp_(-1, 1) for u in zs]
+
+    def decode_to_cpu_uint8(self, zs, tile_size=0, target_frames=None, target_height=None, target_width=None,
+                            any_end_frame=False, frame_start=0):
+        """vae.py:1021-1027 -> :741-767: uint8 CPU frames, round(clamp((clamp(x,-1,1)+1)*127.5, 0, 255))."""
+        if tile_size and tile_size > 0:
+            raise NotImplementedError("tiled decode is a 'next' row (SURVEY.md 8f.3); B200 decodes untiled")
+        outs = []
+        for u in zs:
+            fr = self.model.decode(u.unsqueeze(0), self.scale, any_end_frame)[0]
+            n = fr.shape[1]
+            fs = min(max(0, int(frame_start or 0)), n)
+            fe = n if target_frames is None else min(n, fs + int(target_frames))
+            fr = fr[:, fs:fe, :target_height, :target_width].contiguous()
+            u8 = torch.empty(fr.shape, device=fr.device, dtype=torch.uint8)
+            _lib.call("b200_frames_to_u8", fr.data_ptr(), u8.data_ptr(), fr.numel(), _s())
+            outs.append(u8.cpu())
+        return outs
+
+    def encode(self, videos, tile_size=256, any_end_frame=False):
+        raise NotImplementedError("VAE encode is a 'next' row (SURVEY.md 8f.2)")
