@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- denoise-step throughput of the Wan DiT hot path (+ WanVAE decode frames/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W              (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                        (CPU arm: the oracle port on the host cores)
+
+A "step" is ONE denoise step of BASELINE.json configs[1]: Wan2.2 t2v 14B (high+low-noise experts resident), latent
+[1,16,21,90,160] (720p x 81 frames, L = 75 600 tokens), text context [1,512,4096], CFG => two DiT forwards (cond,
+uncond), CFG combine and the flow-matching Euler update; synthetic latents, random-init weights of that architecture.
+Multi-GPU: every rank denoises its own independent sample (north star: batch split, no data-path collective inside a
+step) => weak scaling; value = total steps/s over all ranks, timed on the device, max over ranks.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config, latent (T,H,W), two experts?, description)
+    "wan22_t2v_14b_720p81": ("t2v_2_2", (21, 90, 160), True, "Wan2.2 t2v 14B, latent [1,16,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 12"),
+    "wan21_t2v_1.3b_p": ("t2v_1.3B", (9, 30, 52), False, "Wan2.1 t2v 1.3B, latent [1,16,9,30,52] (BASELINE config 0), CFG pair"),
+    "tiny": ("small", (5, 16, 24), False, "reduced config for smoke runs"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tensor_burst": p["bf16_tflops"], "tensor_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor_burst": 1590.0, "tensor_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def wan_flops_forward(cfg, L, Lt):
+    D, F, nl = cfg["dim"], cfg["ffn_dim"], cfg["num_layers"]
+    per_block = 4.0 * L * L * D + 8.0 * L * D * D + (4.0 * L * D * D + 4.0 * Lt * D * D + 4.0 * L * Lt * D) + 4.0 * L * D * F
+    return nl * per_block
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_steps_per_sec(cfg, thw, steps=1, warmup=0):
+    """Reference CPU arm / cpu_baseline: the oracle port (oracle/wan_oracle.py, fp32, all host threads) on a BOUNDED sample
+    of the workload -- one transformer block of this architecture on a 1-latent-frame slice -- converted to steps/s of
+    the full workload by algorithmic FLOPs (stated as extrapolated)."""
+    from oracle import wan_oracle
+    from wan2gp_b200 import synth
+    T, H, W = thw
+    Ts = 1 if cfg["dim"] > 2000 else T
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    shapes = synth.wan_param_shapes(cfg)
+    sd = {n: synth.make_wan_tensor(n, s, cfg, 0, "cpu") for n, s in shapes.items() if n.startswith("blocks.0.")}
+    Ls = Ts * (H // 2) * (W // 2)
+    x = torch.randn(Ls, cfg["dim"])
+    e0 = torch.randn(6, cfg["dim"]) * 0.1
+    ctx = torch.randn(cfg["text_len"], cfg["dim"])
+    cos, sin = wan_oracle.rope_tables((Ts, H, W))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.time()
+        with torch.no_grad():
+            wan_oracle.block_forward(sd, cfg, 0, x, e0.reshape(1, 6, -1)[0], ctx, cos, sin, False)
+        times.append(time.time() - t0)
+    dt = sum(times[warmup:]) / steps
+    one = dict(cfg, num_layers=1)
+    sample_flops = wan_flops_forward(one, Ls, cfg["text_len"])
+    full_flops = 2.0 * wan_flops_forward(cfg, T * (H // 2) * (W // 2), cfg["text_len"])
+    cpu_flops = sample_flops / dt
+    return cpu_flops / full_flops, dt, threads, f"1 of {cfg['num_layers']} blocks on {Ts} of {T} latent frames (L={Ls}), fp32, extrapolated to the full step by algorithmic FLOPs ({cpu_flops / 1e12:.2f} TFLOP/s measured)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="wan22_t2v_14b_720p81", choices=list(WORKLOADS))
+    ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from wan2gp_b200 import synth
+    cfg_name, thw, two_experts, desc = WORKLOADS[args.workload]
+    cfg = synth.WAN_CONFIGS[cfg_name]
+    T, H, W = thw
+    L = T * (H // 2) * (W // 2)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": args.workload, "description": desc, "latent": [1, 16, T, H, W], "tokens": L, "context": [1, cfg["text_len"], cfg["text_dim"]],
+              "cfg_pair": True, "parallelism": f"{world} independent samples (batch split), 1 per GPU",
+              "l2_policy": "inputs larger than L2 (weights 28 GB / expert, activations > 1 GB per tensor); no flush needed"}
+
+    if args.impl == "reference":
+        # CPU arm: rank 0 only; other ranks exit without work
+        if rank != 0:
+            return
+        v, dt, threads, sample = cpu_port_steps_per_sec(cfg, thw, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": "denoise_steps_per_sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from wan2gp_b200 import _lib, ops
+    from wan2gp_b200.pipeline import WanDenoiser
+    from wan2gp_b200.wan import WanModel, WanVAE, get_rotary_pos_embed
+
+    model = WanModel(**cfg, device=dev).init_synthetic(seed=1)
+    model2 = WanModel(**cfg, device=dev).init_synthetic(seed=2) if two_experts else None
+    den = WanDenoiser(model, model2, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=875, device=dev)
+    freqs = get_rotary_pos_embed(thw)
+    g = torch.Generator().manual_seed(1000 + rank)
+    lat_host = torch.randn(1, 16, T, H, W, generator=g).pin_memory()
+    ctx_host = torch.randn(1, cfg["text_len"], cfg["text_dim"], generator=g).pin_memory()
+    ctxn_host = torch.zeros(1, cfg["text_len"], cfg["text_dim"]).pin_memory()
+    latents = lat_host.to(dev)
+    ctx, ctxn = ctx_host.to(dev), ctxn_host.to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # steps are taken around the expert switch (t = 875) so both experts are exercised like in the real schedule
+    sched = [i for i, t in enumerate(den.timesteps[:-1])]
+    sw = next((i for i in sched if den.timesteps[i] <= 875), 0)
+    first = max(0, sw - (args.warmup + args.steps) // 2)
+
+    def step_idx(k):
+        return min(first + k, den.num_steps - 1)
+
+    for k in range(args.warmup):
+        den.step(latents, step_idx(k), ctx, ctxn, freqs=freqs)
+    barrier()
+    launches0 = _lib.launch_count()
+    ops.TIMED["attention"] = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for k in range(args.steps):
+            den.step(latents, step_idx(args.warmup + k), ctx, ctxn, freqs=freqs)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    att = ops.TIMED.pop("attention")
+    att_ms = [a.elapsed_time(b) for a, b, _ in att]
+    att_work = att[0][2] if att else 0.0
+    ok = bool(torch.isfinite(latents).all())
+
+    # ---- end to end through the public API with host buffers (H2D of latents+contexts, D2H of the new latents, every step)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(e2e_steps):
+        den.step_host(lat_host, step_idx(args.warmup + k), ctx_host, ctxn_host, freqs=freqs)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+
+    times = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(times[0]), float(times[1])
+    pk = peaks()
+    steps_per_s = world * args.steps / (ms / 1000.0)
+    flops_step = 2.0 * wan_flops_forward(cfg, L, cfg["text_len"])
+    att_avg = sum(att_ms) / max(1, len(att_ms))
+    att_tf = att_work / (att_avg * 1e-3) / 1e12 if att_ms else None
+    result = {
+        "metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": config,
+        "e2e": {"value": world * e2e_steps / (e2e_ms / 1000.0), "unit": "steps/s", "steps": e2e_steps,
+                "h2d_bytes_per_step": lat_host.numel() * 4 + ctx_host.numel() * 4 + ctxn_host.numel() * 4,
+                "d2h_bytes_per_step": lat_host.numel() * 4},
+        "gpu_launches": launches,
+        "finite": ok,
+        "model_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12,
+        "model_tensor_frac": flops_step / (ms / args.steps * 1e-3) / 1e12 / pk["tensor_sustained"],
+        "roofline": {"kernel": "attn_fwd_d128_kernel (self-attention, 72% of step FLOPs)", "bound": "tensor", "achieved": att_tf,
+                     "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": None if att_tf is None else att_tf / pk["tensor_sustained"],
+                     "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                     "launches_timed": len(att_ms), "avg_launch_ms": att_avg,
+                     "share_of_step": sum(att_ms) / ms if att_ms else None,
+                     "algorithmic_flops_per_launch": att_work, "traffic": None},
+        "clocks": clk.summary(),
+    }
+
+    # ---- VAE decode frames/s (second half of the metric), one clip per GPU
+    if not args.no_vae:
+        del den, model, model2
+        torch.cuda.empty_cache()
+        vae = WanVAE(device=dev, state_dict=synth.make_vae_state_dict(seed=0))
+        z = torch.randn(16, T, H, W, generator=g).to(dev)
+        nfr = 4 * (T - 1) + 1
+        vae.decode_to_cpu_uint8([z], 0)
+        barrier()
+        l0 = _lib.launch_count()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        reps = 2
+        for _ in range(reps):
+            fr = vae.model.decode_frames(z, vae.mean, vae.std)
+        v1.record()
+        barrier()
+        vms = torch.tensor([v0.elapsed_time(v1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+        vms = float(vms[0]) / reps
+        # end to end: latent on host -> uint8 frames on host
+        zh = z.cpu().pin_memory()
+        tt0 = time.time()
+        u8 = vae.decode_to_cpu_uint8([zh.to(dev, non_blocking=True)], 0)[0]
+        e2e_v = time.time() - tt0
+        vae_flops = 7.9e12 * nfr * (H * W) / (90 * 160)
+        result["vae_decode"] = {"metric": "vae_decode_frames_per_sec", "value": world * nfr / (vms / 1000.0), "unit": "frames/s",
+                                "frames": nfr, "resolution": [8 * H, 8 * W], "ms_per_clip": vms,
+                                "gpu_launches": (_lib.launch_count() - l0) // reps,
+                                "tflops": vae_flops / (vms * 1e-3) / 1e12, "tensor_frac": vae_flops / (vms * 1e-3) / 1e12 / pk["tensor_burst"],
+                                "e2e": {"value": world * nfr / e2e_v, "unit": "frames/s", "h2d_bytes": zh.numel() * 4, "d2h_bytes": u8.numel()}}
+        if dist is not None:
+            # the single collective of the north star: all-gather of decoded uint8 frames over NVLink
+            gathered = [torch.empty_like(u8, device=dev) for _ in range(world)]
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u8d = u8.to(dev)
+            barrier()
+            g0.record()
+            dist.all_gather(gathered, u8d)
+            g1.record()
+            barrier()
+            result["vae_decode"]["allgather_frames_ms"] = g0.elapsed_time(g1)
+            result["vae_decode"]["allgather_bytes"] = u8.numel() * world
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads, sample = cpu_port_steps_per_sec(cfg, thw)
+        result["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample, "sample_seconds": dt}
+    if rank == 0:
+        print(json.dumps(result))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

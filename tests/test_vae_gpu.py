@@ -1,0 +1,58 @@
+"""GPU parity of the WanVAE decode (B200 kernels through the reference-shaped WanVAE API) against the oracle and
+the golden frames produced by the UNMODIFIED reference's chunked decode.  Tolerances: vs the bf16-emulating oracle
+rel-L2 <= 2.5e-2 (two decorrelated bf16 paths through ~35 layers; each is ~1.2e-2 from fp32); vs the reference fp32 frames PSNR >= 35 dB on [-1,1] data (peak 2) and mean |uint8 diff| <= 1.5."""
+import pytest
+import torch
+
+from tests.helpers import load_golden, psnr, rel_l2, vae_case
+from wan2gp_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+bf16 = torch.bfloat16
+
+
+def test_conv3d_vs_torch():
+    import torch.nn.functional as F
+    from wan2gp_b200.wan.vae import _Conv
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (T, H, W, ci, co, k) in [(3, 9, 20, 64, 128, (3, 3, 3)), (2, 8, 16, 96, 96, (3, 3, 3)), (4, 5, 7, 32, 64, (3, 1, 1)),
+                                 (1, 12, 18, 192, 96, (1, 3, 3)), (2, 6, 6, 16, 384, (3, 3, 3)), (3, 8, 8, 128, 3, (3, 3, 3)),
+                                 (2, 4, 4, 128, 256, (1, 1, 1))]:
+        x = torch.randn(T, H, W, ci, device="cuda", generator=g).to(bf16)
+        w = (torch.randn(co, ci, *k, device="cuda", generator=g) * (ci * k[0] * k[1] * k[2]) ** -0.5)
+        b = torch.randn(co, device="cuda", generator=g)
+        conv = _Conv(w, b, "cuda")
+        xp = F.pad(x.float().permute(3, 0, 1, 2)[None], (k[2] // 2, k[2] // 2, k[1] // 2, k[1] // 2, k[0] - 1, 0))
+        ref = F.conv3d(xp.double(), w.to(bf16).double(), b.double())[0]          # [co, T, H, W]
+        if co == 3:
+            out = conv(x, out_mode=2)
+            assert rel_l2(out, ref) < 1e-3
+        else:
+            r = torch.randn(T, H, W, co, device="cuda", generator=g).to(bf16)
+            out = conv(x, residual=r)
+            assert rel_l2(out.permute(3, 0, 1, 2), ref + r.double().permute(3, 0, 1, 2)) < 4e-3
+
+
+@pytest.mark.parametrize("name", ["vae_tiny", "vae_small", "vae_p"])
+def test_vae_decode(name):
+    from oracle import vae_oracle
+    from wan2gp_b200.wan import WanVAE
+    cfg, sd, z = vae_case(name)
+    vae = WanVAE(device="cuda", state_dict=sd, cfg=cfg)
+    got = vae.model.decode(z[None].cuda(), vae.scale)[0].cpu()
+    g = load_golden(name)["out"][0]
+    assert got.shape == g.shape
+    line = f"{name}: vs reference frames rel-L2 {rel_l2(got, g):.3e}, PSNR {psnr(got.clamp(-1, 1), g.clamp(-1, 1), 2.0):.1f} dB"
+    if name != "vae_p":
+        emu = vae_oracle.vae_decode(sd, z, synth.VAE_MEAN, synth.VAE_STD, cfg, emulate_bf16=True)
+        line += f"; vs bf16-emulating oracle {rel_l2(got, emu):.3e}"
+        assert rel_l2(got, emu) < 2.5e-2
+    u8 = vae.decode_to_cpu_uint8([z.cuda()], 0)[0]
+    ref8 = vae_oracle.frames_to_uint8(g)
+    d = (u8.int() - ref8.int()).abs()
+    print(line + f"; uint8 mean|d| {d.float().mean():.3f} max {int(d.max())}")
+    assert u8.dtype == torch.uint8 and u8.device.type == "cpu" and u8.shape == ref8.shape
+    assert psnr(got.clamp(-1, 1), g.clamp(-1, 1), 2.0) > 35.0
+    assert d.float().mean() <= 1.5
+    fl = vae.decode([z.cuda()], 0)[0]
+    assert fl.min() >= -1 and fl.max() <= 1

@@ -1,0 +1,75 @@
+"""Per-kernel timing at the BASELINE shapes (CUDA events, L2-cold inputs via rotation) -> gpurun_out/kernel_bench.json."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from wan2gp_b200 import ops  # noqa: E402
+
+bf16, f32 = torch.bfloat16, torch.float32
+PEAK_TF, PEAK_HBM = 1654.0, 6567.1
+pk = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    d = json.load(open(pk)); PEAK_TF, PEAK_HBM = d["bf16_tflops"], d["hbm_gbs"]
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+rows = []
+
+
+def rec(name, ms, flops=None, bytes_=None):
+    r = {"kernel": name, "ms": ms}
+    if flops:
+        r["tflops"] = flops / ms / 1e9; r["tensor_frac_of_measured_burst"] = r["tflops"] / PEAK_TF
+    if bytes_:
+        r["gbs"] = bytes_ / ms / 1e6; r["hbm_frac_of_measured"] = r["gbs"] / PEAK_HBM
+    rows.append(r); print(json.dumps(r), flush=True)
+
+
+which = sys.argv[1:] or ["gemm", "attn", "rows"]
+L, D, F, H = 75600, 5120, 13824, 40
+if "gemm" in which:
+    a = torch.randn(L, D, device="cuda").to(bf16)
+    for name, N, K, kw in [("qkv L x 3D x D", 3 * D, D, {}), ("o-proj L x D x D (+gate, +=x fp32)", D, D, {"acc": True}),
+                           ("ffn.0 L x F x D (+GELU)", F, D, {"act": 1}), ("ffn.2 L x D x F (+gate, +=x)", D, F, {"acc": True})]:
+        A = a if K == D else torch.randn(L, K, device="cuda").to(bf16)
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(bf16)
+        bias = torch.randn(N, device="cuda")
+        if kw.get("acc"):
+            x = torch.zeros(L, N, device="cuda", dtype=f32); gate = torch.randn(N, device="cuda")
+            fn = lambda: ops.gemm(A, w, out=x, bias=bias, gate=gate, accumulate=True)
+        else:
+            out = torch.empty(L, N, device="cuda", dtype=bf16)
+            fn = lambda: ops.gemm(A, w, out=out, bias=bias, act=kw.get("act", 0))
+        rec("gemm " + name, timeit(fn), flops=2.0 * L * N * K)
+        del w, A
+if "attn" in which:
+    for (Lq, Lk, tag) in [(L, L, "self L=75600 H=40"), (L, 512, "cross Lk=512 H=40"), (32760, 32760, "self L=32760 (480p) H=40")]:
+        qkv = torch.randn(max(Lq, Lk), 3 * D, device="cuda").to(bf16)
+        out = torch.empty(Lq, D, device="cuda", dtype=bf16)
+        fn = lambda: ops.attention(qkv[:Lq, :D], qkv[:Lk, D:2 * D], qkv[:Lk, 2 * D:], H, out=out)
+        rec("attention " + tag, timeit(fn, iters=3, warm=1), flops=4.0 * Lq * Lk * D)
+        del qkv, out
+if "rows" in which:
+    x = torch.randn(L, D, device="cuda"); sh = torch.randn(D, device="cuda"); sc = torch.randn(D, device="cuda")
+    y = torch.empty(L, D, device="cuda", dtype=bf16)
+    rec("ln_modulate L x D", timeit(lambda: ops.ln_modulate(x, sh, sc, out=y)), bytes_=L * D * 6)
+    qkv = torch.randn(L, 3 * D, device="cuda").to(bf16); w = torch.ones(D, device="cuda")
+    cos = torch.randn(L, 128, device="cuda"); sin = torch.randn(L, 128, device="cuda")
+    rec("rmsnorm_rope L x D (strided in qkv)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6, cos, sin)), bytes_=L * D * 4 + L * 128 * 8)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)

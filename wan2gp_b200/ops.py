@@ -14,6 +14,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).  Disabled by default:
+# when `TIMED` holds a kernel name, every launch of it is bracketed by two event records (no synchronisation here).
+TIMED = {}          # name -> list of (start_event, end_event, work) ; filled only for names present as keys
+
+
+def _timed(name, work, fn):
+    rec = TIMED.get(name)
+    if rec is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    rec.append((e0, e1, work))
+    return out
+
+
 def _p(t):
     return 0 if t is None else t.data_ptr()
 
@@ -42,8 +59,9 @@ def gemm(a, b, out=None, bias=None, gate=None, residual=None, act=0, out_dtype=b
     if residual is not None:
         _chk(residual, bf16, "residual")
         assert residual.shape == (M, N) and residual.stride() == out.stride() and out.dtype == bf16
-    _lib.call("b200_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
-              out.stride(0), _p(bias), _p(gate), _p(residual), int(act), int(out.dtype == f32), int(accumulate), int(b_mn_major), _stream())
+    _timed("gemm", 2.0 * M * N * K, lambda: _lib.call(
+        "b200_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+        _p(bias), _p(gate), _p(residual), int(act), int(out.dtype == f32), int(accumulate), int(b_mn_major), _stream()))
     return out
 
 
@@ -79,8 +97,9 @@ def attention(q, k, v, num_heads, out=None, scale=None):
     if out is None:
         out = torch.empty(Lq, num_heads * 128, device=q.device, dtype=bf16)
     scale = 1.0 / math.sqrt(128) if scale is None else scale
-    _lib.call("b200_attention_d128", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Lq, Lk, num_heads,
-              q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream())
+    _timed("attention" if Lq == Lk else "cross_attention", 4.0 * Lq * Lk * num_heads * 128, lambda: _lib.call(
+        "b200_attention_d128", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Lq, Lk, num_heads,
+        q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream()))
     return out
 
 

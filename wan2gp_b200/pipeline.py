@@ -1,0 +1,91 @@
+"""Sampling-loop call sites of the hot path, B200-native.
+
+Mirrors what `models/wan/any2video.py::WanAny2V.generate` does around the denoiser:
+  * flow-matching Euler schedule (shared/utils/euler_scheduler.py:35-86, `sample_solver="euler"`),
+  * Wan2.2 two-expert switch: the high-noise model while t > switch_threshold, then the low-noise model with its own
+    guidance scale (any2video.py:1437-1443, 1491-1492; defaults/t2v_2_2.json: 875, 4 -> 3, flow_shift 12),
+  * CFG: cond / uncond forwards (any2video.py:1625-1646) and the combine u + g (c - u) (:1722) fused with the
+    scheduler update in one kernel,
+  * VAE decode to uint8 frames (:1784).
+The reference's UniPC solver, CFG-Zero*, sliding windows etc. stay in the reference (adjacent rows).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+f32 = torch.float32
+
+
+def euler_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
+    """EulerScheduler.set_timesteps (euler_scheduler.py:35-51): linspace(1000, 1, n) ++ [0], shifted; returns n+1 values."""
+    t = np.append(np.linspace(num_train_timesteps, 1, num_steps, dtype=np.float32), np.float32(0.0)).astype(np.float64)
+    t = t / num_train_timesteps
+    t = shift * t / (1 + (shift - 1) * t) * num_train_timesteps
+    return [float(v) for v in t]
+
+
+class WanDenoiser:
+    """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
+
+    def __init__(self, model, model2=None, vae=None, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0,
+                 switch_threshold=875, device="cuda"):
+        self.model, self.model2, self.vae = model, model2, vae
+        self.device = torch.device(device)
+        self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
+        self.timesteps = euler_timesteps(num_steps, shift)
+        self.num_steps = num_steps
+        self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
+        self._pred = None
+
+    def expert(self, t):
+        """(model, guidance scale) for timestep t (any2video.py:1437-1443: switch when t <= switch_threshold)."""
+        if self.model2 is not None and t <= self.switch_threshold:
+            return self.model2, self.guide2_scale
+        return self.model, self.guide_scale
+
+    @torch.no_grad()
+    def step(self, latents, i, context, context_null=None, y=None, freqs=None, callback=None):
+        """latents fp32 [B,16,T,H,W] on device, updated IN PLACE; returns latents or None if interrupted."""
+        t = self.timesteps[i]
+        dt = (t - self.timesteps[i + 1]) / 1000.0
+        model, g = self.expert(t)
+        tt = torch.tensor([t], dtype=f32)
+        kw = dict(y=y, freqs=freqs, pipeline=self, current_step_no=i, max_steps=self.num_steps, callback=callback)
+        if context_null is None:
+            cond = model([latents], tt, [context], **kw)[0]
+            uncond = None
+        else:
+            # joint pass: same blocks applied to each branch in turn (any2video.py:1634, model.py:2030-2037)
+            cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
+        if cond is None:
+            return None
+        ops.cfg_euler_step_(latents, cond, uncond, g, dt)
+        return latents
+
+    @torch.no_grad()
+    def step_host(self, latents_host, i, context_host, context_null_host=None, y=None, freqs=None):
+        """End-to-end step with HOST buffers (pinned): H2D of the step's inputs, the step, D2H of the new latents."""
+        lat = latents_host.to(self.device, non_blocking=True)
+        ctx = context_host.to(self.device, non_blocking=True)
+        ctxn = None if context_null_host is None else context_null_host.to(self.device, non_blocking=True)
+        out = self.step(lat, i, ctx, ctxn, y=y, freqs=freqs)
+        if out is None:
+            return None
+        latents_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return latents_host
+
+    @torch.no_grad()
+    def generate(self, context, context_null, latent_shape, seed=0, y=None, callback=None, decode=True):
+        """Full schedule: noise -> denoise loop -> VAE decode; returns {"x": uint8 CPU [3,F,H,W]} or latents, None if aborted
+        (contract of WanAny2V.generate, any2video.py:1810-1826)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        latents = torch.randn(1, *latent_shape, dtype=f32, generator=g).to(self.device)      # any2video.py:1470
+        context, context_null = context.to(self.device), (None if context_null is None else context_null.to(self.device))
+        for i in range(self.num_steps):
+            if self.step(latents, i, context, context_null, y=y, callback=callback) is None:
+                return None
+        if not decode or self.vae is None:
+            return {"latents": latents}
+        return {"x": self.vae.decode_to_cpu_uint8([latents[0]], 0)[0]}
