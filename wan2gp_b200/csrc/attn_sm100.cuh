@@ -1,22 +1,23 @@
 // Flash-attention forward for sm_100a: softmax(Q K^T * scale) V, head dim 128, non-causal, no mask
 // (reference: shared/attention.py:208-225 sdpa_wrapper called from models/wan/modules/model.py:385 / :265).
 //
-// One CTA per (128-row Q tile, head); 256 threads:
-//   warp 0    TMA producer : Q tile once, then K_j / V_j tiles (128 keys) through two 2-deep smem rings
-//   warp 1    MMA issuer   : S_j = Q K_j^T  (tcgen05.mma M=128,N=128,K=16 x8, both operands K-major SW128)
-//                            O  += P_j V_j  (A = P_j read from TMEM, B = V_j as an MN-major SW128 operand)
-//   warp 2    TMEM allocator (S double-buffered: cols 0-127 / 128-255, O: cols 256-383, all fp32; the bf16 P_j
-//                            overwrites the first 64 columns of its own S_j buffer)
-//   warps 4-7 softmax      : thread <-> row.  tcgen05.ld the S row, online softmax in the log2 domain
-//                            (ex2.approx), bf16 P packed 2/column and tcgen05.st back to TMEM (no shared-memory
-//                            round trip: with both MMA operands in smem an M=128,N=128 MMA already consumes the
-//                            full 128 B/clk smem bandwidth, so P-through-smem capped the tensor pipe at ~55%),
-//                            lazy O rescale (only when the running max grows by > 2^8, FA-4
-//                            style; exact because l and O always share the same reference max), epilogue
-//                            O / l -> bf16 -> global.
-// S_{j+1} is issued before the softmax of tile j finishes, so tensor pipe and MUFU/FMA pipes overlap.
-// CTAs are rasterised Q-tile-fastest so all CTAs resident at one time share a head and its K/V
-// (2 * Lk * 256 B = 38.7 MB at L = 75 600) stays in the 126 MB L2.
+// One CTA per (256-row Q block = two 128-row Q tiles, head); 384 threads:
+//   warp 0     TMA producer : both Q tiles once, then K_j / V_j tiles (128 keys) through 2-deep smem rings
+//   warp 1     MMA issuer   : S_i = Q_i K_j^T  (tcgen05.mma M=128,N=128,K=16 x8, both operands K-major SW128 smem)
+//                             O_i += P_i V_j   (A = P_i read from TMEM, B = V_j as an MN-major SW128 smem operand)
+//                             issue order  PV0_j, S0_{j+1}, PV1_j, S1_{j+1}: while one softmax warpgroup works on
+//                             its S tile the tensor pipe runs the other Q tile's MMAs (FA-4 style ping-pong)
+//   warp 2     TMEM allocator: S_0 cols 0-127, S_1 cols 128-255, O_0 cols 256-383, O_1 cols 384-511 (fp32);
+//                             bf16 P_i (two keys per 32-bit column) overwrites columns [0,64) of its own S_i
+//   warps 4-7  softmax warpgroup of Q tile 0,  warps 8-11 softmax warpgroup of Q tile 1: thread <-> row.
+//                             Online softmax in the log2 domain (ex2.approx); the S row is read from TMEM in two
+//                             64-column halves (keeps the thread under 168 registers) and P goes straight back to
+//                             TMEM -- no shared-memory round trip: with both operands in smem an M=128,N=128 MMA
+//                             already consumes the full 128 B/clk smem bandwidth.  Lazy O rescale (only when the
+//                             running max grows by > 2^8; exact because l and O always share the same reference
+//                             max).  Epilogue O / l -> bf16 -> global.
+// CTAs are rasterised Q-block-fastest so all CTAs resident at one time share a head and its K/V
+// (2 * Lk * 256 B = 38.7 MB at L = 75 600) stays in the 126 MB L2; K/V smem tiles are shared by both Q tiles.
 #pragma once
 #include <cuda.h>
 
@@ -32,28 +33,30 @@ struct AttnParams {
 };
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 128;
-constexpr int ATT_TILE_BYTES = 128 * 128 * 2;     // one [128][128] bf16 tile = two [128][64] slabs
-constexpr int ATT_KV_STAGES = 3;
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + 1024 + 256;   // Q, K x3, V x3
+constexpr int ATT_QTILES = 2;                      // Q tiles per CTA
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;      // one [128][128] bf16 tile = two [128][64] slabs
+constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (ATT_QTILES + 2 * ATT_KV_STAGES) + 1024 + 256;
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + ATT_TILE_BYTES;                       // ATT_KV_STAGES stages
+    uint8_t* sQ = smem;                                      // 2 tiles
+    uint8_t* sK = sQ + ATT_QTILES * ATT_TILE_BYTES;          // ATT_KV_STAGES stages
     uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;       // ATT_KV_STAGES stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
     uint64_t* q_full = bars;            // [1]
-    uint64_t* k_full = bars + 1;        // [3]
-    uint64_t* k_empty = bars + 4;       // [3]
-    uint64_t* v_full = bars + 7;        // [3]
-    uint64_t* v_empty = bars + 10;      // [3]
-    uint64_t* s_full = bars + 13;       // [2]  MMA -> softmax
-    uint64_t* p_full = bars + 15;       // [2]  softmax -> MMA (128 arrivals)
-    uint64_t* pv_done = bars + 17;      // [2]  MMA -> softmax (tile j -> barrier j&1)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* k_full = bars + 1;        // [2]
+    uint64_t* k_empty = bars + 3;       // [2]
+    uint64_t* v_full = bars + 5;        // [2]
+    uint64_t* v_empty = bars + 7;       // [2]
+    uint64_t* s_full = bars + 9;        // [2]  per Q tile: MMA -> softmax, one phase per KV tile
+    uint64_t* p_full = bars + 11;       // [2]  per Q tile: softmax -> MMA (128 arrivals)
+    uint64_t* pv_done = bars + 13;      // [2]  per Q tile: MMA -> softmax
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,15 +79,18 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_O = tmem_base + 256;
 
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (elect_one()) {
             const int col = head * ATT_D;
-            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-            tma_load_2d(sQ, &tmap_q, q_full, col, q_blk * ATT_BM);
-            tma_load_2d(sQ + ATT_TILE_BYTES / 2, &tmap_q, q_full, col + 64, q_blk * ATT_BM);
+            mbar_arrive_expect_tx(q_full, ATT_QTILES * ATT_TILE_BYTES);
+            #pragma unroll
+            for (int i = 0; i < ATT_QTILES; ++i) {
+                const int r0 = (q_blk * ATT_QTILES + i) * ATT_BM;
+                tma_load_2d(sQ + i * ATT_TILE_BYTES, &tmap_q, q_full, col, r0);
+                tma_load_2d(sQ + i * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_q, q_full, col + 64, r0);
+            }
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j % ATT_KV_STAGES;
                 const uint32_t ph = (j / ATT_KV_STAGES) & 1;
@@ -104,127 +110,159 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (elect_one()) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN, /*b_mn_major=*/false);
             constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, ATT_D, /*b_mn_major=*/true);
-            const uint32_t aQ = smem_u32(sQ);
-            auto issue_s = [&](int j) {
-                const int st = j % ATT_KV_STAGES, sb = j & 1;
-                mbar_wait(&k_full[st], (j / ATT_KV_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t aK = smem_u32(sK + st * ATT_TILE_BYTES);
+            auto issue_s = [&](int i, int j) {              // S_i = Q_i K_j^T into TMEM cols [128 i, 128 i + 128)
+                const uint32_t aQ = smem_u32(sQ + i * ATT_TILE_BYTES);
+                const uint32_t aK = smem_u32(sK + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
                 #pragma unroll
                 for (int kk = 0; kk < ATT_D / 16; ++kk) {
                     const uint32_t off = (kk >> 2) * (ATT_TILE_BYTES / 2) + (kk & 3) * 32;   // slab, then 32 B per K step
-                    umma_bf16_ss(tmem_base + sb * 128, umma_desc_kmajor_sw128(aQ + off), umma_desc_kmajor_sw128(aK + off),
+                    umma_bf16_ss(tmem_base + i * 128, umma_desc_kmajor_sw128(aQ + off), umma_desc_kmajor_sw128(aK + off),
                                  idesc_s, kk != 0);
                 }
-                umma_commit(&k_empty[st]);
-                umma_commit(&s_full[sb]);
+                umma_commit(&s_full[i]);
             };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < n_kv; ++j) {
-                const int st = j % ATT_KV_STAGES, sb = j & 1;
-                // S buffer (j+1)&1 still holds P_{j-1} in its first 64 columns; PV_{j-1} was issued earlier and
-                // tcgen05.mma executes in issue order, so it has consumed P_{j-1} before S_{j+1} overwrites it.
-                if (j + 1 < n_kv) issue_s(j + 1);
-                mbar_wait(&p_full[sb], (j >> 1) & 1);
-                mbar_wait(&v_full[st], (j / ATT_KV_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t aV = smem_u32(sV + st * ATT_TILE_BYTES);
+            auto issue_pv = [&](int i, int j) {             // O_i += P_i V_j ; P_i = bf16 in TMEM cols [128 i, 128 i + 64)
+                const uint32_t aV = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
                 #pragma unroll
                 for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-                    // A = P_j in TMEM: 16 keys = 8 packed columns per K step.
-                    // V tile: two [128 keys][64 d] slabs; MN-major B: K step of 16 keys = 16 rows = 2048 B
-                    umma_bf16_ts(tmem_O, tmem_base + sb * 128 + kk * 8,
+                    // 16 keys = 8 packed TMEM columns of P; V: two [128 keys][64 d] slabs, 16 keys = 16 rows = 2048 B
+                    umma_bf16_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
                                  umma_desc_mnmajor_sw128(aV + kk * 2048, ATT_TILE_BYTES / 2), idesc_o, (j | kk) != 0);
                 }
+                umma_commit(&pv_done[i]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % ATT_KV_STAGES;
+                const uint32_t kvph = (j / ATT_KV_STAGES) & 1;
+                const bool more = j + 1 < n_kv;
+                // ---- Q tile 0: PV0_j then S0_{j+1} (S0_{j+1} overwrites P0_j: tcgen05.mma executes in issue order)
+                mbar_wait(&p_full[0], j & 1);
+                mbar_wait(&v_full[st], kvph);
+                tc_fence_after();
+                issue_pv(0, j);
+                if (more) {
+                    mbar_wait(&k_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
+                    tc_fence_after();
+                    issue_s(0, j + 1);
+                }
+                // ---- Q tile 1
+                mbar_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, j);
                 umma_commit(&v_empty[st]);
-                umma_commit(&pv_done[sb]);
+                if (more) {
+                    issue_s(1, j + 1);
+                    umma_commit(&k_empty[(j + 1) % ATT_KV_STAGES]);
+                }
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
         // ============================ softmax / correction / epilogue ============================
-        const int wq = warp & 3;
+        const int qi = (warp - 4) >> 2;             // Q tile of this warpgroup
+        const int wq = warp & 3;                    // TMEM lane quarter
         const int row = wq * 32 + lane;
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem_base + lane_off + qi * 128;
+        const uint32_t tO = tmem_base + lane_off + 256 + qi * 128;
         float m_used = -INFINITY;      // reference max (log2 domain) shared by l and O
         float l = 0.f;
         for (int j = 0; j < n_kv; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            mbar_wait(&s_full[st], ph);
+            mbar_wait(&s_full[qi], j & 1);
             tc_fence_after();
-            uint32_t v[128];
-            #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_base + lane_off + st * 128 + c * 32, v + c * 32);
-            tmem_ld_wait();
             const int valid = p.Lk - j * ATT_BN;       // >= 128 except for the last, partial tile
-            if (valid < ATT_BN) {
+            // ---- pass 1: row max (two 64-column halves, 8 independent partial maxima for ILP)
+            float mx;
+            {
+                float mx8[8];
                 #pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i >= valid) v[i] = 0xff800000u;   // -inf: keys beyond Lk (TMA zero-filled rows)
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[64];
+                    tmem_ld_32x32b_x32(tS + h * 64, v);
+                    tmem_ld_32x32b_x32(tS + h * 64 + 32, v + 32);
+                    tmem_ld_wait();
+                    if (valid < ATT_BN) {
+                        #pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            if (h * 64 + i >= valid) v[i] = 0xff800000u;   // -inf: keys beyond Lk (TMA zero-filled rows)
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        if (h == 0 && i < 8) mx8[i] = __uint_as_float(v[i]);
+                        else mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
+                    }
+                }
+                mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+                mx *= p.scale_log2;                    // scale > 0, so max commutes with the scaling
             }
-            // 8 independent partial maxima: this warp is the only softmax warp on its scheduler, so ILP (not TLP)
-            // has to hide the 4-cycle ALU latency
-            float mx8[8];
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(v[i]);
-            #pragma unroll
-            for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
-            float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-            mx *= p.scale_log2;                        // scale > 0, so max commutes with the scaling
-            // lazy rescale: keep the old reference max unless the row max grew by more than 8 (factor 256)
+            // ---- lazy rescale: keep the old reference max unless the row max grew by more than 8 (factor 256)
             const bool need = mx > m_used + 8.0f;
             if (__any_sync(0xffffffffu, need)) {
                 const float m_new = need ? mx : m_used;
                 const float alpha = ex2_approx(m_used - m_new);   // first tile: exp2(-inf) = 0
                 if (j > 0) {
                     // O must be complete (PV_{j-1}) before it is rescaled in TMEM
-                    mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    mbar_wait(&pv_done[qi], (j - 1) & 1);
                     tc_fence_after();
                     #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         uint32_t o[32];
-                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld_32x32b_x32(tO + c * 32, o);
                         tmem_ld_wait();
                         #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, o);
+                        tmem_st_32x32b_x32(tO + c * 32, o);
                     }
                     tmem_st_wait();
                 }
                 l *= alpha;
                 m_used = m_new;
             }
-            // P_j (bf16, two keys per 32-bit column) overwrites columns [0,64) of this thread's own S_j row, which is
-            // already in registers; packed in place: v[c] <- (p[2c], p[2c+1]).
+            // ---- pass 2: P = exp2(s * scale - m) -> bf16, packed two keys per column, written over S columns [0,64)
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = -m_used;
             #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * c]), p.scale_log2, neg_m));
-                const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * c + 1]), p.scale_log2, neg_m));
-                ls[c & 3] += e0 + e1;
-                v[c] = pack_bf16x2(e0, e1);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[64];
+                tmem_ld_32x32b_x32(tS + h * 64, v);
+                tmem_ld_32x32b_x32(tS + h * 64 + 32, v + 32);
+                tmem_ld_wait();
+                if (valid < ATT_BN) {
+                    #pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (h * 64 + i >= valid) v[i] = 0xff800000u;
+                }
+                #pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * c]), p.scale_log2, neg_m));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * c + 1]), p.scale_log2, neg_m));
+                    ls[c & 3] += e0 + e1;
+                    v[c] = pack_bf16x2(e0, e1);
+                }
+                // half 0 overwrites S columns [0,32) (already consumed); half 1 overwrites [32,64) (consumed in half 0)
+                tmem_st_32x32b_x32(tS + h * 32, v);
             }
             l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-            tmem_st_32x32b_x32(tmem_base + lane_off + st * 128, v);
-            tmem_st_32x32b_x32(tmem_base + lane_off + st * 128 + 32, v + 32);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_full[st]);
+            mbar_arrive(&p_full[qi]);
         }
         // ---- epilogue: O / l
-        const int jl = n_kv - 1;
-        mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+        mbar_wait(&pv_done[qi], (n_kv - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l;
-        const long long grow = (long long)q_blk * ATT_BM + row;
+        const long long grow = ((long long)q_blk * ATT_QTILES + qi) * ATT_BM + row;
         __nv_bfloat16* orow = p.out + grow * p.ldo + head * ATT_D;
         #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, o);
+            tmem_ld_32x32b_x32(tO + c * 32, o);
             tmem_ld_wait();
             if (grow < p.Lq) {
                 #pragma unroll

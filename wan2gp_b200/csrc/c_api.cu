@@ -214,8 +214,8 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
     p.Lq = Lq; p.Lk = Lk; p.H = H;
     p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
-    dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H);
-    attn_fwd_d128_kernel<<<grid, 256, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H);
+    attn_fwd_d128_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
     CHECK_LAUNCH("attn_fwd_d128");
     return B200_OK;
 }
