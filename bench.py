@@ -191,12 +191,17 @@ def main():
     launches0 = _lib.launch_count()
     ops.TIMED["attention"] = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = bool(os.environ.get("B200_CUDA_PROFILER_RANGE"))     # ncu --profile-from-start off: only the timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     with ClockSampler(local_rank) as clk:
         ev0.record()
         for k in range(args.steps):
             den.step(latents, step_idx(args.warmup + k), ctx, ctxn, freqs=freqs)
         ev1.record()
         barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     att = ops.TIMED.pop("attention")

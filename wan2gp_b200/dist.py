@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, independent samples per rank
+(batch split of the denoising batch), NO data-path collective inside a denoise step, and ONE collective at the end
+of the schedule: the all-gather of the decoded uint8 frames over NVLink (NCCL; gloo on CPU for the tests).
+
+The reference has no distributed layer at all on this path; nothing here mirrors reference code.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend=None, device=None):
+    """Initialise the default process group from torchrun's env (RANK / WORLD_SIZE / MASTER_*). No-op for 1 process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return int(os.environ.get("RANK", "0")), world
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl" and device is not None:
+        kw["device_id"] = torch.device(device)
+    dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard(n_items, rank, world):
+    """Contiguous split of n_items samples over `world` ranks (first n_items % world ranks get one more)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return list(range(start, start + base + (1 if rank < rem else 0)))
+
+
+def allgather_frames(frames, group=None):
+    """frames: uint8 tensor [n_local, 3, F, H, W] (same F,H,W on every rank; n_local may differ by one).
+    Returns the frames of ALL samples in global sample order on every rank -- the single collective of the schedule."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return frames
+    world = dist.get_world_size(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=frames.device)
+    counts[dist.get_rank(group)] = frames.shape[0]
+    dist.all_reduce(counts, group=group)
+    nmax = int(counts.max())
+    pad = frames
+    if frames.shape[0] < nmax:
+        pad = torch.cat([frames, frames.new_zeros((nmax - frames.shape[0],) + tuple(frames.shape[1:]))], 0)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad.contiguous(), group=group)          # ncclAllGather on GPUs, gloo in the CPU tests
+    return torch.cat([out[r][: int(counts[r])] for r in range(world)], 0)
+
+
+def generate_batch(make_denoiser, contexts, context_null, latent_shape, seeds, device=None):
+    """Batch-split generation: rank r denoises + decodes samples shard(len(seeds), r, world) with its own denoiser
+    (weights replicated; both Wan2.2 experts fit one 180 GB GPU), then all ranks all-gather the uint8 frames.
+    `make_denoiser()` returns a wan2gp_b200.pipeline.WanDenoiser with a VAE attached."""
+    rank, world = init(device=device)
+    mine = shard(len(seeds), rank, world)
+    den = make_denoiser()
+    outs = []
+    for i in mine:
+        res = den.generate(contexts[i], context_null, latent_shape, seed=seeds[i])
+        if res is None:
+            return None
+        outs.append(res["x"])
+    dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
+    local = torch.stack(outs, 0).to(dev) if outs else torch.empty((0, 3, 4 * (latent_shape[1] - 1) + 1, 8 * latent_shape[2], 8 * latent_shape[3]), dtype=torch.uint8, device=dev)
+    return allgather_frames(local)
