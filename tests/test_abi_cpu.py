@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library builds for sm_100a, loads without a GPU and exports every symbol include/wan2gp_b200.h
+declares; the product path refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from wan2gp_b200 import build
+    return ctypes.CDLL(build.build())
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "wan2gp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200_\w+)\s*\(", hdr)))
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    from wan2gp_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == names            # the ctypes table binds exactly the header
+    lib.b200_version.restype = ctypes.c_int
+    assert lib.b200_version() >= 100
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma / tcgen05.ld / TMA appear as UTCHMMA / LDTM / UTMALDG in the SASS (B200_PROFILING.md)."""
+    import subprocess
+    from wan2gp_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+def test_no_cpu_fallback():
+    from wan2gp_b200 import _lib, ops
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(_lib.B200Error):
+        ops.gemm(a, a)
+    with pytest.raises(_lib.B200Error):
+        ops.ln_modulate(torch.zeros(4, 8), torch.zeros(8), torch.zeros(8))
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    lib.b200_last_error.restype = ctypes.c_char_p
+    rc = lib.b200_gemm_bf16(None, None, None, 0, 0, 0, 0, 0, 0, None, None, None, 0, 0, 0, 0, None)
+    assert rc == -1 and b"gemm" in lib.b200_last_error()
+
+
+def test_wanmodel_api_contract():
+    from wan2gp_b200.wan import WanModel
+    from wan2gp_b200.wan.rope import get_rotary_pos_embed
+    m = WanModel(model_type="t2v", dim=256, ffn_dim=768, num_heads=2, num_layers=2, text_dim=128, text_len=64, device="cpu")
+    with pytest.raises(RuntimeError):
+        m([torch.zeros(1, 16, 1, 4, 4)], torch.tensor([1.0]), [torch.zeros(1, 64, 128)])     # weights not loaded
+    with pytest.raises(NotImplementedError):
+        WanModel(model_type="i2v")                           # Wan2.1 i2v (clip cross-attn) is outside the hot path
+    assert WanModel.preprocess_key("model.diffusion_model.blocks.3.block.ffn.0.weight") == "blocks.3.ffn.0.weight"
+    cos, sin = get_rotary_pos_embed((3, 8, 12))
+    assert cos.shape == (3 * 4 * 6, 128) and cos.dtype == torch.float32
+    cos_r, _ = get_rotary_pos_embed((3, 8, 12), enable_RIFLEx=True)
+    assert not torch.equal(cos, cos_r)

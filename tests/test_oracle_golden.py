@@ -55,3 +55,16 @@ def test_cfg_and_euler():
     o2 = wan_oracle.cfg_combine(c, u, 4.0, cfg_star=True, step_no=3)
     alpha = (c * u).sum() / (u.pow(2).sum() + 1e-8)
     assert torch.allclose(o2, alpha * u + 4.0 * (c - alpha * u), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_product_rope_tables_match_reference(name):
+    """wan2gp_b200.wan.rope (product code) reproduces the reference's get_rotary_pos_embed tables bit-exactly."""
+    from tests.helpers import WAN_CASES
+    from wan2gp_b200.wan.rope import get_rotary_pos_embed
+    _, thw, _ = WAN_CASES[name]
+    g = load_golden("wan_" + name)
+    cos, sin = get_rotary_pos_embed(thw)
+    assert torch.equal(cos[:64], g["cos"]) and torch.equal(sin[:64], g["sin"])
+    c2, s2 = wan_oracle.rope_tables(thw)
+    assert torch.equal(cos, c2) and torch.equal(sin, s2)

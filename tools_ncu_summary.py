@@ -1,0 +1,25 @@
+"""Extract the handful of ncu metrics the roofline discussion needs from a .ncu-rep (run where ncu is installed):
+    python tools_ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.per_cycle_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    print("== kernel:", d["Kernel Name"][:100])
+    for k in KEYS:
+        if k in d:
+            print(f"   {k:95s} {d[k]:>16s} {units[hdr.index(k)]}")

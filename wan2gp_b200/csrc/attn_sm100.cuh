@@ -10,10 +10,11 @@
 //   warp 2     TMEM allocator: S_0 cols 0-127, S_1 cols 128-255, O_0 cols 256-383, O_1 cols 384-511 (fp32);
 //                             bf16 P_i (two keys per 32-bit column) overwrites columns [0,64) of its own S_i
 //   warps 4-7  softmax warpgroup of Q tile 0,  warps 8-11 softmax warpgroup of Q tile 1: thread <-> row.
-//                             Online softmax in the log2 domain (ex2.approx); the S row is read from TMEM in two
-//                             64-column halves (keeps the thread under 168 registers) and P goes straight back to
-//                             TMEM -- no shared-memory round trip: with both operands in smem an M=128,N=128 MMA
-//                             already consumes the full 128 B/clk smem bandwidth.  Lazy O rescale (only when the
+//                             Online softmax in the log2 domain (ex2.approx); the whole 128-column S row lives in
+//                             registers (setmaxnreg: 216 for softmax warps, 72 for the service warps) and P goes
+//                             straight back to TMEM in two 64-key halves, each published to the MMA warp as soon as
+//                             it is written -- no shared-memory round trip: with both operands in smem an
+//                             M=128,N=128 MMA already consumes the full 128 B/clk smem bandwidth.  Lazy O rescale (only when the
 //                             running max grows by > 2^8; exact because l and O always share the same reference
 //                             max).  Epilogue O / l -> bf16 -> global.
 // CTAs are rasterised Q-block-fastest so all CTAs resident at one time share a head and its K/V
@@ -39,6 +40,9 @@ constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (ATT_QTILES + 2 * ATT_KV_STAGES) + 1024 + 256;
 
+// POLY: every POLY-th column of a row takes its exp2 on the FMA pipe (0 = all on MUFU).
+// SPLIT: P is handed to the MMA warp in two 64-key halves so P*V starts while the second half is still being computed.
+template <int POLY, bool SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -54,9 +58,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* v_full = bars + 5;        // [2]
     uint64_t* v_empty = bars + 7;       // [2]
     uint64_t* s_full = bars + 9;        // [2]  per Q tile: MMA -> softmax, one phase per KV tile
-    uint64_t* p_full = bars + 11;       // [2]  per Q tile: softmax -> MMA (128 arrivals)
-    uint64_t* pv_done = bars + 13;      // [2]  per Q tile: MMA -> softmax
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* p_full = bars + 11;       // [2][2]  per Q tile, per 64-key half: softmax -> MMA (128 arrivals)
+    uint64_t* pv_done = bars + 15;      // [2]  per Q tile: MMA -> softmax
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,7 +75,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 128);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -80,6 +85,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // softmax threads keep a whole 128-column S row in registers: take registers from the 4 service warps
+    if (warp < 4) {
+    setmaxnreg_dec<72>();
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (elect_one()) {
@@ -125,6 +133,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint32_t aV = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
                 #pragma unroll
                 for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+                    if (kk == 0 || kk == ATT_BN / 32) {     // keys [0,64) / [64,128) of P_i are published separately
+                        mbar_wait(&p_full[i * 2 + (kk != 0)], j & 1);
+                        tc_fence_after();
+                    }
                     // 16 keys = 8 packed TMEM columns of P; V: two [128 keys][64 d] slabs, 16 keys = 16 rows = 2048 B
                     umma_bf16_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
                                  umma_desc_mnmajor_sw128(aV + kk * 2048, ATT_TILE_BYTES / 2), idesc_o, (j | kk) != 0);
@@ -142,9 +154,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint32_t kvph = (j / ATT_KV_STAGES) & 1;
                 const bool more = j + 1 < n_kv;
                 // ---- Q tile 0: PV0_j then S0_{j+1} (S0_{j+1} overwrites P0_j: tcgen05.mma executes in issue order)
-                mbar_wait(&p_full[0], j & 1);
                 mbar_wait(&v_full[st], kvph);
-                tc_fence_after();
                 issue_pv(0, j);
                 if (more) {
                     mbar_wait(&k_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
@@ -152,8 +162,6 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     issue_s(0, j + 1);
                 }
                 // ---- Q tile 1
-                mbar_wait(&p_full[1], j & 1);
-                tc_fence_after();
                 issue_pv(1, j);
                 umma_commit(&v_empty[st]);
                 if (more) {
@@ -163,8 +171,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    }
+    } else {
         // ============================ softmax / correction / epilogue ============================
+        setmaxnreg_inc<216>();
         const int qi = (warp - 4) >> 2;             // Q tile of this warpgroup
         const int wq = warp & 3;                    // TMEM lane quarter
         const int row = wq * 32 + lane;
@@ -177,27 +187,23 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_wait(&s_full[qi], j & 1);
             tc_fence_after();
             const int valid = p.Lk - j * ATT_BN;       // >= 128 except for the last, partial tile
-            // ---- pass 1: row max (two 64-column halves, 8 independent partial maxima for ILP)
+            uint32_t v[128];
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + c * 32, v + c * 32);
+            tmem_ld_wait();
+            if (valid < ATT_BN) {
+                #pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= valid) v[i] = 0xff800000u;   // -inf: keys beyond Lk (TMA zero-filled rows)
+            }
+            // row max with 8 independent partial maxima (ILP: at most two softmax warps share a scheduler)
             float mx;
             {
                 float mx8[8];
                 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[64];
-                    tmem_ld_32x32b_x32(tS + h * 64, v);
-                    tmem_ld_32x32b_x32(tS + h * 64 + 32, v + 32);
-                    tmem_ld_wait();
-                    if (valid < ATT_BN) {
-                        #pragma unroll
-                        for (int i = 0; i < 64; ++i)
-                            if (h * 64 + i >= valid) v[i] = 0xff800000u;   // -inf: keys beyond Lk (TMA zero-filled rows)
-                    }
-                    #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
-                        if (h == 0 && i < 8) mx8[i] = __uint_as_float(v[i]);
-                        else mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
-                    }
-                }
+                for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(v[i]);
+                #pragma unroll
+                for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
                 mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
                 mx *= p.scale_log2;                    // scale > 0, so max commutes with the scaling
             }
@@ -224,34 +230,30 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 l *= alpha;
                 m_used = m_new;
             }
-            // ---- pass 2: P = exp2(s * scale - m) -> bf16, packed two keys per column, written over S columns [0,64)
+            // ---- P = exp2(s * scale - m) -> bf16, two keys per 32-bit column, written over S columns [0,64); packed in
+            //      place (v[h*64 + c] <- keys h*64 + 2c, 2c+1) and published per 64-key half
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = -m_used;
             #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                uint32_t v[64];
-                tmem_ld_32x32b_x32(tS + h * 64, v);
-                tmem_ld_32x32b_x32(tS + h * 64 + 32, v + 32);
-                tmem_ld_wait();
-                if (valid < ATT_BN) {
-                    #pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        if (h * 64 + i >= valid) v[i] = 0xff800000u;
-                }
                 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * c]), p.scale_log2, neg_m));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * c + 1]), p.scale_log2, neg_m));
+                    const float x0 = fmaf(__uint_as_float(v[h * 64 + 2 * c]), p.scale_log2, neg_m);
+                    const float x1 = fmaf(__uint_as_float(v[h * 64 + 2 * c + 1]), p.scale_log2, neg_m);
+                    const float e0 = (POLY > 0 && (2 * c) % POLY == POLY - 1) ? ex2_poly3(x0) : ex2_approx(x0);
+                    const float e1 = (POLY > 0 && (2 * c + 1) % POLY == POLY - 1) ? ex2_poly3(x1) : ex2_approx(x1);
                     ls[c & 3] += e0 + e1;
-                    v[c] = pack_bf16x2(e0, e1);
+                    v[h * 64 + c] = pack_bf16x2(e0, e1);
                 }
-                // half 0 overwrites S columns [0,32) (already consumed); half 1 overwrites [32,64) (consumed in half 0)
-                tmem_st_32x32b_x32(tS + h * 32, v);
+                tmem_st_32x32b_x32(tS + h * 32, v + h * 64);
+                if (SPLIT || h == 1) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    if (SPLIT) mbar_arrive(&p_full[qi * 2 + h]);
+                    else { mbar_arrive(&p_full[qi * 2]); mbar_arrive(&p_full[qi * 2 + 1]); }
+                }
             }
             l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[qi]);
         }
         // ---- epilogue: O / l
         mbar_wait(&pv_done[qi], (n_kv - 1) & 1);

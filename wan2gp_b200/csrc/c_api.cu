@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -204,18 +205,33 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
         uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldv * 2};
         int r = b200_make_tmap_bf16(&tv, v, 2, dims, str, box); if (r) return r;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
     AttnParams p;
     p.Lq = Lq; p.Lk = Lk; p.H = H;
     p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H);
-    attn_fwd_d128_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    // tuning variants (B200_ATT_VARIANT = "<poly><split>", e.g. "41"); the default (1 = no poly, split P) is the measured best
+    static int variant = -1;
+    if (variant < 0) {
+        const char* ev = getenv("B200_ATT_VARIANT");
+        variant = ev ? atoi(ev) : 1;
+    }
+    auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+        kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        return B200_OK;
+    };
+    int rc;
+    switch (variant) {
+        // measured at L=75600, H=40 (profiles/attn_variants_r01.txt): 0: 100.5 ms, 1: 97.3 ms, 41: 98.6 ms, 21: 109.0 ms --
+        // under the 1 kW power cap extra FMA-pipe work for exp2 costs more clock than the MUFU relief buys
+        case 0: rc = launch(attn_fwd_d128_kernel<0, false>); break;
+        case 41: rc = launch(attn_fwd_d128_kernel<4, true>); break;
+        case 21: rc = launch(attn_fwd_d128_kernel<2, true>); break;
+        default: rc = launch(attn_fwd_d128_kernel<0, true>); break;
+    }
+    if (rc) return rc;
     CHECK_LAUNCH("attn_fwd_d128");
     return B200_OK;
 }

@@ -183,6 +183,18 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
     return 0.5f * x * (1.0f + t);
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel err 7.5e-5, far
+// below the bf16 rounding of the softmax probabilities): used for a fraction of each row so MUFU.EX2 (16/clk/SM) is
+// not the only unit the attention softmax depends on.
+__device__ __forceinline__ float ex2_poly3(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
+    const float p = fmaf(fmaf(fmaf(0.05517105758190155f, f, 0.2426096349954605f), f, 0.6932609677314758f), f, 0.9999281764030457f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // p * 2^round(x)
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
