@@ -118,3 +118,72 @@ def load_reference():
 class Pipe:
     """Stand-in for the pipeline object polled at model.py:1997."""
     _interrupt = False
+
+
+# ----------------------------------------------------------------------------- Hunyuan Video
+_loaded_hy = None
+
+
+def load_reference_hy():
+    """Reference HYVideoDiffusionTransformer (models/hyvideo/modules/models.py) importable on CPU.
+    Extra shims: register_to_config must populate self.config (models.py:710), namespace
+    packages for models.hyvideo{,.modules,.utils,.text_encoder}; ByT5Mapper is imported from the reference's own
+    text_encoder/byT5/__init__.py when its imports resolve, else that module is stubbed (byT5 branch unused)."""
+    global _loaded_hy
+    if _loaded_hy is not None:
+        return _loaded_hy
+    import importlib
+    import inspect
+
+    import torch
+    load_reference()          # mmgp / diffusers stubs, namespace package `models`
+    dc = sys.modules["diffusers.configuration_utils"]
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def w(self, *a, **k):
+            ba = inspect.signature(init).bind(self, *a, **k)
+            ba.apply_defaults()
+            self.config = types.SimpleNamespace(**{n: v for n, v in ba.arguments.items() if n != "self"})
+            return init(self, *a, **k)
+        return w
+    dc.register_to_config = register_to_config
+    sys.modules["diffusers"].ModelMixin = sys.modules["diffusers.models"].ModelMixin
+    sys.modules["diffusers"].ConfigMixin = dc.ConfigMixin
+    for name, rel in [("models.hyvideo", "models/hyvideo"), ("models.hyvideo.modules", "models/hyvideo/modules"),
+                      ("models.hyvideo.utils", "models/hyvideo/utils"), ("models.hyvideo.text_encoder", "models/hyvideo/text_encoder")]:
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+        sys.modules[name] = m
+    byt5_real = True
+    try:
+        importlib.import_module("models.hyvideo.text_encoder.byT5")
+    except Exception:
+        byt5_real = False
+
+        class _NNStub(types.ModuleType):
+            def __getattr__(self, k):
+                if k.startswith("__"):
+                    raise AttributeError(k)
+                return type(k, (torch.nn.Module,), {})
+        sys.modules["models.hyvideo.text_encoder.byT5"] = _NNStub("models.hyvideo.text_encoder.byT5")
+    from models.hyvideo.modules.models import HUNYUAN_VIDEO_CONFIG, HYVideoDiffusionTransformer
+    from models.hyvideo.modules.posemb_layers import get_nd_rotary_pos_embed
+    _loaded_hy = types.SimpleNamespace(HYVideoDiffusionTransformer=HYVideoDiffusionTransformer, CONFIGS=HUNYUAN_VIDEO_CONFIG,
+                                       get_nd_rotary_pos_embed=get_nd_rotary_pos_embed, byt5_real=byt5_real)
+    return _loaded_hy
+
+
+def hook_linear_input_cast(model):
+    """The HY blocks hard-cast activations to torch.bfloat16 (models.py:211, 290, 302, 313) so the reference only runs with
+    bf16 weights.  To pin the oracle tightly we run it with fp32 weights and let every nn.Linear/Conv cast its INPUT to the
+    weight dtype (a forward pre-hook; reference code untouched): the run is then fp32 arithmetic with bf16 roundings exactly
+    at the reference's hard-cast points."""
+    import torch
+
+    def pre(m, args):
+        return (args[0].to(m.weight.dtype),) + tuple(args[1:])
+    for mod in model.modules():
+        if isinstance(mod, (torch.nn.Linear, torch.nn.Conv3d)):
+            mod.register_forward_pre_hook(pre)
+    return model
