@@ -26,6 +26,8 @@ extern "C" {
 
 #define B200_ACT_NONE 0
 #define B200_ACT_GELU_TANH 1
+#define B200_ACT_SILU 2
+#define B200_ACT_GELU_ERF 3
 
 const char* b200_last_error(void);
 int b200_version(void);
@@ -44,14 +46,17 @@ int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
                    int out_fp32, int accumulate, int b_mn_major, void* stream);
 
 /* y[L,D] bf16 = LN(x[L,D] fp32) * (1 + scale[D]) + shift[D]   (affine=0: WanLayerNorm + modulation, model.py:634-638,
- * 686-691, 857-861)  or  LN(x) * scale + shift (affine=1: norm3, model.py:664).  D % 4 == 0, D <= 8192. */
-int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, void* y_bf16, int L, int D,
-                     float eps, void* stream);
+ * 686-691, 857-861)  or  LN(x) * scale + shift (affine=1: norm3, model.py:664).  D % 4 == 0, D <= 8192.
+ * pre_round=1 rounds LN(x) to bf16 before the modulation (Hunyuan: hyvideo/modules/models.py:210-216, 289-291). */
+int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, int pre_round, void* y_bf16,
+                     int L, int D, float eps, void* stream);
 
 /* in place on bf16 rows x[L, D] (row stride ld): RoPE(x * rsqrt(mean(x^2)+eps) * w); cos/sin fp32 [L,128] or NULL.
- * WanRMSNorm over the full dim (model.py:152-175) + apply_rotary_emb (posemb_layers.py:251-269). D % 128 == 0. */
+ * WanRMSNorm over the full dim (model.py:152-175) + apply_rotary_emb (posemb_layers.py:251-269). D % 128 == 0.
+ * per_head=1: statistics per 128-wide head with w[128] (Hunyuan RMSNorm.apply_, hyvideo/modules/norm_layers.py:62-70,
+ * used at hyvideo/modules/models.py:226-228, 254-255). */
 int b200_rmsnorm_rope(void* x_bf16, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
-                      const float* sin_t, void* stream);
+                      const float* sin_t, int per_head, void* stream);
 
 /* out[Lq, H*128] = softmax(q k^T / sqrt(128)) v per head; q/k/v/out bf16 with row strides ldq/ldk/ldv/ldo
  * (elements), head h at columns [128h, 128h+128).  Non-causal, no mask.
@@ -63,18 +68,22 @@ int b200_attention_d128(const void* q, const void* k, const void* v, void* out, 
 int b200_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 
 /* Patch embedding Conv3d k=s=(1,2,2) (model.py:1131-1132, 1631, 1731) over cat(x0[C0], x1[C1]) [C,T,H,W] fp32
- * (x1 = i2v `y`, model.py:1597-1600; NULL/0 for t2v) -> out [L=T*H/2*W/2, D] fp32.  w fp32 [D, (C0+C1)*4]. */
+ * (x1 = i2v `y`, model.py:1597-1600; NULL/0 for t2v) -> out [L=T*H/p*W/p, D] fp32.  w fp32 [D, (C0+C1)*p*p].
+ * patch p = 2 (Wan, Hunyuan 1.0) or 1 (Hunyuan 1.5 PatchEmbed, hyvideo/modules/embed_layers.py:9-60). */
 int b200_patch_embed(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out,
-                     int T, int H, int W, int D, void* stream);
+                     int T, int H, int W, int D, int patch, void* stream);
 
-/* unpatchify (model.py:2100-2126): y [L, 4*C] fp32, feature order (ph,pw,c) -> out [C,T,H,W] fp32 */
-int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, void* stream);
+/* unpatchify: y [L, p*p*C] fp32 -> out [C,T,H,W] fp32.  c_major=0: feature order (ph,pw,c) (Wan, model.py:2100-2126);
+ * c_major=1: (c,ph,pw) (Hunyuan, hyvideo/modules/models.py:1235-1248). */
+int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, int patch, int c_major, void* stream);
 
 /* out[N] = act_out(sum_k act_in(x[k]) W[N,K] + b) fp32 GEMV (time_embedding / time_projection, model.py:1815-1818) */
 int b200_gemv_f32(const float* x, const float* w, const float* b, float* out, int N, int K, int silu_in, int silu_out,
                   void* stream);
 /* sinusoidal_embedding_1d (model.py:32-42) */
 int b200_sinusoid(float t, float* out, int dim, void* stream);
+/* out[c] = mean_r x[r, c], fp32 [rows, cols] (masked text mean, hyvideo/modules/token_refiner.py:221-226) */
+int b200_col_mean_f32(const float* x, float* out, int rows, int cols, void* stream);
 /* out[i] = a[i] + b[i % bmod] */
 int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, void* stream);
 

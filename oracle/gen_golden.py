@@ -94,9 +94,36 @@ def run_vae(name):
                         seconds=np.float32(dt), threads=np.int32(torch.get_num_threads()))
 
 
+HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0)}
+
+
+def run_hy(name):
+    from oracle.refshim import hook_linear_input_cast, load_reference_hy
+    hy = load_reference_hy()
+    cfg_name, thw, seed = HY_CASES[name]
+    cfg = synth.HY_CONFIGS[cfg_name]
+    kw = dict(hy.CONFIGS["HYVideo-1_5"])
+    kw.update({k: cfg[k] for k in ("hidden_size", "heads_num", "mlp_width_ratio", "mm_double_blocks_depth", "text_states_dim")})
+    model = hy.HYVideoDiffusionTransformer(i2v_condition_type=None, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], **kw)
+    model = model.eval().requires_grad_(False)
+    sd = synth.make_hy_state_dict(cfg, seed)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.startswith("vision_in") for m in missing), (missing, unexpected)
+    model.cache = None
+    hook_linear_input_cast(model)         # fp32 weights + the reference's own bf16 hard-casts (see oracle/hy_oracle.py)
+    x, t, txt, tm, b5, bm = synth.make_hy_inputs(cfg, thw, seed=seed)
+    cos, sin = hy.get_nd_rotary_pos_embed(cfg["rope_dim_list"], list(thw), theta=256, use_real=True, theta_rescale_factor=1,
+                                             enable_riflex=False)   # as hunyuan.py:716-724 with enable_riflex=False
+    with torch.no_grad():
+        out = model(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Pipe(),
+                    byt5_text_states=b5, byt5_text_mask=bm)
+    print(f"{name}: reference HY forward out {tuple(out.shape)} {out.dtype} absmean {out.float().abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.float().numpy(), cos=cos[:64].numpy(), sin=sin[:64].numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_vae)(n)

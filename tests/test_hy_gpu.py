@@ -1,0 +1,86 @@
+"""GPU parity of the Hunyuan Video 1.5 DiT forward (B200 kernels through the reference-shaped HYVideoDiffusionTransformer
+API) against the bf16-emulating oracle and the golden output of the UNMODIFIED reference (fp32 weights + the reference's
+own bf16 hard-casts, see oracle/hy_oracle.py).  Tolerances: rel-L2 <= 6e-3 vs either."""
+import pytest
+import torch
+
+from tests.helpers import load_golden, psnr, rel_l2
+from wan2gp_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+class Pipe:
+    _interrupt = False
+
+
+def _case():
+    cfg, thw = synth.HY_CONFIGS["hy_tiny"], (3, 6, 10)
+    return cfg, thw, synth.make_hy_state_dict(cfg, 0), synth.make_hy_inputs(cfg, thw, seed=0)
+
+
+def _model(cfg, sd):
+    from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer
+    m = HYVideoDiffusionTransformer(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"],
+                                    out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
+                                    mlp_width_ratio=cfg["mlp_width_ratio"], mm_double_blocks_depth=cfg["mm_double_blocks_depth"],
+                                    mm_single_blocks_depth=0, text_states_dim=cfg["text_states_dim"], text_pool_type=None,
+                                    glyph_byT5_v2=True, use_cond_type_embedding=True, pre_split_qkv=True)
+    m.load_state_dict(sd)
+    return m
+
+
+def test_hy_ops():
+    """per-head RMSNorm + RoPE, SiLU / erf-GELU epilogues, pre-rounded LN modulation, patch-1 embed / unpatchify."""
+    from oracle import hy_oracle, wan_oracle
+    from wan2gp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    L, H = 3 * 6 * 10, 2
+    D = H * 128
+    cos, sin = hy_oracle.rope_tables_hy((3, 6, 10))
+    x = torch.randn(L, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(128, device="cuda", generator=g)
+    ref = hy_oracle.rms_head(x[:, D:2 * D].float().cpu().reshape(L, H, 128), w.cpu())
+    ref = wan_oracle.apply_rope(ref, cos, sin).reshape(L, D)
+    ops.rmsnorm_rope_(x[:, D:2 * D], w, 1e-6, cos.cuda(), sin.cuda(), per_head=True)
+    assert rel_l2(x[:, D:2 * D].cpu(), ref) < 4e-3
+    a = torch.randn(70, 64, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(96, 64, device="cuda", generator=g) / 8).to(torch.bfloat16)
+    lin = a.double() @ b.double().t()
+    assert rel_l2(ops.gemm(a, b, act=2, out_dtype=torch.float32), torch.nn.functional.silu(lin)) < 1e-3
+    assert rel_l2(ops.gemm(a, b, act=3, out_dtype=torch.float32), torch.nn.functional.gelu(lin)) < 1e-3
+    xf = torch.randn(50, 256, device="cuda", generator=g)
+    sh, sc = torch.randn(256, device="cuda", generator=g), torch.randn(256, device="cuda", generator=g) * 0.3
+    ln = torch.nn.functional.layer_norm(xf, (256,), eps=1e-6).to(torch.bfloat16).double()
+    assert rel_l2(ops.ln_modulate(xf, sh, sc, pre_round=True), ln * (1 + sc.double()) + sh.double()) < 4e-3
+    xin = torch.randn(65, 3, 6, 10, device="cuda", generator=g)
+    wpe, bpe = torch.randn(256, 65, device="cuda", generator=g) / 8, torch.randn(256, device="cuda", generator=g)
+    assert rel_l2(ops.patch_embed(xin, None, wpe, bpe, 256, patch=1), xin.reshape(65, -1).t() @ wpe.t() + bpe) < 1e-5
+    y = torch.randn(L, 32, device="cuda", generator=g)
+    assert torch.equal(ops.unpatchify(y, 32, 3, 6, 10, patch=1, c_major=True), y.t().reshape(32, 3, 6, 10))
+    assert rel_l2(ops.col_mean(xf), xf.mean(0)) < 1e-6
+
+
+def test_hy_forward_tiny():
+    from oracle import hy_oracle
+    cfg, thw, sd, (x, t, txt, tm, b5, bm) = _case()
+    m = _model(cfg, sd)
+    cos, sin = hy_oracle.rope_tables_hy(thw)
+    out = m(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Pipe(), byt5_text_states=b5, byt5_text_mask=bm)
+    assert out.shape == (1, cfg["out_channels"]) + thw and out.dtype == torch.float32
+    got = out.cpu()
+    emu = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, emulate_bf16=True)
+    g = load_golden("hy_tiny")["out"]
+    print(f"hy_tiny: vs bf16-emulating oracle {rel_l2(got, emu):.3e}; vs reference {rel_l2(got, g):.3e}, "
+          f"PSNR {psnr(got, g, float(g.abs().max())):.1f} dB")
+    assert rel_l2(got, emu) < 6e-3 and rel_l2(got, g) < 6e-3
+    # rope tables of the product code == reference tables
+    from wan2gp_b200.hyvideo import get_rotary_pos_embed
+    c2, s2 = get_rotary_pos_embed(thw)
+    gg = load_golden("hy_tiny")
+    assert torch.equal(c2[:64], gg["cos"]) and torch.equal(s2[:64], gg["sin"])
+    # interrupt contract (models.py:1146-1149)
+
+    class Stop:
+        _interrupt = True
+    assert m(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Stop(), byt5_text_states=b5, byt5_text_mask=bm) is None

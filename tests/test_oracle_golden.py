@@ -68,3 +68,18 @@ def test_product_rope_tables_match_reference(name):
     assert torch.equal(cos[:64], g["cos"]) and torch.equal(sin[:64], g["sin"])
     c2, s2 = wan_oracle.rope_tables(thw)
     assert torch.equal(cos, c2) and torch.equal(sin, s2)
+
+
+def test_hy_oracle_matches_reference():
+    """Hunyuan Video 1.5 DiT oracle vs the reference run (fp32 weights + the reference's own bf16 hard-casts)."""
+    from oracle import hy_oracle
+    from wan2gp_b200 import synth
+    cfg, thw = synth.HY_CONFIGS["hy_tiny"], (3, 6, 10)
+    sd = synth.make_hy_state_dict(cfg, 0)
+    x, t, txt, tm, b5, bm = synth.make_hy_inputs(cfg, thw, seed=0)
+    g = load_golden("hy_tiny")
+    cos, sin = hy_oracle.rope_tables_hy(thw)
+    assert torch.equal(cos[:64], g["cos"]) and torch.equal(sin[:64], g["sin"])
+    out = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, ref_casts=True)
+    assert rel_l2(out, g["out"]) < 2e-5
+    assert rel_l2(hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, emulate_bf16=True), g["out"]) < 5e-3

@@ -16,16 +16,17 @@ SIGNATURES = {
     "b200_launch_count": [],
     "b200_gemm_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p,
                        c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "b200_ln_modulate": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p],
-    "b200_rmsnorm_rope": [c_void_p, c_ll, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "b200_ln_modulate": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p],
+    "b200_rmsnorm_rope": [c_void_p, c_ll, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "b200_attention_d128": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll,
                             c_float, c_void_p],
     "b200_cast_f32_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "b200_patch_embed": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                         c_void_p],
-    "b200_unpatchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+                         c_int, c_void_p],
+    "b200_unpatchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_gemv_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "b200_sinusoid": [c_float, c_void_p, c_int, c_void_p],
+    "b200_col_mean_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_add_vec": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_ll, c_void_p],
     "b200_conv3d_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -237,21 +237,22 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
 }
 
 // ------------------------------------------------------------------ row / elementwise kernels
-extern "C" int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, void* y, int L, int D,
-                                float eps, void* stream) {
+extern "C" int b200_ln_modulate(const float* x, const float* shift, const float* scale, int affine, int pre_round, void* y,
+                                int L, int D, float eps, void* stream) {
     if (!x || !shift || !scale || !y || L <= 0) return b200_set_error(B200_ERR_ARG, "ln_modulate: null/empty argument");
     if (D % 4 || D > 256 * 4 * LN_MAXV) return b200_set_error(B200_ERR_ARG, "ln_modulate: D=%d unsupported", D);
-    ln_modulate_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, affine, reinterpret_cast<__nv_bfloat16*>(y), D, eps);
+    ln_modulate_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, affine, pre_round, reinterpret_cast<__nv_bfloat16*>(y), D, eps);
     CHECK_LAUNCH("ln_modulate");
     return B200_OK;
 }
 
 extern "C" int b200_rmsnorm_rope(void* x, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
-                                 const float* sin_t, void* stream) {
+                                 const float* sin_t, int per_head, void* stream) {
     if (!x || !w || L <= 0) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: null/empty argument");
     if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
     if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: cos/sin must both be given");
-    rmsnorm_rope_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
+    if (per_head) rmsnorm_rope_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
+    else rmsnorm_rope_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
     CHECK_LAUNCH("rmsnorm_rope");
     return B200_OK;
 }
@@ -265,20 +266,20 @@ extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* st
 }
 
 extern "C" int b200_patch_embed(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias,
-                                float* out, int T, int H, int W, int D, void* stream) {
+                                float* out, int T, int H, int W, int D, int patch, void* stream) {
     if (!x0 || !w || !bias || !out || (C1 > 0 && !x1)) return b200_set_error(B200_ERR_ARG, "patch_embed: null argument");
-    if (H % 2 || W % 2) return b200_set_error(B200_ERR_ARG, "patch_embed: H, W must be even");
-    const int L = T * (H / 2) * (W / 2);
+    if ((patch != 1 && patch != 2) || H % patch || W % patch) return b200_set_error(B200_ERR_ARG, "patch_embed: patch must be 1 or 2 and divide H, W");
+    const int L = T * (H / patch) * (W / patch);
     dim3 grid((L + PE_TOK - 1) / PE_TOK, (D + PE_CH - 1) / PE_CH);
-    patch_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, w, bias, out, T, H, W, D);
+    patch_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, w, bias, out, T, H, W, D, patch);
     CHECK_LAUNCH("patch_embed");
     return B200_OK;
 }
 
-extern "C" int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, void* stream) {
-    if (!y || !out) return b200_set_error(B200_ERR_ARG, "unpatchify: null argument");
+extern "C" int b200_unpatchify(const float* y, float* out, int C, int T, int H, int W, int patch, int c_major, void* stream) {
+    if (!y || !out || (patch != 1 && patch != 2)) return b200_set_error(B200_ERR_ARG, "unpatchify: bad argument");
     const long long n = (long long)C * T * H * W;
-    unpatchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, out, C, T, H, W);
+    unpatchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, out, C, T, H, W, patch, c_major);
     CHECK_LAUNCH("unpatchify");
     return B200_OK;
 }
@@ -302,6 +303,13 @@ extern "C" int b200_add_vec(const float* a, const float* b, float* out, int n, i
     if (!a || !b || !out || n <= 0 || bmod <= 0) return b200_set_error(B200_ERR_ARG, "add_vec: bad argument");
     add_vec_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, out, n, bmod);
     CHECK_LAUNCH("add_vec");
+    return B200_OK;
+}
+
+extern "C" int b200_col_mean_f32(const float* x, float* out, int rows, int cols, void* stream) {
+    if (!x || !out || rows <= 0 || cols <= 0) return b200_set_error(B200_ERR_ARG, "col_mean: bad argument");
+    col_mean_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, out, rows, cols);
+    CHECK_LAUNCH("col_mean");
     return B200_OK;
 }
 

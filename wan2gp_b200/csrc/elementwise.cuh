@@ -13,7 +13,7 @@ namespace b200 {
 constexpr int LN_MAXV = 8;    // float4 per thread, D <= 256*4*8 = 8192
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
-                   int scale_is_affine, __nv_bfloat16* __restrict__ y, int D, float eps) {
+                   int scale_is_affine, int pre_round, __nv_bfloat16* __restrict__ y, int D, float eps) {
     __shared__ float red[8];
     const long long row = blockIdx.x;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
@@ -44,10 +44,15 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
             const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + idx);
             const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + idx);
             const float add = scale_is_affine ? 0.f : 1.f;
-            const float a = (v[i].x - mean) * rstd * (add + sc.x) + sh.x;
-            const float b = (v[i].y - mean) * rstd * (add + sc.y) + sh.y;
-            const float c = (v[i].z - mean) * rstd * (add + sc.z) + sh.z;
-            const float d = (v[i].w - mean) * rstd * (add + sc.w) + sh.w;
+            float n0 = (v[i].x - mean) * rstd, n1 = (v[i].y - mean) * rstd, n2 = (v[i].z - mean) * rstd, n3 = (v[i].w - mean) * rstd;
+            if (pre_round) {     // Hunyuan: LayerNorm output is cast to bf16 BEFORE the modulation (hyvideo/modules/models.py:211)
+                n0 = __bfloat162float(__float2bfloat16_rn(n0)); n1 = __bfloat162float(__float2bfloat16_rn(n1));
+                n2 = __bfloat162float(__float2bfloat16_rn(n2)); n3 = __bfloat162float(__float2bfloat16_rn(n3));
+            }
+            const float a = n0 * (add + sc.x) + sh.x;
+            const float b = n1 * (add + sc.y) + sh.y;
+            const float c = n2 * (add + sc.z) + sh.z;
+            const float d = n3 * (add + sc.w) + sh.w;
             yr[idx] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
         }
     }
@@ -58,7 +63,10 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
 // WanRMSNorm over the FULL dim (model.py:152-175, production semantics) then the interleaved-pair rotation
 // of posemb_layers.py:251-259 in fp32 with the [L,128] cos/sin tables; cos == nullptr skips RoPE
 // (cross-attention q/k, model.py:255-258).
+// PER_HEAD: statistics over each 128-wide head instead (Hunyuan RMSNorm over head_dim, hyvideo/modules/norm_layers.py:62-70;
+// w is then [128]); the 16 lanes that hold one head reduce with shuffles.
 constexpr int RN_MAXV = 4;    // uint4 (8 bf16) per thread, D <= 256*8*4 = 8192
+template <bool PER_HEAD>
 __global__ void __launch_bounds__(256)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __restrict__ w, int D, float eps,
                     const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
@@ -68,27 +76,38 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __
     const int nv = D >> 3;
     uint4 v[RN_MAXV];
     float s = 0.f;
+    float rh[RN_MAXV];
     #pragma unroll
     for (int i = 0; i < RN_MAXV; ++i) {
         const int idx = threadIdx.x + i * 256;
+        float si = 0.f;
         if (idx < nv) {
             v[i] = xr[idx];
             const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
-                s += a * a + b * b;
+                si += a * a + b * b;
             }
         }
+        if (PER_HEAD) {      // 16 consecutive lanes == one head (nv is a multiple of 16, so a head never straddles the tail)
+            #pragma unroll
+            for (int o = 8; o > 0; o >>= 1) si += __shfl_xor_sync(0xffffffffu, si, o);
+            rh[i] = rsqrtf(si / 128.f + eps);
+        }
+        s += si;
     }
-    const float r = rsqrtf(block_sum_256(s, red) / D + eps);
+    float r = 0.f;
+    if (!PER_HEAD) r = rsqrtf(block_sum_256(s, red) / D + eps);
     #pragma unroll
     for (int i = 0; i < RN_MAXV; ++i) {
         const int idx = threadIdx.x + i * 256;
         if (idx < nv) {
             const int col = idx << 3;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col + 4));
+            if (PER_HEAD) r = rh[i];
+            const int wcol = PER_HEAD ? (col & 127) : col;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + wcol));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + wcol + 4));
             const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             float f[8];
@@ -135,11 +154,11 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 constexpr int PE_TOK = 32, PE_CH = 128, PE_KC = 32;
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, const float* __restrict__ w,
-                   const float* __restrict__ bias, float* __restrict__ out, int T, int H, int W, int D) {
+                   const float* __restrict__ bias, float* __restrict__ out, int T, int H, int W, int D, int P /* patch 1 or 2 */) {
     __shared__ float sx[PE_TOK][PE_KC + 1];
     __shared__ float sw[PE_CH][PE_KC + 1];
-    const int K = (C0 + C1) * 4;
-    const int Hp = H >> 1, Wp = W >> 1;
+    const int K = (C0 + C1) * P * P;
+    const int Hp = H / P, Wp = W / P;
     const int L = T * Hp * Wp;
     const int tok0 = blockIdx.x * PE_TOK, ch0 = blockIdx.y * PE_CH;
     // thread -> 4 tokens x 4 channels
@@ -153,9 +172,9 @@ patch_embed_kernel(const float* __restrict__ x0, int C0, const float* __restrict
             float val = 0.f;
             if (l < L && k < K) {
                 const int t = l / (Hp * Wp), r = l - t * (Hp * Wp), hp = r / Wp, wp = r - hp * Wp;
-                const int c = k >> 2, ph = (k >> 1) & 1, pw = k & 1;
+                const int c = k / (P * P), ph = (k / P) % P, pw = k % P;
                 const float* src = c < C0 ? x0 + (long long)c * T * H * W : x1 + (long long)(c - C0) * T * H * W;
-                val = __ldg(src + ((long long)t * H + (2 * hp + ph)) * W + 2 * wp + pw);
+                val = __ldg(src + ((long long)t * H + (P * hp + ph)) * W + P * wp + pw);
             }
             sx[tl][i % PE_KC] = val;
         }
@@ -189,16 +208,18 @@ patch_embed_kernel(const float* __restrict__ x0, int C0, const float* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // unpatchify (model.py:2100-2126): y [L, 4*C] fp32 with feature order (ph, pw, c) -> out [C, T, H, W] fp32
-__global__ void unpatchify_kernel(const float* __restrict__ y, float* __restrict__ out, int C, int T, int H, int W) {
+// c_major = 1: feature order (c, ph, pw) (Hunyuan, hyvideo/modules/models.py:1235-1248); P = patch size 1 or 2
+__global__ void unpatchify_kernel(const float* __restrict__ y, float* __restrict__ out, int C, int T, int H, int W, int P, int c_major) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = (long long)C * T * H * W;
     if (i >= n) return;
     const int w = i % W; long long r = i / W;
     const int h = r % H; r /= H;
     const int t = r % T; const int c = r / T;
-    const int Hp = H >> 1, Wp = W >> 1;
-    const long long l = ((long long)t * Hp + (h >> 1)) * Wp + (w >> 1);
-    out[i] = __ldg(y + l * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c);
+    const int Hp = H / P, Wp = W / P;
+    const long long l = ((long long)t * Hp + (h / P)) * Wp + (w / P);
+    const int sub = (h % P) * P + (w % P);
+    out[i] = __ldg(y + l * (P * P * C) + (c_major ? c * (P * P) + sub : sub * C + c));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -233,6 +254,14 @@ __global__ void sinusoid_kernel(float t, float* __restrict__ out, int dim) {
     const float a = t * powf(10000.f, -(float)i / (float)half);
     out[i] = cosf(a);
     out[half + i] = sinf(a);
+}
+// out[c] = mean over rows of x[rows, cols] (fp32): masked mean of the valid text tokens (hyvideo/modules/token_refiner.py:221-226)
+__global__ void col_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += __ldg(x + (long long)r * cols + c);
+    out[c] = s / rows;
 }
 // out[j] = a[j] + b[j]   (modulation tables: blocks.i.modulation + e0, head.modulation + e)
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n, int bmod) {

@@ -24,7 +24,7 @@
 namespace b200 {
 
 enum { MODE_LINEAR = 0, MODE_CONV = 1 };
-enum { ACT_NONE = 0, ACT_GELU_TANH = 1 };
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_GELU_ERF = 3 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -244,6 +244,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (p.act == ACT_GELU_TANH) {
                     #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+                } else if (p.act == ACT_SILU) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+                } else if (p.act == ACT_GELU_ERF) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.7071067811865476f));
                 }
                 if (p.gate) {
                     #pragma unroll

@@ -65,26 +65,26 @@ def gemm(a, b, out=None, bias=None, gate=None, residual=None, act=0, out_dtype=b
     return out
 
 
-def ln_modulate(x, shift, scale, affine=False, eps=1e-6, out=None):
+def ln_modulate(x, shift, scale, affine=False, eps=1e-6, out=None, pre_round=False):
     _chk(x, f32, "x"), _chk(shift, f32, "shift"), _chk(scale, f32, "scale")
     L, D = x.shape
     assert x.is_contiguous() and shift.numel() == D and scale.numel() == D
     if out is None:
         out = torch.empty(L, D, device=x.device, dtype=bf16)
-    _lib.call("b200_ln_modulate", x.data_ptr(), shift.data_ptr(), scale.data_ptr(), int(affine), out.data_ptr(), L, D,
-              float(eps), _stream())
+    _lib.call("b200_ln_modulate", x.data_ptr(), shift.data_ptr(), scale.data_ptr(), int(affine), int(pre_round), out.data_ptr(),
+              L, D, float(eps), _stream())
     return out
 
 
-def rmsnorm_rope_(x, w, eps=1e-6, cos=None, sin=None):
-    """In place on bf16 x[L, D] (last dim contiguous, arbitrary row stride)."""
+def rmsnorm_rope_(x, w, eps=1e-6, cos=None, sin=None, per_head=False):
+    """In place on bf16 x[L, D] (last dim contiguous, arbitrary row stride); per_head: norm over each 128-wide head, w [128]."""
     _chk(x, bf16, "x"), _chk(w, f32, "w")
     L, D = x.shape
-    assert x.stride(1) == 1 and w.numel() == D
+    assert x.stride(1) == 1 and w.numel() == (128 if per_head else D)
     if cos is not None:
         _chk(cos, f32, "cos"), _chk(sin, f32, "sin")
         assert cos.shape == (L, 128) and sin.shape == (L, 128) and cos.is_contiguous() and sin.is_contiguous()
-    _lib.call("b200_rmsnorm_rope", x.data_ptr(), x.stride(0), w.data_ptr(), L, D, float(eps), _p(cos), _p(sin), _stream())
+    _lib.call("b200_rmsnorm_rope", x.data_ptr(), x.stride(0), w.data_ptr(), L, D, float(eps), _p(cos), _p(sin), int(per_head), _stream())
     return x
 
 
@@ -111,23 +111,23 @@ def cast_bf16(x):
     return y
 
 
-def patch_embed(x, y, w, bias, D):
-    """x [C0,T,H,W] fp32, y [C1,T,H,W] fp32 or None, w [D, (C0+C1)*4] fp32 -> [L, D] fp32."""
+def patch_embed(x, y, w, bias, D, patch=2):
+    """x [C0,T,H,W] fp32, y [C1,T,H,W] fp32 or None, w [D, (C0+C1)*patch^2] fp32 -> [L, D] fp32."""
     _chk(x, f32, "x"), _chk(w, f32, "w"), _chk(bias, f32, "bias")
     C0, T, H, W = x.shape
     C1 = 0 if y is None else y.shape[0]
     assert x.is_contiguous() and (y is None or y.is_contiguous()) and w.is_contiguous()
-    out = torch.empty(T * (H // 2) * (W // 2), D, device=x.device, dtype=f32)
+    out = torch.empty(T * (H // patch) * (W // patch), D, device=x.device, dtype=f32)
     _lib.call("b200_patch_embed", x.data_ptr(), C0, _p(y), C1, w.data_ptr(), bias.data_ptr(), out.data_ptr(), T, H, W, D,
-              _stream())
+              int(patch), _stream())
     return out
 
 
-def unpatchify(y, C, T, H, W):
+def unpatchify(y, C, T, H, W, patch=2, c_major=False):
     _chk(y, f32, "y")
-    assert y.is_contiguous() and y.shape == (T * (H // 2) * (W // 2), 4 * C)
+    assert y.is_contiguous() and y.shape == (T * (H // patch) * (W // patch), patch * patch * C)
     out = torch.empty(C, T, H, W, device=y.device, dtype=f32)
-    _lib.call("b200_unpatchify", y.data_ptr(), out.data_ptr(), C, T, H, W, _stream())
+    _lib.call("b200_unpatchify", y.data_ptr(), out.data_ptr(), C, T, H, W, int(patch), int(c_major), _stream())
     return out
 
 
@@ -144,6 +144,14 @@ def gemv(x, w, b, silu_in=False, silu_out=False):
 def sinusoid(t, dim, device):
     out = torch.empty(dim, device=device, dtype=f32)
     _lib.call("b200_sinusoid", float(t), out.data_ptr(), dim, _stream())
+    return out
+
+
+def col_mean(x):
+    _chk(x, f32, "x")
+    assert x.dim() == 2 and x.is_contiguous()
+    out = torch.empty(x.shape[1], device=x.device, dtype=f32)
+    _lib.call("b200_col_mean_f32", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream())
     return out
 
 

@@ -210,3 +210,80 @@ def make_wan_inputs(cfg, latent_shape, seed=0, batch=1):
         y = _normal((cfg["in_dim"] - 16, T, H, W), 1.0, seed, "input.y", "cpu")
         y[:4] = (y[:4] > 0).float()
     return x, t, ctx, y
+
+
+# --------------------------------------------------------------------------- Hunyuan Video 1.5 (double-stream DiT)
+
+HY_CONFIGS = {
+    # models/hyvideo/modules/models.py:1345-1363 'HYVideo-1_5' + hunyuan.py:230-233 (in 65 / out 32 channels)
+    "HYVideo-1_5": dict(hidden_size=2048, heads_num=16, mlp_width_ratio=4, mm_double_blocks_depth=54, in_channels=65,
+                        out_channels=32, text_states_dim=3584, patch_size=[1, 1, 1], rope_dim_list=[16, 56, 56]),
+    "hy_tiny": dict(hidden_size=256, heads_num=2, mlp_width_ratio=4, mm_double_blocks_depth=2, in_channels=65,
+                    out_channels=32, text_states_dim=96, patch_size=[1, 1, 1], rope_dim_list=[16, 56, 56]),
+}
+HY_BYT5_DIMS = (1472, 2048, 2048)      # ByT5Mapper(in_dim, hidden_dim, out_dim) constants, models.py:647-653
+
+
+def hy_param_shapes(cfg):
+    """name -> shape of HYVideoDiffusionTransformer('HYVideo-1_5' family: pre-split qkv, byT5 mapper, cond-type embedding,
+    token refiner depth 2), SURVEY.md Appendix B.  vision_in.* is not listed (only used with vision_states)."""
+    D, Td, Cin, Co = cfg["hidden_size"], cfg["text_states_dim"], cfg["in_channels"], cfg["out_channels"]
+    F = int(D * cfg["mlp_width_ratio"])
+    bi, bh, bo = HY_BYT5_DIMS
+    pp = cfg["patch_size"][0] * cfg["patch_size"][1] * cfg["patch_size"][2]
+    s = {"byt5_in.layernorm.weight": (bi,), "byt5_in.layernorm.bias": (bi,)}
+
+    def lin(name, o, i):
+        s[name + ".weight"] = (o, i)
+        s[name + ".bias"] = (o,)
+    lin("byt5_in.fc1", bh, bi), lin("byt5_in.fc2", bo, bh), lin("byt5_in.fc3", D, bo)
+    s["img_in.proj.weight"] = (D, Cin, *cfg["patch_size"])
+    s["img_in.proj.bias"] = (D,)
+    lin("txt_in.input_embedder", D, Td)
+    lin("txt_in.t_embedder.mlp.0", D, 256), lin("txt_in.t_embedder.mlp.2", D, D)
+    lin("txt_in.c_embedder.linear_1", D, Td), lin("txt_in.c_embedder.linear_2", D, D)
+    for j in range(2):
+        p = f"txt_in.individual_token_refiner.blocks.{j}."
+        s[p + "norm1.weight"] = s[p + "norm1.bias"] = s[p + "norm2.weight"] = s[p + "norm2.bias"] = (D,)
+        lin(p + "self_attn_qkv", 3 * D, D), lin(p + "self_attn_proj", D, D)
+        lin(p + "mlp.fc1", F, D), lin(p + "mlp.fc2", D, F), lin(p + "adaLN_modulation.1", 2 * D, D)
+    lin("time_in.mlp.0", D, 256), lin("time_in.mlp.2", D, D)
+    for i in range(cfg["mm_double_blocks_depth"]):
+        for st in ("img", "txt"):
+            p = f"double_blocks.{i}.{st}_"
+            lin(p + "mod.linear", 6 * D, D)
+            for l in "qkv":
+                lin(p + "attn_" + l, D, D)
+            s[p + "attn_q_norm.weight"] = s[p + "attn_k_norm.weight"] = (D // cfg["heads_num"],)
+            lin(p + "attn_proj", D, D), lin(p + "mlp.fc1", F, D), lin(p + "mlp.fc2", D, F)
+    lin("final_layer.linear", pp * Co, D), lin("final_layer.adaLN_modulation.1", 2 * D, D)
+    s["cond_type_embedding.weight"] = (3, D)
+    return s
+
+
+def make_hy_tensor(name, shape, seed=0, device="cpu"):
+    if name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight"):
+        return 1.0 + _normal(shape, 0.1, seed, name, device)
+    if name.endswith("bias"):
+        return _normal(shape, 0.02, seed, name, device)
+    if "mod.linear" in name or "adaLN_modulation" in name or name.startswith(("final_layer.linear", "cond_type_embedding")):
+        return _normal(shape, 0.02, seed, name, device)          # zero-initialised in the reference; randomised so they matter
+    fan_in = math.prod(shape[1:])
+    return _normal(shape, 1.0 / math.sqrt(fan_in), seed, name, device)
+
+
+def make_hy_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    return {n: make_hy_tensor(n, s, seed, device).to(dtype) for n, s in hy_param_shapes(cfg).items()}
+
+
+def make_hy_inputs(cfg, latent_thw, n_txt=24, n_txt_valid=17, n_byt5=12, n_byt5_valid=5, seed=0):
+    """x [1,Cin,T,H,W], t=[500], LLM states [1,n_txt,text_dim] + mask (valid prefix), byT5 states [1,n_byt5,1472] + mask."""
+    T, H, W = latent_thw
+    x = _normal((1, cfg["in_channels"], T, H, W), 1.0, seed, "hy.x", "cpu")
+    txt = _normal((1, n_txt, cfg["text_states_dim"]), 1.0, seed, "hy.txt", "cpu")
+    byt5 = _normal((1, n_byt5, HY_BYT5_DIMS[0]), 1.0, seed, "hy.byt5", "cpu")
+    tm = torch.zeros(1, n_txt, dtype=torch.long)
+    tm[:, :n_txt_valid] = 1
+    bm = torch.zeros(1, n_byt5, dtype=torch.long)
+    bm[:, :n_byt5_valid] = 1
+    return x, torch.tensor([500.0]), txt, tm, byt5, bm
