@@ -29,7 +29,109 @@ WORKLOADS = {
     "wan22_t2v_14b_720p81": ("t2v_2_2", (21, 90, 160), True, "Wan2.2 t2v 14B, latent [1,16,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 12"),
     "wan21_t2v_1.3b_p": ("t2v_1.3B", (9, 30, 52), False, "Wan2.1 t2v 1.3B, latent [1,16,9,30,52] (BASELINE config 0), CFG pair"),
     "tiny": ("small", (5, 16, 24), False, "reduced config for smoke runs"),
+    # BASELINE configs[3]: Hunyuan Video 1.5 t2v 720p, 129 frames -> latent [1,32,33,45,80] (+33 cond channels), 54 double blocks
+    "hy15_t2v_720p129": ("HYVideo-1_5", (33, 45, 80), False, "Hunyuan Video 1.5 t2v 720p x 129f, latent [1,32,33,45,80]+33 cond ch, L=118800 (+767 text), CFG pair, 30-step Euler shift 9"),
+    "hy15_tiny": ("hy_tiny", (3, 6, 10), False, "reduced Hunyuan config for smoke runs"),
 }
+
+
+def hy_flops_forward(cfg, L, Lt):
+    D, nl = cfg["hidden_size"], cfg["mm_double_blocks_depth"]
+    n = L + Lt
+    return nl * (4.0 * n * n * D + 8.0 * n * D * D + 16.0 * n * D * D)
+
+
+def run_hunyuan(args, rank, world, local_rank, dev, dist):
+    """Hunyuan Video 1.5 denoise-step bench (same JSON contract, steps of cond+uncond forwards + CFG + Euler)."""
+    from wan2gp_b200 import _lib, ops, synth
+    from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer, get_rotary_pos_embed
+    from wan2gp_b200.pipeline import HunyuanDenoiser
+    cfg_name, thw, _, desc = WORKLOADS[args.workload]
+    cfg = synth.HY_CONFIGS[cfg_name]
+    T, H, W = thw
+    L, Lt, Lb = T * H * W, 511, 256
+    if cfg_name == "hy_tiny":
+        Lt, Lb = 24, 12
+    model = HYVideoDiffusionTransformer(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"],
+                                        out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
+                                        mm_double_blocks_depth=cfg["mm_double_blocks_depth"], mm_single_blocks_depth=0,
+                                        text_states_dim=cfg["text_states_dim"], text_pool_type=None, glyph_byT5_v2=True,
+                                        use_cond_type_embedding=True, pre_split_qkv=True, device=dev).init_synthetic(seed=1)
+    den = HunyuanDenoiser(model, num_steps=30, shift=9.0, guide_scale=6.0, device=dev)
+    g = torch.Generator().manual_seed(1000 + rank)
+    lat_host = torch.randn(1, cfg["out_channels"], T, H, W, generator=g).pin_memory()
+    latents = lat_host.to(dev)
+    cond = torch.zeros(1, cfg["in_channels"] - cfg["out_channels"], T, H, W, device=dev)
+    txt = torch.randn(1, Lt, cfg["text_states_dim"], generator=g).to(dev)
+    txt0 = torch.randn(1, Lt, cfg["text_states_dim"], generator=g).to(dev)
+    tm = torch.ones(1, Lt, dtype=torch.long)
+    b5 = torch.randn(1, Lb, synth.HY_BYT5_DIMS[0], generator=g).to(dev)
+    bm = torch.ones(1, Lb, dtype=torch.long)
+    freqs = get_rotary_pos_embed(thw)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(k, lat):
+        return den.step(lat, cond, min(k, den.num_steps - 1), txt, tm, txt0, tm, b5, bm, freqs)
+    for k in range(args.warmup):
+        one(k, latents)
+    barrier()
+    l0 = _lib.launch_count()
+    ops.TIMED["attention"] = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for k in range(args.steps):
+            one(args.warmup + k, latents)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    att = [(a.elapsed_time(b), w) for a, b, w in ops.TIMED.pop("attention") if w > 1e12]
+    # end to end with host buffers
+    n_e2e = max(1, min(args.steps, 3))
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(n_e2e):
+        lat = lat_host.to(dev, non_blocking=True)
+        one(args.warmup + k, lat)
+        lat_host.copy_(lat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    barrier()
+    tms = torch.tensor([ms, t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    pk = peaks()
+    fl = 2.0 * hy_flops_forward(cfg, L, Lt + Lb)
+    att_ms = sum(a for a, _ in att) / max(1, len(att))
+    att_tf = (att[0][1] / (att_ms * 1e-3) / 1e12) if att else None
+    res = {"metric": "denoise_steps_per_sec", "value": world * args.steps / (ms / 1e3), "unit": "steps/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": args.workload, "description": desc, "latent": [1, cfg["out_channels"], T, H, W], "tokens": L,
+                      "text_tokens": Lt + Lb, "cfg_pair": True, "parallelism": f"{world} independent samples (batch split), 1 per GPU",
+                      "l2_policy": "inputs larger than L2; no flush needed"},
+           "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "steps/s", "steps": n_e2e,
+                   "h2d_bytes_per_step": lat_host.numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 4},
+           "gpu_launches": launches, "finite": bool(torch.isfinite(latents).all()),
+           "model_tflops": fl / (ms / args.steps * 1e-3) / 1e12,
+           "model_tensor_frac": fl / (ms / args.steps * 1e-3) / 1e12 / pk["tensor_sustained"],
+           "roofline": {"kernel": "attn_fwd_d128_kernel (joint img+txt attention)", "bound": "tensor", "achieved": att_tf,
+                        "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": None if att_tf is None else att_tf / pk["tensor_sustained"],
+                        "peak_source": pk["source"] + ", sustained figure", "launches_timed": len(att), "avg_launch_ms": att_ms,
+                        "share_of_step": (sum(a for a, _ in att) / ms) if att else None, "traffic": None},
+           "clocks": clk.summary()}
+    if rank == 0:
+        print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
+
 
 
 def peaks():
@@ -128,6 +230,18 @@ def main():
 
     from wan2gp_b200 import synth
     cfg_name, thw, two_experts, desc = WORKLOADS[args.workload]
+    if args.workload.startswith("hy15"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "CPU arm is implemented for the Wan workloads only"}))
+            return
+        rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=dev)
+        return run_hunyuan(args, rank, world, local_rank, dev, dist)
     cfg = synth.WAN_CONFIGS[cfg_name]
     T, H, W = thw
     L = T * (H // 2) * (W // 2)

@@ -89,3 +89,34 @@ class WanDenoiser:
         if not decode or self.vae is None:
             return {"latents": latents}
         return {"x": self.vae.decode_to_cpu_uint8([latents[0]], 0)[0]}
+
+
+class HunyuanDenoiser:
+    """Denoise-loop call site of the Hunyuan Video 1.5 pipeline (models/hyvideo/diffusion/pipelines/pipeline_hunyuan_video.py
+    :1597-1763): latent_model_input = cat(latents, cond_latents) (:1640-1650), transformer(cond) / transformer(uncond)
+    (:1655/:1687), CFG combine (:1719-1743) and the flow-matching scheduler step (:1755), here the Euler update fused with
+    the combine.  guidance 6.0 / shift 9 are defaults/hunyuan_1_5_t2v.json."""
+
+    def __init__(self, model, num_steps=30, shift=9.0, guide_scale=6.0, device="cuda"):
+        self.model, self.device, self.guide_scale = model, torch.device(device), guide_scale
+        self.timesteps = euler_timesteps(num_steps, shift)
+        self.num_steps = num_steps
+        self._interrupt = False
+
+    @torch.no_grad()
+    def step(self, latents, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=None, byt5_mask=None, freqs=None):
+        """latents fp32 [1,32,T,H,W] (updated in place), cond_latents fp32 [1,33,T,H,W] (concat mask/cond channels)."""
+        t = self.timesteps[i]
+        dt = (t - self.timesteps[i + 1]) / 1000.0
+        x = torch.cat([latents, cond_latents], 1)
+        tt = torch.tensor([t], dtype=f32)
+        kw = dict(freqs_cos=None if freqs is None else freqs[0], freqs_sin=None if freqs is None else freqs[1], pipeline=self,
+                  step_no=i, byt5_text_states=byt5, byt5_text_mask=byt5_mask)
+        cond = self.model(x, tt, text_states=text, text_mask=text_mask, **kw)
+        if cond is None:
+            return None
+        uncond = self.model(x, tt, text_states=text_null, text_mask=text_null_mask, **kw)
+        if uncond is None:
+            return None
+        ops.cfg_euler_step_(latents, cond.contiguous(), uncond.contiguous(), self.guide_scale, dt)
+        return latents
