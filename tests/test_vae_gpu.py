@@ -16,7 +16,7 @@ def test_conv3d_vs_torch():
     from wan2gp_b200.wan.vae import _Conv
     g = torch.Generator(device="cuda").manual_seed(0)
     for (T, H, W, ci, co, k) in [(3, 9, 20, 64, 128, (3, 3, 3)), (2, 8, 16, 96, 96, (3, 3, 3)), (4, 5, 7, 32, 64, (3, 1, 1)),
-                                 (1, 12, 18, 192, 96, (1, 3, 3)), (2, 6, 6, 16, 384, (3, 3, 3)), (3, 8, 8, 128, 3, (3, 3, 3)),
+                                 (1, 12, 18, 192, 96, (1, 3, 3)), (2, 6, 6, 16, 384, (3, 3, 3)), (3, 8, 8, 128, 3, (3, 3, 3)), (2, 9, 17, 96, 3, (3, 3, 3)), (3, 10, 33, 96, 96, (3, 3, 3)),
                                  (2, 4, 4, 128, 256, (1, 1, 1))]:
         x = torch.randn(T, H, W, ci, device="cuda", generator=g).to(bf16)
         w = (torch.randn(co, ci, *k, device="cuda", generator=g) * (ci * k[0] * k[1] * k[2]) ** -0.5)

@@ -73,3 +73,24 @@ if "rows" in which:
     rec("rmsnorm_rope L x D (strided in qkv)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6, cos, sin)), bytes_=L * D * 4 + L * 128 * 8)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)
+if "conv" in which:
+    from wan2gp_b200.wan.vae import _Conv, rms_silu, upsample2x
+    shapes = [("s0 res 384->384 3x3x3", 21, 90, 160, 384, 384, (3, 3, 3)), ("s1 res 384->384 3x3x3", 41, 180, 320, 384, 384, (3, 3, 3)),
+              ("s1 res 192->384 3x3x3", 41, 180, 320, 192, 384, (3, 3, 3)), ("up1 conv2d 384->192 3x3", 41, 180, 320, 384, 192, (1, 3, 3)),
+              ("time_conv 384->768 3x1x1", 40, 180, 320, 384, 768, (3, 1, 1)), ("s2 res 192->192 3x3x3", 81, 360, 640, 192, 192, (3, 3, 3)),
+              ("up2 conv2d 384->192 3x3", 81, 360, 640, 384, 192, (1, 3, 3)), ("s3 res 96->96 3x3x3", 81, 720, 1280, 96, 96, (3, 3, 3)),
+              ("up3 conv2d 192->96 3x3", 81, 720, 1280, 192, 96, (1, 3, 3)), ("head 96->3 3x3x3", 81, 720, 1280, 96, 3, (3, 3, 3))]
+    for name, T, H, W, ci, co, k in shapes:
+        x = torch.randn(T, H, W, ci, device="cuda", dtype=bf16)
+        conv = _Conv(torch.randn(co, ci, *k, device="cuda") * 0.02, torch.randn(co, device="cuda"), "cuda")
+        mode = 2 if co == 3 else 0
+        out = conv(x, out_mode=mode)
+        fl = 2.0 * T * H * W * ci * co * k[0] * k[1] * k[2]
+        rec("conv " + name, timeit(lambda: conv(x, out=out, out_mode=mode), iters=3, warm=1), flops=fl, bytes_=x.numel() * 2 + out.numel() * out.element_size())
+        del x, out, conv
+    x = torch.randn(81, 720, 1280, 96, device="cuda", dtype=bf16); gmm = torch.ones(96, device="cuda")
+    rec("rms_silu 81x720x1280x96", timeit(lambda: rms_silu(x, gmm), iters=3, warm=1), bytes_=x.numel() * 4)
+    del x
+    x = torch.randn(81, 360, 640, 192, device="cuda", dtype=bf16)
+    rec("upsample2x 81x360x640x192", timeit(lambda: upsample2x(x), iters=3, warm=1), bytes_=x.numel() * 2 * 5)
+    json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)

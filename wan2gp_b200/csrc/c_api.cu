@@ -65,7 +65,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // bf16 tensor, dims[0] is the contiguous dimension; strides (bytes) for dims 1..rank-1; 128B swizzle.
 int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box) {
+                        const uint32_t* box, int swizzle_bytes) {
     auto enc = get_encode();
     if (!enc) return b200_set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5], gstr[4];
@@ -73,7 +73,8 @@ int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return b200_set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,..] box=[%u,%u,..]", (int)r,
@@ -90,20 +91,29 @@ int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_
     } while (0)
 
 // ------------------------------------------------------------------ GEMM
-template <int BN, bool MN>
+template <int BN, bool MN, int BKC = 64, int NBOX = 1>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_tcgen05_kernel<BN, MN>;
+    auto kern = gemm_tcgen05_kernel<BN, MN, BKC, NBOX>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BKC, NBOX>::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
         attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
-    kern<<<grid, 256, GemmSmem<BN>::kBytes, st>>>(ta, tb, p);
+    kern<<<grid, 256, GemmSmem<BN, BKC, NBOX>::kBytes, st>>>(ta, tb, p);
     CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
+}
+
+// conv layers with Cin = 96: three 32-channel boxes (64B swizzle) per tap => K = 96 exactly, no zero-padded MMAs
+int b200_launch_gemm_k96(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    switch (BN) {
+        case 96: return launch_gemm_inst<96, false, 32, 3>(ta, tb, p, st);
+        case 16: return launch_gemm_inst<16, false, 32, 3>(ta, tb, p, st);
+    }
+    return b200_set_error(B200_ERR_ARG, "no K=96 GEMM instance for BN=%d", BN);
 }
 
 int b200_launch_gemm(int BN, bool mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
@@ -157,20 +167,20 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
         uint64_t str[1] = {(uint64_t)lda * 2};
         uint32_t box[2] = {GEMM_BK, GEMM_BM};
-        int r = b200_make_tmap_bf16(&ta, A, 2, dims, str, box);
+        int r = b200_make_tmap_bf16(&ta, A, 2, dims, str, box, 128);
         if (r) return r;
     }
     if (!mn) {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
         uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
-        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box);
+        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
         if (r) return r;
     } else {
         uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
         uint64_t str[1] = {(uint64_t)ldb * 2};
         uint32_t box[2] = {64, GEMM_BK};
-        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box);
+        int r = b200_make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
         if (r) return r;
     }
     GemmParams p;
@@ -195,15 +205,15 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
     uint32_t box[2] = {64, 128};
     {
         uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lq}; uint64_t str[1] = {(uint64_t)ldq * 2};
-        int r = b200_make_tmap_bf16(&tq, q, 2, dims, str, box); if (r) return r;
+        int r = b200_make_tmap_bf16(&tq, q, 2, dims, str, box, 128); if (r) return r;
     }
     {
         uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldk * 2};
-        int r = b200_make_tmap_bf16(&tk, k, 2, dims, str, box); if (r) return r;
+        int r = b200_make_tmap_bf16(&tk, k, 2, dims, str, box, 128); if (r) return r;
     }
     {
         uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldv * 2};
-        int r = b200_make_tmap_bf16(&tv, v, 2, dims, str, box); if (r) return r;
+        int r = b200_make_tmap_bf16(&tv, v, 2, dims, str, box, 128); if (r) return r;
     }
     AttnParams p;
     p.Lq = Lq; p.Lk = Lk; p.H = H;

@@ -57,19 +57,25 @@ struct GemmParams {
     int act;
 };
 
-template <int BN>
+// BKC = K elements per TMA box (64 -> 128B swizzle, 32 -> 64B swizzle); NBOX boxes of A and of B form one pipeline stage
+template <int BN, int BKC = 64, int NBOX = 1>
 struct GemmSmem {
-    static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;          // 16 KB
-    static constexpr int kBBytes = BN * GEMM_BK * 2;
+    static constexpr int kABox = GEMM_BM * BKC * 2;
+    static constexpr int kBBox = BN * BKC * 2;
+    static constexpr int kABytes = NBOX * kABox;                   // 16 KB for the default 128 x 64 tile
+    static constexpr int kBBytes = NBOX * kBBox;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool B_MN_MAJOR>
+template <int BN, bool B_MN_MAJOR, int BKC = 64, int NBOX = 1>
 __global__ void __launch_bounds__(256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, BKC, NBOX>;
+    static_assert(BKC == 64 || BKC == 32, "K box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements");
+    static_assert(!(B_MN_MAJOR && (BKC != 64 || NBOX != 1)), "MN-major B only with the default K box");
+    constexpr int BKS = BKC * NBOX;                  // K elements per pipeline stage
     constexpr int kStages = S::kStages;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
     static_assert(!B_MN_MAJOR || BN % 64 == 0, "MN-major B needs 64-wide slabs");
@@ -132,10 +138,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint8_t* sb = sa + S::kABytes;
                     mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
                     if (p.mode == MODE_LINEAR) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k * GEMM_BK, m_blk * GEMM_BM);
                         if constexpr (!B_MN_MAJOR) {
-                            tma_load_2d(sb, &tmap_b, &full_bar[stage], k * GEMM_BK, n_blk * BN);
+                            #pragma unroll
+                            for (int b = 0; b < NBOX; ++b) {
+                                tma_load_2d(sa + b * S::kABox, &tmap_a, &full_bar[stage], k * BKS + b * BKC, m_blk * GEMM_BM);
+                                tma_load_2d(sb + b * S::kBBox, &tmap_b, &full_bar[stage], k * BKS + b * BKC, n_blk * BN);
+                            }
                         } else {
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], k * GEMM_BK, m_blk * GEMM_BM);
                             // B is [K][N] (N contiguous): one [64 k-rows][64 n] slab per 64 columns
                             #pragma unroll
                             for (int s = 0; s < BN / 64; ++s)
@@ -149,9 +159,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         const int dh = rr / p.kw;
                         const int dw = rr - dh * p.kw;
                         // causal in time (all padding in front), centred in space; OOB -> zero fill
-                        tma_load_4d(sa, &tmap_a, &full_bar[stage], cc * GEMM_BK, w0 + dw - (p.kw >> 1), h0 + dh - (p.kh >> 1),
-                                    t0 + dt - (p.kt - 1));
-                        tma_load_3d(sb, &tmap_b, &full_bar[stage], cc * GEMM_BK, tap, n_blk * BN);
+                        #pragma unroll
+                        for (int b = 0; b < NBOX; ++b) {
+                            tma_load_4d(sa + b * S::kABox, &tmap_a, &full_bar[stage], cc * BKS + b * BKC, w0 + dw - (p.kw >> 1),
+                                        h0 + dh - (p.kh >> 1), t0 + dt - (p.kt - 1));
+                            tma_load_3d(sb + b * S::kBBox, &tmap_b, &full_bar[stage], cc * BKS + b * BKC, tap, n_blk * BN);
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -174,11 +187,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
                     const uint32_t sb = sa + S::kABytes;
                     #pragma unroll
-                    for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-                        const uint64_t da = umma_desc_kmajor_sw128(sa + kk * 32);
-                        const uint64_t db = B_MN_MAJOR ? umma_desc_mnmajor_sw128(sb + kk * 2048, GEMM_BK * 128)
-                                                       : umma_desc_kmajor_sw128(sb + kk * 32);
-                        umma_bf16_ss(d_tmem, da, db, idesc, (k | kk) != 0);
+                    for (int b = 0; b < NBOX; ++b) {
+                        #pragma unroll
+                        for (int kk = 0; kk < BKC / 16; ++kk) {
+                            const uint32_t aa = sa + b * S::kABox + kk * 32, bb = sb + b * S::kBBox + kk * 32;
+                            const uint64_t da = BKC == 64 ? umma_desc_kmajor_sw128(aa) : umma_desc_kmajor_sw64(aa);
+                            const uint64_t db = B_MN_MAJOR ? umma_desc_mnmajor_sw128(sb + kk * 2048, GEMM_BK * 128)
+                                                           : (BKC == 64 ? umma_desc_kmajor_sw128(bb) : umma_desc_kmajor_sw64(bb));
+                            umma_bf16_ss(d_tmem, da, db, idesc, (k | b | kk) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
                     if (k == p.num_k_iters - 1) umma_commit(&tfull_bar[acc]);

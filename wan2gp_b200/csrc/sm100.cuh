@@ -100,6 +100,16 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same, 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B, tile [rows][32] bf16, row pitch 64 B, 8-row groups of 512 B): used when
+// the K extent per step is 32 elements (conv layers with Cin = 96 = 3 x 32, so no zero-padded K is multiplied).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // MN-major operand (the MN index is contiguous in memory): tile stored as slabs [K rows][64] bf16
 // (128-B rows, SWIZZLE_128B), one slab per 64 MN elements.  SBO = 1024 (8 K-rows), LBO = slab bytes.
 // Advancing K by 16 = +16 rows = +2048 B on the start address.
