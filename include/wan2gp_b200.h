@@ -103,6 +103,12 @@ int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, floa
 int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                    int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream);
 
+/* Resample 'upsample2d/3d' spatial part (vae.py:124-133: nearest-exact 2x then Conv2d 3x3 pad 1) as four 2x2 sub-pixel
+ * convolutions on the low-resolution input: x bf16 [T,H,W,Cin]; w4 bf16 [4][Cout][4][Cin] = per output parity (py,px) the 3x3
+ * taps that hit the same source pixel summed; out bf16 [T,2H,2W,Cout]. */
+int b200_upconv2x_cl(const void* x, const void* w4, const float* bias, void* out, int T, int H, int W, int Cin, int Cout,
+                     void* stream);
+
 /* y = silu(x / max(||x||_2 over C, 1e-12) * sqrt(C) * gamma) per pixel (vae.py:85-103 RMS_norm + nn.SiLU),
  * bf16 [P, C] -> bf16 [P, C]; silu=0 skips the activation (AttentionBlock norm, vae.py:293). */
 int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream);

@@ -56,3 +56,19 @@ def test_vae_decode(name):
     assert d.float().mean() <= 1.5
     fl = vae.decode([z.cuda()], 0)[0]
     assert fl.min() >= -1 and fl.max() <= 1
+
+
+def test_upconv_subpixel_vs_torch():
+    """nearest-exact 2x + Conv2d 3x3 (vae.py:124-133) computed as four 2x2 sub-pixel convs on the low-res input."""
+    import torch.nn.functional as F
+    from wan2gp_b200.wan.vae import _UpConv
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (T, H, W, ci, co) in [(2, 5, 7, 64, 32), (1, 9, 20, 192, 96), (3, 8, 16, 384, 192)]:
+        x = torch.randn(T, H, W, ci, device="cuda", generator=g).to(bf16)
+        w = torch.randn(co, ci, 3, 3, device="cuda", generator=g) * (ci * 9) ** -0.5
+        b = torch.randn(co, device="cuda", generator=g)
+        out = _UpConv(w, b, "cuda")(x)
+        up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact")
+        ref = F.conv2d(up.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+        assert out.shape == (T, 2 * H, 2 * W, co)
+        assert rel_l2(out, ref) < 5e-3

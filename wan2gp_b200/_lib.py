@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_ll, c_void_p],
     "b200_conv3d_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_int, c_int, c_int, c_int, c_void_p],
+    "b200_upconv2x_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_rms_silu_cl": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     "b200_upsample2x_cl": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "b200_vae_prologue": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

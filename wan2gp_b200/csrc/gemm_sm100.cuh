@@ -38,6 +38,7 @@ struct GemmParams {
     // ---- conv geometry (input and output share the T,H,W pixel grid)
     int T, H, W;
     int kt, kh, kw;           // taps
+    int pad_h, pad_w;         // taps start at (h - pad_h, w - pad_w): kh/2, kw/2 for centred convs
     int cin_chunks;           // ceil(Cin / 64)
     int tiles_h, tiles_w;     // ceil(H/8), ceil(W/16)
     // ---- tile rasterisation
@@ -161,8 +162,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         // causal in time (all padding in front), centred in space; OOB -> zero fill
                         #pragma unroll
                         for (int b = 0; b < NBOX; ++b) {
-                            tma_load_4d(sa + b * S::kABox, &tmap_a, &full_bar[stage], cc * BKS + b * BKC, w0 + dw - (p.kw >> 1),
-                                        h0 + dh - (p.kh >> 1), t0 + dt - (p.kt - 1));
+                            tma_load_4d(sa + b * S::kABox, &tmap_a, &full_bar[stage], cc * BKS + b * BKC, w0 + dw - p.pad_w,
+                                        h0 + dh - p.pad_h, t0 + dt - (p.kt - 1));
                             tma_load_3d(sb + b * S::kBBox, &tmap_b, &full_bar[stage], cc * BKS + b * BKC, tap, n_blk * BN);
                         }
                     }

@@ -172,8 +172,34 @@ extern "C" int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void
 
 // ---------------------------------------------------------------------------------------------
 // causal conv as implicit GEMM
+static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
+                        int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
+                        void* stream);
+
 extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                               int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
+    return conv_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, out_mode, t_off, kh >> 1, kw >> 1, -1, -1, stream);
+}
+
+// nearest-exact 2x upsample followed by a 3x3 conv (vae.py:124-133) == four 2x2 convs on the LOW-resolution input, one per
+// output parity (py, px), with pre-summed taps (w4: [4 phases][Cout][4 taps][Cin], phase = 2*py+px, taps (a,b) row-major):
+// 2.25x fewer FLOPs and the 4x larger up-sampled tensor is never written.  out: bf16 [T, 2H, 2W, Cout].
+extern "C" int b200_upconv2x_cl(const void* x, const void* w4, const float* bias, void* out, int T, int H, int W, int Cin, int Cout,
+                                void* stream) {
+    if (!x || !w4 || !out) return b200_set_error(B200_ERR_ARG, "upconv2x_cl: null argument");
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w4) + (long long)(2 * py + px) * Cout * 4 * Cin;
+            // parity 0 reads source rows (h-1, h); parity 1 reads (h, h+1)
+            int r = conv_cl_impl(x, wp, bias, nullptr, out, T, H, W, Cin, Cout, 1, 2, 2, 0, 0, 1 - py, 1 - px, py, px, stream);
+            if (r) return r;
+        }
+    return B200_OK;
+}
+
+static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
+                        int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
+                        void* stream) {
     if (!x || !w || !out || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
     if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
     if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
@@ -204,6 +230,7 @@ extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, c
     p.mode = MODE_CONV;
     p.N = Cout;
     p.T = T; p.H = H; p.W = W; p.kt = kt; p.kh = kh; p.kw = kw;
+    p.pad_h = pad_h; p.pad_w = pad_w;
     p.cin_chunks = k96 ? 1 : (Cin + 63) / 64;
     p.num_k_iters = taps * p.cin_chunks;
     p.tiles_h = (H + CONV_BH - 1) / CONV_BH;
@@ -214,7 +241,11 @@ extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, c
     p.n_group = p.n_tiles;            // weights are small: all N tiles of one pixel tile run back to back
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-    if (out_mode == 0) {
+    if (out_mode == 0 && up_py >= 0) {
+        // output pixel (t, 2h + py, 2w + px) of a [T, 2H, 2W, Cout] tensor
+        p.out = reinterpret_cast<__nv_bfloat16*>(out) + ((long long)up_py * 2 * W + up_px) * Cout;
+        p.st_w = 2LL * Cout; p.st_h = 4LL * W * Cout; p.st_t = 4LL * H * W * Cout;
+    } else if (out_mode == 0) {
         p.out = out;
         p.st_w = Cout; p.st_h = (long long)W * Cout; p.st_t = (long long)H * W * Cout;
     } else if (out_mode == 1) {

@@ -49,6 +49,35 @@ class _Conv:
         return out
 
 
+class _UpConv:
+    """nearest-exact 2x + Conv2d 3x3 (vae.py:124-133) folded into four 2x2 sub-pixel convs (csrc/vae_ops.cu::b200_upconv2x_cl)."""
+
+    def __init__(self, w, b, device):
+        co, ci = w.shape[:2]
+        w = w.detach().to(device, f32)                      # [Co, Ci, 3, 3]
+        self.cout, self.cin = co, ci
+        # parity 0 reads source offsets (-1, 0): taps {0} | {1,2};  parity 1 reads (0, +1): taps {0,1} | {2}
+        groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+        phases = []
+        for py in (0, 1):
+            for px in (0, 1):
+                taps = []
+                for a in range(2):
+                    for bb in range(2):
+                        taps.append(sum(w[:, :, dy, dx] for dy in groups[py][a] for dx in groups[px][bb]))   # [Co, Ci]
+                phases.append(torch.stack(taps, 1))           # [Co, 4, Ci]
+        self.w4 = torch.stack(phases, 0).to(bf16).contiguous()  # [4, Co, 4, Ci]
+        self.b = b.detach().to(device, f32).contiguous()
+
+    def __call__(self, x):
+        T, H, W, C = x.shape
+        assert C == self.cin and x.is_contiguous() and x.dtype == bf16
+        out = torch.empty(T, 2 * H, 2 * W, self.cout, device=x.device, dtype=bf16)
+        _lib.call("b200_upconv2x_cl", x.data_ptr(), self.w4.data_ptr(), self.b.data_ptr(), out.data_ptr(), T, H, W, self.cin,
+                  self.cout, _s())
+        return out
+
+
 def rms_silu(x, gamma, silu=True):
     y = torch.empty_like(x)
     C = x.shape[-1]
@@ -100,7 +129,7 @@ class WanVAEDecoder(torch.nn.Module):
             if u[0] == "res":
                 self.ups.append(("res", res(p)))
             else:
-                d = {"conv": _Conv(sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], dev)}
+                d = {"conv": _UpConv(sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], dev)}
                 if u[0] == "up3d":
                     d["time"] = _Conv(sd[p + "time_conv.weight"], sd[p + "time_conv.bias"], dev)
                 self.ups.append((u[0], d))
@@ -136,7 +165,7 @@ class WanVAEDecoder(torch.nn.Module):
             y[0].copy_(x[0])                                                 # frame 0 bypasses time_conv (vae.py:155-158)
             d["time"](x[1:], out=y, out_mode=1, t_off=1)                     # causal over frames 1.., interleaved store
             x = y
-        return d["conv"](upsample2x(x))
+        return d["conv"](x)                                             # 2x nearest + 3x3 conv as sub-pixel convs
 
     @torch.no_grad()
     def decode_frames(self, z, mean, std):
