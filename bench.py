@@ -359,7 +359,11 @@ def main():
                      "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                      "launches_timed": len(att_ms), "avg_launch_ms": att_avg,
                      "share_of_step": sum(att_ms) / ms if att_ms else None,
-                     "algorithmic_flops_per_launch": att_work, "traffic": None},
+                     "algorithmic_flops_per_launch": att_work,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full capture
+                     # summarised in profiles/ncu_r01_attn_v3.txt (algorithmic minimum q+k+v+o = 4 * L * D * 2 B = 3.10e9)
+                     "traffic": 3.35e9 if (L == 75600 and cfg["dim"] == 5120) else None,
+                     "traffic_unit": "bytes/launch (ncu dram read+write)"},
         "clocks": clk.summary(),
     }
 

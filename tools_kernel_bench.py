@@ -57,6 +57,17 @@ if "gemm" in which:
             fn = lambda: ops.gemm(A, w, out=out, bias=bias, act=kw.get("act", 0))
         rec("gemm " + name, timeit(fn), flops=2.0 * L * N * K)
         del w, A
+if "gemm_epi" in which:
+    # epilogue cost probe on the o-proj shape (M=L, N=K=D)
+    a = torch.randn(L, D, device="cuda").to(bf16); w = (torch.randn(D, D, device="cuda") * D ** -0.5).to(bf16)
+    bias = torch.randn(D, device="cuda"); gate = torch.randn(D, device="cuda")
+    ob = torch.empty(L, D, device="cuda", dtype=bf16); of = torch.zeros(L, D, device="cuda", dtype=f32)
+    for name, fn in [("bf16 out + bias", lambda: ops.gemm(a, w, out=ob, bias=bias)),
+                     ("fp32 out + bias", lambda: ops.gemm(a, w, out=of, bias=bias)),
+                     ("fp32 out + bias + gate", lambda: ops.gemm(a, w, out=of, bias=bias, gate=gate)),
+                     ("fp32 accumulate + bias + gate", lambda: ops.gemm(a, w, out=of, bias=bias, gate=gate, accumulate=True))]:
+        rec("gemm o-proj L x D x D, " + name, timeit(fn), flops=2.0 * L * D * D)
+    del a, w, ob, of
 if "attn" in which:
     for (Lq, Lk, tag) in [(L, L, "self L=75600 H=40"), (L, 512, "cross Lk=512 H=40"), (32760, 32760, "self L=32760 (480p) H=40")]:
         qkv = torch.randn(max(Lq, Lk), 3 * D, device="cuda").to(bf16)
