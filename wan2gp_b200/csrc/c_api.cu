@@ -64,15 +64,21 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // bf16 tensor, dims[0] is the contiguous dimension; strides (bytes) for dims 1..rank-1; 128B swizzle.
+int b200_make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes, int is_f32);
 int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, int swizzle_bytes) {
+    return b200_make_tmap(m, ptr, rank, dims, strides_bytes, box, swizzle_bytes, 0);
+}
+int b200_make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes, int is_f32) {
     auto enc = get_encode();
     if (!enc) return b200_set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+    CUresult r = enc(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -91,18 +97,19 @@ int b200_make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_
     } while (0)
 
 // ------------------------------------------------------------------ GEMM
-template <int BN, bool MN, int BKC = 64, int NBOX = 1>
-static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_tcgen05_kernel<BN, MN, BKC, NBOX>;
+template <int BN, bool MN, int BKC = 64, int NBOX = 1, bool EPI_TMA = false>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st,
+                            const CUtensorMap* tc = nullptr) {
+    auto kern = gemm_tcgen05_kernel<BN, MN, BKC, NBOX, EPI_TMA>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BKC, NBOX>::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BKC, NBOX, EPI_TMA>::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
         attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
-    kern<<<grid, 256, GemmSmem<BN, BKC, NBOX>::kBytes, st>>>(ta, tb, p);
+    kern<<<grid, 256, GemmSmem<BN, BKC, NBOX, EPI_TMA>::kBytes, st>>>(ta, tb, tc ? *tc : ta, p);
     CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }
@@ -193,6 +200,19 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
     p.n_group = 16;
     p.out = out; p.out_fp32 = out_fp32; p.accumulate = accumulate; p.ldc = ldc;
     p.bias = bias; p.gate = gate; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16); p.act = act;
+    // residual-stream accumulate: L2-side reduce-add through TMA (B200_GEMM_TMA_REDUCE=0 selects the LDG/STG epilogue)
+    static int use_tma_reduce = -1;
+    if (use_tma_reduce < 0) { const char* ev = getenv("B200_GEMM_TMA_REDUCE"); use_tma_reduce = ev ? atoi(ev) : 1; }
+    if (use_tma_reduce && accumulate && out_fp32 && !mn && BN == 256 && N % 32 == 0 && !residual_bf16 && act == 0 && ldc % 4 == 0) {
+        CUtensorMap tc;
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldc * 4};
+        uint32_t box[2] = {32, GEMM_BM};
+        int r = b200_make_tmap(&tc, out, 2, dims, str, box, 128, 1);
+        if (r) return r;
+        p.tma_reduce = 1;
+        return launch_gemm_inst<256, false, 64, 1, true>(ta, tb, p, (cudaStream_t)stream, &tc);
+    }
     return b200_launch_gemm(BN, mn, ta, tb, p, (cudaStream_t)stream);
 }
 

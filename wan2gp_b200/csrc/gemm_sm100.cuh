@@ -47,6 +47,7 @@ struct GemmParams {
     void* out;                // bf16 or fp32
     int out_fp32;
     int accumulate;           // out (fp32) += value   (DiT residual stream)
+    int tma_reduce;           // accumulate through cp.reduce.async.bulk.tensor (EPI_TMA instantiation)
     long long ldc;            // linear: row stride (elements)
     long long st_t, st_h, st_w;   // conv: pixel strides (elements)
     int csplit;               // conv: columns >= csplit go to a second plane (time_conv interleave)
@@ -59,7 +60,8 @@ struct GemmParams {
 };
 
 // BKC = K elements per TMA box (64 -> 128B swizzle, 32 -> 64B swizzle); NBOX boxes of A and of B form one pipeline stage
-template <int BN, int BKC = 64, int NBOX = 1>
+// EPI_TMA: 2 x 16 KB staging tiles for the TMA reduce-add epilogue (fp32 residual-stream accumulate)
+template <int BN, int BKC = 64, int NBOX = 1, bool EPI_TMA = false>
 struct GemmSmem {
     static constexpr int kABox = GEMM_BM * BKC * 2;
     static constexpr int kBBox = BN * BKC * 2;
@@ -67,13 +69,18 @@ struct GemmSmem {
     static constexpr int kBBytes = NBOX * kBBox;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-    static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = EPI_TMA ? 2 * GEMM_BM * 128 : 0;
+    static constexpr int kBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool B_MN_MAJOR, int BKC = 64, int NBOX = 1>
+// EPI_TMA (linear mode, fp32 accumulate): the epilogue stages each 128 x 32 fp32 chunk in 128B-swizzled smem and issues
+// cp.reduce.async.bulk.tensor (.add): the read-modify-write of the residual stream happens in L2, fully coalesced, instead
+// of per-thread row-strided LDG/STG (which cost 30% of the GEMM: 4.37 ms vs 2.98 ms at M=75600, N=K=5120).
+template <int BN, bool B_MN_MAJOR, int BKC = 64, int NBOX = 1, bool EPI_TMA = false>
 __global__ void __launch_bounds__(256, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using S = GemmSmem<BN, BKC, NBOX>;
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+    using S = GemmSmem<BN, BKC, NBOX, EPI_TMA>;
     static_assert(BKC == 64 || BKC == 32, "K box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements");
     static_assert(!(B_MN_MAJOR && (BKC != 64 || NBOX != 1)), "MN-major B only with the default K box");
     constexpr int BKS = BKC * NBOX;                  // K elements per pipeline stage
@@ -83,7 +90,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+    uint8_t* epi_smem = smem + kStages * S::kStageBytes;          // [2][128 rows][128 B], EPI_TMA only
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + S::kEpiBytes);
     uint64_t* full_bar = bars;                    // [kStages]
     uint64_t* empty_bar = bars + kStages;         // [kStages]
     uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
@@ -231,6 +239,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(wq * 32) << 16);
+            if constexpr (EPI_TMA) {
+                const bool leader = (warp == 4 && lane == 0);
+                #pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int n0 = n_blk * BN + c * 32;
+                    float f[32];
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (n0 < p.N) {        // N % 32 == 0 is required by the host for this path
+                        if (p.bias) {
+                            #pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                            }
+                        }
+                        if (p.gate) {
+                            #pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + n0 + j));
+                                f[j] *= g.x; f[j + 1] *= g.y; f[j + 2] *= g.z; f[j + 3] *= g.w;
+                            }
+                        }
+                    }
+                    uint8_t* buf = epi_smem + (c & 1) * (GEMM_BM * 128);
+                    // buffer (c & 1) was handed to the TMA two chunks ago: wait until that store has READ it
+                    if (leader) bulk_wait_group_read<1>();
+                    named_bar_sync(1, 128);
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j)            // 128-B row, 16-B chunks XOR-swizzled by (row & 7): conflict-free
+                        *reinterpret_cast<float4*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) =
+                            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (leader && n0 < p.N) {
+                        tma_reduce_add_2d(&tmap_c, buf, n0, m_blk * GEMM_BM);     // rows >= M are clipped by the tensor map
+                        bulk_commit_group();
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             #pragma unroll 1
             for (int c = 0; c < BN / 32 + (BN % 32 ? 1 : 0); ++c) {
                 uint32_t v[32];
@@ -331,6 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     }
 
+    if (EPI_TMA && warp == 4 && lane == 0) bulk_wait_group<0>();   // smem staging tiles must outlive the reduce-stores
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {

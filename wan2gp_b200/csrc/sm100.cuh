@@ -73,6 +73,16 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const void* tmap, uint64
         ::"r"(smem_u32(smem)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+// ------------------------------------------------------------------ TMA reduce-store (smem tile -> global += tile, done at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ------------------------------------------------------------------ TMEM allocation (cta_group::1)
 // Must be executed by one full warp; the same warp deallocates.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
