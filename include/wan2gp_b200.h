@@ -88,9 +88,10 @@ int b200_col_mean_f32(const float* x, float* out, int rows, int cols, void* stre
 int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, void* stream);
 
 /* lat -= dt * (u + g (c - u)); uncond may be NULL (no CFG); pred_out optional.  any2video.py:1701-1722 +
- * euler_scheduler.py:67-86.  n % 4 == 0. */
+ * euler_scheduler.py:67-86.  n % 4 == 0.  star_dots (device float[2] scratch, or NULL): CFG-Zero* -- u is first rescaled by
+ * alpha = <c,u> / (||u||^2 + 1e-8) computed over the whole sample (any2video.py:1706-1714, steps > cfg_zero_step). */
 int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt, float* pred_out,
-                        long long n, void* stream);
+                        float* star_dots, long long n, void* stream);
 
 /* ---- WanVAE decode (channels-last bf16 activations [T,H,W,C]) ---- */
 

@@ -147,5 +147,10 @@ def test_cfg_euler(ops):
     from oracle import wan_oracle
     lat, c, u = (_randn(1, 16, 3, 8, 12, seed=s) for s in (1, 2, 3))
     ref = wan_oracle.euler_step(lat.cpu(), wan_oracle.cfg_combine(c.cpu(), u.cpu(), 4.0), 0.9, 0.85)
+    lat0 = lat.clone()
     ops.cfg_euler_step_(lat, c, u, 4.0, 0.05)
     assert rel_l2(lat.cpu(), ref) < 1e-6
+    # CFG-Zero* (any2video.py:1706-1714)
+    ref = wan_oracle.euler_step(lat0.cpu(), wan_oracle.cfg_combine(c.cpu(), u.cpu(), 4.0, cfg_star=True, step_no=3), 0.9, 0.85)
+    ops.cfg_euler_step_(lat0, c, u, 4.0, 0.05, cfg_star=True)
+    assert rel_l2(lat0.cpu(), ref) < 1e-5

@@ -344,10 +344,16 @@ extern "C" int b200_col_mean_f32(const float* x, float* out, int rows, int cols,
 }
 
 extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt,
-                                   float* pred_out, long long n, void* stream) {
-    if (!lat || !cond || n <= 0 || n % 4) return b200_set_error(B200_ERR_ARG, "cfg_euler_step: bad argument");
+                                   float* pred_out, float* star_dots, long long n, void* stream) {
+    if (!lat || !cond || n <= 0 || n % 4 || (star_dots && !uncond)) return b200_set_error(B200_ERR_ARG, "cfg_euler_step: bad argument");
     const long long n4 = n / 4;
-    cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, pred_out, n4);
+    if (star_dots) {
+        cudaMemsetAsync(star_dots, 0, 2 * sizeof(float), (cudaStream_t)stream);
+        const unsigned blocks = (unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+        cfg_dots_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond, uncond, star_dots, n4);
+        CHECK_LAUNCH("cfg_dots");
+    }
+    cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, pred_out, star_dots, n4);
     CHECK_LAUNCH("cfg_euler_step");
     return B200_OK;
 }

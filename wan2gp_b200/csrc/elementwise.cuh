@@ -272,12 +272,33 @@ __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restr
 // ---------------------------------------------------------------------------------------------
 // CFG combine + flow-matching Euler update (any2video.py:1701-1722 plain CFG; euler_scheduler.py:67-86):
 // lat <- lat - dt * (u + g (c - u)); also writes the combined prediction (optional)
+// CFG-Zero* (any2video.py:1701-1722): alpha = <c,u> / (||u||^2 + 1e-8) over the whole sample, uncond *= alpha before the
+// combine.  dots[0] += sum c*u, dots[1] += sum u*u  (caller zeroes dots).
+__global__ void __launch_bounds__(256)
+cfg_dots_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float* __restrict__ dots, long long n4) {
+    __shared__ float red[8];
+    float cu = 0.f, uu = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
+        const float4 u = __ldg(reinterpret_cast<const float4*>(uncond) + i);
+        cu += c.x * u.x + c.y * u.y + c.z * u.z + c.w * u.w;
+        uu += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+    }
+    cu = block_sum_256(cu, red);
+    uu = block_sum_256(uu, red);
+    if (threadIdx.x == 0) { atomicAdd(dots, cu); atomicAdd(dots + 1, uu); }
+}
+
 __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond,
-                                 float g, float dt, float* __restrict__ pred_out, long long n4) {
+                                 float g, float dt, float* __restrict__ pred_out, const float* __restrict__ star_dots, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
     float4 u = uncond ? __ldg(reinterpret_cast<const float4*>(uncond) + i) : c;
+    if (star_dots) {
+        const float alpha = __ldg(star_dots) / (__ldg(star_dots + 1) + 1e-8f);
+        u.x *= alpha; u.y *= alpha; u.z *= alpha; u.w *= alpha;
+    }
     float4 p = make_float4(u.x + g * (c.x - u.x), u.y + g * (c.y - u.y), u.z + g * (c.z - u.z), u.w + g * (c.w - u.w));
     float4 x = reinterpret_cast<float4*>(lat)[i];
     x.x -= dt * p.x; x.y -= dt * p.y; x.z -= dt * p.z; x.w -= dt * p.w;

@@ -162,9 +162,11 @@ def add_vec(a, b):
     return out
 
 
-def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None):
+def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None, cfg_star=False):
+    """lat -= dt * (u + g (c - u)); cfg_star=True applies the CFG-Zero* rescale of u (any2video.py:1706-1714)."""
     _chk(lat, f32, "lat"), _chk(cond, f32, "cond")
     assert lat.is_contiguous() and cond.is_contiguous() and (uncond is None or uncond.is_contiguous())
+    dots = torch.empty(2, device=lat.device, dtype=f32) if cfg_star else None
     _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
-              lat.numel(), _stream())
+              _p(dots), lat.numel(), _stream())
     return lat

@@ -29,8 +29,9 @@ class WanDenoiser:
     """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
 
     def __init__(self, model, model2=None, vae=None, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0,
-                 switch_threshold=875, device="cuda"):
+                 switch_threshold=875, device="cuda", cfg_star_switch=False, cfg_zero_step=-1):
         self.model, self.model2, self.vae = model, model2, vae
+        self.cfg_star_switch, self.cfg_zero_step = cfg_star_switch, cfg_zero_step      # CFG-Zero* (any2video.py:1701-1722)
         self.device = torch.device(device)
         self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
         self.timesteps = euler_timesteps(num_steps, shift)
@@ -60,7 +61,8 @@ class WanDenoiser:
             cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
         if cond is None:
             return None
-        ops.cfg_euler_step_(latents, cond, uncond, g, dt)
+        # NB any2video.py:1719 is overwritten by :1722, so steps <= cfg_zero_step are ordinary un-rescaled CFG
+        ops.cfg_euler_step_(latents, cond, uncond, g, dt, cfg_star=self.cfg_star_switch and uncond is not None and i > self.cfg_zero_step)
         return latents
 
     @torch.no_grad()
