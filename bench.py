@@ -277,6 +277,10 @@ def main():
 
     model = WanModel(**cfg, device=dev).init_synthetic(seed=1)
     model2 = WanModel(**cfg, device=dev).init_synthetic(seed=2) if two_experts else None
+    if L <= 16384:          # launch-bound configs: replay one captured CUDA graph per block
+        model.use_cuda_graphs = True
+        if model2 is not None:
+            model2.use_cuda_graphs = True
     den = WanDenoiser(model, model2, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=875, device=dev)
     freqs = get_rotary_pos_embed(thw)
     g = torch.Generator().manual_seed(1000 + rank)

@@ -123,7 +123,8 @@ int b200_vae_prologue(const float* z, const float* mean, const float* std, const
 
 /* single-head attention, head dim C <= 512 (C % 64 == 0), per frame over N tokens: qkv bf16 [F, N, 3C];
  * out bf16 [F, N, C] (vae.py:276-315 AttentionBlock core, F.scaled_dot_product_attention).
- * workspace: caller-owned, >= N * roundup(N,64) * 6 bytes (fp32 scores + bf16 probabilities of one frame). */
+ * workspace: caller-owned, >= N * roundup(N,64) * 6 bytes (fp32 scores + bf16 probabilities of one frame).
+ * qkv must have 8 readable (finite) rows after the last frame when N % 8 != 0 (the GEMM extents are rounded up to 8). */
 int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
                          float scale, void* stream);
 

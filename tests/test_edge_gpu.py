@@ -1,0 +1,76 @@
+"""GPU edge cases of the hot path: ragged / minimal shapes, batch > 1, single-frame decode, frame cropping, error behaviour."""
+import math
+
+import pytest
+import torch
+
+from tests.helpers import rel_l2, vae_case, wan_case
+from wan2gp_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+bf16 = torch.bfloat16
+
+
+class Pipe:
+    _interrupt = False
+
+
+def test_attention_ragged_minimal():
+    from wan2gp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for Lq, Lk, H in [(1, 1, 1), (3, 129, 2), (257, 7, 1), (255, 511, 3), (8, 8, 5)]:
+        q, k, v = (torch.randn(L, H * 128, device="cuda", generator=g).to(bf16) for L in (Lq, Lk, Lk))
+        out = ops.attention(q, k, v, H)
+        qh, kh, vh = (t.double().reshape(-1, H, 128).permute(1, 0, 2) for t in (q, k, v))
+        ref = (torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128), -1) @ vh).permute(1, 0, 2).reshape(Lq, -1)
+        assert torch.isfinite(out).all() and rel_l2(out, ref) < 4e-3
+
+
+def test_wan_batch2_and_single_frame():
+    """x entries with B = 2 (any2video.py:1470 batch_size) and a single latent frame (image generation)."""
+    from oracle import wan_oracle
+    from wan2gp_b200.wan import WanModel
+    cfg, thw, sd, x, t, ctx, y = wan_case("tiny")
+    m = WanModel(**cfg)
+    m.load_state_dict(sd)
+    x2 = torch.cat([x, x.flip(2)], 0)
+    out = m([x2.clone()], t, [ctx], pipeline=Pipe())[0].cpu()
+    ref = wan_oracle.wan_forward(sd, cfg, x2, t, ctx, emulate_bf16=True)
+    assert out.shape == ref.shape == (2, 16) + thw and rel_l2(out, ref) < 5e-3
+    x1 = x[:, :, :1, :6, :10].contiguous()                      # T=1, H=6, W=10 -> L = 15 tokens
+    out1 = m([x1.clone()], t, [ctx], pipeline=Pipe())[0].cpu()  # freqs=None -> tables computed by the product code
+    assert rel_l2(out1, wan_oracle.wan_forward(sd, cfg, x1, t, ctx, emulate_bf16=True)) < 5e-3
+
+
+def test_vae_single_frame_odd_sizes_and_crop():
+    """Tl = 1 (no temporal up-sampling at all), spatial sizes that are not multiples of the 8x16 conv tile, frame cropping."""
+    from oracle import vae_oracle
+    from wan2gp_b200.wan import WanVAE
+    cfg, sd, _ = vae_case("vae_tiny")
+    vae = WanVAE(device="cuda", state_dict=sd, cfg=cfg)
+    for shape in [(16, 1, 5, 7), (16, 2, 3, 9)]:
+        z = synth._normal(shape, 1.0, 7, "edge.z", "cpu")
+        got = vae.model.decode(z[None].cuda(), vae.scale)[0].cpu()
+        ref = vae_oracle.vae_decode(sd, z, synth.VAE_MEAN, synth.VAE_STD, cfg, emulate_bf16=True)
+        assert got.shape == ref.shape == (3, 4 * (shape[1] - 1) + 1, 8 * shape[2], 8 * shape[3])
+        assert rel_l2(got, ref) < 2.5e-2
+    z = synth._normal((16, 3, 4, 6), 1.0, 8, "edge.z2", "cpu")
+    full = vae.decode_to_cpu_uint8([z.cuda()], 0)[0]
+    crop = vae.decode_to_cpu_uint8([z.cuda()], 0, target_frames=4, target_height=24, target_width=40, frame_start=2)[0]
+    assert crop.shape == (3, 4, 24, 40) and torch.equal(crop, full[:, 2:6, :24, :40])
+
+
+def test_error_behaviour():
+    from wan2gp_b200 import _lib, ops
+    from wan2gp_b200.wan import WanModel, WanVAE
+    cfg, thw, sd, x, t, ctx, y = wan_case("tiny")
+    m = WanModel(**cfg)
+    m.load_state_dict(sd)
+    with pytest.raises(NotImplementedError):
+        m([x.clone()], t, [ctx], vace_context=[x], pipeline=Pipe())
+    with pytest.raises(NotImplementedError):
+        m([x.clone()], torch.tensor([1.0, 2.0, 3.0]), [ctx], pipeline=Pipe())
+    with pytest.raises(_lib.B200Error):
+        ops.gemm(torch.zeros(4, 12, device="cuda", dtype=bf16), torch.zeros(8, 12, device="cuda", dtype=bf16))     # K % 8
+    with pytest.raises(NotImplementedError):
+        WanVAE(device="cuda").decode([torch.zeros(16, 1, 2, 2)], tile_size=256)

@@ -269,6 +269,8 @@ __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int N, long long lds, long long ldp, float scale_log2) {
     extern __shared__ float row[];
     __shared__ float red[8];
+    // N = real keys; N8 = columns of the score row that exist (N rounded up to 8): the tail gets probability 0
+    const int N8 = (N + 7) & ~7;
     const float* sr = s + (long long)blockIdx.x * lds;
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < N; i += 256) { const float v = sr[i] * scale_log2; row[i] = v; mx = fmaxf(mx, v); }
@@ -283,13 +285,15 @@ softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, 
     for (int i = threadIdx.x; i < N; i += 256) { const float e = exp2f(row[i] - mx); row[i] = e; sum += e; }
     const float inv = 1.f / block_sum_256(sum, red);
     __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
-    for (int i = threadIdx.x; i < N; i += 256) pr[i] = __float2bfloat16_rn(row[i] * inv);
+    for (int i = threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? row[i] * inv : 0.f);
 }
 
 extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
                                     float scale, void* stream) {
     if (!qkv || !out || !workspace) return b200_set_error(B200_ERR_ARG, "attention_1head: null argument");
-    if (C % 64 || N % 8) return b200_set_error(B200_ERR_ARG, "attention_1head: C %% 64 or N %% 8 != 0");
+    if (C % 64) return b200_set_error(B200_ERR_ARG, "attention_1head: C %% 64 != 0");
+    const int N8 = (N + 7) & ~7;      // GEMM extents are multiples of 8: the key tail [N, N8) gets probability 0 (the caller
+                                      // guarantees 8 readable rows after the last frame of qkv)
     const long long Np = (N + 63) / 64 * 64;          // padded row pitch so P is a legal GEMM operand
     const long long need = (long long)N * Np * 4 + (long long)N * Np * 2;
     if (workspace_bytes < need) return b200_set_error(B200_ERR_ARG, "attention_1head: workspace %lld < %lld bytes", workspace_bytes, need);
@@ -305,11 +309,11 @@ extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace,
     if ((long long)N * 4 > 200 * 1024) return b200_set_error(B200_ERR_ARG, "attention_1head: N=%d too large", N);
     for (int f = 0; f < F; ++f) {
         const __nv_bfloat16* q = base + (long long)f * N * 3 * C;
-        int r = b200_gemm_bf16(q, q + C, S, N, N, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
+        int r = b200_gemm_bf16(q, q + C, S, N, N8, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
         if (r) return r;
         softmax_rows_kernel<<<N, 256, N * sizeof(float), st>>>(S, P, N, Np, Np, scale * 1.4426950408889634f);
         CHECK_LAUNCH("softmax_rows");
-        r = b200_gemm_bf16(P, q + 2 * C, reinterpret_cast<__nv_bfloat16*>(out) + (long long)f * N * C, N, C, N, Np, 3LL * C, C,
+        r = b200_gemm_bf16(P, q + 2 * C, reinterpret_cast<__nv_bfloat16*>(out) + (long long)f * N * C, N, C, N8, Np, 3LL * C, C,
                            nullptr, nullptr, nullptr, 0, 0, 0, 1, stream);
         if (r) return r;
     }

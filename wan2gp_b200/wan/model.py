@@ -64,6 +64,10 @@ class WanModel(torch.nn.Module):
         self._freqs_cache = {}
         self._ctx_cache = None
         self.cache_context = False              # optional: reuse step-invariant text projections
+        # optional: one CUDA graph per transformer block (launch-bound small configs); the per-block
+        # interrupt poll of the reference stays between graph replays
+        self.use_cuda_graphs = False
+        self._graphs = {}
         self._ready = False
 
     # ------------------------------------------------------------------ weights
@@ -214,6 +218,37 @@ class WanModel(torch.nn.Module):
         o = ops.gemm(y, g["head_w"], bias=g["head_b"], out_dtype=f32)
         return ops.unpatchify(o, self.out_dim, T, H, W)
 
+    def _block_graphs(self, streams, e0, ctx_emb, cos, sin):
+        """Static input buffers + one captured CUDA graph per block for this (token count, entries, text length) signature.
+        Capture records the same C-ABI launches as the eager path (tensor maps are encoded at capture time on static
+        addresses); all graphs share one memory pool, so the temporaries of one block are reused by the next."""
+        key = (tuple(len(s) for s in streams), streams[0][0].shape, tuple(c.shape for c in ctx_emb), cos.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"x": [[torch.empty_like(s) for s in ss] for ss in streams], "e0": torch.empty_like(e0),
+                 "ctx": [torch.empty_like(c) for c in ctx_emb], "g": []}
+            pool = torch.cuda.graph_pool_handle()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for blk in self.blocks:
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg, pool=pool, stream=side):
+                        for i, ss in enumerate(g["x"]):
+                            ckv = self._cross_kv(blk, g["ctx"][i])
+                            for s in ss:
+                                self._block(blk, s, g["e0"], g["ctx"][i], cos, sin, ckv)
+                    g["g"].append(cg)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graphs = {key: g}
+        for dst, src in zip(g["x"], streams):
+            for d, s_ in zip(dst, src):
+                d.copy_(s_)
+        g["e0"].copy_(e0)
+        for d, c in zip(g["ctx"], ctx_emb):
+            d.copy_(c)
+        return g
+
     # ------------------------------------------------------------------ forward (reference contract)
     @torch.no_grad()
     def forward(self, x, t, context, y=None, freqs=None, pipeline=None, current_step_no=0, real_step_no=0, x_id=0,
@@ -261,16 +296,22 @@ class WanModel(torch.nn.Module):
             xi = xi.to(self.device, f32)
             streams.append([ops.patch_embed(xi[b].contiguous(), yd, self._g["pe_w"], self._g["pe_b"], self.dim) for b in range(xi.shape[0])])
         del x_list
+        graphs = self._block_graphs(streams, e0, ctx_emb, cos, sin) if self.use_cuda_graphs else None
         for idx, blk in enumerate(self.blocks):
             shared_state["layer"] = idx
             if callback is not None:
                 callback(-1, None, False, True)
             if pipeline is not None and getattr(pipeline, "_interrupt", False):
                 return [None] * n
+            if graphs is not None:
+                graphs["g"][idx].replay()
+                continue
             for i in range(n):
                 ckv = self._cross_kv(blk, ctx_emb[i])
                 for s in streams[i]:
                     self._block(blk, s, e0, ctx_emb[i], cos, sin, ckv)
+        if graphs is not None:
+            streams = list(graphs["x"])
         outs = []
         for i in range(n):
             outs.append(torch.stack([self._head(s, e, thw) for s in streams[i]], 0))

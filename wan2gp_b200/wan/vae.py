@@ -149,8 +149,9 @@ class WanVAEDecoder(torch.nn.Module):
         T, H, W, C = x.shape
         a = self.attn
         xn = rms_silu(x, a["g"], silu=False).reshape(T * H * W, C)
-        qkv = ops.gemm(xn, a["wqkv"], bias=a["bqkv"])                        # 1x1 conv == GEMM over pixels
         N = H * W
+        buf = torch.zeros(T * N + 8, 3 * C, device=x.device, dtype=bf16)    # 8 spare rows: key tail when N % 8 != 0
+        qkv = ops.gemm(xn, a["wqkv"], out=buf[:T * N], bias=a["bqkv"])      # 1x1 conv == GEMM over pixels
         npad = (N + 63) // 64 * 64
         ws = torch.empty(N * npad * 6, device=x.device, dtype=torch.uint8)
         o = torch.empty(T * N, C, device=x.device, dtype=bf16)
