@@ -94,7 +94,7 @@ def run_vae(name):
                         seconds=np.float32(dt), threads=np.int32(torch.get_num_threads()))
 
 
-HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0)}
+HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0), "hy10_tiny": ("hy10_tiny", (2, 8, 12), 1)}
 
 
 def run_hy(name):
@@ -102,21 +102,35 @@ def run_hy(name):
     hy = load_reference_hy()
     cfg_name, thw, seed = HY_CASES[name]
     cfg = synth.HY_CONFIGS[cfg_name]
-    kw = dict(hy.CONFIGS["HYVideo-1_5"])
+    v10 = cfg.get("family") == "1.0"
+    kw = dict(hy.CONFIGS["HYVideo-T/2-cfgdistill" if v10 else "HYVideo-1_5"])
     kw.update({k: cfg[k] for k in ("hidden_size", "heads_num", "mlp_width_ratio", "mm_double_blocks_depth", "text_states_dim")})
+    if v10:
+        kw.update(mm_single_blocks_depth=cfg["mm_single_blocks_depth"], text_states_dim_2=cfg["text_states_dim_2"])
     model = hy.HYVideoDiffusionTransformer(i2v_condition_type=None, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], **kw)
     model = model.eval().requires_grad_(False)
     sd = synth.make_hy_state_dict(cfg, seed)
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected and all(m.startswith("vision_in") for m in missing), (missing, unexpected)
     model.cache = None
+    if v10:
+        # hunyuan_handler.py:274-278: mmgp splits img_attn_qkv / linear1 into per-projection Linears at load time
+        from models.hyvideo.modules.models import get_linear_split_map
+        from oracle.refshim import split_linear_modules
+        split_linear_modules(model, get_linear_split_map())
     hook_linear_input_cast(model)         # fp32 weights + the reference's own bf16 hard-casts (see oracle/hy_oracle.py)
     x, t, txt, tm, b5, bm = synth.make_hy_inputs(cfg, thw, seed=seed)
-    cos, sin = hy.get_nd_rotary_pos_embed(cfg["rope_dim_list"], list(thw), theta=256, use_real=True, theta_rescale_factor=1,
-                                             enable_riflex=False)   # as hunyuan.py:716-724 with enable_riflex=False
+    P = cfg["patch_size"][1]
+    cos, sin = hy.get_nd_rotary_pos_embed(cfg["rope_dim_list"], [thw[0], thw[1] // P, thw[2] // P], theta=256, use_real=True,
+                                             theta_rescale_factor=1, enable_riflex=False)   # hunyuan.py:716-724
+    extra = {}
+    if v10:
+        extra = dict(text_states_2=synth._normal((1, cfg["text_states_dim_2"]), 1.0, seed, "hy.txt2", "cpu"),
+                     guidance=torch.tensor([6000.0]))
+    else:
+        extra = dict(byt5_text_states=b5, byt5_text_mask=bm)
     with torch.no_grad():
-        out = model(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Pipe(),
-                    byt5_text_states=b5, byt5_text_mask=bm)
+        out = model(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Pipe(), **extra)
     print(f"{name}: reference HY forward out {tuple(out.shape)} {out.dtype} absmean {out.float().abs().mean():.6f}")
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.float().numpy(), cos=cos[:64].numpy(), sin=sin[:64].numpy())
 

@@ -112,9 +112,12 @@ def double_block(sd, cfg, i, img, txt, vec, cos, sin, n_txt_valid, ref_casts, em
         if st == "img":
             xm = _q(xm, rc)                                     # img_modulated.to(torch.bfloat16), models.py:211
         xm = _q(xm * (1 + sc1) + sh1, em or (rc and st == "img"))   # modulate_ writes into the bf16 tensor (:216)
-        q = _q(lin(sd, p + "attn_q", xm, em), em).reshape(-1, H, hd)
-        k = _q(lin(sd, p + "attn_k", xm, em), em).reshape(-1, H, hd)
-        v = _q(lin(sd, p + "attn_v", xm, em), em).reshape(-1, H, hd)
+        if p + "attn_qkv.weight" in sd:                          # HunyuanVideo 1.0 keeps q|k|v fused (split by mmgp at load)
+            q, k, v = (u.reshape(-1, H, hd) for u in _q(lin(sd, p + "attn_qkv", xm, em), em).chunk(3, -1))
+        else:
+            q = _q(lin(sd, p + "attn_q", xm, em), em).reshape(-1, H, hd)
+            k = _q(lin(sd, p + "attn_k", xm, em), em).reshape(-1, H, hd)
+            v = _q(lin(sd, p + "attn_v", xm, em), em).reshape(-1, H, hd)
         q, k = rms_head(q, sd[p + "attn_q_norm.weight"]), rms_head(k, sd[p + "attn_k_norm.weight"])
         if st == "img":
             q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
@@ -139,24 +142,67 @@ def double_block(sd, cfg, i, img, txt, vec, cos, sin, n_txt_valid, ref_casts, em
     return out["img"], out["txt"]
 
 
-def hy_forward(sd, cfg, x, t, text_states, text_mask, byt5_states, byt5_mask, freqs=None, ref_casts=True, emulate_bf16=False,
-               num_blocks=None):
+def single_block(sd, cfg, i, img, txt, vec, cos, sin, n_txt_valid, ref_casts, em):
+    """MMSingleStreamBlock.forward (models.py:393-508): one modulation for both streams, linear1 = q|k|v|mlp_in, joint
+    attention, linear2(cat(attn, gelu(mlp))) stored into the bf16 buffer, gated accumulate."""
+    D, H = cfg["hidden_size"], cfg["heads_num"]
+    hd = D // H
+    rc = ref_casts or em
+    p = f"single_blocks.{i}."
+    sh, sc, gate = (F.silu(vec) @ sd[p + "modulation.linear.weight"].float().t() + sd[p + "modulation.linear.bias"].float()).chunk(3)
+    L = img.shape[0]
+    x = torch.cat([img, txt], 0)
+    xm = _q(_q(F.layer_norm(x, (D,), eps=1e-6), rc) * (1 + sc) + sh, rc)      # pre_norm -> bf16 -> modulate_ (:427-435)
+    h1 = lin(sd, p + "linear1", xm, em)
+    q, k, v = (_q(u, em).reshape(-1, H, hd) for u in h1[:, :3 * D].chunk(3, -1))
+    q, k = rms_head(q, sd[p + "q_norm.weight"]), rms_head(k, sd[p + "k_norm.weight"])
+    q = torch.cat([apply_rope(q[:L], cos, sin), q[L:]], 0)
+    k = torch.cat([apply_rope(k[:L], cos, sin), k[L:]], 0)
+    n = L + n_txt_valid
+    attn = _q(attention(_q(q, em)[:n], _q(k, em)[:n], v[:n], em).reshape(n, D), em)
+    attn = torch.cat([attn, attn.new_zeros(x.shape[0] - n, D)], 0)
+    mlp = _q(F.gelu(h1[:, 3 * D:], approximate="tanh"), em)
+    y = _q(lin(sd, p + "linear2", torch.cat([attn, mlp], -1), em), rc)       # x_chunk[...] = linear2(...) into bf16 (:493)
+    x = x + y * gate
+    return x[:L], x[L:]
+
+
+def hy_forward(sd, cfg, x, t, text_states, text_mask, byt5_states=None, byt5_mask=None, freqs=None, ref_casts=True,
+               emulate_bf16=False, num_blocks=None, text_states_2=None, guidance=None):
     """x [1,Cin,T,H,W] -> [1,Cout,T,H,W]; masks must mark a valid PREFIX (as the reference's encoders produce)."""
     em = emulate_bf16
     D = cfg["hidden_size"]
     _, Cin, T, H, W = x.shape
-    cos, sin = freqs if freqs is not None else rope_tables_hy((T, H, W))
+    P = cfg["patch_size"][1]
+    cos, sin = freqs if freqs is not None else rope_tables_hy((T, H // P, W // P))
     vec = timestep_embedder(sd, "time_in.", t)[0]
-    img = x[0].reshape(Cin, -1).t() @ sd["img_in.proj.weight"].float().reshape(D, Cin).t() + sd["img_in.proj.bias"].float()
-    nt, nb = int(text_mask[0].sum()), int(byt5_mask[0].sum())
-    txt = token_refiner(sd, cfg, text_states[0, :nt].float(), t, nt, em) + sd["cond_type_embedding.weight"][0].float()
-    b5 = byt5_mapper(sd, byt5_states[0, :nb].float(), em) + sd["cond_type_embedding.weight"][1].float()
-    n_pad = (text_states.shape[1] - nt) + (byt5_states.shape[1] - nb)
-    txt = torch.cat([b5, txt, txt.new_zeros(n_pad, D)], 0)      # reorder_txt_token(zero_feat=True), models.py:910-935
+    if text_states_2 is not None:                              # pooled-text vector (models.py:1012-1019, MLPEmbedder)
+        h = F.silu(text_states_2[0].float() @ sd["vector_in.in_layer.weight"].float().t() + sd["vector_in.in_layer.bias"].float())
+        vec = vec + h @ sd["vector_in.out_layer.weight"].float().t() + sd["vector_in.out_layer.bias"].float()
+    if guidance is not None:                                   # guidance-distilled models (models.py:1021-1029)
+        vec = vec + timestep_embedder(sd, "guidance_in.", guidance)[0]
+    # PatchEmbed (embed_layers.py:9-60): Conv3d k = s = patch; K order (c, ph, pw), tokens (t, h', w')
+    xp = x[0].reshape(Cin, T, H // P, P, W // P, P).permute(1, 2, 4, 0, 3, 5).reshape(T * (H // P) * (W // P), Cin * P * P)
+    img = xp @ sd["img_in.proj.weight"].float().reshape(D, -1).t() + sd["img_in.proj.bias"].float()
+    nt = int(text_mask[0].sum())
+    txt = token_refiner(sd, cfg, text_states[0, :nt].float(), t, nt, em)
+    n_valid, n_pad = nt, text_states.shape[1] - nt
+    if "cond_type_embedding.weight" in sd:
+        txt = txt + sd["cond_type_embedding.weight"][0].float()
+    if byt5_states is not None:
+        nb = int(byt5_mask[0].sum())
+        b5 = byt5_mapper(sd, byt5_states[0, :nb].float(), em) + sd["cond_type_embedding.weight"][1].float()
+        txt = torch.cat([b5, txt], 0)                           # reorder_txt_token(zero_feat=True), models.py:910-935
+        n_valid, n_pad = n_valid + nb, n_pad + byt5_states.shape[1] - nb
+    txt = torch.cat([txt, txt.new_zeros(n_pad, D)], 0)
     nblk = cfg["mm_double_blocks_depth"] if num_blocks is None else num_blocks
     for i in range(nblk):
-        img, txt = double_block(sd, cfg, i, img, txt, vec, cos, sin, nt + nb, ref_casts, em)
+        img, txt = double_block(sd, cfg, i, img, txt, vec, cos, sin, n_valid, ref_casts, em)
+    for i in range(cfg.get("mm_single_blocks_depth", 0)):
+        img, txt = single_block(sd, cfg, i, img, txt, vec, cos, sin, n_valid, ref_casts, em)
     sh, sc = (F.silu(vec) @ sd["final_layer.adaLN_modulation.1.weight"].float().t() + sd["final_layer.adaLN_modulation.1.bias"].float()).chunk(2)
     y = _q(F.layer_norm(img, (D,), eps=1e-6) * (1 + sc) + sh, em)
-    y = lin(sd, "final_layer.linear", y, em)                     # [L, Cout] (patch 1,1,1)
-    return y.t().reshape(1, -1, T, H, W)
+    y = lin(sd, "final_layer.linear", y, em)                     # [L, Cout * P * P], feature order (c, ph, pw)
+    C = cfg["out_channels"]
+    y = y.reshape(T, H // P, W // P, C, 1, P, P)
+    return torch.einsum("thwcopq->ctohpwq", y).reshape(1, C, T, H, W)   # unpatchify, models.py:1235-1248

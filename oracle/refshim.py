@@ -187,3 +187,28 @@ def hook_linear_input_cast(model):
         if isinstance(mod, (torch.nn.Linear, torch.nn.Conv3d)):
             mod.register_forward_pre_hook(pre)
     return model
+
+
+def split_linear_modules(model, split_map):
+    """Restatement of mmgp.offload.split_linear_modules (mmgp==3.7.12, requirements.txt:2 -- third-party, NOT in the reference
+    tree) as used at models/hyvideo/hunyuan_handler.py:274-278: every sub-module that owns a Linear named <key> gets extra
+    Linear children `mapped_modules[i]` holding consecutive row slices (`split_sizes`) of its weight / bias.  No arithmetic."""
+    import torch
+    for mod in list(model.modules()):
+        for key, spec in split_map.items():
+            lin = getattr(mod, key, None)
+            if not isinstance(lin, torch.nn.Linear):
+                continue
+            sizes = spec["split_sizes"]
+            total = lin.weight.shape[0]
+            if sum(sizes) != total:                      # the map is written for hidden_size 3072: rescale for reduced configs
+                sizes = [s * total // sum(sizes) for s in sizes]
+            off = 0
+            for name, n in zip(spec["mapped_modules"], sizes):
+                sub = torch.nn.Linear(lin.in_features, n, bias=lin.bias is not None)
+                sub.weight = torch.nn.Parameter(lin.weight[off:off + n].detach().clone(), requires_grad=False)
+                if lin.bias is not None:
+                    sub.bias = torch.nn.Parameter(lin.bias[off:off + n].detach().clone(), requires_grad=False)
+                setattr(mod, name, sub)
+                off += n
+    return model

@@ -84,3 +84,24 @@ def test_hy_forward_tiny():
     class Stop:
         _interrupt = True
     assert m(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Stop(), byt5_text_states=b5, byt5_text_mask=bm) is None
+
+
+def test_hy10_forward_tiny():
+    """HunyuanVideo 1.0 family: fused qkv double block + single-stream blocks (H3), pooled-text vector, guidance embed, patch 2."""
+    from oracle import hy_oracle
+    from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer
+    cfg, thw, seed = synth.HY_CONFIGS["hy10_tiny"], (2, 8, 12), 1
+    sd = synth.make_hy_state_dict(cfg, seed)
+    x, t, txt, tm, _, _ = synth.make_hy_inputs(cfg, thw, seed=seed)
+    t2 = synth._normal((1, cfg["text_states_dim_2"]), 1.0, seed, "hy.txt2", "cpu")
+    gd = torch.tensor([6000.0])
+    m = HYVideoDiffusionTransformer(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=16, out_channels=16,
+                                    hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"], mm_double_blocks_depth=1,
+                                    mm_single_blocks_depth=2, text_states_dim=cfg["text_states_dim"],
+                                    text_states_dim_2=cfg["text_states_dim_2"], guidance_embed=True)
+    m.load_state_dict(sd)
+    out = m(x, t, text_states=txt, text_mask=tm, text_states_2=t2, guidance=gd, pipeline=Pipe()).cpu()
+    emu = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, emulate_bf16=True, text_states_2=t2, guidance=gd)
+    g = load_golden("hy10_tiny")["out"]
+    print(f"hy10_tiny: vs bf16-emulating oracle {rel_l2(out, emu):.3e}; vs reference {rel_l2(out, g):.3e}")
+    assert out.shape == g.shape and rel_l2(out, emu) < 6e-3 and rel_l2(out, g) < 6e-3

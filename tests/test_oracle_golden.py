@@ -83,3 +83,15 @@ def test_hy_oracle_matches_reference():
     out = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, ref_casts=True)
     assert rel_l2(out, g["out"]) < 2e-5
     assert rel_l2(hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, emulate_bf16=True), g["out"]) < 5e-3
+
+
+def test_hy10_oracle_matches_reference():
+    """HunyuanVideo 1.0 family (double + single-stream blocks; mmgp's load-time Linear split restated in oracle/refshim.py)."""
+    from oracle import hy_oracle
+    from wan2gp_b200 import synth
+    cfg, thw, seed = synth.HY_CONFIGS["hy10_tiny"], (2, 8, 12), 1
+    sd = synth.make_hy_state_dict(cfg, seed)
+    x, t, txt, tm, _, _ = synth.make_hy_inputs(cfg, thw, seed=seed)
+    t2 = synth._normal((1, cfg["text_states_dim_2"]), 1.0, seed, "hy.txt2", "cpu")
+    out = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, ref_casts=True, text_states_2=t2, guidance=torch.tensor([6000.0]))
+    assert rel_l2(out, load_golden("hy10_tiny")["out"]) < 3e-5

@@ -1,4 +1,6 @@
-"""B200-native HYVideoDiffusionTransformer for the 'HYVideo-1_5' family (hot-path rows H1-H4 of SURVEY.md section 8a):
+"""B200-native HYVideoDiffusionTransformer (hot-path rows H1-H4 of SURVEY.md section 8a) for the 'HYVideo-1_5' family (54
+double-stream blocks) and the HunyuanVideo 1.0 family ('HYVideo-T/2[-cfgdistill]': 20 double + 40 single-stream blocks,
+fused qkv, pooled-text and guidance vectors, patch (1,2,2)):
 same constructor arguments, state-dict names and forward() contract as the reference
 `models/hyvideo/modules/models.py::HYVideoDiffusionTransformer` (:946-1233) -- double-stream blocks (:158-318) with per-head
 QK RMSNorm, RoPE on the image stream, joint attention over cat(img, txt) trimmed to the valid text length, token refiner
@@ -38,6 +40,10 @@ class _Stream:
     __slots__ = ("mod_w", "mod_b", "w_qkv", "b_qkv", "qn", "kn", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")
 
 
+class _Single:
+    __slots__ = ("mod_w", "mod_b", "w1", "b1", "w2", "b2", "qn", "kn")
+
+
 class HYVideoDiffusionTransformer(torch.nn.Module):
     def __init__(self, i2v_condition_type=None, patch_size=(1, 2, 2), in_channels=4, out_channels=None, hidden_size=3072,
                  heads_num=24, mlp_width_ratio=4.0, mlp_act_type="gelu_tanh", mm_double_blocks_depth=20,
@@ -46,9 +52,8 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
                  text_states_dim_2=768, text_pool_type=True, glyph_byT5_v2=False, use_cond_type_embedding=False,
                  use_meanflow=False, vision_projection=False, pre_split_qkv=False, device="cuda", **unused):
         super().__init__()
-        if mm_single_blocks_depth != 0 or text_pool_type is not None or guidance_embed or use_meanflow or i2v_condition_type:
-            raise NotImplementedError("only the HYVideo-1_5 family (double-stream blocks only, no pooled-text / guidance / "
-                                      "token-replace conditioning) is implemented; HunyuanVideo 1.0 single blocks are a next row")
+        if use_meanflow or i2v_condition_type:
+            raise NotImplementedError("meanflow / token-replace (i2v) conditioning is outside the t2v hot path")
         if hidden_size // heads_num != 128 or not qk_norm or qk_norm_type != "rms" or text_projection != "single_refiner":
             raise NotImplementedError("HY hot path requires head_dim 128, RMS qk-norm and the single_refiner text projection")
         if tuple(patch_size) not in ((1, 1, 1), (1, 2, 2)):
@@ -56,6 +61,8 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         self.patch_size, self.in_channels = list(patch_size), in_channels
         self.out_channels = in_channels if out_channels is None else out_channels
         self.hidden_size, self.heads_num, self.depth = hidden_size, heads_num, mm_double_blocks_depth
+        self.single_depth, self.mlp_hidden = mm_single_blocks_depth, int(hidden_size * mlp_width_ratio)
+        self.text_pool_type, self.text_states_dim_2 = text_pool_type, text_states_dim_2
         self.rope_dim_list, self.text_states_dim = list(rope_dim_list), text_states_dim
         self.glyph_byT5_v2, self.use_cond = glyph_byT5_v2, use_cond_type_embedding
         self.i2v_condition_type, self.guidance_embed = i2v_condition_type, guidance_embed
@@ -109,8 +116,22 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
                 g["byt5_" + n] = self._lin(sd, "byt5_in." + n)
         if self.use_cond:
             g["cond"] = self._d(sd["cond_type_embedding.weight"], f32)
+        if self.text_pool_type is not None:
+            g["vector_in.in_layer"] = self._lin(sd, "vector_in.in_layer", f32)
+            g["vector_in.out_layer"] = self._lin(sd, "vector_in.out_layer", f32)
+        if self.guidance_embed:
+            g["guidance_in.mlp.0"] = self._lin(sd, "guidance_in.mlp.0", f32)
+            g["guidance_in.mlp.2"] = self._lin(sd, "guidance_in.mlp.2", f32)
         self.double_blocks = [(self._pack_stream(sd, f"double_blocks.{i}.img_"), self._pack_stream(sd, f"double_blocks.{i}.txt_"))
                               for i in range(self.depth)]
+        self.single_blocks = []
+        for i in range(self.single_depth):
+            p, b = f"single_blocks.{i}.", _Single()
+            b.mod_w, b.mod_b = self._lin(sd, p + "modulation.linear", f32)
+            b.w1, b.b1 = self._lin(sd, p + "linear1")          # rows: q | k | v | mlp_in  (split by mmgp in the reference)
+            b.w2, b.b2 = self._lin(sd, p + "linear2")
+            b.qn, b.kn = self._d(sd[p + "q_norm.weight"], f32), self._d(sd[p + "k_norm.weight"], f32)
+            self.single_blocks.append(b)
         self._ready = True
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
@@ -118,7 +139,8 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         from .. import synth
         cfg = dict(hidden_size=self.hidden_size, heads_num=self.heads_num, mlp_width_ratio=4, mm_double_blocks_depth=self.depth,
                    in_channels=self.in_channels, out_channels=self.out_channels, text_states_dim=self.text_states_dim,
-                   patch_size=self.patch_size)
+                   patch_size=self.patch_size, mm_single_blocks_depth=self.single_depth, guidance_embed=self.guidance_embed,
+                   text_states_dim_2=self.text_states_dim_2, family="1.0" if self.text_pool_type is not None else "1.5")
         self.load_state_dict({n: synth.make_hy_tensor(n, s, seed, self.device) for n, s in synth.hy_param_shapes(cfg).items()})
         return self
 
@@ -197,6 +219,22 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
             h = ops.gemm(a, s.w_fc1, bias=s.b_fc1, act=ACT_GELU_TANH)
             ops.gemm(h, s.w_fc2, out=x, bias=s.b_fc2, gate=m[5 * D:], accumulate=True)
 
+    def _single_block(self, b, img, txt, vec, cos, sin, n_valid, qkv, cat):
+        """MMSingleStreamBlock (models.py:393-508): shared modulation, linear1 = q|k|v|mlp_in, joint attention written straight
+        into the first D columns of the [attn | gelu(mlp)] buffer that feeds linear2, gated accumulate into both streams."""
+        D, H, L = self.hidden_size, self.heads_num, img.shape[0]
+        m = ops.gemv(vec, b.mod_w, b.mod_b, silu_in=True)
+        for x, rows, rope in ((img, slice(0, L), (cos, sin)), (txt, slice(L, None), (None, None))):
+            a = ops.ln_modulate(x, m[0:D], m[D:2 * D], pre_round=True)
+            ops.gemm(a, b.w1[:3 * D], out=qkv[rows], bias=b.b1[:3 * D])
+            ops.gemm(a, b.w1[3 * D:], out=cat[rows, D:], bias=b.b1[3 * D:], act=ACT_GELU_TANH)
+            ops.rmsnorm_rope_(qkv[rows, :D], b.qn, 1e-6, *rope, per_head=True)
+            ops.rmsnorm_rope_(qkv[rows, D:2 * D], b.kn, 1e-6, *rope, per_head=True)
+        n = L + n_valid
+        ops.attention(qkv[:n, :D], qkv[:n, D:2 * D], qkv[:n, 2 * D:], H, out=cat[:n, :D])
+        for x, rows in ((img, slice(0, L)), (txt, slice(L, None))):
+            ops.gemm(cat[rows], b.w2, out=x, bias=b.b2, gate=m[2 * D:], accumulate=True)
+
     # ------------------------------------------------------------------ forward (reference contract)
     @torch.no_grad()
     def forward(self, x, t, ref_latents=None, text_states=None, text_mask=None, text_states_2=None, freqs_cos=None,
@@ -207,7 +245,11 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         [B,Cout,T,H,W] fp32, or None when `pipeline._interrupt` is raised (polled once per block, models.py:1146-1149)."""
         if not self._ready:
             raise RuntimeError("HYVideoDiffusionTransformer: load_state_dict() / init_synthetic() must be called before forward()")
-        for name, v in (("ref_latents", ref_latents), ("text_states_2", text_states_2), ("audio_prompts", audio_prompts),
+        if (text_states_2 is None) != (self.text_pool_type is None):
+            raise ValueError("text_states_2 must be given exactly when the model has a pooled-text vector_in (text_pool_type)")
+        if self.guidance_embed and guidance is None:
+            raise ValueError("Didn't get guidance strength for guidance distilled model.")       # models.py:1023-1026
+        for name, v in (("ref_latents", ref_latents), ("audio_prompts", audio_prompts),
                         ("motion_exp", motion_exp), ("motion_pose", motion_pose), ("fps", fps), ("bg_latents", bg_latents),
                         ("vision_states", vision_states), ("timesteps_r", timesteps_r)):
             if v is not None:
@@ -223,22 +265,37 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         for i in range(B):
             ti = float(t.flatten()[i] if t.numel() > 1 else t.flatten()[0])
             vec = self._tembed("time_in", ti)
+            if text_states_2 is not None:                       # vector_in MLPEmbedder (models.py:1012-1019)
+                (w1, b1), (w2, b2) = self._g["vector_in.in_layer"], self._g["vector_in.out_layer"]
+                pooled = text_states_2[i].to(self.device, f32).contiguous()
+                vec = ops.add_vec(vec, ops.gemv(ops.gemv(pooled, w1, b1, silu_out=True), w2, b2))
+            if self.guidance_embed:                             # guidance_in TimestepEmbedder (models.py:1021-1029)
+                gi = float(guidance.flatten()[i] if guidance.numel() > 1 else guidance.flatten()[0])
+                vec = ops.add_vec(vec, self._tembed("guidance_in", gi))
             img = ops.patch_embed(x[i].to(self.device, f32).contiguous(), None, self._g["img_w"], self._g["img_b"], D, patch=P)
             txt, n_valid = self._text(text_states[i], None if text_mask is None else text_mask[i],
                                       None if byt5_text_states is None else byt5_text_states[i],
                                       None if byt5_text_mask is None else byt5_text_mask[i], ti)
             Lt = txt.shape[0]
+            cat = torch.zeros(L + Lt, D + self.mlp_hidden, device=self.device, dtype=bf16) if self.single_blocks else None
             streams.append((img, txt, vec, n_valid, torch.empty(L + Lt, 3 * D, device=self.device, dtype=bf16),
-                            torch.zeros(L + Lt, D, device=self.device, dtype=bf16)))
+                            torch.zeros(L + Lt, D, device=self.device, dtype=bf16), cat))
         for blk in self.double_blocks:
-            for (img, txt, vec, n_valid, qkv, attn) in streams:
+            for (img, txt, vec, n_valid, qkv, attn, cat) in streams:
                 if callback is not None:
                     callback(-1, None, False, True)
                 if pipeline is not None and getattr(pipeline, "_interrupt", False):
                     return None
                 self._double_block(blk, img, txt, vec, cos, sin, n_valid, qkv, attn)
+        for blk in self.single_blocks:
+            for (img, txt, vec, n_valid, qkv, attn, cat) in streams:
+                if callback is not None:
+                    callback(-1, None, False, True)
+                if pipeline is not None and getattr(pipeline, "_interrupt", False):
+                    return None
+                self._single_block(blk, img, txt, vec, cos, sin, n_valid, qkv, cat)
         fw, fb = self._g["final_layer.adaLN_modulation.1"]
-        for (img, txt, vec, n_valid, qkv, attn) in streams:
+        for (img, txt, vec, n_valid, qkv, attn, cat) in streams:
             m = ops.gemv(vec, fw, fb, silu_in=True)                          # FinalLayer (mlp_layers.py:127-131): shift, scale
             y = ops.ln_modulate(img, m[:D], m[D:])
             o = ops.gemm(y, self._g["final"][0], bias=self._g["final"][1], out_dtype=f32)

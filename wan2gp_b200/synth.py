@@ -221,6 +221,14 @@ HY_CONFIGS = {
     "hy_tiny": dict(hidden_size=256, heads_num=2, mlp_width_ratio=4, mm_double_blocks_depth=2, in_channels=65,
                     out_channels=32, text_states_dim=96, patch_size=[1, 1, 1], rope_dim_list=[16, 56, 56]),
 }
+HY_CONFIGS["hy10_tiny"] = dict(hidden_size=256, heads_num=2, mlp_width_ratio=4, mm_double_blocks_depth=1, mm_single_blocks_depth=2,
+                               in_channels=16, out_channels=16, text_states_dim=96, text_states_dim_2=64, patch_size=[1, 2, 2],
+                               rope_dim_list=[16, 56, 56], guidance_embed=True, family="1.0")
+# models/hyvideo/modules/models.py:1287-1295 'HYVideo-T/2-cfgdistill' (HunyuanVideo 1.0: 20 double + 40 single blocks)
+HY_CONFIGS["HYVideo-T/2-cfgdistill"] = dict(hidden_size=3072, heads_num=24, mlp_width_ratio=4, mm_double_blocks_depth=20,
+                                            mm_single_blocks_depth=40, in_channels=16, out_channels=16, text_states_dim=4096,
+                                            text_states_dim_2=768, patch_size=[1, 2, 2], rope_dim_list=[16, 56, 56],
+                                            guidance_embed=True, family="1.0")
 HY_BYT5_DIMS = (1472, 2048, 2048)      # ByT5Mapper(in_dim, hidden_dim, out_dim) constants, models.py:647-653
 
 
@@ -231,12 +239,19 @@ def hy_param_shapes(cfg):
     F = int(D * cfg["mlp_width_ratio"])
     bi, bh, bo = HY_BYT5_DIMS
     pp = cfg["patch_size"][0] * cfg["patch_size"][1] * cfg["patch_size"][2]
-    s = {"byt5_in.layernorm.weight": (bi,), "byt5_in.layernorm.bias": (bi,)}
+    v10 = cfg.get("family") == "1.0"          # HunyuanVideo 1.0: fused qkv, single-stream blocks, pooled-text + guidance vectors
+    s = {}
 
     def lin(name, o, i):
         s[name + ".weight"] = (o, i)
         s[name + ".bias"] = (o,)
-    lin("byt5_in.fc1", bh, bi), lin("byt5_in.fc2", bo, bh), lin("byt5_in.fc3", D, bo)
+    if not v10:
+        s["byt5_in.layernorm.weight"] = s["byt5_in.layernorm.bias"] = (bi,)
+        lin("byt5_in.fc1", bh, bi), lin("byt5_in.fc2", bo, bh), lin("byt5_in.fc3", D, bo)
+    else:
+        lin("vector_in.in_layer", D, cfg["text_states_dim_2"]), lin("vector_in.out_layer", D, D)
+        if cfg.get("guidance_embed"):
+            lin("guidance_in.mlp.0", D, 256), lin("guidance_in.mlp.2", D, D)
     s["img_in.proj.weight"] = (D, Cin, *cfg["patch_size"])
     s["img_in.proj.bias"] = (D,)
     lin("txt_in.input_embedder", D, Td)
@@ -252,12 +267,20 @@ def hy_param_shapes(cfg):
         for st in ("img", "txt"):
             p = f"double_blocks.{i}.{st}_"
             lin(p + "mod.linear", 6 * D, D)
-            for l in "qkv":
-                lin(p + "attn_" + l, D, D)
+            if v10:
+                lin(p + "attn_qkv", 3 * D, D)
+            else:
+                for l in "qkv":
+                    lin(p + "attn_" + l, D, D)
             s[p + "attn_q_norm.weight"] = s[p + "attn_k_norm.weight"] = (D // cfg["heads_num"],)
             lin(p + "attn_proj", D, D), lin(p + "mlp.fc1", F, D), lin(p + "mlp.fc2", D, F)
+    for i in range(cfg.get("mm_single_blocks_depth", 0)):
+        p = f"single_blocks.{i}."
+        lin(p + "linear1", 3 * D + F, D), lin(p + "linear2", D, D + F), lin(p + "modulation.linear", 3 * D, D)
+        s[p + "q_norm.weight"] = s[p + "k_norm.weight"] = (D // cfg["heads_num"],)
     lin("final_layer.linear", pp * Co, D), lin("final_layer.adaLN_modulation.1", 2 * D, D)
-    s["cond_type_embedding.weight"] = (3, D)
+    if not v10:
+        s["cond_type_embedding.weight"] = (3, D)
     return s
 
 
@@ -266,7 +289,7 @@ def make_hy_tensor(name, shape, seed=0, device="cpu"):
         return 1.0 + _normal(shape, 0.1, seed, name, device)
     if name.endswith("bias"):
         return _normal(shape, 0.02, seed, name, device)
-    if "mod.linear" in name or "adaLN_modulation" in name or name.startswith(("final_layer.linear", "cond_type_embedding")):
+    if "mod.linear" in name or "modulation.linear" in name or "adaLN_modulation" in name or name.startswith(("final_layer.linear", "cond_type_embedding")):
         return _normal(shape, 0.02, seed, name, device)          # zero-initialised in the reference; randomised so they matter
     fan_in = math.prod(shape[1:])
     return _normal(shape, 1.0 / math.sqrt(fan_in), seed, name, device)
