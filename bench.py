@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (config, latent (T,H,W), two experts?, description)
     "wan22_t2v_14b_720p81": ("t2v_2_2", (21, 90, 160), True, "Wan2.2 t2v 14B, latent [1,16,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 12"),
+    # BASELINE configs[2]: Wan2.2 i2v 14B (in_dim 36: 16 latent + 4 mask + 16 image-latent channels), CFG pair
+    "wan22_i2v_14b_720p81": ("i2v_2_2", (21, 90, 160), True, "Wan2.2 i2v 14B, latent [1,16,21,90,160] + y [20,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 5"),
     "wan21_t2v_1.3b_p": ("t2v_1.3B", (9, 30, 52), False, "Wan2.1 t2v 1.3B, latent [1,16,9,30,52] (BASELINE config 0), CFG pair"),
     "tiny": ("small", (5, 16, 24), False, "reduced config for smoke runs"),
     # BASELINE configs[3]: Hunyuan Video 1.5 t2v 720p, 129 frames -> latent [1,32,33,45,80] (+33 cond channels), 54 double blocks
@@ -225,6 +227,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wan22_t2v_14b_720p81", choices=list(WORKLOADS))
     ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--cfg-split", action="store_true", help="split each CFG pair over 2 GPUs (one 19 MB exchange per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -281,9 +284,21 @@ def main():
         model.use_cuda_graphs = True
         if model2 is not None:
             model2.use_cuda_graphs = True
-    den = WanDenoiser(model, model2, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=875, device=dev)
+    i2v = cfg["in_dim"] > 16
+    n_samples, sample_id, cfg_kw = world, rank, {}
+    if args.cfg_split and world > 1:
+        from wan2gp_b200 import dist as wdist
+        grp, cfg_rank, sample_id, n_samples = wdist.make_cfg_pairs()
+        cfg_kw = dict(cfg_group=grp, cfg_rank=cfg_rank)
+        config["parallelism"] = f"{n_samples} samples, each CFG pair split over 2 GPUs (per-step 2-rank all-gather of the prediction)"
+    den = WanDenoiser(model, model2, num_steps=50, shift=5.0 if i2v else 12.0, guide_scale=3.5 if i2v else 4.0,
+                      guide2_scale=3.5 if i2v else 3.0, switch_threshold=900 if i2v else 875, device=dev, **cfg_kw)
     freqs = get_rotary_pos_embed(thw)
-    g = torch.Generator().manual_seed(1000 + rank)
+    g = torch.Generator().manual_seed(1000 + sample_id)
+    y_dev = None
+    if i2v:
+        y_dev = torch.randn(cfg["in_dim"] - 16, T, H, W, generator=g).to(dev)
+        y_dev[:4] = (y_dev[:4] > 0).float()
     lat_host = torch.randn(1, 16, T, H, W, generator=g).pin_memory()
     ctx_host = torch.randn(1, cfg["text_len"], cfg["text_dim"], generator=g).pin_memory()
     ctxn_host = torch.zeros(1, cfg["text_len"], cfg["text_dim"]).pin_memory()
@@ -297,14 +312,14 @@ def main():
 
     # steps are taken around the expert switch (t = 875) so both experts are exercised like in the real schedule
     sched = [i for i, t in enumerate(den.timesteps[:-1])]
-    sw = next((i for i in sched if den.timesteps[i] <= 875), 0)
+    sw = next((i for i in sched if den.timesteps[i] <= den.switch_threshold), 0)
     first = max(0, sw - (args.warmup + args.steps) // 2)
 
     def step_idx(k):
         return min(first + k, den.num_steps - 1)
 
     for k in range(args.warmup):
-        den.step(latents, step_idx(k), ctx, ctxn, freqs=freqs)
+        den.step(latents, step_idx(k), ctx, ctxn, y=y_dev, freqs=freqs)
     barrier()
     launches0 = _lib.launch_count()
     ops.TIMED["attention"] = []
@@ -315,7 +330,7 @@ def main():
     with ClockSampler(local_rank) as clk:
         ev0.record()
         for k in range(args.steps):
-            den.step(latents, step_idx(args.warmup + k), ctx, ctxn, freqs=freqs)
+            den.step(latents, step_idx(args.warmup + k), ctx, ctxn, y=y_dev, freqs=freqs)
         ev1.record()
         barrier()
     if prof_range:
@@ -333,7 +348,7 @@ def main():
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for k in range(e2e_steps):
-        den.step_host(lat_host, step_idx(args.warmup + k), ctx_host, ctxn_host, freqs=freqs)
+        den.step_host(lat_host, step_idx(args.warmup + k), ctx_host, ctxn_host, y=y_dev, freqs=freqs)
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
@@ -343,15 +358,15 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(times[0]), float(times[1])
     pk = peaks()
-    steps_per_s = world * args.steps / (ms / 1000.0)
-    flops_step = 2.0 * wan_flops_forward(cfg, L, cfg["text_len"])
+    steps_per_s = n_samples * args.steps / (ms / 1000.0)
+    flops_step = 2.0 * wan_flops_forward(cfg, L, cfg["text_len"]) * (n_samples / world)      # per GPU
     att_avg = sum(att_ms) / max(1, len(att_ms))
     att_tf = att_work / (att_avg * 1e-3) / 1e12 if att_ms else None
     result = {
         "metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config,
-        "e2e": {"value": world * e2e_steps / (e2e_ms / 1000.0), "unit": "steps/s", "steps": e2e_steps,
+        "e2e": {"value": n_samples * e2e_steps / (e2e_ms / 1000.0), "unit": "steps/s", "steps": e2e_steps,
                 "h2d_bytes_per_step": lat_host.numel() * 4 + ctx_host.numel() * 4 + ctxn_host.numel() * 4,
                 "d2h_bytes_per_step": lat_host.numel() * 4},
         "gpu_launches": launches,

@@ -50,3 +50,45 @@ def test_euler_schedule_matches_reference_formula():
     t = 1000.0 - 999.0 / 49.0          # second linspace point
     assert abs(ts[1] - 12 * (t / 1000) / (1 + 11 * (t / 1000)) * 1000) < 1e-2
     assert sum(1 for v in ts[:-1] if v > 875) >= 1       # both Wan2.2 experts are used
+
+
+class _FakeModel:
+    """Stands in for WanModel on CPU: a deterministic function of (latents, context)."""
+
+    def __call__(self, x, t, context, **kw):
+        return [xi * 0.5 + ci.mean() * 0.1 + float(t[0]) * 1e-4 for xi, ci in zip(list(x), context)]
+
+
+def _cfg_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import wan_oracle
+    from wan2gp_b200.pipeline import WanDenoiser
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    wd.init(backend="gloo")
+    group, cfg_rank, sample, n_pairs = wd.make_cfg_pairs()
+    g = torch.Generator().manual_seed(100 + sample)
+    lat = torch.randn(1, 16, 2, 4, 4, generator=g)
+    ctx, ctxn = torch.randn(1, 8, 16, generator=g), torch.zeros(1, 8, 16)
+    den = WanDenoiser(_FakeModel(), num_steps=4, shift=5.0, guide_scale=4.0, device="cpu", cfg_group=group, cfg_rank=cfg_rank)
+    den._combine_step = lambda latents, c, u, gs, dt, star: latents.sub_(dt * wan_oracle.cfg_combine(c, u, gs))
+    ref = WanDenoiser(_FakeModel(), num_steps=4, shift=5.0, guide_scale=4.0, device="cpu")
+    ref._combine_step = den._combine_step
+    a, b = lat.clone(), lat.clone()
+    for i in range(4):
+        den.step(a, i, ctx, ctxn)
+        ref.step(b, i, ctx, ctxn)
+    q.put((rank, sample, n_pairs, bool(torch.allclose(a, b, atol=1e-6)), float(a.sum())))
+    dist.destroy_process_group()
+
+
+def test_cfg_pair_split_gloo():
+    """4 ranks = 2 CFG pairs: each rank runs one branch, the pair all-gathers the prediction, latents stay replicated and equal
+    the single-process joint-pass result."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 4, 29641, q)) for r in range(4)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert [r[1] for r in res] == [0, 0, 1, 1] and all(r[2] == 2 and r[3] for r in res)
+    assert res[0][4] == res[1][4] and res[2][4] == res[3][4] and res[0][4] != res[2][4]

@@ -31,6 +31,20 @@ def shard(n_items, rank, world):
     return list(range(start, start + base + (1 if rank < rem else 0)))
 
 
+def make_cfg_pairs():
+    """CFG-pair split: ranks (2k, 2k+1) form one pair working on sample k.  Every rank must call this (new_group is
+    collective).  Returns (pair_group, cfg_rank, sample_index, n_pairs)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world % 2:
+        raise ValueError("CFG-pair split needs an even number of ranks")
+    mine = None
+    for k in range(world // 2):
+        g = dist.new_group([2 * k, 2 * k + 1])
+        if rank // 2 == k:
+            mine = g
+    return mine, rank % 2, rank // 2, world // 2
+
+
 def allgather_frames(frames, group=None):
     """frames: uint8 tensor [n_local, 3, F, H, W] (same F,H,W on every rank; n_local may differ by one).
     Returns the frames of ALL samples in global sample order on every rank -- the single collective of the schedule."""

@@ -29,8 +29,12 @@ class WanDenoiser:
     """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
 
     def __init__(self, model, model2=None, vae=None, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0,
-                 switch_threshold=875, device="cuda", cfg_star_switch=False, cfg_zero_step=-1):
+                 switch_threshold=875, device="cuda", cfg_star_switch=False, cfg_zero_step=-1, cfg_group=None, cfg_rank=0):
         self.model, self.model2, self.vae = model, model2, vae
+        # CFG-pair split (SURVEY.md section 8e, BASELINE configs[2]): the two ranks of `cfg_group` each run ONE branch
+        # (cfg_rank 0 = cond, 1 = uncond) and exchange the fp32 prediction (19 MB at 720p x 81f) once per step; both then
+        # apply the identical combine + scheduler update, so the latents stay replicated without a second collective.
+        self.cfg_group, self.cfg_rank = cfg_group, cfg_rank
         self.cfg_star_switch, self.cfg_zero_step = cfg_star_switch, cfg_zero_step      # CFG-Zero* (any2video.py:1701-1722)
         self.device = torch.device(device)
         self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
@@ -56,14 +60,26 @@ class WanDenoiser:
         if context_null is None:
             cond = model([latents], tt, [context], **kw)[0]
             uncond = None
+        elif self.cfg_group is not None:
+            import torch.distributed as dist
+            mine = model([latents], tt, [context if self.cfg_rank == 0 else context_null], **kw)[0]
+            if mine is None:
+                return None
+            both = [torch.empty_like(mine), torch.empty_like(mine)]
+            dist.all_gather(both, mine.contiguous(), group=self.cfg_group)        # ncclAllGather inside the 2-rank pair
+            cond, uncond = both
         else:
             # joint pass: same blocks applied to each branch in turn (any2video.py:1634, model.py:2030-2037)
             cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
         if cond is None:
             return None
         # NB any2video.py:1719 is overwritten by :1722, so steps <= cfg_zero_step are ordinary un-rescaled CFG
-        ops.cfg_euler_step_(latents, cond, uncond, g, dt, cfg_star=self.cfg_star_switch and uncond is not None and i > self.cfg_zero_step)
+        self._combine_step(latents, cond, uncond, g, dt, self.cfg_star_switch and uncond is not None and i > self.cfg_zero_step)
         return latents
+
+    @staticmethod
+    def _combine_step(latents, cond, uncond, g, dt, cfg_star):
+        ops.cfg_euler_step_(latents, cond, uncond, g, dt, cfg_star=cfg_star)
 
     @torch.no_grad()
     def step_host(self, latents_host, i, context_host, context_null_host=None, y=None, freqs=None):
