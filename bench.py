@@ -419,17 +419,32 @@ def main():
                                 "tflops": vae_flops / (vms * 1e-3) / 1e12, "tensor_frac": vae_flops / (vms * 1e-3) / 1e12 / pk["tensor_burst"],
                                 "e2e": {"value": world * nfr / e2e_v, "unit": "frames/s", "h2d_bytes": zh.numel() * 4, "d2h_bytes": u8.numel()}}
         if dist is not None:
-            # the single collective of the north star: all-gather of decoded uint8 frames over NVLink
+            # the single collective of the north star: all-gather of the decoded uint8 frames over NVLink.
+            # (a) baseline: frames_to_u8 kernel + ncclAllGather; (b) fused quantise + all-gather over peer memory
             gathered = [torch.empty_like(u8, device=dev) for _ in range(world)]
+            u8d = torch.empty(fr.shape, device=dev, dtype=torch.uint8)
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            u8d = u8.to(dev)
             barrier()
             g0.record()
+            _lib.call("b200_frames_to_u8", fr.data_ptr(), u8d.data_ptr(), fr.numel(), torch.cuda.current_stream().cuda_stream)
             dist.all_gather(gathered, u8d)
             g1.record()
             barrier()
-            result["vae_decode"]["allgather_frames_ms"] = g0.elapsed_time(g1)
+            result["vae_decode"]["u8_plus_nccl_allgather_ms"] = g0.elapsed_time(g1)
             result["vae_decode"]["allgather_bytes"] = u8.numel() * world
+            try:
+                from wan2gp_b200 import dist as wdist
+                fg = wdist.FusedFrameGather(fr.numel(), dev)
+                fg.gather(fr)
+                barrier()
+                g0.record()
+                allf = fg.gather(fr)
+                g1.record()
+                barrier()
+                result["vae_decode"]["fused_u8_allgather_ms"] = g0.elapsed_time(g1)
+                result["vae_decode"]["fused_matches_nccl"] = bool(all(torch.equal(allf[r], gathered[r].reshape(-1)) for r in range(world)))
+            except Exception as e:           # symmetric memory unavailable on this box: the NCCL path above stands
+                result["vae_decode"]["fused_u8_allgather_error"] = repr(e)[:200]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads, sample = cpu_port_steps_per_sec(cfg, thw)

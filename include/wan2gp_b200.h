@@ -131,6 +131,12 @@ int b200_attention_1head(const void* qkv, void* out, void* workspace, long long 
 /* frames fp32 planar [3,T,H,W] -> uint8 [3,T,H,W]: round(clamp((clamp(x,-1,1)+1)*127.5,0,255)) (vae.py:18-20) */
 int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void* stream);
 
+/* Fused quantise + all-gather of decoded frames (the one collective of the schedule): x fp32 [n] (this
+ * rank's frames) -> uint8 written into slot `rank` (byte offset rank*n) of EVERY peer's gather buffer.  peer_bufs: HOST array
+ * of n_peers device pointers (peer-mapped, e.g. torch symmetric memory buffer_ptrs); the caller issues the cross-GPU barrier.
+ * The reference has no multi-GPU path; this replaces frames_to_u8 + ncclAllGather. */
+int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_bufs, int n_peers, int rank, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_vae_prologue": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "b200_attention_1head": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
     "b200_frames_to_u8": [c_void_p, c_void_p, c_ll, c_void_p],
+    "b200_frames_to_u8_allgather": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
 }
 _RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_launch_count": c_ll}
 

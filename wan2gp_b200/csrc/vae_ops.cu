@@ -171,6 +171,42 @@ extern "C" int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused frame quantisation + all-gather over NVLink peer memory: every rank converts its fp32 frames to uint8 ONCE and
+// stores the bytes straight into slot `rank` of the gather buffer of EVERY GPU of the box (peer-mapped pointers from the
+// symmetric-memory rendezvous; NVSwitch gives each peer full bandwidth), instead of frames_to_u8 -> HBM -> ncclAllGather.
+// A cross-GPU barrier (symmetric-memory signal pads) after the launch publishes the data.
+struct PeerPtrs { uint8_t* p[16]; };
+__global__ void frames_to_u8_allgather_kernel(const float4* __restrict__ x, PeerPtrs peers, int n_peers, long long slot_off, long long n16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    auto cvt = [](float f) -> uint32_t {
+        f = fminf(fmaxf(f, -1.f), 1.f);
+        f = rintf((f + 1.f) * 127.5f);
+        return (uint32_t)fminf(fmaxf(f, 0.f), 255.f);
+    };
+    uint32_t w[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {                      // 16 floats -> 16 bytes
+        const float4 v = __ldg(x + 4 * i + k);
+        w[k] = cvt(v.x) | (cvt(v.y) << 8) | (cvt(v.z) << 16) | (cvt(v.w) << 24);
+    }
+    const uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int r = 0; r < n_peers; ++r) reinterpret_cast<uint4*>(peers.p[r] + slot_off)[i] = o;      // 16-B st.global on peer apertures
+}
+extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_bufs, int n_peers, int rank, long long n,
+                                           void* stream) {
+    if (!x || !peer_bufs || n_peers <= 0 || n_peers > 16 || rank < 0 || rank >= n_peers || n <= 0 || n % 16)
+        return b200_set_error(B200_ERR_ARG, "frames_to_u8_allgather: bad argument");
+    PeerPtrs pp;
+    for (int r = 0; r < 16; ++r) pp.p[r] = r < n_peers ? reinterpret_cast<uint8_t*>(peer_bufs[r]) : nullptr;
+    const long long n16 = n / 16;
+    frames_to_u8_allgather_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), pp, n_peers, (long long)rank * n, n16);
+    CHECK_LAUNCH("frames_to_u8_allgather");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // causal conv as implicit GEMM
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,

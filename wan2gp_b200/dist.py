@@ -79,3 +79,35 @@ def generate_batch(make_denoiser, contexts, context_null, latent_shape, seeds, d
     dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
     local = torch.stack(outs, 0).to(dev) if outs else torch.empty((0, 3, 4 * (latent_shape[1] - 1) + 1, 8 * latent_shape[2], 8 * latent_shape[3]), dtype=torch.uint8, device=dev)
     return allgather_frames(local)
+
+
+class FusedFrameGather:
+    """Fused `frames -> uint8 -> all-gather` over NVLink peer memory (csrc/vae_ops.cu::frames_to_u8_allgather_kernel).
+
+    One symmetric buffer [world, n] uint8 per GPU (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into
+    every peer); each rank's quantisation kernel stores its bytes into slot `rank` of ALL buffers, then a signal-pad barrier
+    makes them visible.  Replaces frames_to_u8 + ncclAllGather (allgather_frames) when all ranks share one NVSwitch box."""
+
+    def __init__(self, n_bytes_per_rank, device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = int(n_bytes_per_rank)
+        self.buf = symm_mem.empty(self.world * self.n, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = list(self.hdl.buffer_ptrs)
+        self._ptrs = (ctypes.c_uint64 * len(ptrs))(*ptrs)
+
+    def gather(self, frames_fp32):
+        """frames_fp32: this rank's fp32 frames (numel == n).  Returns uint8 [world, n] on this GPU (all ranks' frames)."""
+        import ctypes
+
+        from . import _lib
+        assert frames_fp32.numel() == self.n and frames_fp32.is_contiguous() and frames_fp32.dtype == torch.float32
+        self.hdl.barrier(channel=0)                 # every rank has finished reading the previous contents
+        _lib.call("b200_frames_to_u8_allgather", frames_fp32.data_ptr(), ctypes.cast(self._ptrs, ctypes.c_void_p), self.world,
+                  self.rank, self.n, torch.cuda.current_stream().cuda_stream)
+        self.hdl.barrier(channel=1)                 # all peers' stores have landed
+        return self.buf.view(self.world, self.n)
