@@ -34,13 +34,16 @@ WORKLOADS = {
     # BASELINE configs[3]: Hunyuan Video 1.5 t2v 720p, 129 frames -> latent [1,32,33,45,80] (+33 cond channels), 54 double blocks
     "hy15_t2v_720p129": ("HYVideo-1_5", (33, 45, 80), False, "Hunyuan Video 1.5 t2v 720p x 129f, latent [1,32,33,45,80]+33 cond ch, L=118800 (+767 text), CFG pair, 30-step Euler shift 9"),
     "hy15_tiny": ("hy_tiny", (3, 6, 10), False, "reduced Hunyuan config for smoke runs"),
+    # HunyuanVideo 1.0 (guidance-distilled: ONE forward per step), 720p x 129f: latent [1,16,33,90,160], patch (1,2,2) -> L = 118800
+    "hy10_t2v_720p129": ("HYVideo-T/2-cfgdistill", (33, 90, 160), False, "HunyuanVideo 1.0 cfg-distilled t2v 720p x 129f, latent [1,16,33,90,160], L=118800 (+256 text), 20 double + 40 single blocks, one forward per step"),
+    "hy10_tiny": ("hy10_tiny", (2, 8, 12), False, "reduced HunyuanVideo 1.0 config for smoke runs"),
 }
 
 
 def hy_flops_forward(cfg, L, Lt):
-    D, nl = cfg["hidden_size"], cfg["mm_double_blocks_depth"]
+    D, nl, ns = cfg["hidden_size"], cfg["mm_double_blocks_depth"], cfg.get("mm_single_blocks_depth", 0)
     n = L + Lt
-    return nl * (4.0 * n * n * D + 8.0 * n * D * D + 16.0 * n * D * D)
+    return (nl + ns) * (4.0 * n * n * D + 8.0 * n * D * D + 16.0 * n * D * D)
 
 
 def run_hunyuan(args, rank, world, local_rank, dev, dist):
@@ -50,26 +53,33 @@ def run_hunyuan(args, rank, world, local_rank, dev, dist):
     from wan2gp_b200.pipeline import HunyuanDenoiser
     cfg_name, thw, _, desc = WORKLOADS[args.workload]
     cfg = synth.HY_CONFIGS[cfg_name]
+    v10 = cfg.get("family") == "1.0"
     T, H, W = thw
-    L, Lt, Lb = T * H * W, 511, 256
-    if cfg_name == "hy_tiny":
-        Lt, Lb = 24, 12
+    P = cfg["patch_size"][1]
+    L, Lt, Lb = T * (H // P) * (W // P), 511, 256
+    if v10:
+        Lt, Lb = 256, 0
+    if cfg_name in ("hy_tiny", "hy10_tiny"):
+        Lt, Lb = 24, (0 if v10 else 12)
+    kw = dict(mm_single_blocks_depth=cfg["mm_single_blocks_depth"], text_states_dim_2=cfg["text_states_dim_2"], guidance_embed=True) if v10 \
+        else dict(mm_single_blocks_depth=0, text_pool_type=None, glyph_byT5_v2=True, use_cond_type_embedding=True, pre_split_qkv=True)
     model = HYVideoDiffusionTransformer(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"],
                                         out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
-                                        mm_double_blocks_depth=cfg["mm_double_blocks_depth"], mm_single_blocks_depth=0,
-                                        text_states_dim=cfg["text_states_dim"], text_pool_type=None, glyph_byT5_v2=True,
-                                        use_cond_type_embedding=True, pre_split_qkv=True, device=dev).init_synthetic(seed=1)
-    den = HunyuanDenoiser(model, num_steps=30, shift=9.0, guide_scale=6.0, device=dev)
+                                        mm_double_blocks_depth=cfg["mm_double_blocks_depth"], text_states_dim=cfg["text_states_dim"],
+                                        device=dev, **kw).init_synthetic(seed=1)
+    den = HunyuanDenoiser(model, num_steps=30, shift=9.0 if not v10 else 7.0, guide_scale=6.0, device=dev)
     g = torch.Generator().manual_seed(1000 + rank)
     lat_host = torch.randn(1, cfg["out_channels"], T, H, W, generator=g).pin_memory()
     latents = lat_host.to(dev)
-    cond = torch.zeros(1, cfg["in_channels"] - cfg["out_channels"], T, H, W, device=dev)
+    cond = torch.zeros(1, cfg["in_channels"] - cfg["out_channels"], T, H, W, device=dev) if cfg["in_channels"] > cfg["out_channels"] else None
+    t2 = torch.randn(1, cfg["text_states_dim_2"], generator=g).to(dev) if v10 else None
+    gd = torch.tensor([6000.0]) if v10 else None
     txt = torch.randn(1, Lt, cfg["text_states_dim"], generator=g).to(dev)
     txt0 = torch.randn(1, Lt, cfg["text_states_dim"], generator=g).to(dev)
     tm = torch.ones(1, Lt, dtype=torch.long)
-    b5 = torch.randn(1, Lb, synth.HY_BYT5_DIMS[0], generator=g).to(dev)
-    bm = torch.ones(1, Lb, dtype=torch.long)
-    freqs = get_rotary_pos_embed(thw)
+    b5 = torch.randn(1, Lb, synth.HY_BYT5_DIMS[0], generator=g).to(dev) if Lb else None
+    bm = torch.ones(1, Lb, dtype=torch.long) if Lb else None
+    freqs = get_rotary_pos_embed((T, H // P, W // P))
 
     def barrier():
         if dist is not None:
@@ -77,7 +87,7 @@ def run_hunyuan(args, rank, world, local_rank, dev, dist):
         torch.cuda.synchronize()
 
     def one(k, lat):
-        return den.step(lat, cond, min(k, den.num_steps - 1), txt, tm, txt0, tm, b5, bm, freqs)
+        return den.step(lat, cond, min(k, den.num_steps - 1), txt, tm, None if v10 else txt0, tm, b5, bm, freqs, text_states_2=t2, guidance=gd)
     for k in range(args.warmup):
         one(k, latents)
     barrier()
@@ -110,14 +120,14 @@ def run_hunyuan(args, rank, world, local_rank, dev, dist):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
     pk = peaks()
-    fl = 2.0 * hy_flops_forward(cfg, L, Lt + Lb)
+    fl = (1.0 if v10 else 2.0) * hy_flops_forward(cfg, L, Lt + Lb)
     att_ms = sum(a for a, _ in att) / max(1, len(att))
     att_tf = (att[0][1] / (att_ms * 1e-3) / 1e12) if att else None
     res = {"metric": "denoise_steps_per_sec", "value": world * args.steps / (ms / 1e3), "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "latent": [1, cfg["out_channels"], T, H, W], "tokens": L,
-                      "text_tokens": Lt + Lb, "cfg_pair": True, "parallelism": f"{world} independent samples (batch split), 1 per GPU",
+                      "text_tokens": Lt + Lb, "cfg_pair": not v10, "parallelism": f"{world} independent samples (batch split), 1 per GPU",
                       "l2_policy": "inputs larger than L2; no flush needed"},
            "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "steps/s", "steps": n_e2e,
                    "h2d_bytes_per_step": lat_host.numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 4},
@@ -233,7 +243,7 @@ def main():
 
     from wan2gp_b200 import synth
     cfg_name, thw, two_experts, desc = WORKLOADS[args.workload]
-    if args.workload.startswith("hy15"):
+    if args.workload.startswith("hy1"):
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "CPU arm is implemented for the Wan workloads only"}))
             return

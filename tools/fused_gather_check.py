@@ -5,7 +5,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wan2gp_b200 import _lib  # noqa: E402
 from wan2gp_b200 import dist as wd  # noqa: E402
 

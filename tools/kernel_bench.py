@@ -5,12 +5,12 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wan2gp_b200 import ops  # noqa: E402
 
 bf16, f32 = torch.bfloat16, torch.float32
 PEAK_TF, PEAK_HBM = 1654.0, 6567.1
-pk = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(pk):
     d = json.load(open(pk)); PEAK_TF, PEAK_HBM = d["bf16_tflops"], d["hbm_gbs"]
 

@@ -1,5 +1,5 @@
 """Extract the handful of ncu metrics the roofline discussion needs from a .ncu-rep (run where ncu is installed):
-    python tools_ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
 import csv
 import subprocess
 import sys

@@ -4,7 +4,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wan2gp_b200 import ops  # noqa: E402
 from wan2gp_b200.wan.vae import _Conv  # noqa: E402
 

@@ -122,19 +122,24 @@ class HunyuanDenoiser:
         self._interrupt = False
 
     @torch.no_grad()
-    def step(self, latents, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=None, byt5_mask=None, freqs=None):
-        """latents fp32 [1,32,T,H,W] (updated in place), cond_latents fp32 [1,33,T,H,W] (concat mask/cond channels)."""
+    def step(self, latents, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=None, byt5_mask=None, freqs=None,
+             text_states_2=None, guidance=None):
+        """latents fp32 [1,C,T,H,W] (updated in place); cond_latents fp32 [1,C2,T,H,W] (Hunyuan 1.5 concat mask/cond channels) or
+        None; text_null=None => no CFG (guidance-distilled HunyuanVideo 1.0: one forward with the guidance embedding)."""
         t = self.timesteps[i]
         dt = (t - self.timesteps[i + 1]) / 1000.0
-        x = torch.cat([latents, cond_latents], 1)
+        x = latents if cond_latents is None else torch.cat([latents, cond_latents], 1)
         tt = torch.tensor([t], dtype=f32)
         kw = dict(freqs_cos=None if freqs is None else freqs[0], freqs_sin=None if freqs is None else freqs[1], pipeline=self,
-                  step_no=i, byt5_text_states=byt5, byt5_text_mask=byt5_mask)
+                  step_no=i, byt5_text_states=byt5, byt5_text_mask=byt5_mask, text_states_2=text_states_2, guidance=guidance)
         cond = self.model(x, tt, text_states=text, text_mask=text_mask, **kw)
         if cond is None:
             return None
-        uncond = self.model(x, tt, text_states=text_null, text_mask=text_null_mask, **kw)
-        if uncond is None:
-            return None
-        ops.cfg_euler_step_(latents, cond.contiguous(), uncond.contiguous(), self.guide_scale, dt)
+        uncond = None
+        if text_null is not None:
+            uncond = self.model(x, tt, text_states=text_null, text_mask=text_null_mask, **kw)
+            if uncond is None:
+                return None
+            uncond = uncond.contiguous()
+        ops.cfg_euler_step_(latents, cond.contiguous(), uncond, self.guide_scale, dt)
         return latents
