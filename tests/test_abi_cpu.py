@@ -67,3 +67,15 @@ def test_wanmodel_api_contract():
     assert cos.shape == (3 * 4 * 6, 128) and cos.dtype == torch.float32
     cos_r, _ = get_rotary_pos_embed((3, 8, 12), enable_RIFLEx=True)
     assert not torch.equal(cos, cos_r)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under wan2gp_b200/ may import or reference it."""
+    import pathlib
+    bad = []
+    for f in pathlib.Path(ROOT, "wan2gp_b200").rglob("*.py"):
+        for i, line in enumerate(f.read_text().splitlines(), 1):
+            s = line.strip()
+            if (s.startswith("import ") or s.startswith("from ")) and "oracle" in s:
+                bad.append(f"{f}:{i}: {s}")
+    assert not bad, bad
