@@ -123,13 +123,28 @@ int b200_vae_prologue(const float* z, const float* mean, const float* std, const
 
 /* single-head attention, head dim C <= 512 (C % 64 == 0), per frame over N tokens: qkv bf16 [F, N, 3C];
  * out bf16 [F, N, C] (vae.py:276-315 AttentionBlock core, F.scaled_dot_product_attention).
+ * causal_frames=1: frame f attends to all tokens of frames 0..f (Hunyuan 1.5 VAE AttnBlock with prepare_causal_attention_mask,
+ * hyvideo/vae/hunyuanvideo_15_vae.py:161-214); the workspace pitch is then roundup(F*N,64).
  * workspace: caller-owned, >= N * roundup(N,64) * 6 bytes (fp32 scores + bf16 probabilities of one frame).
  * qkv must have 8 readable (finite) rows after the last frame when N % 8 != 0 (the GEMM extents are rounded up to 8). */
 int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
-                         float scale, void* stream);
+                         float scale, int causal_frames, void* stream);
 
 /* frames fp32 planar [3,T,H,W] -> uint8 [3,T,H,W]: round(clamp((clamp(x,-1,1)+1)*127.5,0,255)) (vae.py:18-20) */
 int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void* stream);
+
+/* ---- Hunyuan Video 1.5 VAE decode helpers (hyvideo/vae/hunyuanvideo_15_vae.py) ---- */
+/* replicate padding of a channels-last bf16 tensor: [T,H,W,C] -> [T+pt, H+2ph, W+2pw, C], pt frames in front (CausalConv3d :137-158) */
+int b200_pad_replicate_cl(const void* x, void* y, int T, int H, int W, int C, int pt, int ph, int pw, void* stream);
+/* "valid" conv over an explicitly padded input xpad [T+kt-1, H+kh-1, W+kw-1, Cin]; T,H,W = output dims; other arguments as
+ * b200_conv3d_cl (out_mode 0 or 2) */
+int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const float* bias, const void* residual, void* out, int T, int H,
+                             int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, void* stream);
+/* planar fp32 [C,P] -> channels-last bf16 [P, C*rep] with each channel repeated rep times (z.repeat_interleave, :489-490) */
+int b200_planar_to_cl(const float* x, void* y_bf16, int C, long long P, int rep, void* stream);
+/* Upsample tail (:309-338): channel -> (time,) space shuffle of the conv output h [T,H,W,F*Co] plus the repeat-interleaved
+ * shortcut of x [T,H,W,Ci] -> out bf16 [2T-1 | T, 2H, 2W, Co] */
+int b200_hy_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream);
 
 /* Fused quantise + all-gather of decoded frames (the one collective of the schedule): x fp32 [n] (this
  * rank's frames) -> uint8 written into slot `rank` (byte offset rank*n) of EVERY peer's gather buffer.  peer_bufs: HOST array

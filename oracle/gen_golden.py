@@ -135,9 +135,26 @@ def run_hy(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.float().numpy(), cos=cos[:64].numpy(), sin=sin[:64].numpy())
 
 
+HYVAE_CASES = {"hyvae_tiny": ("hyvae_tiny", (8, 3, 4, 6), 0), "hyvae_small": ("hyvae_small", (16, 3, 2, 3), 1)}
+
+
+def run_hyvae(name):
+    from oracle.refshim import load_reference_hyvae
+    hv = load_reference_hyvae()
+    cfg_name, zshape, seed = HYVAE_CASES[name]
+    cfg = synth.HYVAE_CONFIGS[cfg_name]
+    dec = hv.Decoder(**cfg).eval().requires_grad_(False)
+    dec.load_state_dict(synth.make_hyvae_state_dict(cfg, seed))
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    with torch.no_grad():
+        out = dec(z)
+    print(f"{name}: reference HY-1.5 VAE Decoder out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_vae)(n)

@@ -212,3 +212,29 @@ def split_linear_modules(model, split_map):
                 setattr(mod, name, sub)
                 off += n
     return model
+
+
+_loaded_hyvae = None
+
+
+def load_reference_hyvae():
+    """Reference Hunyuan Video 1.5 VAE decoder (models/hyvideo/vae/hunyuanvideo_15_vae.py::Decoder) importable on CPU: extra
+    diffusers stubs (BaseOutput, DiagonalGaussianDistribution, AutoencoderKLOutput) -- none of them carries arithmetic."""
+    global _loaded_hyvae
+    if _loaded_hyvae is not None:
+        return _loaded_hyvae
+    load_reference_hy()
+    for name in ["diffusers.models.autoencoders", "diffusers.models.autoencoders.vae", "diffusers.models.modeling_outputs", "diffusers.utils"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+
+    class BaseOutput(dict):
+        pass
+    sys.modules["diffusers.models.autoencoders.vae"].BaseOutput = BaseOutput
+    sys.modules["diffusers.models.autoencoders.vae"].DiagonalGaussianDistribution = type("DiagonalGaussianDistribution", (), {})
+    sys.modules["diffusers.models.modeling_outputs"].AutoencoderKLOutput = type("AutoencoderKLOutput", (BaseOutput,), {})
+    m = types.ModuleType("models.hyvideo.vae")
+    m.__path__ = [os.path.join(REFERENCE_ROOT, "models/hyvideo/vae")]
+    sys.modules["models.hyvideo.vae"] = m
+    from models.hyvideo.vae.hunyuanvideo_15_vae import Decoder
+    _loaded_hyvae = types.SimpleNamespace(Decoder=Decoder)
+    return _loaded_hyvae

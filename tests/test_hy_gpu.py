@@ -105,3 +105,22 @@ def test_hy10_forward_tiny():
     g = load_golden("hy10_tiny")["out"]
     print(f"hy10_tiny: vs bf16-emulating oracle {rel_l2(out, emu):.3e}; vs reference {rel_l2(out, g):.3e}")
     assert out.shape == g.shape and rel_l2(out, emu) < 6e-3 and rel_l2(out, g) < 6e-3
+
+
+@pytest.mark.parametrize("name,zshape,seed", [("hyvae_tiny", (8, 3, 4, 6), 0), ("hyvae_small", (16, 3, 2, 3), 1)])
+def test_hyvae_decode(name, zshape, seed):
+    """Hunyuan 1.5 VAE decoder (row H6, un-tiled): replicate-padded convs, frame-causal mid attention, shuffle up-sampling.
+    Tolerances as for the Wan VAE: vs the bf16-emulating oracle rel-L2 <= 2.5e-2; vs reference frames PSNR >= 35 dB."""
+    from oracle import hyvae_oracle
+    from wan2gp_b200.hyvideo import HYVAEDecoder
+    cfg = synth.HYVAE_CONFIGS[name]
+    sd = synth.make_hyvae_state_dict(cfg, seed)
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    dec = HYVAEDecoder(cfg)
+    dec.load_state_dict(sd)
+    got = dec(z.cuda())[0].cpu()
+    g = load_golden(name)["out"][0]
+    emu = hyvae_oracle.hyvae_decode(sd, cfg, z[0], emulate_bf16=True)
+    print(f"{name}: vs reference {rel_l2(got, g):.3e}, PSNR {psnr(got.clamp(-1, 1), g.clamp(-1, 1), 2.0):.1f} dB; vs bf16-emulating oracle {rel_l2(got, emu):.3e}")
+    assert got.shape == g.shape
+    assert rel_l2(got, emu) < 2.5e-2 and psnr(got.clamp(-1, 1), g.clamp(-1, 1), 2.0) > 35.0

@@ -95,3 +95,13 @@ def test_hy10_oracle_matches_reference():
     t2 = synth._normal((1, cfg["text_states_dim_2"]), 1.0, seed, "hy.txt2", "cpu")
     out = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, ref_casts=True, text_states_2=t2, guidance=torch.tensor([6000.0]))
     assert rel_l2(out, load_golden("hy10_tiny")["out"]) < 3e-5
+
+
+@pytest.mark.parametrize("name,zshape,seed", [("hyvae_tiny", (8, 3, 4, 6), 0), ("hyvae_small", (16, 3, 2, 3), 1)])
+def test_hyvae_oracle_matches_reference(name, zshape, seed):
+    from oracle import hyvae_oracle
+    from wan2gp_b200 import synth
+    cfg = synth.HYVAE_CONFIGS[name]
+    sd = synth.make_hyvae_state_dict(cfg, seed)
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")[0]
+    assert rel_l2(hyvae_oracle.hyvae_decode(sd, cfg, z), load_golden(name)["out"][0]) < 1e-5

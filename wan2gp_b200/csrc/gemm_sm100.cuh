@@ -39,6 +39,7 @@ struct GemmParams {
     int T, H, W;
     int kt, kh, kw;           // taps
     int pad_h, pad_w;         // taps start at (h - pad_h, w - pad_w): kh/2, kw/2 for centred convs
+    int pad_t;                // taps start at t - pad_t: kt-1 (causal); 0 when the input was padded explicitly (replicate)
     int cin_chunks;           // ceil(Cin / 64)
     int tiles_h, tiles_w;     // ceil(H/8), ceil(W/16)
     // ---- tile rasterisation
@@ -175,7 +176,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         #pragma unroll
                         for (int b = 0; b < NBOX; ++b) {
                             tma_load_4d(sa + b * S::kABox, &tmap_a, &full_bar[stage], cc * BKS + b * BKC, w0 + dw - p.pad_w,
-                                        h0 + dh - p.pad_h, t0 + dt - (p.kt - 1));
+                                        h0 + dh - p.pad_h, t0 + dt - p.pad_t);
                             tma_load_3d(sb + b * S::kBBox, &tmap_b, &full_bar[stage], cc * BKS + b * BKC, tap, n_blk * BN);
                         }
                     }

@@ -171,6 +171,86 @@ extern "C" int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hunyuan VAE helpers (channels-last bf16)
+// replicate padding: out [T+pt, H+2ph, W+2pw, C] (pt frames in FRONT), 16-byte chunks
+__global__ void pad_replicate_cl_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int C8, int pt, int ph, int pw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int To = T + pt, Ho = H + 2 * ph, Wo = W + 2 * pw;
+    if (i >= (long long)To * Ho * Wo * C8) return;
+    const int c = i % C8; long long r = i / C8;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; const int t = r / Ho;
+    const int ts = max(t - pt, 0), hs = min(max(h - ph, 0), H - 1), ws = min(max(w - pw, 0), W - 1);
+    y[i] = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c);
+}
+extern "C" int b200_pad_replicate_cl(const void* x, void* y, int T, int H, int W, int C, int pt, int ph, int pw, void* stream) {
+    if (!x || !y || C % 8) return b200_set_error(B200_ERR_ARG, "pad_replicate_cl: bad argument");
+    const long long n = (long long)(T + pt) * (H + 2 * ph) * (W + 2 * pw) * (C / 8);
+    pad_replicate_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), T, H, W, C / 8, pt, ph, pw);
+    CHECK_LAUNCH("pad_replicate_cl");
+    return B200_OK;
+}
+
+// planar fp32 [C, P] -> channels-last bf16 [P, C*rep], channel c repeated rep times (z -> z.repeat_interleave(rep, dim=1),
+// hunyuanvideo_15_vae.py:489-490; rep = 1 is a plain layout change)
+__global__ void planar_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, long long P, int rep) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = P * C * rep;
+    if (i >= n) return;
+    const int co = i % (C * rep); const long long p = i / (C * rep);
+    y[i] = __float2bfloat16_rn(__ldg(x + (long long)(co / rep) * P + p));
+}
+extern "C" int b200_planar_to_cl(const float* x, void* y, int C, long long P, int rep, void* stream) {
+    if (!x || !y || C <= 0 || P <= 0 || rep <= 0) return b200_set_error(B200_ERR_ARG, "planar_to_cl: bad argument");
+    const long long n = P * C * rep;
+    planar_to_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), C, P, rep);
+    CHECK_LAUNCH("planar_to_cl");
+    return B200_OK;
+}
+
+// Hunyuan 1.5 VAE Upsample tail (hunyuanvideo_15_vae.py:309-338): h = conv output [T,H,W,F*Co] (F = 8 with temporal up-sampling,
+// else 4), x = block input [T,H,W,Ci].  out [To, 2H, 2W, Co] = shuffle(h) + shuffle(repeat_interleave(x)), To = 2T-1 | T.
+// The first frame of a temporal up-sample only unfolds in space: its channels are read as (r2 r3 c') with c' < 2Co and the
+// first Co kept; the shortcut repeats by rep/2 there.
+__global__ void hy_upsample_cl_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                      int T, int H, int W, int Ci, int Co, int temporal) {
+    const int C8 = Co >> 3;
+    const int To = temporal ? 2 * T - 1 : T;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)To * 2 * H * 2 * W * C8) return;
+    const int c0 = (i % C8) * 8; long long r = i / C8;
+    const int wo = r % (2 * W); r /= (2 * W);
+    const int ho = r % (2 * H); const int to = r / (2 * H);
+    const int r2 = ho & 1, r3 = wo & 1, hh = ho >> 1, ww = wo >> 1;
+    const int F = temporal ? 8 : 4;
+    const int rep = F * Co / Ci;
+    int f, hch, xbase, xrep;
+    if (temporal && to == 0) { f = 0; hch = (r2 * 2 + r3) * (2 * Co); xbase = (r2 * 2 + r3) * (Ci / 4); xrep = rep / 2; }
+    else if (temporal) { f = 1 + (to - 1) / 2; const int r1 = (to - 1) & 1; const int g = (r1 * 2 + r2) * 2 + r3; hch = g * Co; xbase = g * (Ci / 8); xrep = rep; }
+    else { f = to; const int g = r2 * 2 + r3; hch = g * Co; xbase = g * (Ci / 4); xrep = rep; }
+    const long long pix = ((long long)f * H + hh) * W + ww;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h + pix * (F * Co) + hch + c0));
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    const __nv_bfloat16* xp = x + pix * Ci + xbase;
+    float o[8];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) { o[2 * k] = __uint_as_float(hw[k] << 16); o[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u); }
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += __bfloat162float(xp[(c0 + k) / xrep]);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+}
+extern "C" int b200_hy_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream) {
+    const int F = temporal ? 8 : 4;
+    if (!h || !x || !out || Co % 8 || (F * Co) % Ci || (temporal && (F * Co / Ci) % 2)) return b200_set_error(B200_ERR_ARG, "hy_upsample_cl: bad argument");
+    const long long n = (long long)(temporal ? 2 * T - 1 : T) * 4 * H * W * (Co / 8);
+    hy_upsample_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), T, H, W, Ci, Co, temporal);
+    CHECK_LAUNCH("hy_upsample_cl");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused frame quantisation + all-gather over NVLink peer memory: every rank converts its fp32 frames to uint8 ONCE and
 // stores the bytes straight into slot `rank` of the gather buffer of EVERY GPU of the box (peer-mapped pointers from the
 // symmetric-memory rendezvous; NVSwitch gives each peer full bandwidth), instead of frames_to_u8 -> HBM -> ncclAllGather.
@@ -210,7 +290,7 @@ extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_
 // causal conv as implicit GEMM
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream);
+                        void* stream, int prepadded = 0);
 
 extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                               int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
@@ -233,9 +313,17 @@ extern "C" int b200_upconv2x_cl(const void* x, const void* w4, const float* bias
     return B200_OK;
 }
 
+// Replicate-padded causal conv (Hunyuan VAEs, hunyuanvideo_15_vae.py:124-158): TMA zero fill cannot replicate, so the
+// caller materialises the padded tensor once (b200_pad_replicate_cl) and this runs a "valid" conv over it.
+// xpad bf16 [T+kt-1, H+kh-1, W+kw-1, Cin]; T,H,W are the OUTPUT dims.
+extern "C" int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const float* bias, const void* residual, void* out, int T,
+                                        int H, int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, void* stream) {
+    return conv_cl_impl(xpad, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, out_mode, 0, 0, 0, -1, -1, stream, 1);
+}
+
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream) {
+                        void* stream, int prepadded) {
     if (!x || !w || !out || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
     if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
     if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
@@ -248,8 +336,9 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
-        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const uint64_t Ti = prepadded ? T + kt - 1 : T, Hi = prepadded ? H + kh - 1 : H, Wi = prepadded ? W + kw - 1 : W;
+        uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, Ti};
+        uint64_t str[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
         uint32_t box[4] = {kbox, CONV_BW, CONV_BH, 1};
         int r = b200_make_tmap_bf16(&ta, x, 4, dims, str, box, k96 ? 64 : 128);
         if (r) return r;
@@ -266,7 +355,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.mode = MODE_CONV;
     p.N = Cout;
     p.T = T; p.H = H; p.W = W; p.kt = kt; p.kh = kh; p.kw = kw;
-    p.pad_h = pad_h; p.pad_w = pad_w;
+    p.pad_h = pad_h; p.pad_w = pad_w; p.pad_t = prepadded ? 0 : kt - 1;
     p.cin_chunks = k96 ? 1 : (Cin + 63) / 64;
     p.num_k_iters = taps * p.cin_chunks;
     p.tiles_h = (H + CONV_BH - 1) / CONV_BH;
@@ -324,14 +413,40 @@ softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, 
     for (int i = threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? row[i] * inv : 0.f);
 }
 
+// same for rows that do not fit the shared-memory row buffer: three passes over the (L2-resident) global row
+__global__ void __launch_bounds__(256)
+softmax_rows_long_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int N, long long lds, long long ldp, float scale_log2) {
+    __shared__ float red[8];
+    const int N8 = (N + 7) & ~7;
+    const float* sr = s + (long long)blockIdx.x * lds;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += 256) mx = fmaxf(mx, sr[i] * scale_log2);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    #pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) sum += exp2f(sr[i] * scale_log2 - mx);
+    const float inv = 1.f / block_sum_256(sum, red);
+    __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
+    for (int i = threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? exp2f(sr[i] * scale_log2 - mx) * inv : 0.f);
+}
+
 extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
-                                    float scale, void* stream) {
+                                    float scale, int causal_frames, void* stream) {
     if (!qkv || !out || !workspace) return b200_set_error(B200_ERR_ARG, "attention_1head: null argument");
     if (C % 64) return b200_set_error(B200_ERR_ARG, "attention_1head: C %% 64 != 0");
     const int N8 = (N + 7) & ~7;      // GEMM extents are multiples of 8: the key tail [N, N8) gets probability 0 (the caller
                                       // guarantees 8 readable rows after the last frame of qkv)
-    const long long Np = (N + 63) / 64 * 64;          // padded row pitch so P is a legal GEMM operand
+    // causal_frames: frame f attends to the tokens of frames 0..f (Hunyuan 1.5 VAE mid block, hunyuanvideo_15_vae.py:161-214);
+    // otherwise every frame attends to itself only (Wan VAE).
+    const long long Lk_max = causal_frames ? (long long)F * N : N;
+    const long long Np = (Lk_max + 63) / 64 * 64;     // padded row pitch so P is a legal GEMM operand
     const long long need = (long long)N * Np * 4 + (long long)N * Np * 2;
+    (void)N8;
     if (workspace_bytes < need) return b200_set_error(B200_ERR_ARG, "attention_1head: workspace %lld < %lld bytes", workspace_bytes, need);
     float* S = reinterpret_cast<float*>(workspace);
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + (long long)N * Np);
@@ -342,14 +457,18 @@ extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace,
         cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    if ((long long)N * 4 > 200 * 1024) return b200_set_error(B200_ERR_ARG, "attention_1head: N=%d too large", N);
+
     for (int f = 0; f < F; ++f) {
         const __nv_bfloat16* q = base + (long long)f * N * 3 * C;
-        int r = b200_gemm_bf16(q, q + C, S, N, N8, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
+        const __nv_bfloat16* kv = causal_frames ? base : q;                 // keys/values start at frame 0 when causal
+        const int Lk = causal_frames ? (f + 1) * N : N;
+        const int Lk8 = (Lk + 7) & ~7;
+        int r = b200_gemm_bf16(q, kv + C, S, N, Lk8, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
         if (r) return r;
-        softmax_rows_kernel<<<N, 256, N * sizeof(float), st>>>(S, P, N, Np, Np, scale * 1.4426950408889634f);
+        if ((long long)Lk * 4 <= 200 * 1024) softmax_rows_kernel<<<N, 256, Lk * sizeof(float), st>>>(S, P, Lk, Np, Np, scale * 1.4426950408889634f);
+        else softmax_rows_long_kernel<<<N, 256, 0, st>>>(S, P, Lk, Np, Np, scale * 1.4426950408889634f);
         CHECK_LAUNCH("softmax_rows");
-        r = b200_gemm_bf16(P, q + 2 * C, reinterpret_cast<__nv_bfloat16*>(out) + (long long)f * N * C, N, C, N8, Np, 3LL * C, C,
+        r = b200_gemm_bf16(P, kv + 2 * C, reinterpret_cast<__nv_bfloat16*>(out) + (long long)f * N * C, N, C, Lk8, Np, 3LL * C, C,
                            nullptr, nullptr, nullptr, 0, 0, 0, 1, stream);
         if (r) return r;
     }

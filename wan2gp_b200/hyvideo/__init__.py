@@ -1,1 +1,2 @@
 from .model import HYVideoDiffusionTransformer, get_rotary_pos_embed  # noqa: F401
+from .vae import AutoencoderKLConv3D, HYVAEDecoder  # noqa: F401

@@ -1,0 +1,165 @@
+"""B200-native Hunyuan Video 1.5 VAE decode (hot-path row H6 of SURVEY.md section 8a): the `AutoencoderKLConv3D` surface the
+pipeline uses (`.decode(z, return_dict=False)[0]`, `.enable_tiling()`, `.config.scaling_factor / .shift_factor`,
+models/hyvideo/diffusion/pipelines/pipeline_hunyuan_video.py:1790-1812) over the reference Decoder
+(models/hyvideo/vae/hunyuanvideo_15_vae.py:432-520), UN-TILED: one B200 holds the whole clip, so `enable_tiling()` is a
+no-op (the reference tiles only to fit small GPUs; tiled + blended output differs from the plain decoder near tile seams).
+
+Channels-last bf16 activations [T,H,W,C].  Replicate-padded causal convs (CausalConv3d :124-158) = one `pad_replicate` pass +
+the tcgen05 implicit-GEMM conv over the padded tensor (TMA zero fill cannot replicate); 1x1x1 convs are plain GEMMs over
+pixels; the mid block's single-head, frame-causal attention runs per query frame over keys of frames <= f.
+"""
+import math
+import types
+
+import torch
+
+from .. import _lib, ops, synth
+from ..wan.vae import _Conv, rms_silu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _RepConv(_Conv):
+    """3x3x3 causal conv with replicate padding: pad (2 frames in front, 1 pixel around) then a 'valid' conv."""
+
+    def __call__(self, x, residual=None, out_mode=0):
+        T, H, W, C = x.shape
+        kt, kh, kw = self.k
+        xp = torch.empty(T + kt - 1, H + kh - 1, W + kw - 1, C, device=x.device, dtype=bf16)
+        _lib.call("b200_pad_replicate_cl", x.data_ptr(), xp.data_ptr(), T, H, W, C, kt - 1, kh // 2, kw // 2, _s())
+        out = (torch.empty(self.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
+               else torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16))
+        _lib.call("b200_conv3d_cl_prepadded", xp.data_ptr(), self.w.data_ptr(), self.b.data_ptr(),
+                  0 if residual is None else residual.data_ptr(), out.data_ptr(), T, H, W, self.cin, self.cout, kt, kh, kw,
+                  out_mode, _s())
+        return out
+
+
+class HYVAEDecoder(torch.nn.Module):
+    def __init__(self, cfg, device="cuda"):
+        super().__init__()
+        self.cfg, self.device = dict(cfg), torch.device(device)
+        self._ready = False
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        dev = self.device
+        gam = lambda k: sd[k].detach().to(dev, f32).reshape(-1).contiguous()                      # noqa: E731
+        rc = lambda p: _RepConv(sd[p + ".weight"], sd[p + ".bias"], dev)                           # noqa: E731
+        lin = lambda p: (sd[p + ".weight"].detach().to(dev, bf16).reshape(sd[p + ".weight"].shape[0], -1).contiguous(),  # noqa: E731
+                         sd[p + ".bias"].detach().to(dev, f32).contiguous())
+
+        def res(p):
+            d = {"g1": gam(p + "norm1.gamma"), "c1": rc(p + "conv1.conv"), "g2": gam(p + "norm2.gamma"), "c2": rc(p + "conv2.conv")}
+            if p + "nin_shortcut.weight" in sd:
+                d["nin"] = lin(p + "nin_shortcut")
+            return d
+        self.conv_in = rc("conv_in.conv")
+        self.mid1, self.mid2 = res("mid.block_1."), res("mid.block_2.")
+        a = "mid.attn_1."
+        self.attn = {"g": gam(a + "norm.gamma"),
+                     "wqkv": torch.cat([lin(a + n)[0] for n in "qkv"], 0).contiguous(), "bqkv": torch.cat([lin(a + n)[1] for n in "qkv"], 0).contiguous(),
+                     "proj": lin(a + "proj_out")}
+        self.levels = []
+        levels, _ = synth.hyvae_layout(self.cfg)
+        for i, (blocks, up) in enumerate(levels):
+            self.levels.append(([res(f"up.{i}.block.{j}.") for j in range(len(blocks))],
+                                None if up is None else (rc(f"up.{i}.upsample.conv.conv"), up[1], up[2])))
+        self.g_out = gam("norm_out.gamma")
+        self.conv_out = rc("conv_out.conv")
+        self._ready = True
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    @staticmethod
+    def _res(d, x):
+        T, H, W, C = x.shape
+        h = d["c1"](rms_silu(x, d["g1"]))
+        sc = x
+        if "nin" in d:                                                       # 1x1x1 conv == GEMM over pixels
+            sc = ops.gemm(x.reshape(-1, C), d["nin"][0], bias=d["nin"][1]).reshape(T, H, W, -1)
+        return d["c2"](rms_silu(h, d["g2"]), residual=sc)                    # h += x fused in the conv epilogue
+
+    def _attn(self, x):
+        T, H, W, C = x.shape
+        a, N = self.attn, H * W
+        xn = rms_silu(x, a["g"], silu=False).reshape(T * N, C)
+        buf = torch.zeros(T * N + 8, 3 * C, device=x.device, dtype=bf16)
+        qkv = ops.gemm(xn, a["wqkv"], out=buf[:T * N], bias=a["bqkv"])
+        npad = (T * N + 63) // 64 * 64
+        ws = torch.empty(N * npad * 6, device=x.device, dtype=torch.uint8)
+        o = torch.empty(T * N, C, device=x.device, dtype=bf16)
+        _lib.call("b200_attention_1head", qkv.data_ptr(), o.data_ptr(), ws.data_ptr(), ws.numel(), T, N, C, float(C) ** -0.5, 1, _s())
+        return ops.gemm(o, a["proj"][0], bias=a["proj"][1], residual=x.reshape(T * N, C)).reshape(T, H, W, C)
+
+    @staticmethod
+    def _up(up, x):
+        conv, cout, temporal = up
+        T, H, W, Ci = x.shape
+        h = conv(x)
+        out = torch.empty((2 * T - 1) if temporal else T, 2 * H, 2 * W, cout, device=x.device, dtype=bf16)
+        _lib.call("b200_hy_upsample_cl", h.data_ptr(), x.data_ptr(), out.data_ptr(), T, H, W, Ci, cout, int(temporal), _s())
+        return out
+
+    @torch.no_grad()
+    def forward(self, z):
+        """z [B, zc, T, h, w] -> frames fp32 [B, 3, ft*(T-1)+1, fs*h, fs*w] (Decoder.forward, :486-520)."""
+        if not self._ready:
+            raise RuntimeError("HYVAEDecoder: load_state_dict() must be called before decode")
+        outs = []
+        c0, zc = self.cfg["block_out_channels"][0], self.cfg["z_channels"]
+        for zi in z:
+            zi = zi.to(self.device, f32).contiguous()
+            _, T, H, W = zi.shape
+            P = T * H * W
+            zcl = torch.empty(T, H, W, zc, device=self.device, dtype=bf16)
+            zrep = torch.empty(T, H, W, c0, device=self.device, dtype=bf16)
+            _lib.call("b200_planar_to_cl", zi.data_ptr(), zcl.data_ptr(), zc, P, 1, _s())
+            _lib.call("b200_planar_to_cl", zi.data_ptr(), zrep.data_ptr(), zc, P, c0 // zc, _s())
+            h = self.conv_in(zcl, residual=zrep)                               # conv_in(z) + z.repeat_interleave (:489-490)
+            h = self._res(self.mid1, h)
+            h = self._attn(h)
+            h = self._res(self.mid2, h)
+            for blocks, up in self.levels:
+                for d in blocks:
+                    h = self._res(d, h)
+                if up is not None:
+                    h = self._up(up, h)
+            outs.append(self.conv_out(rms_silu(h, self.g_out), out_mode=2))
+        return torch.stack(outs, 0)
+
+
+class AutoencoderKLConv3D(torch.nn.Module):
+    """Decode surface of models/hyvideo/vae/hunyuanvideo_15_vae.py::AutoencoderKLConv3D (:523-907)."""
+
+    def __init__(self, in_channels=3, out_channels=3, latent_channels=32, block_out_channels=(128, 256, 512, 1024, 1024),
+                 layers_per_block=2, ffactor_spatial=16, ffactor_temporal=4, sample_size=256, sample_tsize=64, scaling_factor=None,
+                 shift_factor=None, device="cuda", **unused):
+        super().__init__()
+        self.ffactor_spatial, self.ffactor_temporal = ffactor_spatial, ffactor_temporal
+        self.scaling_factor, self.shift_factor = scaling_factor, shift_factor
+        self.config = types.SimpleNamespace(scaling_factor=scaling_factor, shift_factor=shift_factor, latent_channels=latent_channels)
+        self.decoder = HYVAEDecoder(dict(z_channels=latent_channels, out_channels=out_channels,
+                                         block_out_channels=list(reversed(list(block_out_channels))), num_res_blocks=layers_per_block,
+                                         ffactor_spatial=ffactor_spatial, ffactor_temporal=ffactor_temporal), device)
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        return self.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+
+    def enable_tiling(self, *a, **k):          # un-tiled whole-clip decode on a 180 GB GPU
+        return None
+
+    def enable_spatial_tiling(self, *a, **k):
+        return None
+
+    def enable_temporal_tiling(self, *a, **k):
+        return None
+
+    def decode(self, z, return_dict=True, generator=None):
+        out = self.decoder(z)
+        return types.SimpleNamespace(sample=out) if return_dict else (out,)
+
+    def encode(self, *a, **k):
+        raise NotImplementedError("Hunyuan VAE encode is outside the decode hot path")

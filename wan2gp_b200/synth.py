@@ -310,3 +310,72 @@ def make_hy_inputs(cfg, latent_thw, n_txt=24, n_txt_valid=17, n_byt5=12, n_byt5_
     bm = torch.zeros(1, n_byt5, dtype=torch.long)
     bm[:, :n_byt5_valid] = 1
     return x, torch.tensor([500.0]), txt, tm, byt5, bm
+
+
+# --------------------------------------------------------------------------- Hunyuan Video 1.5 VAE decoder (AutoencoderKLConv3D)
+
+HYVAE_CONFIGS = {
+    # hunyuan_video_1_5_VAE.json is a DOWNLOAD (hunyuan.py:329-336), not in the reference tree: these are the upstream values
+    # (SURVEY.md section 8c), block_out_channels given in DECODER order
+    "hyvae15": dict(z_channels=32, out_channels=3, block_out_channels=[1024, 1024, 512, 256, 128], num_res_blocks=2,
+                    ffactor_spatial=16, ffactor_temporal=4),
+    "hyvae_tiny": dict(z_channels=8, out_channels=3, block_out_channels=[64, 64, 32], num_res_blocks=1, ffactor_spatial=4,
+                       ffactor_temporal=2),
+    "hyvae_small": dict(z_channels=16, out_channels=3, block_out_channels=[128, 128, 64, 64, 32], num_res_blocks=2,
+                        ffactor_spatial=16, ffactor_temporal=4),
+}
+
+
+def hyvae_layout(cfg):
+    """Per level: (list of (cin, cout) resnet blocks, upsample (cin, cout, temporal) or None) -- Decoder.__init__
+    (hunyuanvideo_15_vae.py:432-484)."""
+    boc = cfg["block_out_channels"]
+    n_sp, n_t = int(math.log2(cfg["ffactor_spatial"])), int(math.log2(cfg["ffactor_temporal"]))
+    levels, cin = [], boc[0]
+    for i, ch in enumerate(boc):
+        blocks = []
+        for _ in range(cfg["num_res_blocks"] + 1):
+            blocks.append((cin, ch))
+            cin = ch
+        up = None
+        if i < n_sp or i < n_t:
+            up = (cin, boc[i + 1], i < n_t)
+            cin = boc[i + 1]
+        levels.append((blocks, up))
+    return levels, cin
+
+
+def hyvae_param_shapes(cfg):
+    s = {}
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k, k)
+        s[name + ".bias"] = (co,)
+
+    def res(p, ci, co):
+        s[p + "norm1.gamma"] = (ci, 1, 1, 1)
+        conv(p + "conv1.conv", co, ci, 3)
+        s[p + "norm2.gamma"] = (co, 1, 1, 1)
+        conv(p + "conv2.conv", co, co, 3)
+        if ci != co:
+            conv(p + "nin_shortcut", co, ci, 1)
+    c0 = cfg["block_out_channels"][0]
+    conv("conv_in.conv", c0, cfg["z_channels"], 3)
+    res("mid.block_1.", c0, c0)
+    s["mid.attn_1.norm.gamma"] = (c0, 1, 1, 1)
+    for n in ("q", "k", "v", "proj_out"):
+        conv("mid.attn_1." + n, c0, c0, 1)
+    res("mid.block_2.", c0, c0)
+    levels, c_last = hyvae_layout(cfg)
+    for i, (blocks, up) in enumerate(levels):
+        for j, (ci, co) in enumerate(blocks):
+            res(f"up.{i}.block.{j}.", ci, co)
+        if up is not None:
+            conv(f"up.{i}.upsample.conv.conv", up[1] * (8 if up[2] else 4), up[0], 3)
+    s["norm_out.gamma"] = (c_last, 1, 1, 1)
+    conv("conv_out.conv", cfg["out_channels"], c_last, 3)
+    return s
+
+
+def make_hyvae_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in hyvae_param_shapes(cfg).items()}

@@ -155,7 +155,7 @@ class WanVAEDecoder(torch.nn.Module):
         npad = (N + 63) // 64 * 64
         ws = torch.empty(N * npad * 6, device=x.device, dtype=torch.uint8)
         o = torch.empty(T * N, C, device=x.device, dtype=bf16)
-        _lib.call("b200_attention_1head", qkv.data_ptr(), o.data_ptr(), ws.data_ptr(), ws.numel(), T, N, C, float(C) ** -0.5, _s())
+        _lib.call("b200_attention_1head", qkv.data_ptr(), o.data_ptr(), ws.data_ptr(), ws.numel(), T, N, C, float(C) ** -0.5, 0, _s())
         return ops.gemm(o, a["wproj"], bias=a["bproj"], residual=x.reshape(T * N, C)).reshape(T, H, W, C)
 
     @staticmethod
