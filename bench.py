@@ -139,6 +139,61 @@ def run_hunyuan(args, rank, world, local_rank, dev, dist):
                         "peak_source": pk["source"] + ", sustained figure", "launches_timed": len(att), "avg_launch_ms": att_ms,
                         "share_of_step": (sum(a for a, _ in att) / ms) if att else None, "traffic": None},
            "clocks": clk.summary()}
+
+    # ---- VAE decode of the finished clip (second half of the metric): un-tiled Hunyuan decoder, one clip per GPU
+    if not args.no_vae:
+        from wan2gp_b200.hyvideo import HYVAE10Decoder, HYVAEDecoder
+        del den, model
+        torch.cuda.empty_cache()
+        tiny = cfg_name in ("hy_tiny", "hy10_tiny")
+        if v10:
+            vname = "hyvae10_tiny" if tiny else "hyvae10"
+            vcfg = synth.HYVAE10_CONFIGS[vname]
+            dec = HYVAE10Decoder(vcfg, dev)
+            dec.load_state_dict(synth.make_hyvae10_state_dict(vcfg, 0, device=dev))
+            zc, fs = vcfg["latent_channels"], 8
+        else:
+            vname = "hyvae_tiny" if tiny else "hyvae15"
+            vcfg = synth.HYVAE_CONFIGS[vname]
+            dec = HYVAEDecoder(vcfg, dev)
+            dec.load_state_dict(synth.make_hyvae_state_dict(vcfg, 0, device=dev))
+            zc, fs = vcfg["z_channels"], vcfg["ffactor_spatial"]
+        zh = torch.randn(1, zc, T, H, W, generator=g).pin_memory()
+        try:
+            z = zh.to(dev)
+            torch.cuda.reset_peak_memory_stats()
+            fr = dec(z)                                      # warm-up
+            nfr = fr.shape[2]
+            del fr
+            barrier()
+            l0 = _lib.launch_count()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            fr = dec(z)
+            v1.record()
+            barrier()
+            vlaunch = _lib.launch_count() - l0
+            del fr
+            # end to end: latent on host -> uint8 frames on host
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            fr = dec(zh.to(dev, non_blocking=True))[0]
+            u8 = torch.empty(fr.shape, device=dev, dtype=torch.uint8)
+            _lib.call("b200_frames_to_u8", fr.data_ptr(), u8.data_ptr(), fr.numel(), torch.cuda.current_stream().cuda_stream)
+            u8h = u8.cpu()
+            w1.record()
+            barrier()
+            vt = torch.tensor([v0.elapsed_time(v1), w0.elapsed_time(w1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(vt, op=dist.ReduceOp.MAX)
+            res["vae_decode"] = {"metric": "vae_decode_frames_per_sec", "decoder": vname, "value": world * nfr / (float(vt[0]) / 1e3),
+                                 "unit": "frames/s", "frames": nfr, "resolution": [fs * H, fs * W], "ms_per_clip": float(vt[0]),
+                                 "gpu_launches": vlaunch, "tiling": "none (whole clip resident)",
+                                 "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                                 "e2e": {"value": world * nfr / (float(vt[1]) / 1e3), "unit": "frames/s", "h2d_bytes": zh.numel() * 4,
+                                         "d2h_bytes": u8h.numel()}}
+        except Exception as e:                               # noqa: BLE001  (e.g. out of memory on a smaller GPU)
+            res["vae_decode"] = {"decoder": vname, "error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(res))
     if dist is not None:

@@ -111,7 +111,7 @@ int b200_upconv2x_cl(const void* x, const void* w4, const float* bias, void* out
                      void* stream);
 
 /* y = silu(x / max(||x||_2 over C, 1e-12) * sqrt(C) * gamma) per pixel (vae.py:85-103 RMS_norm + nn.SiLU),
- * bf16 [P, C] -> bf16 [P, C]; silu=0 skips the activation (AttentionBlock norm, vae.py:293). */
+ * bf16 [P, C] -> bf16 [P, C], C % 8 == 0 and C <= 1024; silu=0 skips the activation (AttentionBlock norm, vae.py:293). */
 int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream);
 
 /* nearest-exact 2x spatial upsample (vae.py:105-111, 124-127), bf16 [T,H,W,C] -> [T,2H,2W,C] */
@@ -124,7 +124,9 @@ int b200_vae_prologue(const float* z, const float* mean, const float* std, const
 /* single-head attention, head dim C <= 512 (C % 64 == 0), per frame over N tokens: qkv bf16 [F, N, 3C];
  * out bf16 [F, N, C] (vae.py:276-315 AttentionBlock core, F.scaled_dot_product_attention).
  * causal_frames=1: frame f attends to all tokens of frames 0..f (Hunyuan 1.5 VAE AttnBlock with prepare_causal_attention_mask,
- * hyvideo/vae/hunyuanvideo_15_vae.py:161-214); the workspace pitch is then roundup(F*N,64).
+ * hyvideo/vae/hunyuanvideo_15_vae.py:161-214; HunyuanVideo 1.0 VAE mid block, unet_causal_3d_blocks.py:21-30, 728-736);
+ * causal_frames=2: every frame attends to all F*N tokens (same mid block with mid_block_causal_attn off); for 1 and 2 the
+ * workspace pitch is roundup(F*N,64).
  * workspace: caller-owned, >= N * roundup(N,64) * 6 bytes (fp32 scores + bf16 probabilities of one frame).
  * qkv must have 8 readable (finite) rows after the last frame when N % 8 != 0 (the GEMM extents are rounded up to 8). */
 int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
@@ -136,6 +138,10 @@ int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void* stream);
 /* ---- Hunyuan Video 1.5 VAE decode helpers (hyvideo/vae/hunyuanvideo_15_vae.py) ---- */
 /* replicate padding of a channels-last bf16 tensor: [T,H,W,C] -> [T+pt, H+2ph, W+2pw, C], pt frames in front (CausalConv3d :137-158) */
 int b200_pad_replicate_cl(const void* x, void* y, int T, int H, int W, int C, int pt, int ph, int pw, void* stream);
+/* RMS_norm -> SiLU -> replicate padding in one pass for frames [t0, t0+Tc) of x [T,H,W,C]: y = [Tc+pt, H+2ph, W+2pw, C]
+ * (ResnetBlock norm -> swish -> CausalConv3d pad, hunyuanvideo_15_vae.py:107-158, 217-250); C % 8 == 0, C <= 1024 */
+int b200_rms_silu_pad_cl(const void* x, const float* gamma, void* y, int T, int H, int W, int C, int silu, int t0, int Tc, int pt,
+                         int ph, int pw, void* stream);
 /* "valid" conv over an explicitly padded input xpad [T+kt-1, H+kh-1, W+kw-1, Cin]; T,H,W = output dims; other arguments as
  * b200_conv3d_cl (out_mode 0 or 2) */
 int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const float* bias, const void* residual, void* out, int T, int H,
@@ -145,6 +151,24 @@ int b200_planar_to_cl(const float* x, void* y_bf16, int C, long long P, int rep,
 /* Upsample tail (:309-338): channel -> (time,) space shuffle of the conv output h [T,H,W,F*Co] plus the repeat-interleaved
  * shortcut of x [T,H,W,Ci] -> out bf16 [2T-1 | T, 2H, 2W, Co] */
 int b200_hy_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream);
+
+/* ---- HunyuanVideo 1.0 VAE decode helpers (hyvideo/vae/unet_causal_3d_blocks.py, vae/vae.py) ---- */
+/* GroupNorm statistics of a channels-last bf16 tensor [P, C] over all P pixels of the clip (torch.nn.GroupNorm on [B,C,T,H,W],
+ * unet_causal_3d_blocks.py:378,399; vae.py:292): stats[2g] = mean, stats[2g+1] = 1/sqrt(var + eps); workspace >= B200_GROUP_STATS_WS_BYTES(G);
+ * C/8 must divide 256; fixed summation order (bit-reproducible) */
+#define B200_GROUP_STATS_WS_BYTES(G) (148LL * 8 * (G) * 2 * 4)
+int b200_group_stats_cl(const void* x, float* stats, void* workspace, long long P, int C, int G, float eps, void* stream);
+/* y = [silu]((x - mean_g) * rstd_g * gamma + beta) for frames [t0, t0+Tc) of x [T,H,W,C], written replicate-padded as
+ * [Tc+pt, H+2ph, W+2pw, C] (pt frames in front, taken from the frames before t0 or frame 0): GroupNorm -> SiLU ->
+ * CausalConv3d's F.pad(mode="replicate") (unet_causal_3d_blocks.py:63-66, 455-480) in one pass */
+int b200_group_norm_apply_cl(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int T, int H, int W,
+                             int C, int G, int silu, int t0, int Tc, int pt, int ph, int pw, void* stream);
+/* "valid" conv over a window of x [Ti,Hi,Wi,Cin] starting at (off_t,off_h,off_w), T x H x W outputs stored bf16 with element
+ * strides (ost_t, ost_h, ost_w): one phase of nearest-up-sample + CausalConv3d (UpsampleCausal3D, unet_causal_3d_blocks.py
+ * :196-222) evaluated on the low-resolution tensor with pre-summed taps */
+int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int off_h, int off_w, const void* w, const float* bias,
+                        void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t, long long ost_h,
+                        long long ost_w, void* stream);
 
 /* Fused quantise + all-gather of decoded frames (the one collective of the schedule): x fp32 [n] (this
  * rank's frames) -> uint8 written into slot `rank` (byte offset rank*n) of EVERY peer's gather buffer.  peer_bufs: HOST array

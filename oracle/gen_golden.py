@@ -152,9 +152,30 @@ def run_hyvae(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
 
 
+HYVAE10_CASES = {"hyvae10_tiny": ("hyvae10_tiny", (8, 3, 2, 3), 0), "hyvae10_small": ("hyvae10_small", (16, 2, 2, 2), 1)}
+
+
+def run_hyvae10(name):
+    """Reference AutoencoderKLCausal3D.decode, un-tiled (autoencoder_kl_causal_3d.py:474-493); the mid-block `Attention` is the
+    restated third-party class of refshim.load_reference_hyvae10."""
+    from oracle.refshim import load_reference_hyvae10
+    hv = load_reference_hyvae10()
+    cfg_name, zshape, seed = HYVAE10_CASES[name]
+    cfg = synth.HYVAE10_CONFIGS[cfg_name]
+    vae = hv.AutoencoderKLCausal3D(in_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4,
+                                   up_block_types=("UpDecoderBlockCausal3D",) * 4, **cfg).eval().requires_grad_(False)
+    missing = vae.load_state_dict(synth.make_hyvae10_state_dict(cfg, seed), strict=False)
+    assert not missing.unexpected_keys and all(k.startswith(("encoder.", "quant_conv.")) for k in missing.missing_keys)
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    with torch.no_grad():
+        out = vae.decode(z, return_dict=False)[0]
+    print(f"{name}: reference HY-1.0 VAE decode out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae)(n)

@@ -238,3 +238,70 @@ def load_reference_hyvae():
     from models.hyvideo.vae.hunyuanvideo_15_vae import Decoder
     _loaded_hyvae = types.SimpleNamespace(Decoder=Decoder)
     return _loaded_hyvae
+
+
+_loaded_hyvae10 = None
+
+
+def load_reference_hyvae10():
+    """Reference HunyuanVideo 1.0 VAE decoder (models/hyvideo/vae/vae.py::DecoderCausal3D + unet_causal_3d_blocks.py).
+    Its mid block uses `diffusers.models.attention_processor.Attention` -- THIRD-PARTY code (diffusers==0.36.0,
+    requirements.txt:4) that is not in the reference tree.  `_Attention` below restates the published behaviour of
+    Attention(+AttnProcessor2_0) for the exact constructor call at unet_causal_3d_blocks.py:690-703 (single head,
+    GroupNorm over tokens, to_q/to_k/to_v/to_out Linears with bias, residual connection, rescale_output_factor): parity of
+    that one block is pinned to this restatement, not to diffusers itself ("parity unpinned" at that boundary)."""
+    global _loaded_hyvae10
+    if _loaded_hyvae10 is not None:
+        return _loaded_hyvae10
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    load_reference_hyvae()
+
+    class _Attention(nn.Module):
+        def __init__(self, query_dim, heads=8, dim_head=64, rescale_output_factor=1.0, eps=1e-5, norm_num_groups=None,
+                     spatial_norm_dim=None, residual_connection=False, bias=False, upcast_softmax=False,
+                     _from_deprecated_attn_block=False, **kw):
+            super().__init__()
+            inner = heads * dim_head
+            self.heads, self.rescale, self.residual = heads, rescale_output_factor, residual_connection
+            self.group_norm = nn.GroupNorm(norm_num_groups, query_dim, eps=eps, affine=True) if norm_num_groups else None
+            self.to_q, self.to_k, self.to_v = (nn.Linear(query_dim, inner, bias=bias) for _ in range(3))
+            self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(0.0)])
+
+        def forward(self, hidden_states, temb=None, attention_mask=None, **kw):
+            residual = hidden_states
+            b, n, c = hidden_states.shape
+            if self.group_norm is not None:
+                hidden_states = self.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+            q, k, v = (f(hidden_states).view(b, n, self.heads, -1).transpose(1, 2) for f in (self.to_q, self.to_k, self.to_v))
+            if attention_mask is not None:
+                attention_mask = attention_mask.view(b, 1, n, n)
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask)
+            o = self.to_out[0](o.transpose(1, 2).reshape(b, n, -1))
+            if self.residual:
+                o = o + residual
+            return o / self.rescale
+
+    def mod(name, **attrs):
+        m = sys.modules.setdefault(name, types.ModuleType(name))
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+    blank = lambda n: type(n, (nn.Module,), {})                                      # noqa: E731
+    logging = types.SimpleNamespace(get_logger=lambda *a, **k: types.SimpleNamespace(warn=print, warning=print, info=print))
+    mod("diffusers.utils", is_torch_version=lambda *a: True, logging=logging, BaseOutput=dict)
+    mod("diffusers.utils.torch_utils", randn_tensor=lambda *a, **k: torch.randn(*a))
+    mod("diffusers.utils.accelerate_utils", apply_forward_hook=lambda f: f)
+    mod("diffusers.models.activations", get_activation=lambda n: {"swish": nn.SiLU(), "silu": nn.SiLU()}[n])
+    mod("diffusers.models.attention_processor", Attention=_Attention, SpatialNorm=blank("SpatialNorm"), AttentionProcessor=object,
+        AttnAddedKVProcessor=object, AttnProcessor=object, ADDED_KV_ATTENTION_PROCESSORS=(), CROSS_ATTENTION_PROCESSORS=())
+    mod("diffusers.models.normalization", AdaGroupNorm=blank("AdaGroupNorm"), RMSNorm=blank("RMSNorm"))
+    mod("diffusers.loaders", FromOriginalVAEMixin=object, FromOriginalModelMixin=object)
+    mod("diffusers.loaders.single_file_model", FromOriginalModelMixin=object)
+    load_reference_hy()                              # ConfigMixin / ModelMixin / register_to_config shims
+    sys.modules.setdefault("loguru", types.SimpleNamespace(logger=types.SimpleNamespace(warning=print, info=print)))
+    from models.hyvideo.vae.vae import DecoderCausal3D
+    from models.hyvideo.vae.autoencoder_kl_causal_3d import AutoencoderKLCausal3D
+    _loaded_hyvae10 = types.SimpleNamespace(DecoderCausal3D=DecoderCausal3D, AutoencoderKLCausal3D=AutoencoderKLCausal3D)
+    return _loaded_hyvae10

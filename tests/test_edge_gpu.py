@@ -74,3 +74,45 @@ def test_error_behaviour():
         ops.gemm(torch.zeros(4, 12, device="cuda", dtype=bf16), torch.zeros(8, 12, device="cuda", dtype=bf16))     # K % 8
     with pytest.raises(NotImplementedError):
         WanVAE(device="cuda").decode([torch.zeros(16, 1, 2, 2)], tile_size=256)
+
+
+@pytest.mark.parametrize("C", [16, 96, 384, 1024])
+def test_rms_silu_widths(C):
+    """RMS_norm + SiLU over channels up to the 1024-channel levels of the Hunyuan 1.5 VAE, vs a plain torch fp32 reference."""
+    from wan2gp_b200.wan.vae import rms_silu
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(3, 5, 7, C, device="cuda", generator=g) * 1.5).to(bf16)
+    gam = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    for silu in (True, False):
+        y = rms_silu(x, gam, silu=silu).float()
+        ref = torch.nn.functional.normalize(x.float(), dim=-1) * C ** 0.5 * gam
+        ref = torch.nn.functional.silu(ref) if silu else ref
+        assert rel_l2(y, ref) < 4e-3
+
+
+@pytest.mark.parametrize("C,G", [(32, 8), (64, 32), (128, 32), (512, 32)])
+def test_group_norm_cl(C, G):
+    """Clip-wide GroupNorm statistics + fused normalise/SiLU/replicate-pad slice writer vs torch.nn.functional.group_norm."""
+    import torch.nn.functional as F
+    from wan2gp_b200.hyvideo.vae10 import _GroupNorm
+    g = torch.Generator(device="cuda").manual_seed(C + G)
+    T, H, W = 5, 6, 7
+    x = (torch.randn(T, H, W, C, device="cuda", generator=g) * 2 + 0.7).to(bf16)
+    w, b = 1 + 0.1 * torch.randn(C, device="cuda", generator=g), 0.1 * torch.randn(C, device="cuda", generator=g)
+    gn = _GroupNorm(w, b, G, "cuda")
+    st = gn.stats(x)
+    assert torch.equal(st, gn.stats(x))                                   # fixed summation order: bit-reproducible
+    xc = x.float().permute(3, 0, 1, 2)[None]                               # [1,C,T,H,W]
+    ref = F.group_norm(xc, G, w, b, 1e-6)
+    mean = xc.reshape(G, -1).mean(1)
+    assert torch.allclose(st[0::2], mean, atol=1e-4, rtol=1e-4)
+    y = gn.apply(x, st, False).float().permute(3, 0, 1, 2)[None]
+    assert rel_l2(y, ref) < 4e-3
+    # SiLU + replicate padding of the time slice [2, 5): 2 frames in front come from frames 0..1, 1 pixel around
+    yp = gn.apply(x, st, True, 2, 3, (2, 1, 1)).float().permute(3, 0, 1, 2)[None]
+    refp = F.pad(F.silu(ref), (1, 1, 1, 1, 0, 0), mode="replicate")
+    assert yp.shape == (1, C, 5, H + 2, W + 2) and rel_l2(yp, refp) < 4e-3
+    # slice starting at frame 0: the 2 front frames replicate frame 0
+    y0 = gn.apply(x, st, True, 0, 2, (2, 1, 1)).float().permute(3, 0, 1, 2)[None]
+    ref0 = F.pad(F.silu(ref[:, :, :2]), (1, 1, 1, 1, 2, 0), mode="replicate")
+    assert rel_l2(y0, ref0) < 4e-3

@@ -1,0 +1,78 @@
+"""CPU tests for hot-path row H5 (HunyuanVideo 1.0 VAE decode): oracle vs the reference fixtures, and the host-side algebra of
+the phase-decomposed up-sampling conv (no GPU, no compute calls into the C ABI)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import load_golden, rel_l2
+from wan2gp_b200 import synth
+
+
+@pytest.mark.parametrize("name,zshape,seed", [("hyvae10_tiny", (8, 3, 2, 3), 0), ("hyvae10_small", (16, 2, 2, 2), 1)])
+def test_hyvae10_oracle_matches_reference(name, zshape, seed):
+    """fp32 oracle == reference AutoencoderKLCausal3D.decode (un-tiled) on the committed fixture."""
+    from oracle import hyvae10_oracle
+    cfg = synth.HYVAE10_CONFIGS[name]
+    sd = synth.make_hyvae10_state_dict(cfg, seed)
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")[0]
+    g = load_golden(name)["out"][0]
+    assert rel_l2(hyvae10_oracle.hyvae10_decode(sd, cfg, z), g) < 1e-5
+
+
+def test_hyvae10_layout_884():
+    """Up-sampling plan of the 884 decoder (vae/vae.py:259-261): x(1,2,2), x(2,2,2), x(2,2,2), none."""
+    blocks, c_last = synth.hyvae10_layout(synth.HYVAE10_CONFIGS["hyvae10"])
+    assert [up for _, up in blocks] == [(False, True), (True, True), (True, True), None]
+    assert [rs[0] for rs, _ in blocks] == [(512, 512), (512, 512), (512, 256), (256, 128)] and c_last == 128
+
+
+def _reference_upsample(x, w, b, up_t):
+    """UpsampleCausal3D.forward (unet_causal_3d_blocks.py:196-222) in plain torch: x [C,T,H,W]."""
+    if up_t:
+        first = F.interpolate(x[None, :, :1], scale_factor=(1, 2, 2), mode="nearest")[0]
+        x = torch.cat([first, F.interpolate(x[None, :, 1:], scale_factor=(2, 2, 2), mode="nearest")[0]], 1) if x.shape[1] > 1 else first
+    else:
+        x = F.interpolate(x[None], scale_factor=(1, 2, 2), mode="nearest")[0]
+    return F.conv3d(F.pad(x[None], (1, 1, 1, 1, 2, 0), mode="replicate"), w, b)[0]
+
+
+def _phase_convs_cpu(up, x):
+    """What _UpConvNearest.__call__ asks b200_conv3d_cl_view to do, restated with F.conv3d (same windows, strides, weights)."""
+    C, T, H, W = x.shape
+    ptf = 1 if up.up_t else 2
+    xp = F.pad(x[None], (1, 1, 1, 1, ptf, 0), mode="replicate")[0]
+    out = torch.zeros(up.cout, 2 * T - 1 if up.up_t else T, 2 * H, 2 * W)
+    for (pt, py, px), w in up.w.items():
+        kt = 3 if pt is None else 2
+        wk = w.float().reshape(up.cout, kt, 2, 2, up.cin).permute(0, 4, 1, 2, 3)
+        n_t, off_t, o_t, s_t = (T, 0, 0, 1) if pt is None else (T, 0, 0, 2) if pt == 0 else (T - 1, 1, 1, 2)
+        if n_t <= 0:
+            continue
+        win = xp[:, off_t:off_t + n_t + kt - 1, py:py + H + 1, px:px + W + 1]
+        out[:, o_t::s_t, py::2, px::2][:, :n_t] = F.conv3d(win[None], wk, up.b)[0]
+    return out
+
+
+@pytest.mark.parametrize("up_t", [False, True])
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_upsample_phase_decomposition(up_t, T):
+    """nearest x(1|2,2,2) + replicate-padded causal 3x3x3 conv == 4|8 phase convs with pre-summed taps on the low-res tensor."""
+    from wan2gp_b200.hyvideo.vae10 import _UpConvNearest
+    g = torch.Generator().manual_seed(T + 10 * up_t)
+    w, b, x = torch.randn(16, 8, 3, 3, 3, generator=g) * 0.2, torch.randn(16, generator=g), torch.randn(8, T, 3, 4, generator=g)
+    up = _UpConvNearest(w, b, up_t, "cpu", dtype=torch.float32)
+    assert len(up.w) == (8 if up_t else 4)
+    assert rel_l2(_phase_convs_cpu(up, x), _reference_upsample(x, w, b, up_t)) < 1e-5
+
+
+def test_post_quant_fold():
+    """conv_in(replicate_pad(post_quant_conv(z))) == folded conv (vae10.HYVAE10Decoder.load_state_dict)."""
+    g = torch.Generator().manual_seed(3)
+    zc, c0 = 8, 16
+    wq, bq = torch.randn(zc, zc, 1, 1, 1, generator=g) * 0.3, torch.randn(zc, generator=g)
+    wi, bi = torch.randn(c0, zc, 3, 3, 3, generator=g) * 0.1, torch.randn(c0, generator=g)
+    z = torch.randn(1, zc, 3, 4, 5, generator=g)
+    pad = lambda t: F.pad(t, (1, 1, 1, 1, 2, 0), mode="replicate")                                    # noqa: E731
+    want = F.conv3d(pad(F.conv3d(z, wq, bq)), wi, bi)
+    wf, bf = torch.einsum("omtyx,mi->oityx", wi, wq.reshape(zc, zc)), bi + torch.einsum("omtyx,m->o", wi, bq)
+    assert rel_l2(F.conv3d(pad(z), wf, bf), want) < 1e-5

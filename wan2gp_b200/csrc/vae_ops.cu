@@ -20,20 +20,30 @@ using namespace b200;
 
 // ---------------------------------------------------------------------------------------------
 // RMS_norm over channels (vae.py:85-103: F.normalize(x, dim=C) * sqrt(C) * gamma) + SiLU, per pixel.
-// LPP lanes cooperate on one pixel, each holding up to two 16-byte chunks (C <= 16 * LPP).
-template <int LPP>
+// LPP lanes cooperate on one pixel, each holding up to NCH 16-byte chunks (C <= 8 * NCH * LPP).
+// optional output geometry: write frames [t0, t0+Tc) of [T,H,W,C] replicate-padded as [Tc+pt, H+2ph, W+2pw, C]
+struct RmsPad { int on, H, W, t0, pt, ph, pw; };
+template <int LPP, int NCH>
 __global__ void __launch_bounds__(256)
 rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ y,
-                   long long P, int C, int do_silu) {
+                   long long P, int C, int do_silu, RmsPad g) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pix = gt / LPP;
+    const long long opix = gt / LPP;               // output pixel (of the padded slice when g.on)
     const int sub = (int)(gt % LPP);
     const int nchunk = C >> 3;
-    const bool active = pix < P;
-    uint4 v[2];
+    const bool active = opix < P;
+    long long pix = opix;                          // source pixel
+    if (g.on && active) {
+        const int Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
+        const int w = (int)(opix % Wo); const long long r = opix / Wo;
+        const int h = (int)(r % Ho), t = (int)(r / Ho);
+        const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
+        pix = ((long long)ts * g.H + hs) * g.W + ws;
+    }
+    uint4 v[NCH];
     float ss = 0.f;
     #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NCH; ++i) {
         const int ch = sub + i * LPP;
         if (active && ch < nchunk) {
             v[i] = __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch);
@@ -49,7 +59,7 @@ rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
     #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NCH; ++i) {
         const int ch = sub + i * LPP;
         if (active && ch < nchunk) {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
@@ -66,30 +76,43 @@ rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
             }
-            reinterpret_cast<uint4*>(y + pix * C)[ch] =
+            reinterpret_cast<uint4*>(y + opix * C)[ch] =
                 make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
     }
 }
 
-template <int LPP>
-static int launch_rms(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st) {
+template <int LPP, int NCH = 2>
+static int launch_rms(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st, RmsPad g = RmsPad{}) {
     const long long threads = P * LPP;
-    rms_silu_cl_kernel<LPP><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), P, C, silu);
+    if ((threads + 255) / 256 > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: too many pixels for one launch");
+    rms_silu_cl_kernel<LPP, NCH><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), P, C, silu, g);
     CHECK_LAUNCH("rms_silu_cl");
     return B200_OK;
 }
 
-extern "C" int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream) {
-    if (!x || !gamma || !y || P <= 0 || C % 8 || C > 512) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: bad argument (C=%d)", C);
-    cudaStream_t st = (cudaStream_t)stream;
+static int rms_dispatch(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st, RmsPad g) {
     const int nchunk = C / 8;
-    if (nchunk <= 4) return launch_rms<2>(x, gamma, y, P, C, silu, st);
-    if (nchunk <= 8) return launch_rms<4>(x, gamma, y, P, C, silu, st);
-    if (nchunk <= 16) return launch_rms<8>(x, gamma, y, P, C, silu, st);
-    if (nchunk <= 32) return launch_rms<16>(x, gamma, y, P, C, silu, st);
-    return launch_rms<32>(x, gamma, y, P, C, silu, st);
+    if (nchunk <= 4) return launch_rms<2>(x, gamma, y, P, C, silu, st, g);
+    if (nchunk <= 8) return launch_rms<4>(x, gamma, y, P, C, silu, st, g);
+    if (nchunk <= 16) return launch_rms<8>(x, gamma, y, P, C, silu, st, g);
+    if (nchunk <= 32) return launch_rms<16>(x, gamma, y, P, C, silu, st, g);
+    if (nchunk <= 64) return launch_rms<32>(x, gamma, y, P, C, silu, st, g);
+    return launch_rms<32, 4>(x, gamma, y, P, C, silu, st, g);       // C <= 1024 (Hunyuan 1.5 VAE, 1024-channel levels)
+}
+extern "C" int b200_rms_silu_cl(const void* x, const float* gamma, void* y, long long P, int C, int silu, void* stream) {
+    if (!x || !gamma || !y || P <= 0 || C % 8 || C > 1024) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: bad argument (C=%d)", C);
+    return rms_dispatch(x, gamma, y, P, C, silu, (cudaStream_t)stream, RmsPad{});
+}
+// RMS_norm -> SiLU -> F.pad(mode="replicate") of CausalConv3d (hunyuanvideo_15_vae.py:107-158, 217-250) in one pass, for the time
+// slice [t0, t0+Tc): the normalised tensor is only ever written in the padded layout the conv reads.
+extern "C" int b200_rms_silu_pad_cl(const void* x, const float* gamma, void* y, int T, int H, int W, int C, int silu, int t0, int Tc,
+                                    int pt, int ph, int pw, void* stream) {
+    if (!x || !gamma || !y || C % 8 || C > 1024 || T <= 0 || H <= 0 || W <= 0 || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
+        return b200_set_error(B200_ERR_ARG, "rms_silu_pad_cl: bad argument (C=%d)", C);
+    const long long P = (long long)(Tc + pt) * (H + 2 * ph) * (W + 2 * pw);
+    return rms_dispatch(x, gamma, y, P, C, silu, (cudaStream_t)stream, RmsPad{1, H, W, t0, pt, ph, pw});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,10 +310,122 @@ extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_
 }
 
 // ---------------------------------------------------------------------------------------------
+// HunyuanVideo 1.0 VAE helpers: GroupNorm over the WHOLE clip (torch.nn.GroupNorm on [B,C,T,H,W], unet_causal_3d_blocks.py
+// :378/:399, vae.py:292) on channels-last bf16.  Pass 1: per-group sum / sum-of-squares (fp32 per thread and block, fp64
+// across blocks, fixed summation order).  Pass 2 (apply) normalises, optionally applies SiLU and writes straight into the replicate-PADDED layout
+// the following causal conv reads, for a time slice [t0, t0+Tc) of the clip -- the un-padded normalised tensor never exists.
+__global__ void __launch_bounds__(256)
+group_stats_kernel(const uint4* __restrict__ x, float* __restrict__ part, long long P, int C8, int Cg, int G) {
+    __shared__ float sh[2][256][8];
+    const int tid = threadIdx.x;
+    const int rows = 256 / C8;                      // C8 divides 256 (host-checked)
+    const int c8 = tid % C8, r = tid / C8;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+        const uint4 v = __ldg(x + p * C8 + c8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+            s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sh[0][tid][j] = s[j]; sh[1][tid][j] = q[j]; }
+    __syncthreads();
+    // fixed-order reduction (no atomics: the statistics, hence the decode, are bit-reproducible run to run)
+    if (tid < G) {
+        float a = 0.f, b = 0.f;
+        const int c_lo = tid * Cg, c_hi = c_lo + Cg;
+        for (int rr = 0; rr < rows; ++rr)
+            for (int c = c_lo; c < c_hi; ++c) { a += sh[0][rr * C8 + (c >> 3)][c & 7]; b += sh[1][rr * C8 + (c >> 3)][c & 7]; }
+        part[((long long)blockIdx.x * G + tid) * 2] = a;
+        part[((long long)blockIdx.x * G + tid) * 2 + 1] = b;
+    }
+}
+__global__ void group_stats_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int nblocks, double inv_n, float eps, int G) {
+    const int g = threadIdx.x;
+    if (g >= G) return;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblocks; ++i) { a += (double)part[((long long)i * G + g) * 2]; b += (double)part[((long long)i * G + g) * 2 + 1]; }
+    const double mean = a * inv_n;
+    const double var = fmax(b * inv_n - mean * mean, 0.0);    // biased variance, as torch group_norm
+    stats[2 * g] = (float)mean;
+    stats[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+#define GROUP_STATS_MAX_BLOCKS (148 * 8)
+extern "C" int b200_group_stats_cl(const void* x, float* stats, void* workspace, long long P, int C, int G, float eps, void* stream) {
+    if (!x || !stats || !workspace || P <= 0 || G <= 0 || G > 256 || C % 8 || C % G) return b200_set_error(B200_ERR_ARG, "group_stats_cl: bad argument");
+    const int C8 = C / 8, Cg = C / G;
+    if (C8 > 256 || 256 % C8) return b200_set_error(B200_ERR_ARG, "group_stats_cl: C/8 = %d must divide 256", C8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = 256 / C8;
+    const long long want = (P + rows - 1) / rows;
+    const unsigned grid = (unsigned)(want < GROUP_STATS_MAX_BLOCKS ? want : GROUP_STATS_MAX_BLOCKS);
+    group_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<float*>(workspace), P, C8, Cg, G);
+    CHECK_LAUNCH("group_stats_cl");
+    group_stats_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), stats, (int)grid, 1.0 / ((double)P * Cg), eps, G);
+    CHECK_LAUNCH("group_stats_finalize");
+    return B200_OK;
+}
+
+__global__ void __launch_bounds__(256)
+group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, uint4* __restrict__ y, int H, int W, int C8, int Cg, int silu, int t0, int Tc,
+                        int pt, int ph, int pw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int To = Tc + pt, Ho = H + 2 * ph, Wo = W + 2 * pw;
+    if (i >= (long long)To * Ho * Wo * C8) return;
+    const int c8 = i % C8; long long r = i / C8;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; const int t = r / Ho;
+    const int ts = max(t0 + t - pt, 0), hs = min(max(h - ph, 0), H - 1), ws = min(max(w - pw, 0), W - 1);
+    const uint4 v = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c8);
+    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + 1);
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 a = __bfloat1622float2(hv[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c8 * 8 + j) / Cg;
+        float u = (f[j] - __ldg(stats + 2 * g)) * __ldg(stats + 2 * g + 1) * ga[j] + be[j];
+        if (silu) u = u / (1.f + __expf(-u));
+        f[j] = u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    y[i] = o;
+}
+extern "C" int b200_group_norm_apply_cl(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int T, int H,
+                                        int W, int C, int G, int silu, int t0, int Tc, int pt, int ph, int pw, void* stream) {
+    if (!x || !stats || !gamma || !beta || !y || C % 8 || G <= 0 || C % G || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
+        return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: bad argument");
+    const int Cg = C / G;
+    const long long n = (long long)(Tc + pt) * (H + 2 * ph) * (W + 2 * pw) * (C / 8);
+    if ((n + 255) / 256 > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: slice too large");
+    group_norm_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x), stats, gamma, beta, reinterpret_cast<uint4*>(y), H, W, C / 8, Cg, silu, t0, Tc, pt, ph, pw);
+    CHECK_LAUNCH("group_norm_apply_cl");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // causal conv as implicit GEMM
+// optional explicit view for conv_cl_impl: input extents + tap origin offsets, output strides (elements) -- used by the
+// phase-decomposed up-sampling convs of the HunyuanVideo 1.0 VAE
+struct ConvView { int Ti, Hi, Wi, off_t, off_h, off_w; long long ost_t, ost_h, ost_w; };
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream, int prepadded = 0);
+                        void* stream, int prepadded = 0, const ConvView* view = nullptr);
 
 extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                               int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
@@ -321,9 +456,22 @@ extern "C" int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const f
     return conv_cl_impl(xpad, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, out_mode, 0, 0, 0, -1, -1, stream, 1);
 }
 
+// "valid" conv over an arbitrary window of a channels-last tensor x [Ti,Hi,Wi,Cin]: output pixel (t,h,w), t<T, h<H, w<W, reads
+// taps at x[off_t + t + dt, off_h + h + dh, off_w + w + dw] and is stored (bf16) at out + t*ost_t + h*ost_h + w*ost_w (elements).
+// One launch per phase of a nearest-up-sample + conv pair (UpsampleCausal3D, unet_causal_3d_blocks.py:196-222): the conv
+// over the 2x (x2x2) up-sampled tensor equals 4 (8) small convs with pre-summed taps over the LOW-resolution tensor.
+extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int off_h, int off_w, const void* w, const float* bias,
+                                   void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t,
+                                   long long ost_h, long long ost_w, void* stream) {
+    if (off_t < 0 || off_h < 0 || off_w < 0 || off_t + T + kt - 1 > Ti || off_h + H + kh - 1 > Hi || off_w + W + kw - 1 > Wi)
+        return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: window outside the input");
+    ConvView v{Ti, Hi, Wi, off_t, off_h, off_w, ost_t, ost_h, ost_w};
+    return conv_cl_impl(x, w, bias, nullptr, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, 0, 0, -1, -1, stream, 1, &v);
+}
+
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream, int prepadded) {
+                        void* stream, int prepadded, const ConvView* view) {
     if (!x || !w || !out || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
     if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
     if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
@@ -336,7 +484,8 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
-        const uint64_t Ti = prepadded ? T + kt - 1 : T, Hi = prepadded ? H + kh - 1 : H, Wi = prepadded ? W + kw - 1 : W;
+        uint64_t Ti = prepadded ? T + kt - 1 : T, Hi = prepadded ? H + kh - 1 : H, Wi = prepadded ? W + kw - 1 : W;
+        if (view) { Ti = view->Ti; Hi = view->Hi; Wi = view->Wi; }
         uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, Ti};
         uint64_t str[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
         uint32_t box[4] = {kbox, CONV_BW, CONV_BH, 1};
@@ -366,7 +515,12 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.n_group = p.n_tiles;            // weights are small: all N tiles of one pixel tile run back to back
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-    if (out_mode == 0 && up_py >= 0) {
+    if (view) {
+        if (out_mode != 0 || residual) return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: bf16 output without residual only");
+        p.pad_t = -view->off_t; p.pad_h = -view->off_h; p.pad_w = -view->off_w;
+        p.out = out;
+        p.st_t = view->ost_t; p.st_h = view->ost_h; p.st_w = view->ost_w;
+    } else if (out_mode == 0 && up_py >= 0) {
         // output pixel (t, 2h + py, 2w + px) of a [T, 2H, 2W, Cout] tensor
         p.out = reinterpret_cast<__nv_bfloat16*>(out) + ((long long)up_py * 2 * W + up_px) * Cout;
         p.st_w = 2LL * Cout; p.st_h = 4LL * W * Cout; p.st_t = 4LL * H * W * Cout;
@@ -442,7 +596,8 @@ extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace,
     const int N8 = (N + 7) & ~7;      // GEMM extents are multiples of 8: the key tail [N, N8) gets probability 0 (the caller
                                       // guarantees 8 readable rows after the last frame of qkv)
     // causal_frames: frame f attends to the tokens of frames 0..f (Hunyuan 1.5 VAE mid block, hunyuanvideo_15_vae.py:161-214);
-    // otherwise every frame attends to itself only (Wan VAE).
+    // 2: full attention over all F*N tokens (HunyuanVideo 1.0 VAE with mid_block_causal_attn off); 0: every frame attends to
+    // itself only (Wan VAE).
     const long long Lk_max = causal_frames ? (long long)F * N : N;
     const long long Np = (Lk_max + 63) / 64 * 64;     // padded row pitch so P is a legal GEMM operand
     const long long need = (long long)N * Np * 4 + (long long)N * Np * 2;
@@ -461,7 +616,7 @@ extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace,
     for (int f = 0; f < F; ++f) {
         const __nv_bfloat16* q = base + (long long)f * N * 3 * C;
         const __nv_bfloat16* kv = causal_frames ? base : q;                 // keys/values start at frame 0 when causal
-        const int Lk = causal_frames ? (f + 1) * N : N;
+        const int Lk = causal_frames == 1 ? (f + 1) * N : causal_frames == 2 ? F * N : N;   // 2: every frame sees all frames
         const int Lk8 = (Lk + 7) & ~7;
         int r = b200_gemm_bf16(q, kv + C, S, N, Lk8, C, 3LL * C, 3LL * C, Np, nullptr, nullptr, nullptr, 0, 1, 0, 0, stream);
         if (r) return r;

@@ -23,6 +23,9 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+PAD_SLICE_BYTES = 8 << 30            # budget for one padded, normalised time slice of a full-resolution activation
+
+
 class _RepConv(_Conv):
     """3x3x3 causal conv with replicate padding: pad (2 frames in front, 1 pixel around) then a 'valid' conv."""
 
@@ -31,12 +34,58 @@ class _RepConv(_Conv):
         kt, kh, kw = self.k
         xp = torch.empty(T + kt - 1, H + kh - 1, W + kw - 1, C, device=x.device, dtype=bf16)
         _lib.call("b200_pad_replicate_cl", x.data_ptr(), xp.data_ptr(), T, H, W, C, kt - 1, kh // 2, kw // 2, _s())
-        out = (torch.empty(self.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
-               else torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16))
+        return self.prepadded(xp, T, H, W, residual, None, out_mode)
+
+    def prepadded(self, xp, T, H, W, residual, out, out_mode):
+        """'valid' conv over an already padded operand xp [T+kt-1, H+kh-1, W+kw-1, Cin]."""
+        kt, kh, kw = self.k
+        if out is None:
+            out = (torch.empty(self.cout, T, H, W, device=xp.device, dtype=f32) if out_mode == 2
+                   else torch.empty(T, H, W, self.cout, device=xp.device, dtype=bf16))
         _lib.call("b200_conv3d_cl_prepadded", xp.data_ptr(), self.w.data_ptr(), self.b.data_ptr(),
-                  0 if residual is None else residual.data_ptr(), out.data_ptr(), T, H, W, self.cin, self.cout, kt, kh, kw,
-                  out_mode, _s())
+                  0 if residual is None else residual.data_ptr(), out.data_ptr(), T, H, W, self.cin, self.cout, kt, kh, kw, out_mode, _s())
         return out
+
+
+class _RMSNorm:
+    """RMS_norm (hunyuanvideo_15_vae.py:107-122) with the norm_act_conv interface: no clip-wide statistics."""
+
+    def __init__(self, gamma):
+        self.g = gamma
+
+    def stats(self, x):
+        return None
+
+    def apply(self, x, st, silu, t0=0, tc=None, pad=(0, 0, 0)):
+        T, H, W, C = x.shape
+        tc = T if tc is None else tc
+        y = torch.empty(tc + pad[0], H + 2 * pad[1], W + 2 * pad[2], C, device=x.device, dtype=bf16)
+        _lib.call("b200_rms_silu_pad_cl", x.data_ptr(), self.g.data_ptr(), y.data_ptr(), T, H, W, C, int(silu), t0, tc, pad[0], pad[1], pad[2], _s())
+        return y
+
+
+def norm_act_conv(x, norm, conv, residual=None, out_mode=0, out=None):
+    """conv(replicate_pad(silu(norm(x)))) [+ residual].  norm -> SiLU -> pad is ONE pass that writes the padded operand of the
+    tcgen05 implicit-GEMM conv, in time slices of <= PAD_SLICE_BYTES so the padded copy stays a few GB at 720p x 129 frames
+    (a full-resolution activation is 30-61 GB).  `out` may alias `residual`: each epilogue thread reads its residual chunk
+    before storing the same chunk."""
+    T, H, W, C = x.shape
+    kt, kh, kw = conv.k
+    st = norm.stats(x)
+    frame_bytes = (H + kh - 1) * (W + kw - 1) * C * 2
+    tc_max = max(1, min(T, PAD_SLICE_BYTES // frame_bytes - (kt - 1)))
+    if out is None:
+        out = (torch.empty(conv.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
+               else torch.empty(T, H, W, conv.cout, device=x.device, dtype=bf16))
+    for t0 in range(0, T, tc_max):
+        tc = min(tc_max, T - t0)
+        xp = norm.apply(x, st, True, t0, tc, (kt - 1, kh // 2, kw // 2))
+        if out_mode == 2 and tc != T:                       # planar fp32 head: the channel stride is the slice's, so copy it in
+            out[:, t0:t0 + tc].copy_(conv.prepadded(xp, tc, H, W, None, None, 2))
+        else:
+            conv.prepadded(xp, tc, H, W, None if residual is None else residual[t0:t0 + tc], out if out_mode == 2 else out[t0:t0 + tc], out_mode)
+        del xp
+    return out
 
 
 class HYVAEDecoder(torch.nn.Module):
@@ -48,12 +97,13 @@ class HYVAEDecoder(torch.nn.Module):
     def load_state_dict(self, sd, strict=True, assign=False):
         dev = self.device
         gam = lambda k: sd[k].detach().to(dev, f32).reshape(-1).contiguous()                      # noqa: E731
+        rms = lambda k: _RMSNorm(gam(k))                                                           # noqa: E731
         rc = lambda p: _RepConv(sd[p + ".weight"], sd[p + ".bias"], dev)                           # noqa: E731
         lin = lambda p: (sd[p + ".weight"].detach().to(dev, bf16).reshape(sd[p + ".weight"].shape[0], -1).contiguous(),  # noqa: E731
                          sd[p + ".bias"].detach().to(dev, f32).contiguous())
 
         def res(p):
-            d = {"g1": gam(p + "norm1.gamma"), "c1": rc(p + "conv1.conv"), "g2": gam(p + "norm2.gamma"), "c2": rc(p + "conv2.conv")}
+            d = {"g1": rms(p + "norm1.gamma"), "c1": rc(p + "conv1.conv"), "g2": rms(p + "norm2.gamma"), "c2": rc(p + "conv2.conv")}
             if p + "nin_shortcut.weight" in sd:
                 d["nin"] = lin(p + "nin_shortcut")
             return d
@@ -68,19 +118,23 @@ class HYVAEDecoder(torch.nn.Module):
         for i, (blocks, up) in enumerate(levels):
             self.levels.append(([res(f"up.{i}.block.{j}.") for j in range(len(blocks))],
                                 None if up is None else (rc(f"up.{i}.upsample.conv.conv"), up[1], up[2])))
-        self.g_out = gam("norm_out.gamma")
+        self.g_out = rms("norm_out.gamma")
         self.conv_out = rc("conv_out.conv")
         self._ready = True
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
     @staticmethod
-    def _res(d, x):
+    def _res(d, hold):
+        """ResnetBlock.forward (:217-250).  `hold` is a one-element list that is CONSUMED: the block input is freed (or
+        overwritten in place by the output) as soon as the shortcut exists."""
+        x = hold.pop()
         T, H, W, C = x.shape
-        h = d["c1"](rms_silu(x, d["g1"]))
+        h = norm_act_conv(x, d["g1"], d["c1"])
         sc = x
         if "nin" in d:                                                       # 1x1x1 conv == GEMM over pixels
             sc = ops.gemm(x.reshape(-1, C), d["nin"][0], bias=d["nin"][1]).reshape(T, H, W, -1)
-        return d["c2"](rms_silu(h, d["g2"]), residual=sc)                    # h += x fused in the conv epilogue
+        del x
+        return norm_act_conv(h, d["g2"], d["c2"], residual=sc, out=sc)       # h += x fused in the conv epilogue, in place
 
     def _attn(self, x):
         T, H, W, C = x.shape
@@ -118,16 +172,17 @@ class HYVAEDecoder(torch.nn.Module):
             zrep = torch.empty(T, H, W, c0, device=self.device, dtype=bf16)
             _lib.call("b200_planar_to_cl", zi.data_ptr(), zcl.data_ptr(), zc, P, 1, _s())
             _lib.call("b200_planar_to_cl", zi.data_ptr(), zrep.data_ptr(), zc, P, c0 // zc, _s())
-            h = self.conv_in(zcl, residual=zrep)                               # conv_in(z) + z.repeat_interleave (:489-490)
-            h = self._res(self.mid1, h)
-            h = self._attn(h)
-            h = self._res(self.mid2, h)
+            hold = [self.conv_in(zcl, residual=zrep)]                          # conv_in(z) + z.repeat_interleave (:489-490)
+            del zcl, zrep
+            hold.append(self._res(self.mid1, hold))
+            hold.append(self._attn(hold.pop()))
+            hold.append(self._res(self.mid2, hold))
             for blocks, up in self.levels:
                 for d in blocks:
-                    h = self._res(d, h)
+                    hold.append(self._res(d, hold))
                 if up is not None:
-                    h = self._up(up, h)
-            outs.append(self.conv_out(rms_silu(h, self.g_out), out_mode=2))
+                    hold.append(self._up(up, hold.pop()))
+            outs.append(norm_act_conv(hold.pop(), self.g_out, self.conv_out, out_mode=2))
         return torch.stack(outs, 0)
 
 

@@ -379,3 +379,78 @@ def hyvae_param_shapes(cfg):
 
 def make_hyvae_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
     return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in hyvae_param_shapes(cfg).items()}
+
+
+# --------------------------------------------------------------------------- HunyuanVideo 1.0 VAE decoder (AutoencoderKLCausal3D)
+
+HYVAE10_CONFIGS = {
+    # "884-16c-hy" (models/hyvideo/vae/__init__.py:8; config.json is a DOWNLOAD): upstream values, block_out_channels in
+    # ENCODER order as in the reference config
+    "hyvae10": dict(latent_channels=16, out_channels=3, block_out_channels=[128, 256, 512, 512], layers_per_block=2,
+                    norm_num_groups=32, time_compression_ratio=4, spatial_compression_ratio=8, mid_block_causal_attn=True),
+    "hyvae10_tiny": dict(latent_channels=8, out_channels=3, block_out_channels=[32, 64, 64, 64], layers_per_block=1,
+                         norm_num_groups=8, time_compression_ratio=4, spatial_compression_ratio=8, mid_block_causal_attn=True),
+    "hyvae10_small": dict(latent_channels=16, out_channels=3, block_out_channels=[64, 128, 256, 256], layers_per_block=2,
+                          norm_num_groups=32, time_compression_ratio=4, spatial_compression_ratio=8, mid_block_causal_attn=True),
+}
+
+
+def hyvae10_layout(cfg):
+    """Per up block: (list of (cin, cout) resnets, (up_t, up_s) or None) -- DecoderCausal3D.__init__ (vae/vae.py:248-286),
+    time_compression_ratio 4 rule."""
+    boc = list(reversed(cfg["block_out_channels"]))
+    assert cfg["time_compression_ratio"] == 4
+    n_sp, n_t = int(math.log2(cfg["spatial_compression_ratio"])), int(math.log2(cfg["time_compression_ratio"]))
+    blocks, cin = [], boc[0]
+    for i, ch in enumerate(boc):
+        res = []
+        for _ in range(cfg["layers_per_block"] + 1):
+            res.append((cin, ch))
+            cin = ch
+        sp, tm = i < n_sp, (i >= len(boc) - 1 - n_t and i != len(boc) - 1)
+        blocks.append((res, (tm, sp) if (sp or tm) else None))
+    return blocks, cin
+
+
+def hyvae10_param_shapes(cfg):
+    """State-dict names of AutoencoderKLCausal3D's decode half: post_quant_conv + decoder.* (vae/vae.py, unet_causal_3d_blocks.py)."""
+    s = {}
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k, k)
+        s[name + ".bias"] = (co,)
+
+    def norm(name, c):
+        s[name + ".weight"] = s[name + ".bias"] = (c,)
+
+    def res(p, ci, co):
+        norm(p + "norm1", ci), conv(p + "conv1.conv", co, ci, 3), norm(p + "norm2", co), conv(p + "conv2.conv", co, co, 3)
+        if ci != co:
+            conv(p + "conv_shortcut.conv", co, ci, 1)
+    zc, c0 = cfg["latent_channels"], cfg["block_out_channels"][-1]
+    conv("post_quant_conv", zc, zc, 1)
+    conv("decoder.conv_in.conv", c0, zc, 3)
+    res("decoder.mid_block.resnets.0.", c0, c0), res("decoder.mid_block.resnets.1.", c0, c0)
+    a = "decoder.mid_block.attentions.0."
+    norm(a + "group_norm", c0)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[a + n + ".weight"], s[a + n + ".bias"] = (c0, c0), (c0,)
+    blocks, c_last = hyvae10_layout(cfg)
+    for i, (rs, up) in enumerate(blocks):
+        for j, (ci, co) in enumerate(rs):
+            res(f"decoder.up_blocks.{i}.resnets.{j}.", ci, co)
+        if up is not None:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv.conv", rs[-1][1], rs[-1][1], 3)
+    norm("decoder.conv_norm_out", c_last)
+    conv("decoder.conv_out.conv", cfg["out_channels"], c_last, 3)
+    return s
+
+
+def make_hyvae10_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    out = {}
+    for n, s in hyvae10_param_shapes(cfg).items():
+        if "norm" in n and n.endswith(".weight"):
+            out[n] = (1.0 + _normal(s, 0.1, seed, n, device)).to(dtype)
+        else:
+            out[n] = make_vae_tensor(n, s, seed, device).to(dtype)
+    return out
