@@ -116,3 +116,25 @@ def test_group_norm_cl(C, G):
     y0 = gn.apply(x, st, True, 0, 2, (2, 1, 1)).float().permute(3, 0, 1, 2)[None]
     ref0 = F.pad(F.silu(ref[:, :, :2]), (1, 1, 1, 1, 2, 0), mode="replicate")
     assert rel_l2(y0, ref0) < 4e-3
+
+
+@pytest.mark.parametrize("mode,F,N,C", [(0, 2, 100, 64), (1, 3, 60, 128), (2, 3, 60, 64), (1, 2, 25700, 64)])
+def test_attention_1head_modes(mode, F, N, C):
+    """b200_attention_1head: per-frame (Wan VAE), frame-causal (Hunyuan VAEs) and full attention, N % 8 != 0, and key rows longer
+    than the shared-memory softmax buffer (> 51200 keys -> the two-pass online softmax) -- vs torch fp32 softmax(QK^T)V."""
+    from wan2gp_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(F * N + C)
+    L = F * N
+    buf = torch.zeros(L + 8, 3 * C, device="cuda", dtype=bf16)
+    buf[:L] = torch.randn(L, 3 * C, device="cuda", generator=g).to(bf16)
+    lk_max = L if mode else N
+    npad = (lk_max + 63) // 64 * 64
+    ws = torch.empty(N * npad * 6, device="cuda", dtype=torch.uint8)
+    out = torch.empty(L, C, device="cuda", dtype=bf16)
+    _lib.call("b200_attention_1head", buf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), F, N, C, C ** -0.5, mode,
+              torch.cuda.current_stream().cuda_stream)
+    q, k, v = (buf[:L, i * C:(i + 1) * C].float() for i in range(3))
+    for f in range(F):
+        lo, hi = (f * N, (f + 1) * N) if mode == 0 else (0, (f + 1) * N) if mode == 1 else (0, L)
+        ref = torch.softmax(q[f * N:(f + 1) * N] @ k[lo:hi].t() * C ** -0.5, -1) @ v[lo:hi]
+        assert rel_l2(out[f * N:(f + 1) * N].float(), ref) < 8e-3, (mode, f)

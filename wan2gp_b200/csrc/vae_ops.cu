@@ -34,9 +34,10 @@ rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     const bool active = opix < P;
     long long pix = opix;                          // source pixel
     if (g.on && active) {
-        const int Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
-        const int w = (int)(opix % Wo); const long long r = opix / Wo;
-        const int h = (int)(r % Ho), t = (int)(r / Ho);
+        const unsigned Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
+        const unsigned op = (unsigned)opix;         // < 2^31 (host-checked): 32-bit divisions only
+        const unsigned r = op / Wo;
+        const int w = (int)(op - r * Wo), t = (int)(r / Ho), h = (int)(r - (unsigned)t * Ho);
         const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
         pix = ((long long)ts * g.H + hs) * g.W + ws;
     }
@@ -112,6 +113,7 @@ extern "C" int b200_rms_silu_pad_cl(const void* x, const float* gamma, void* y, 
     if (!x || !gamma || !y || C % 8 || C > 1024 || T <= 0 || H <= 0 || W <= 0 || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
         return b200_set_error(B200_ERR_ARG, "rms_silu_pad_cl: bad argument (C=%d)", C);
     const long long P = (long long)(Tc + pt) * (H + 2 * ph) * (W + 2 * pw);
+    if (P > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "rms_silu_pad_cl: slice too large");
     return rms_dispatch(x, gamma, y, P, C, silu, (cudaStream_t)stream, RmsPad{1, H, W, t0, pt, ph, pw});
 }
 
@@ -197,19 +199,20 @@ extern "C" int b200_frames_to_u8(const float* x, uint8_t* out, long long n, void
 // Hunyuan VAE helpers (channels-last bf16)
 // replicate padding: out [T+pt, H+2ph, W+2pw, C] (pt frames in FRONT), 16-byte chunks
 __global__ void pad_replicate_cl_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int C8, int pt, int ph, int pw) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int To = T + pt, Ho = H + 2 * ph, Wo = W + 2 * pw;
-    if (i >= (long long)To * Ho * Wo * C8) return;
-    const int c = i % C8; long long r = i / C8;
-    const int w = r % Wo; r /= Wo;
-    const int h = r % Ho; const int t = r / Ho;
+    // grid: x = 16-byte chunks of one padded row, y = padded row, z = padded frame
+    const int Ho = H + 2 * ph, Wo = W + 2 * pw;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Wo * C8) return;
+    const int w = idx / C8, c = idx - w * C8;
+    const int h = blockIdx.y, t = blockIdx.z;
     const int ts = max(t - pt, 0), hs = min(max(h - ph, 0), H - 1), ws = min(max(w - pw, 0), W - 1);
-    y[i] = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c);
+    y[(((long long)t * Ho + h) * Wo + w) * C8 + c] = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c);
 }
 extern "C" int b200_pad_replicate_cl(const void* x, void* y, int T, int H, int W, int C, int pt, int ph, int pw, void* stream) {
-    if (!x || !y || C % 8) return b200_set_error(B200_ERR_ARG, "pad_replicate_cl: bad argument");
-    const long long n = (long long)(T + pt) * (H + 2 * ph) * (W + 2 * pw) * (C / 8);
-    pad_replicate_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    if (!x || !y || C % 8 || T <= 0 || H <= 0 || W <= 0 || pt < 0 || ph < 0 || pw < 0 || H + 2 * ph > 65535 || T + pt > 65535)
+        return b200_set_error(B200_ERR_ARG, "pad_replicate_cl: bad argument");
+    const dim3 grid((unsigned)(((long long)(W + 2 * pw) * (C / 8) + 255) / 256), (unsigned)(H + 2 * ph), (unsigned)(T + pt));
+    pad_replicate_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), T, H, W, C / 8, pt, ph, pw);
     CHECK_LAUNCH("pad_replicate_cl");
     return B200_OK;
@@ -239,12 +242,12 @@ extern "C" int b200_planar_to_cl(const float* x, void* y, int C, long long P, in
 __global__ void hy_upsample_cl_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                       int T, int H, int W, int Ci, int Co, int temporal) {
     const int C8 = Co >> 3;
-    const int To = temporal ? 2 * T - 1 : T;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)To * 2 * H * 2 * W * C8) return;
-    const int c0 = (i % C8) * 8; long long r = i / C8;
-    const int wo = r % (2 * W); r /= (2 * W);
-    const int ho = r % (2 * H); const int to = r / (2 * H);
+    // grid: x = 16-byte chunks of one output row (2W * C8), y = output row, z = output frame (32-bit index math only)
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= 2 * W * C8) return;
+    const int wo = idx / C8, c0 = (idx - wo * C8) * 8;
+    const int ho = blockIdx.y, to = blockIdx.z;
+    const long long i = (((long long)to * 2 * H + ho) * 2 * W + wo) * C8 + (c0 >> 3);
     const int r2 = ho & 1, r3 = wo & 1, hh = ho >> 1, ww = wo >> 1;
     const int F = temporal ? 8 : 4;
     const int rep = F * Co / Ci;
@@ -266,8 +269,10 @@ __global__ void hy_upsample_cl_kernel(const __nv_bfloat16* __restrict__ h, const
 extern "C" int b200_hy_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream) {
     const int F = temporal ? 8 : 4;
     if (!h || !x || !out || Co % 8 || (F * Co) % Ci || (temporal && (F * Co / Ci) % 2)) return b200_set_error(B200_ERR_ARG, "hy_upsample_cl: bad argument");
-    const long long n = (long long)(temporal ? 2 * T - 1 : T) * 4 * H * W * (Co / 8);
-    hy_upsample_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    const int To = temporal ? 2 * T - 1 : T;
+    if (T <= 0 || H <= 0 || W <= 0 || 2 * H > 65535 || To > 65535) return b200_set_error(B200_ERR_ARG, "hy_upsample_cl: bad extent");
+    const dim3 grid((unsigned)((2LL * W * (Co / 8) + 255) / 256), (unsigned)(2 * H), (unsigned)To);
+    hy_upsample_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), T, H, W, Ci, Co, temporal);
     CHECK_LAUNCH("hy_upsample_cl");
     return B200_OK;
@@ -374,14 +379,14 @@ extern "C" int b200_group_stats_cl(const void* x, float* stats, void* workspace,
 
 __global__ void __launch_bounds__(256)
 group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, uint4* __restrict__ y, int H, int W, int C8, int Cg, int silu, int t0, int Tc,
+                        const float* __restrict__ beta, uint4* __restrict__ y, int H, int W, int C8, int Cg, int silu, int t0,
                         int pt, int ph, int pw) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int To = Tc + pt, Ho = H + 2 * ph, Wo = W + 2 * pw;
-    if (i >= (long long)To * Ho * Wo * C8) return;
-    const int c8 = i % C8; long long r = i / C8;
-    const int w = r % Wo; r /= Wo;
-    const int h = r % Ho; const int t = r / Ho;
+    // grid: x = 16-byte chunks of one padded output row (Wo * C8), y = padded row h, z = padded frame t (32-bit index math only)
+    const int Wo = W + 2 * pw, Ho = H + 2 * ph;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Wo * C8) return;
+    const int w = idx / C8, c8 = idx - w * C8;
+    const int h = blockIdx.y, t = blockIdx.z;
     const int ts = max(t0 + t - pt, 0), hs = min(max(h - ph, 0), H - 1), ws = min(max(w - pw, 0), W - 1);
     const uint4 v = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c8);
     const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -392,28 +397,38 @@ group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ s
     float f[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 a = __bfloat1622float2(hv[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
+    if (Cg >= 8) {                                   // Cg % 8 == 0 (host-checked): one group per chunk
+        const int g = (c8 * 8) / Cg;
+        const float mean = __ldg(stats + 2 * g), rstd = __ldg(stats + 2 * g + 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * ga[j] + be[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c8 * 8 + j) / Cg;
+            f[j] = (f[j] - __ldg(stats + 2 * g)) * __ldg(stats + 2 * g + 1) * ga[j] + be[j];
+        }
+    }
+    if (silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+    }
     uint4 o;
     __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int g = (c8 * 8 + j) / Cg;
-        float u = (f[j] - __ldg(stats + 2 * g)) * __ldg(stats + 2 * g + 1) * ga[j] + be[j];
-        if (silu) u = u / (1.f + __expf(-u));
-        f[j] = u;
-    }
-#pragma unroll
     for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    y[i] = o;
+    y[(((long long)t * Ho + h) * Wo + w) * C8 + c8] = o;
 }
 extern "C" int b200_group_norm_apply_cl(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int T, int H,
                                         int W, int C, int G, int silu, int t0, int Tc, int pt, int ph, int pw, void* stream) {
     if (!x || !stats || !gamma || !beta || !y || C % 8 || G <= 0 || C % G || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
         return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: bad argument");
     const int Cg = C / G;
-    const long long n = (long long)(Tc + pt) * (H + 2 * ph) * (W + 2 * pw) * (C / 8);
-    if ((n + 255) / 256 > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: slice too large");
-    group_norm_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(x), stats, gamma, beta, reinterpret_cast<uint4*>(y), H, W, C / 8, Cg, silu, t0, Tc, pt, ph, pw);
+    if (Cg >= 8 && Cg % 8) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: channels per group %d", Cg);
+    if (H + 2 * ph > 65535 || Tc + pt > 65535) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: slice too large");
+    const dim3 grid((unsigned)(((long long)(W + 2 * pw) * (C / 8) + 255) / 256), (unsigned)(H + 2 * ph), (unsigned)(Tc + pt));
+    group_norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x), stats, gamma, beta, reinterpret_cast<uint4*>(y), H, W, C / 8, Cg, silu, t0, pt, ph, pw);
     CHECK_LAUNCH("group_norm_apply_cl");
     return B200_OK;
 }
@@ -567,26 +582,48 @@ softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, 
     for (int i = threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? row[i] * inv : 0.f);
 }
 
-// same for rows that do not fit the shared-memory row buffer: three passes over the (L2-resident) global row
+// same for rows that do not fit the shared-memory row buffer: TWO passes over the global row -- pass 1 keeps an online
+// (max, sum) pair per thread (flash-style rescale), pass 2 writes the probabilities; 16-byte loads, 8-byte stores.
 __global__ void __launch_bounds__(256)
 softmax_rows_long_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int N, long long lds, long long ldp, float scale_log2) {
     __shared__ float red[8];
+    __shared__ float red_m[8];
     const int N8 = (N + 7) & ~7;
+    const int N4 = N & ~3;
     const float* sr = s + (long long)blockIdx.x * lds;
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < N; i += 256) mx = fmaxf(mx, sr[i] * scale_log2);
+    const float4* sr4 = reinterpret_cast<const float4*>(sr);
+    float mx = -INFINITY, sum = 0.f;
+    for (int i = threadIdx.x; i < N4 / 4; i += 256) {
+        const float4 v = sr4[i];
+        const float a = v.x * scale_log2, b = v.y * scale_log2, c = v.z * scale_log2, d = v.w * scale_log2;
+        const float m4 = fmaxf(fmaxf(a, b), fmaxf(c, d));
+        if (m4 > mx) { sum *= exp2f(mx - m4); mx = m4; }
+        sum += exp2f(a - mx) + exp2f(b - mx) + exp2f(c - mx) + exp2f(d - mx);
+    }
+    for (int i = N4 + threadIdx.x; i < N; i += 256) {
+        const float a = sr[i] * scale_log2;
+        if (a > mx) { sum *= exp2f(mx - a); mx = a; }
+        sum += exp2f(a - mx);
+    }
+    // block combine: global max, then rescaled sums
+    float gm = mx;
     #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    if ((threadIdx.x & 31) == 0) red_m[threadIdx.x >> 5] = gm;
     __syncthreads();
-    mx = red[0];
+    gm = red_m[0];
     #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < N; i += 256) sum += exp2f(sr[i] * scale_log2 - mx);
+    for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red_m[i]);
+    sum = (mx == -INFINITY) ? 0.f : sum * exp2f(mx - gm);
     const float inv = 1.f / block_sum_256(sum, red);
     __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
-    for (int i = threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? exp2f(sr[i] * scale_log2 - mx) * inv : 0.f);
+    uint2* pr4 = reinterpret_cast<uint2*>(pr);
+    for (int i = threadIdx.x; i < N4 / 4; i += 256) {
+        const float4 v = sr4[i];
+        pr4[i] = make_uint2(pack_bf16x2(exp2f(v.x * scale_log2 - gm) * inv, exp2f(v.y * scale_log2 - gm) * inv),
+                            pack_bf16x2(exp2f(v.z * scale_log2 - gm) * inv, exp2f(v.w * scale_log2 - gm) * inv));
+    }
+    for (int i = N4 + threadIdx.x; i < N8; i += 256) pr[i] = __float2bfloat16_rn(i < N ? exp2f(sr[i] * scale_log2 - gm) * inv : 0.f);
 }
 
 extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace, long long workspace_bytes, int F, int N, int C,
