@@ -33,6 +33,60 @@ def test_conv3d_vs_torch():
             assert rel_l2(out.permute(3, 0, 1, 2), ref + r.double().permute(3, 0, 1, 2)) < 4e-3
 
 
+def test_conv3d_row_kernel_vs_torch():
+    """Image rows >= ~103 pixels take the row-tiled kernel (csrc/conv_sm100.cuh: one halo tile per frame tap, all kh x kw taps
+    from shifted shared-memory descriptors).  Zero-padded (Wan) and replicate-padded (Hunyuan) convs, ragged W / odd H, two N
+    tiles, Cin not a multiple of 64, the planar fp32 head, the residual epilogue -- vs torch conv3d in fp64."""
+    import torch.nn.functional as F
+    from wan2gp_b200.hyvideo.vae import _RepConv
+    from wan2gp_b200.wan.vae import _Conv
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (T, H, W, ci, co, k) in [(3, 5, 130, 64, 128, (3, 3, 3)), (2, 3, 256, 96, 96, (3, 3, 3)), (2, 4, 300, 128, 3, (3, 3, 3)),
+                                 (2, 5, 128, 256, 256, (1, 3, 3)), (2, 7, 200, 16, 384, (3, 3, 3)), (1, 2, 330, 32, 64, (3, 3, 3)),
+                                 (4, 1, 110, 128, 32, (3, 3, 3))]:
+        x = torch.randn(T, H, W, ci, device="cuda", generator=g).to(bf16)
+        w = (torch.randn(co, ci, *k, device="cuda", generator=g) * (ci * k[0] * k[1] * k[2]) ** -0.5)
+        b = torch.randn(co, device="cuda", generator=g)
+        xc = x.float().permute(3, 0, 1, 2)[None]
+        pads = (k[2] // 2, k[2] // 2, k[1] // 2, k[1] // 2, k[0] - 1, 0)
+        for cls, mode in ((_Conv, "constant"), (_RepConv, "replicate")):
+            conv = cls(w, b, "cuda")
+            ref = F.conv3d(F.pad(xc, pads, mode=mode).double(), w.to(bf16).double(), b.double())[0]          # [co, T, H, W]
+            if co == 3:
+                assert rel_l2(conv(x, out_mode=2), ref) < 1e-3, (cls.__name__, T, H, W, ci, co)
+            else:
+                r = torch.randn(T, H, W, co, device="cuda", generator=g).to(bf16)
+                out = conv(x, residual=r)
+                assert rel_l2(out.permute(3, 0, 1, 2), ref + r.double().permute(3, 0, 1, 2)) < 4e-3, (cls.__name__, T, H, W, ci, co)
+
+
+def test_upsample_convs_row_kernel():
+    """Phase-decomposed up-sampling convs (Wan 2x2 sub-pixel; Hunyuan 1.0 nearest x(1|2,2,2) with 2x2(x2) phases) on rows wide
+    enough for the row-tiled kernel."""
+    import torch.nn.functional as F
+    from wan2gp_b200.hyvideo.vae10 import _UpConvNearest
+    from wan2gp_b200.wan.vae import _UpConv
+    g = torch.Generator(device="cuda").manual_seed(6)
+    T, H, W, ci, co = 3, 5, 136, 64, 32
+    x = torch.randn(T, H, W, ci, device="cuda", generator=g).to(bf16)
+    w2 = torch.randn(co, ci, 3, 3, device="cuda", generator=g) * (ci * 9) ** -0.5
+    b = torch.randn(co, device="cuda", generator=g)
+    out = _UpConv(w2, b, "cuda")(x)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact")
+    assert rel_l2(out, F.conv2d(up.double(), w2.double(), b.double(), padding=1).permute(0, 2, 3, 1)) < 5e-3
+    w3 = torch.randn(co, ci, 3, 3, 3, device="cuda", generator=g) * (ci * 27) ** -0.5
+    xc = x.float().permute(3, 0, 1, 2)[None]
+    for up_t in (False, True):
+        out = _UpConvNearest(w3, b, up_t, "cuda")(x)
+        if up_t:
+            u = torch.cat([F.interpolate(xc[:, :, :1], scale_factor=(1, 2, 2), mode="nearest"),
+                           F.interpolate(xc[:, :, 1:], scale_factor=(2, 2, 2), mode="nearest")], 2)
+        else:
+            u = F.interpolate(xc, scale_factor=(1, 2, 2), mode="nearest")
+        ref = F.conv3d(F.pad(u, (1, 1, 1, 1, 2, 0), mode="replicate").double(), w3.double(), b.double())[0]
+        assert rel_l2(out.permute(3, 0, 1, 2), ref) < 6e-3, up_t
+
+
 @pytest.mark.parametrize("name", ["vae_tiny", "vae_small", "vae_p"])
 def test_vae_decode(name):
     from oracle import vae_oracle

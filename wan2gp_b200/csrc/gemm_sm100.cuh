@@ -58,6 +58,7 @@ struct GemmParams {
     const float* gate;        // [N] or null : value *= gate[n]
     const __nv_bfloat16* residual;   // same mapping as out (bf16) or null : value += residual
     int act;
+    int conv_base_offset;     // conv_sm100.cuh: put (addr >> 7) & 7 into the A descriptors' base-offset field
 };
 
 // BKC = K elements per TMA box (64 -> 128B swizzle, 32 -> 64B swizzle); NBOX boxes of A and of B form one pipeline stage

@@ -6,6 +6,9 @@
 #include <string.h>
 
 #include "../../include/wan2gp_b200.h"
+#include <stdlib.h>
+
+#include "conv_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -484,6 +487,48 @@ extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int of
     return conv_cl_impl(x, w, bias, nullptr, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, 0, 0, -1, -1, stream, 1, &v);
 }
 
+// ---- row-tiled conv kernel (conv_sm100.cuh): instances and selection
+template <int BN, int ROWS>
+static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = conv_row_tcgen05_kernel<BN, ROWS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS>::kBytes);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row smem attr: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
+    kern<<<grid, 256, ConvRowSmem<BN, ROWS>::kBytes, st>>>(ta, tb, p);
+    CHECK_LAUNCH("conv_row_tcgen05");
+    return B200_OK;
+}
+static int conv_row_rows(int BN) { return BN <= 128 ? 2 : 1; }
+static int launch_conv_row(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    switch (BN) {
+        case 256: return launch_conv_row_inst<256, 1>(ta, tb, p, st);
+        case 192: return launch_conv_row_inst<192, 1>(ta, tb, p, st);
+        case 128: return launch_conv_row_inst<128, 2>(ta, tb, p, st);
+        case 96: return launch_conv_row_inst<96, 2>(ta, tb, p, st);
+        case 64: return launch_conv_row_inst<64, 2>(ta, tb, p, st);
+        case 32: return launch_conv_row_inst<32, 2>(ta, tb, p, st);
+        case 16: return launch_conv_row_inst<16, 2>(ta, tb, p, st);
+    }
+    return b200_set_error(B200_ERR_ARG, "no row-conv instance for BN=%d", BN);
+}
+// B200_CONV_ROW=0 forces the per-tap kernel (A/B measurements); B200_CONV_ROW_BASEOFF=0 leaves the descriptor base offset 0
+static int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+// the row tile is 128 pixels wide: use it when at most ~20% of the last tile is padding and there are spatial taps to share
+static bool conv_row_wanted(int W, int kh, int kw) {
+    static const int on = env_flag("B200_CONV_ROW", 1);
+    if (!on || kh * kw <= 1) return false;
+    const int tiles = (W + CONVR_BW - 1) / CONVR_BW;
+    return on == 2 || (double)W >= 0.8 * tiles * CONVR_BW;
+}
+
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
                         void* stream, int prepadded, const ConvView* view) {
@@ -493,9 +538,11 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     if (out_mode == 1 && (Cout % 64 || residual)) return b200_set_error(B200_ERR_ARG, "conv3d_cl: bad interleave arguments");
     const int taps = kt * kh * kw;
     const int BN = b200_pick_bn(out_mode == 2 ? 16 : Cout, false);
+    const bool row = conv_row_wanted(W, kh, kw);
+    const int ROWS = conv_row_rows(BN);
     // Cin = 96 (the full-resolution stage): K per tap is walked as 3 x 32 channels with 64B-swizzled boxes instead of
     // 2 x 64 with a half-empty second box (25% fewer MMAs and smem bytes)
-    const bool k96 = (Cin == 96) && (BN == 96 || BN == 16);
+    const bool k96 = !row && (Cin == 96) && (BN == 96 || BN == 16);
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
@@ -504,6 +551,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, Ti};
         uint64_t str[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
         uint32_t box[4] = {kbox, CONV_BW, CONV_BH, 1};
+        if (row) { box[1] = CONVR_BW + kw - 1; box[2] = ROWS + kh - 1; }      // halo tile shared by all kh x kw taps
         int r = b200_make_tmap_bf16(&ta, x, 4, dims, str, box, k96 ? 64 : 128);
         if (r) return r;
     }
@@ -522,8 +570,8 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.pad_h = pad_h; p.pad_w = pad_w; p.pad_t = prepadded ? 0 : kt - 1;
     p.cin_chunks = k96 ? 1 : (Cin + 63) / 64;
     p.num_k_iters = taps * p.cin_chunks;
-    p.tiles_h = (H + CONV_BH - 1) / CONV_BH;
-    p.tiles_w = (W + CONV_BW - 1) / CONV_BW;
+    p.tiles_h = row ? (H + ROWS - 1) / ROWS : (H + CONV_BH - 1) / CONV_BH;
+    p.tiles_w = row ? (W + CONVR_BW - 1) / CONVR_BW : (W + CONV_BW - 1) / CONV_BW;
     p.m_tiles = T * p.tiles_h * p.tiles_w;
     p.M = p.m_tiles * GEMM_BM;
     p.n_tiles = (Cout + BN - 1) / BN;
@@ -552,6 +600,11 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         p.st_w = 1; p.st_h = W; p.st_t = (long long)H * W; p.st_split = (long long)T * H * W;
     } else {
         return b200_set_error(B200_ERR_ARG, "conv3d_cl: out_mode %d", out_mode);
+    }
+    if (row) {
+        static const int base_off = env_flag("B200_CONV_ROW_BASEOFF", 1);
+        p.conv_base_offset = base_off;
+        return launch_conv_row(BN, ta, tb, p, (cudaStream_t)stream);
     }
     return k96 ? b200_launch_gemm_k96(BN, ta, tb, p, (cudaStream_t)stream) : b200_launch_gemm(BN, false, ta, tb, p, (cudaStream_t)stream);
 }
