@@ -5,8 +5,10 @@
 // L2->SMEM bound (ncu launch list, profiles/: the 128->128 and the 128->3 full-resolution convs of the Hunyuan VAEs take the
 // same 33 ms per 34-frame slice, i.e. the time is the A traffic of 216 GB per launch, not the MMAs).  Here the M tile is
 // 128 CONSECUTIVE pixels of one image row (x ROWS rows), so the A tile of tap (dh, dw) is the same smem box shifted by
-// (dh * WB + dw) rows of 128 B: a legal K-major SWIZZLE_128B operand whose start address is not 1024-B aligned (the
-// descriptor's base-offset field carries (addr >> 7) & 7).  A traffic drops 9x (3x3 taps) / (halo overhead 1.02-2x), and
+// (dh * WB + dw) rows of 128 B: a legal K-major SWIZZLE_128B operand whose start address is not 1024-B aligned.  The 128B
+// swizzle of both the TMA write and the tcgen05.mma read is a function of the ABSOLUTE smem address bits, so the shifted
+// descriptor needs no fix-up: measured on B200, parity holds with the base-offset field 0 and breaks when it is set to
+// (addr >> 7) & 7.  A traffic drops 9x (3x3 taps) / (halo overhead 1.02-2x), and
 // with ROWS = 2 each weight tile B feeds two accumulators.
 //
 //   warp 0   TMA producer: per (dt, chunk) one 4-D box {64 ch, 128+kw-1, ROWS+kh-1, 1}; per tap one weight box {64, 1, BN}
@@ -34,8 +36,8 @@ struct ConvRowSmem {
     static constexpr int kBytes = kAStages * kAStage + kBStages * kBStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// K-major SWIZZLE_128B operand whose first row is NOT at a 1024-B boundary: rows stay 128 B apart (SBO = 1024 per 8 rows),
-// the swizzle phase of the first row goes into the base-offset field (bits 49-51)
+// K-major SWIZZLE_128B operand whose first row is NOT at a 1024-B boundary: rows stay 128 B apart (SBO = 1024 per 8 rows).
+// use_base_offset (bits 49-51 = swizzle phase of the first row) exists for the A/B experiment only; the correct value is 0.
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_rowoff(uint32_t smem_addr, int use_base_offset) {
     uint64_t d = umma_desc_kmajor_sw128(smem_addr);
     if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
