@@ -153,16 +153,18 @@ int b200_planar_to_cl(const float* x, void* y_bf16, int C, long long P, int rep,
 int b200_hy_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream);
 
 /* ---- HunyuanVideo 1.0 VAE decode helpers (hyvideo/vae/unet_causal_3d_blocks.py, vae/vae.py) ---- */
-/* GroupNorm statistics of a channels-last bf16 tensor [P, C] over all P pixels of the clip (torch.nn.GroupNorm on [B,C,T,H,W],
- * unet_causal_3d_blocks.py:378,399; vae.py:292): stats[2g] = mean, stats[2g+1] = 1/sqrt(var + eps); workspace >= B200_GROUP_STATS_WS_BYTES(G);
- * C/8 must divide 256; fixed summation order (bit-reproducible) */
+/* GroupNorm of a channels-last bf16 tensor [P, C] over all P pixels of the clip (torch.nn.GroupNorm on [B,C,T,H,W],
+ * unet_causal_3d_blocks.py:378,399; vae.py:292), pass 1: per-group mean / biased variance folded with the affine parameters
+ * into scale_shift[0..C) = gamma[c] / sqrt(var_g + eps) and scale_shift[C..2C) = beta[c] - mean_g * scale[c];
+ * workspace >= B200_GROUP_STATS_WS_BYTES(G); C/8 must divide 256; fixed summation order (bit-reproducible) */
 #define B200_GROUP_STATS_WS_BYTES(G) (148LL * 8 * (G) * 2 * 4)
-int b200_group_stats_cl(const void* x, float* stats, void* workspace, long long P, int C, int G, float eps, void* stream);
-/* y = [silu]((x - mean_g) * rstd_g * gamma + beta) for frames [t0, t0+Tc) of x [T,H,W,C], written replicate-padded as
+int b200_group_stats_cl(const void* x, const float* gamma, const float* beta, float* scale_shift, void* workspace, long long P, int C,
+                        int G, float eps, void* stream);
+/* pass 2: y = [silu](x * scale[c] + shift[c]) for frames [t0, t0+Tc) of x [T,H,W,C], written replicate-padded as
  * [Tc+pt, H+2ph, W+2pw, C] (pt frames in front, taken from the frames before t0 or frame 0): GroupNorm -> SiLU ->
  * CausalConv3d's F.pad(mode="replicate") (unet_causal_3d_blocks.py:63-66, 455-480) in one pass */
-int b200_group_norm_apply_cl(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int T, int H, int W,
-                             int C, int G, int silu, int t0, int Tc, int pt, int ph, int pw, void* stream);
+int b200_group_norm_apply_cl(const void* x, const float* scale_shift, void* y, int T, int H, int W, int C, int silu, int t0, int Tc,
+                             int pt, int ph, int pw, void* stream);
 /* "valid" conv over a window of x [Ti,Hi,Wi,Cin] starting at (off_t,off_h,off_w), T x H x W outputs stored bf16 with element
  * strides (ost_t, ost_h, ost_w): one phase of nearest-up-sample + CausalConv3d (UpsampleCausal3D, unet_causal_3d_blocks.py
  * :196-222) evaluated on the low-resolution tensor with pre-summed taps */

@@ -104,8 +104,10 @@ def test_group_norm_cl(C, G):
     assert torch.equal(st, gn.stats(x))                                   # fixed summation order: bit-reproducible
     xc = x.float().permute(3, 0, 1, 2)[None]                               # [1,C,T,H,W]
     ref = F.group_norm(xc, G, w, b, 1e-6)
-    mean = xc.reshape(G, -1).mean(1)
-    assert torch.allclose(st[0::2], mean, atol=1e-4, rtol=1e-4)
+    mean, var = xc.reshape(G, -1).mean(1), xc.reshape(G, -1).var(1, unbiased=False)
+    scale = (w.reshape(G, -1) / (var[:, None] + 1e-6).sqrt()).reshape(-1)
+    assert torch.allclose(st[:C], scale, atol=1e-5, rtol=1e-4)                       # scale = gamma * rstd
+    assert torch.allclose(st[C:], b - (mean[:, None] * scale.reshape(G, -1)).reshape(-1), atol=1e-4, rtol=1e-4)
     y = gn.apply(x, st, False).float().permute(3, 0, 1, 2)[None]
     assert rel_l2(y, ref) < 4e-3
     # SiLU + replicate padding of the time slice [2, 5): 2 frames in front come from frames 0..1, 1 pixel around

@@ -24,11 +24,16 @@ namespace b200 {
 
 constexpr int CONVR_BW = 128;                 // M tile = 128 consecutive pixels of an image row
 
-template <int BN, int ROWS>
+// BKC = channels per K chunk: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B: Cin = 96 = 3 x 32 exactly,
+// no zero-padded K is multiplied)
+template <int BN, int ROWS, int BKC = 64>
 struct ConvRowSmem {
     static_assert(ROWS * BN <= 256, "ROWS accumulators of BN columns per TMEM buffer");
-    static constexpr int kAStage = (((CONVR_BW + 2) * (ROWS + 2) * 128) + 1023) / 1024 * 1024;     // sized for 3x3 taps
-    static constexpr int kBStage = BN * 128;
+    static_assert(BKC == 64 || BKC == 32, "K chunk");
+    static constexpr int kRowBytes = BKC * 2;
+    static constexpr int kAStage = (((CONVR_BW + 2) * (ROWS + 2) * kRowBytes) + 1023) / 1024 * 1024;     // sized for 3x3 taps
+    static constexpr int kBStage = (BN * kRowBytes + 1023) / 1024 * 1024;
+    static constexpr int kBBytes = BN * kRowBytes;
     static constexpr int kAStages = 2;
     static constexpr int kBMax = (200 * 1024 - kAStages * kAStage) / kBStage;
     static constexpr int kBStages = kBMax > 8 ? 8 : kBMax;
@@ -44,10 +49,11 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_rowoff(uint32_t smem_
     return d;
 }
 
-template <int BN, int ROWS>
+template <int BN, int ROWS, int BKC = 64>
 __global__ void __launch_bounds__(256, 1)
 conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using S = ConvRowSmem<BN, ROWS>;
+    using S = ConvRowSmem<BN, ROWS, BKC>;
+    constexpr int RB = S::kRowBytes;                          // bytes per pixel row of the smem tiles
     constexpr int SA = S::kAStages, SB = S::kBStages;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 
@@ -102,7 +108,7 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         // ============================ TMA producer ============================
         if (elect_one()) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            const uint32_t a_bytes = (uint32_t)WB * (ROWS + p.kh - 1) * 128;
+            const uint32_t a_bytes = (uint32_t)WB * (ROWS + p.kh - 1) * RB;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int n_blk, t0, h0, w0; tile_coords(tile, n_blk, t0, h0, w0);
                 for (int dt = 0; dt < p.kt; ++dt) {
@@ -110,12 +116,12 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         mbar_wait(&a_empty[sa], pa ^ 1);
                         mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                         // causal in time (all padding in front), centred in space; OOB -> zero fill
-                        tma_load_4d(smem_a + sa * S::kAStage, &tmap_a, &a_full[sa], cc * 64, w0 - p.pad_w, h0 - p.pad_h, t0 + dt - p.pad_t);
+                        tma_load_4d(smem_a + sa * S::kAStage, &tmap_a, &a_full[sa], cc * BKC, w0 - p.pad_w, h0 - p.pad_h, t0 + dt - p.pad_t);
                         if (++sa == SA) { sa = 0; pa ^= 1; }
                         for (int tap = 0; tap < taps_hw; ++tap) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
-                            mbar_arrive_expect_tx(&b_full[sb], S::kBStage);
-                            tma_load_3d(smem_b + sb * S::kBStage, &tmap_b, &b_full[sb], cc * 64, dt * taps_hw + tap, n_blk * BN);
+                            mbar_arrive_expect_tx(&b_full[sb], S::kBBytes);
+                            tma_load_3d(smem_b + sb * S::kBStage, &tmap_b, &b_full[sb], cc * BKC, dt * taps_hw + tap, n_blk * BN);
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -147,11 +153,12 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                 const uint32_t b_base = smem_u32(smem_b + sb * S::kBStage);
                                 #pragma unroll
                                 for (int r = 0; r < ROWS; ++r) {
-                                    const uint32_t a_row = a_base + (uint32_t)((r + dh) * WB + dw) * 128;
+                                    const uint32_t a_row = a_base + (uint32_t)((r + dh) * WB + dw) * RB;
                                     #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        const uint64_t da = umma_desc_kmajor_sw128_rowoff(a_row + kk * 32, use_bo);
-                                        const uint64_t db = umma_desc_kmajor_sw128(b_base + kk * 32);
+                                    for (int kk = 0; kk < BKC / 16; ++kk) {
+                                        const uint64_t da = BKC == 64 ? umma_desc_kmajor_sw128_rowoff(a_row + kk * 32, use_bo)
+                                                                      : umma_desc_kmajor_sw64(a_row + kk * 32);
+                                        const uint64_t db = BKC == 64 ? umma_desc_kmajor_sw128(b_base + kk * 32) : umma_desc_kmajor_sw64(b_base + kk * 32);
                                         umma_bf16_ss(d_tmem + r * BN, da, db, idesc, !(first && kk == 0));
                                     }
                                 }

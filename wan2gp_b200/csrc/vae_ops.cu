@@ -26,61 +26,76 @@ using namespace b200;
 // LPP lanes cooperate on one pixel, each holding up to NCH 16-byte chunks (C <= 8 * NCH * LPP).
 // optional output geometry: write frames [t0, t0+Tc) of [T,H,W,C] replicate-padded as [Tc+pt, H+2ph, W+2pw, C]
 struct RmsPad { int on, H, W, t0, pt, ph, pw; };
-template <int LPP, int NCH>
-__global__ void __launch_bounds__(256)
+template <int LPP, int NCH, int PIXB>
+__global__ void __launch_bounds__(256, NCH <= 2 ? 3 : 2)
 rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ y,
                    long long P, int C, int do_silu, RmsPad g) {
+    // each group of LPP lanes owns PIXB consecutive output pixels: all their 16-byte loads are issued before any arithmetic
+    // (one load per thread left the kernel latency-bound at ~2 TB/s; ncu launch list round 1)
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long opix = gt / LPP;               // output pixel (of the padded slice when g.on)
+    const long long grp = gt / LPP;
     const int sub = (int)(gt % LPP);
     const int nchunk = C >> 3;
-    const bool active = opix < P;
-    long long pix = opix;                          // source pixel
-    if (g.on && active) {
-        const unsigned Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
-        const unsigned op = (unsigned)opix;         // < 2^31 (host-checked): 32-bit divisions only
-        const unsigned r = op / Wo;
-        const int w = (int)(op - r * Wo), t = (int)(r / Ho), h = (int)(r - (unsigned)t * Ho);
-        const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
-        pix = ((long long)ts * g.H + hs) * g.W + ws;
-    }
-    uint4 v[NCH];
-    float ss = 0.f;
+    uint4 v[PIXB][NCH];
+    bool act[PIXB];
     #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int ch = sub + i * LPP;
-        if (active && ch < nchunk) {
-            v[i] = __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch);
-            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    for (int q = 0; q < PIXB; ++q) {
+        const long long opix = grp * PIXB + q;     // output pixel (of the padded slice when g.on)
+        act[q] = opix < P;
+        long long pix = opix;                      // source pixel
+        if (g.on && act[q]) {
+            const unsigned Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
+            const unsigned op = (unsigned)opix;     // < 2^31 (host-checked): 32-bit divisions only
+            const unsigned r = op / Wo;
+            const int w = (int)(op - r * Wo), t = (int)(r / Ho), h = (int)(r - (unsigned)t * Ho);
+            const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
+            pix = ((long long)ts * g.H + hs) * g.W + ws;
+        }
+        #pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int ch = sub + i * LPP;
+            v[q][i] = (act[q] && ch < nchunk) ? __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    float inv[PIXB];
+    #pragma unroll
+    for (int q = 0; q < PIXB; ++q) {
+        float ss = 0.f;
+        #pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const uint32_t u[4] = {v[q][i].x, v[q][i].y, v[q][i].z, v[q][i].w};
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
                 ss += a * a + b * b;
             }
         }
+        #pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        inv[q] = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
     }
-    #pragma unroll
-    for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
     #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int ch = sub + i * LPP;
-        if (active && ch < nchunk) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if (ch >= nchunk) continue;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        #pragma unroll
+        for (int q = 0; q < PIXB; ++q) {
+            if (!act[q]) continue;
+            const uint32_t u[4] = {v[q][i].x, v[q][i].y, v[q][i].z, v[q][i].w};
             float f[8];
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                f[2 * k] = __uint_as_float(u[k] << 16) * inv * g[2 * k];
-                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * inv * g[2 * k + 1];
+                f[2 * k] = __uint_as_float(u[k] << 16) * inv[q] * gm[2 * k];
+                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * inv[q] * gm[2 * k + 1];
             }
             if (do_silu) {
                 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
             }
-            reinterpret_cast<uint4*>(y + opix * C)[ch] =
+            reinterpret_cast<uint4*>(y + (grp * PIXB + q) * C)[ch] =
                 make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
     }
@@ -88,9 +103,10 @@ rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
 template <int LPP, int NCH = 2>
 static int launch_rms(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st, RmsPad g = RmsPad{}) {
-    const long long threads = P * LPP;
+    constexpr int PIXB = NCH <= 2 ? 4 : 2;
+    const long long threads = (P + PIXB - 1) / PIXB * LPP;
     if ((threads + 255) / 256 > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: too many pixels for one launch");
-    rms_silu_cl_kernel<LPP, NCH><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+    rms_silu_cl_kernel<LPP, NCH, PIXB><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), P, C, silu, g);
     CHECK_LAUNCH("rms_silu_cl");
     return B200_OK;
@@ -354,19 +370,31 @@ group_stats_kernel(const uint4* __restrict__ x, float* __restrict__ part, long l
         part[((long long)blockIdx.x * G + tid) * 2 + 1] = b;
     }
 }
-__global__ void group_stats_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int nblocks, double inv_n, float eps, int G) {
+// per-channel affine of the normalisation: y = x * scale[c] + shift[c], scale = rstd_g * gamma[c], shift = beta[c] - mean_g * scale
+__global__ void group_stats_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float* __restrict__ scale_shift, int nblocks, double inv_n, float eps, int G, int Cg) {
+    __shared__ float s_mean[256], s_rstd[256];
     const int g = threadIdx.x;
-    if (g >= G) return;
-    double a = 0.0, b = 0.0;
-    for (int i = 0; i < nblocks; ++i) { a += (double)part[((long long)i * G + g) * 2]; b += (double)part[((long long)i * G + g) * 2 + 1]; }
-    const double mean = a * inv_n;
-    const double var = fmax(b * inv_n - mean * mean, 0.0);    // biased variance, as torch group_norm
-    stats[2 * g] = (float)mean;
-    stats[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (g < G) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nblocks; ++i) { a += (double)part[((long long)i * G + g) * 2]; b += (double)part[((long long)i * G + g) * 2 + 1]; }
+        const double mean = a * inv_n;
+        const double var = fmax(b * inv_n - mean * mean, 0.0);    // biased variance, as torch group_norm
+        s_mean[g] = (float)mean;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int C = G * Cg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = s_rstd[c / Cg] * gamma[c];
+        scale_shift[c] = sc;
+        scale_shift[C + c] = beta[c] - s_mean[c / Cg] * sc;
+    }
 }
 #define GROUP_STATS_MAX_BLOCKS (148 * 8)
-extern "C" int b200_group_stats_cl(const void* x, float* stats, void* workspace, long long P, int C, int G, float eps, void* stream) {
-    if (!x || !stats || !workspace || P <= 0 || G <= 0 || G > 256 || C % 8 || C % G) return b200_set_error(B200_ERR_ARG, "group_stats_cl: bad argument");
+extern "C" int b200_group_stats_cl(const void* x, const float* gamma, const float* beta, float* stats, void* workspace, long long P, int C,
+                                   int G, float eps, void* stream) {
+    if (!x || !gamma || !beta || !stats || !workspace || P <= 0 || G <= 0 || G > 256 || C % 8 || C % G) return b200_set_error(B200_ERR_ARG, "group_stats_cl: bad argument");
     const int C8 = C / 8, Cg = C / G;
     if (C8 > 256 || 256 % C8) return b200_set_error(B200_ERR_ARG, "group_stats_cl: C/8 = %d must divide 256", C8);
     cudaStream_t st = (cudaStream_t)stream;
@@ -375,63 +403,64 @@ extern "C" int b200_group_stats_cl(const void* x, float* stats, void* workspace,
     const unsigned grid = (unsigned)(want < GROUP_STATS_MAX_BLOCKS ? want : GROUP_STATS_MAX_BLOCKS);
     group_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<float*>(workspace), P, C8, Cg, G);
     CHECK_LAUNCH("group_stats_cl");
-    group_stats_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), stats, (int)grid, 1.0 / ((double)P * Cg), eps, G);
+    group_stats_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), gamma, beta, stats, (int)grid,
+                                                   1.0 / ((double)P * Cg), eps, G, Cg);
     CHECK_LAUNCH("group_stats_finalize");
     return B200_OK;
 }
 
+constexpr int GN_CPT = 4;          // 16-byte chunks per thread, all loaded before any arithmetic (bytes in flight)
 __global__ void __launch_bounds__(256)
-group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, uint4* __restrict__ y, int H, int W, int C8, int Cg, int silu, int t0,
-                        int pt, int ph, int pw) {
-    // grid: x = 16-byte chunks of one padded output row (Wo * C8), y = padded row h, z = padded frame t (32-bit index math only)
-    const int Wo = W + 2 * pw, Ho = H + 2 * ph;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= Wo * C8) return;
-    const int w = idx / C8, c8 = idx - w * C8;
+group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale_shift, uint4* __restrict__ y, int H, int W, int C8,
+                        int silu, int t0, int pt, int ph, int pw) {
+    // grid: x = 16-byte chunks of one padded output row (Wo * C8) / (256 * GN_CPT), y = padded row h, z = padded frame t
+    const int Wo = W + 2 * pw, Ho = H + 2 * ph, n = Wo * C8, C = C8 * 8;
     const int h = blockIdx.y, t = blockIdx.z;
-    const int ts = max(t0 + t - pt, 0), hs = min(max(h - ph, 0), H - 1), ws = min(max(w - pw, 0), W - 1);
-    const uint4 v = __ldg(x + (((long long)ts * H + hs) * W + ws) * C8 + c8);
-    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + 1);
-    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 a = __bfloat1622float2(hv[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
-    if (Cg >= 8) {                                   // Cg % 8 == 0 (host-checked): one group per chunk
-        const int g = (c8 * 8) / Cg;
-        const float mean = __ldg(stats + 2 * g), rstd = __ldg(stats + 2 * g + 1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * ga[j] + be[j];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (c8 * 8 + j) / Cg;
-            f[j] = (f[j] - __ldg(stats + 2 * g)) * __ldg(stats + 2 * g + 1) * ga[j] + be[j];
+    const int ts = max(t0 + t - pt, 0), hs = min(max(h - ph, 0), H - 1);
+    const uint4* xrow = x + ((long long)ts * H + hs) * W * C8;
+    uint4* yrow = y + ((long long)t * Ho + h) * Wo * C8;
+    uint4 v[GN_CPT];
+    int c8s[GN_CPT];
+    #pragma unroll
+    for (int k = 0; k < GN_CPT; ++k) {
+        const int idx = (blockIdx.x * GN_CPT + k) * 256 + threadIdx.x;
+        const int w = idx / C8;
+        c8s[k] = idx - w * C8;
+        const int ws = min(max(w - pw, 0), W - 1);
+        v[k] = idx < n ? __ldg(xrow + (long long)ws * C8 + c8s[k]) : make_uint4(0, 0, 0, 0);
+    }
+    #pragma unroll
+    for (int k = 0; k < GN_CPT; ++k) {
+        const int idx = (blockIdx.x * GN_CPT + k) * 256 + threadIdx.x;
+        if (idx >= n) continue;
+        const float4* sc = reinterpret_cast<const float4*>(scale_shift + c8s[k] * 8);
+        const float4* sh = reinterpret_cast<const float4*>(scale_shift + C + c8s[k] * 8);
+        const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+        const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        float f[8];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = fmaf(__uint_as_float(u[j] << 16), A[2 * j], B[2 * j]);
+            f[2 * j + 1] = fmaf(__uint_as_float(u[j] & 0xffff0000u), A[2 * j + 1], B[2 * j + 1]);
         }
+        if (silu) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+        }
+        yrow[idx] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
-    if (silu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
-    }
-    uint4 o;
-    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    y[(((long long)t * Ho + h) * Wo + w) * C8 + c8] = o;
 }
-extern "C" int b200_group_norm_apply_cl(const void* x, const float* stats, const float* gamma, const float* beta, void* y, int T, int H,
-                                        int W, int C, int G, int silu, int t0, int Tc, int pt, int ph, int pw, void* stream) {
-    if (!x || !stats || !gamma || !beta || !y || C % 8 || G <= 0 || C % G || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
+extern "C" int b200_group_norm_apply_cl(const void* x, const float* scale_shift, void* y, int T, int H, int W, int C, int silu, int t0,
+                                        int Tc, int pt, int ph, int pw, void* stream) {
+    if (!x || !scale_shift || !y || C % 8 || T <= 0 || H <= 0 || W <= 0 || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
         return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: bad argument");
-    const int Cg = C / G;
-    if (Cg >= 8 && Cg % 8) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: channels per group %d", Cg);
     if (H + 2 * ph > 65535 || Tc + pt > 65535) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: slice too large");
-    const dim3 grid((unsigned)(((long long)(W + 2 * pw) * (C / 8) + 255) / 256), (unsigned)(H + 2 * ph), (unsigned)(Tc + pt));
+    const long long chunks = (long long)(W + 2 * pw) * (C / 8);
+    const dim3 grid((unsigned)((chunks + 256 * GN_CPT - 1) / (256 * GN_CPT)), (unsigned)(H + 2 * ph), (unsigned)(Tc + pt));
     group_norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(x), stats, gamma, beta, reinterpret_cast<uint4*>(y), H, W, C / 8, Cg, silu, t0, pt, ph, pw);
+        reinterpret_cast<const uint4*>(x), scale_shift, reinterpret_cast<uint4*>(y), H, W, C / 8, silu, t0, pt, ph, pw);
     CHECK_LAUNCH("group_norm_apply_cl");
     return B200_OK;
 }
@@ -488,23 +517,30 @@ extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int of
 }
 
 // ---- row-tiled conv kernel (conv_sm100.cuh): instances and selection
-template <int BN, int ROWS>
+template <int BN, int ROWS, int BKC = 64>
 static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = conv_row_tcgen05_kernel<BN, ROWS>;
+    auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS>::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS, BKC>::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row smem attr: %s", cudaGetErrorString(e));
         attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
-    kern<<<grid, 256, ConvRowSmem<BN, ROWS>::kBytes, st>>>(ta, tb, p);
+    kern<<<grid, 256, ConvRowSmem<BN, ROWS, BKC>::kBytes, st>>>(ta, tb, p);
     CHECK_LAUNCH("conv_row_tcgen05");
     return B200_OK;
 }
 static int conv_row_rows(int BN) { return BN <= 128 ? 2 : 1; }
-static int launch_conv_row(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_conv_row(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    if (k32) {                                    // Cin = 96: three 32-channel chunks (64B swizzle)
+        switch (BN) {
+            case 96: return launch_conv_row_inst<96, 2, 32>(ta, tb, p, st);
+            case 16: return launch_conv_row_inst<16, 2, 32>(ta, tb, p, st);
+        }
+        return b200_set_error(B200_ERR_ARG, "no K=32 row-conv instance for BN=%d", BN);
+    }
     switch (BN) {
         case 256: return launch_conv_row_inst<256, 1>(ta, tb, p, st);
         case 192: return launch_conv_row_inst<192, 1>(ta, tb, p, st);
@@ -545,7 +581,8 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     const int ROWS = conv_row_rows(BN);
     // Cin = 96 (the full-resolution stage): K per tap is walked as 3 x 32 channels with 64B-swizzled boxes instead of
     // 2 x 64 with a half-empty second box (25% fewer MMAs and smem bytes)
-    const bool k96 = !row && (Cin == 96) && (BN == 96 || BN == 16);
+    static const int row_k32 = env_flag("B200_CONV_ROW_K32", 1);
+    const bool k96 = (Cin == 96) && (BN == 96 || BN == 16) && (!row || row_k32);
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
@@ -571,7 +608,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.N = Cout;
     p.T = T; p.H = H; p.W = W; p.kt = kt; p.kh = kh; p.kw = kw;
     p.pad_h = pad_h; p.pad_w = pad_w; p.pad_t = prepadded ? 0 : kt - 1;
-    p.cin_chunks = k96 ? 1 : (Cin + 63) / 64;
+    p.cin_chunks = k96 ? (row ? 3 : 1) : (Cin + 63) / 64;      // row kernel: three 32-channel chunks; per-tap k96: one 3-box stage
     p.num_k_iters = taps * p.cin_chunks;
     p.tiles_h = row ? (H + ROWS - 1) / ROWS : (H + CONV_BH - 1) / CONV_BH;
     p.tiles_w = row ? (W + CONVR_BW - 1) / CONVR_BW : (W + CONV_BW - 1) / CONV_BW;
@@ -607,7 +644,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     if (row) {
         static const int base_off = env_flag("B200_CONV_ROW_BASEOFF", 0);
         p.conv_base_offset = base_off;
-        return launch_conv_row(BN, ta, tb, p, (cudaStream_t)stream);
+        return launch_conv_row(BN, k96, ta, tb, p, (cudaStream_t)stream);
     }
     return k96 ? b200_launch_gemm_k96(BN, ta, tb, p, (cudaStream_t)stream) : b200_launch_gemm(BN, false, ta, tb, p, (cudaStream_t)stream);
 }

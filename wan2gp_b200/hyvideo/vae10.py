@@ -36,16 +36,17 @@ class _GroupNorm:
 
     def stats(self, x):
         T, H, W, C = x.shape
-        st = torch.empty(2 * self.groups, device=x.device, dtype=f32)
-        _lib.call("b200_group_stats_cl", x.data_ptr(), st.data_ptr(), self.ws.data_ptr(), T * H * W, C, self.groups, self.eps, _s())
+        st = torch.empty(2 * C, device=x.device, dtype=f32)                  # per-channel (scale, shift) of the normalisation
+        _lib.call("b200_group_stats_cl", x.data_ptr(), self.g.data_ptr(), self.b.data_ptr(), st.data_ptr(), self.ws.data_ptr(),
+                  T * H * W, C, self.groups, self.eps, _s())
         return st
 
     def apply(self, x, st, silu, t0=0, tc=None, pad=(0, 0, 0)):
         T, H, W, C = x.shape
         tc = T if tc is None else tc
         y = torch.empty(tc + pad[0], H + 2 * pad[1], W + 2 * pad[2], C, device=x.device, dtype=bf16)
-        _lib.call("b200_group_norm_apply_cl", x.data_ptr(), st.data_ptr(), self.g.data_ptr(), self.b.data_ptr(), y.data_ptr(),
-                  T, H, W, C, self.groups, int(silu), t0, tc, pad[0], pad[1], pad[2], _s())
+        _lib.call("b200_group_norm_apply_cl", x.data_ptr(), st.data_ptr(), y.data_ptr(), T, H, W, C, int(silu), t0, tc,
+                  pad[0], pad[1], pad[2], _s())
         return y
 
 
