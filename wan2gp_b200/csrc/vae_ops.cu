@@ -26,76 +26,61 @@ using namespace b200;
 // LPP lanes cooperate on one pixel, each holding up to NCH 16-byte chunks (C <= 8 * NCH * LPP).
 // optional output geometry: write frames [t0, t0+Tc) of [T,H,W,C] replicate-padded as [Tc+pt, H+2ph, W+2pw, C]
 struct RmsPad { int on, H, W, t0, pt, ph, pw; };
-template <int LPP, int NCH, int PIXB>
-__global__ void __launch_bounds__(256, NCH <= 2 ? 3 : 2)
+template <int LPP, int NCH>
+__global__ void __launch_bounds__(256)
 rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ y,
                    long long P, int C, int do_silu, RmsPad g) {
-    // each group of LPP lanes owns PIXB consecutive output pixels: all their 16-byte loads are issued before any arithmetic
-    // (one load per thread left the kernel latency-bound at ~2 TB/s; ncu launch list round 1)
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long grp = gt / LPP;
+    const long long opix = gt / LPP;               // output pixel (of the padded slice when g.on)
     const int sub = (int)(gt % LPP);
     const int nchunk = C >> 3;
-    uint4 v[PIXB][NCH];
-    bool act[PIXB];
-    #pragma unroll
-    for (int q = 0; q < PIXB; ++q) {
-        const long long opix = grp * PIXB + q;     // output pixel (of the padded slice when g.on)
-        act[q] = opix < P;
-        long long pix = opix;                      // source pixel
-        if (g.on && act[q]) {
-            const unsigned Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
-            const unsigned op = (unsigned)opix;     // < 2^31 (host-checked): 32-bit divisions only
-            const unsigned r = op / Wo;
-            const int w = (int)(op - r * Wo), t = (int)(r / Ho), h = (int)(r - (unsigned)t * Ho);
-            const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
-            pix = ((long long)ts * g.H + hs) * g.W + ws;
-        }
-        #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const int ch = sub + i * LPP;
-            v[q][i] = (act[q] && ch < nchunk) ? __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch) : make_uint4(0, 0, 0, 0);
-        }
+    const bool active = opix < P;
+    long long pix = opix;                          // source pixel
+    if (g.on && active) {
+        const unsigned Ho = g.H + 2 * g.ph, Wo = g.W + 2 * g.pw;
+        const unsigned op = (unsigned)opix;         // < 2^31 (host-checked): 32-bit divisions only
+        const unsigned r = op / Wo;
+        const int w = (int)(op - r * Wo), t = (int)(r / Ho), h = (int)(r - (unsigned)t * Ho);
+        const int ts = max(g.t0 + t - g.pt, 0), hs = min(max(h - g.ph, 0), g.H - 1), ws = min(max(w - g.pw, 0), g.W - 1);
+        pix = ((long long)ts * g.H + hs) * g.W + ws;
     }
-    float inv[PIXB];
+    uint4 v[NCH];
+    float ss = 0.f;
     #pragma unroll
-    for (int q = 0; q < PIXB; ++q) {
-        float ss = 0.f;
-        #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const uint32_t u[4] = {v[q][i].x, v[q][i].y, v[q][i].z, v[q][i].w};
+    for (int i = 0; i < NCH; ++i) {
+        const int ch = sub + i * LPP;
+        if (active && ch < nchunk) {
+            v[i] = __ldg(reinterpret_cast<const uint4*>(x + pix * C) + ch);
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
                 ss += a * a + b * b;
             }
         }
-        #pragma unroll
-        for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        inv[q] = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
     }
+    #pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
     #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int ch = sub + i * LPP;
-        if (ch >= nchunk) continue;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        #pragma unroll
-        for (int q = 0; q < PIXB; ++q) {
-            if (!act[q]) continue;
-            const uint32_t u[4] = {v[q][i].x, v[q][i].y, v[q][i].z, v[q][i].w};
+        if (active && ch < nchunk) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             float f[8];
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                f[2 * k] = __uint_as_float(u[k] << 16) * inv[q] * gm[2 * k];
-                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * inv[q] * gm[2 * k + 1];
+                f[2 * k] = __uint_as_float(u[k] << 16) * inv * g[2 * k];
+                f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * inv * g[2 * k + 1];
             }
             if (do_silu) {
                 #pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
+                for (int k = 0; k < 8; ++k) f[k] = silu_fast(f[k]);
             }
-            reinterpret_cast<uint4*>(y + (grp * PIXB + q) * C)[ch] =
+            reinterpret_cast<uint4*>(y + opix * C)[ch] =
                 make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
     }
@@ -103,10 +88,9 @@ rms_silu_cl_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
 template <int LPP, int NCH = 2>
 static int launch_rms(const void* x, const float* gamma, void* y, long long P, int C, int silu, cudaStream_t st, RmsPad g = RmsPad{}) {
-    constexpr int PIXB = NCH <= 2 ? 4 : 2;
-    const long long threads = (P + PIXB - 1) / PIXB * LPP;
+    const long long threads = P * LPP;
     if ((threads + 255) / 256 > 0x7fffffffLL) return b200_set_error(B200_ERR_ARG, "rms_silu_cl: too many pixels for one launch");
-    rms_silu_cl_kernel<LPP, NCH, PIXB><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+    rms_silu_cl_kernel<LPP, NCH><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), P, C, silu, g);
     CHECK_LAUNCH("rms_silu_cl");
     return B200_OK;
@@ -412,7 +396,7 @@ extern "C" int b200_group_stats_cl(const void* x, const float* gamma, const floa
 constexpr int GN_CPT = 4;          // 16-byte chunks per thread, all loaded before any arithmetic (bytes in flight)
 __global__ void __launch_bounds__(256)
 group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale_shift, uint4* __restrict__ y, int H, int W, int C8,
-                        int silu, int t0, int pt, int ph, int pw) {
+                        int c8_shift, int silu, int t0, int pt, int ph, int pw) {
     // grid: x = 16-byte chunks of one padded output row (Wo * C8) / (256 * GN_CPT), y = padded row h, z = padded frame t
     const int Wo = W + 2 * pw, Ho = H + 2 * ph, n = Wo * C8, C = C8 * 8;
     const int h = blockIdx.y, t = blockIdx.z;
@@ -424,7 +408,7 @@ group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ s
     #pragma unroll
     for (int k = 0; k < GN_CPT; ++k) {
         const int idx = (blockIdx.x * GN_CPT + k) * 256 + threadIdx.x;
-        const int w = idx / C8;
+        const int w = c8_shift >= 0 ? (idx >> c8_shift) : idx / C8;
         c8s[k] = idx - w * C8;
         const int ws = min(max(w - pw, 0), W - 1);
         v[k] = idx < n ? __ldg(xrow + (long long)ws * C8 + c8s[k]) : make_uint4(0, 0, 0, 0);
@@ -447,7 +431,7 @@ group_norm_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ s
         }
         if (silu) {
             #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+            for (int j = 0; j < 8; ++j) f[j] = silu_fast(f[j]);
         }
         yrow[idx] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
@@ -457,10 +441,13 @@ extern "C" int b200_group_norm_apply_cl(const void* x, const float* scale_shift,
     if (!x || !scale_shift || !y || C % 8 || T <= 0 || H <= 0 || W <= 0 || t0 < 0 || Tc <= 0 || t0 + Tc > T || pt < 0 || ph < 0 || pw < 0)
         return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: bad argument");
     if (H + 2 * ph > 65535 || Tc + pt > 65535) return b200_set_error(B200_ERR_ARG, "group_norm_apply_cl: slice too large");
-    const long long chunks = (long long)(W + 2 * pw) * (C / 8);
+    const int C8 = C / 8;
+    int shift = -1;                                   // C/8 a power of two: index split by shift instead of a division
+    if ((C8 & (C8 - 1)) == 0) { shift = 0; while ((1 << shift) < C8) ++shift; }
+    const long long chunks = (long long)(W + 2 * pw) * C8;
     const dim3 grid((unsigned)((chunks + 256 * GN_CPT - 1) / (256 * GN_CPT)), (unsigned)(H + 2 * ph), (unsigned)(Tc + pt));
     group_norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(x), scale_shift, reinterpret_cast<uint4*>(y), H, W, C / 8, silu, t0, pt, ph, pw);
+        reinterpret_cast<const uint4*>(x), scale_shift, reinterpret_cast<uint4*>(y), H, W, C8, shift, silu, t0, pt, ph, pw);
     CHECK_LAUNCH("group_norm_apply_cl");
     return B200_OK;
 }
