@@ -455,7 +455,7 @@ def main():
     if not args.no_vae:
         del den, model, model2
         torch.cuda.empty_cache()
-        vae = WanVAE(device=dev, state_dict=synth.make_vae_state_dict(seed=0))
+        vae = WanVAE(device=dev, state_dict=synth.make_vae_state_dict(seed=0, encoder=True))
         z = torch.randn(16, T, H, W, generator=g).to(dev)
         nfr = 4 * (T - 1) + 1
         vae.decode_to_cpu_uint8([z], 0)
@@ -483,6 +483,26 @@ def main():
                                 "gpu_launches": (_lib.launch_count() - l0) // reps,
                                 "tflops": vae_flops / (vms * 1e-3) / 1e12, "tensor_frac": vae_flops / (vms * 1e-3) / 1e12 / pk["tensor_burst"],
                                 "e2e": {"value": world * nfr / e2e_v, "unit": "frames/s", "h2d_bytes": zh.numel() * 4, "d2h_bytes": u8.numel()}}
+        # VAE encode of the same clip size (every i2v generation encodes its conditioning frames), device-resident video
+        try:
+            vid = (torch.rand(3, nfr, 8 * H, 8 * W, generator=g) * 2 - 1).to(dev)
+            vae.encode([vid], tile_size=0)
+            barrier()
+            l1 = _lib.launch_count()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            mu = vae.encode([vid], tile_size=0)[0]
+            q1.record()
+            barrier()
+            ems = torch.tensor([q0.elapsed_time(q1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            result["vae_encode"] = {"metric": "vae_encode_frames_per_sec", "value": world * nfr / (float(ems[0]) / 1e3), "unit": "frames/s",
+                                    "frames": nfr, "resolution": [8 * H, 8 * W], "ms_per_clip": float(ems[0]),
+                                    "gpu_launches": _lib.launch_count() - l1, "latent": list(mu.shape), "finite": bool(torch.isfinite(mu).all())}
+            del vid, mu
+        except Exception as e:                                   # noqa: BLE001
+            result["vae_encode"] = {"error": repr(e)[:300]}
         if dist is not None:
             # the single collective of the north star: all-gather of the decoded uint8 frames over NVLink.
             # (a) baseline: frames_to_u8 kernel + ncclAllGather; (b) fused quantise + all-gather over peer memory

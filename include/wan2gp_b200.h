@@ -165,12 +165,20 @@ int b200_group_stats_cl(const void* x, const float* gamma, const float* beta, fl
  * CausalConv3d's F.pad(mode="replicate") (unet_causal_3d_blocks.py:63-66, 455-480) in one pass */
 int b200_group_norm_apply_cl(const void* x, const float* scale_shift, void* y, int T, int H, int W, int C, int silu, int t0, int Tc,
                              int pt, int ph, int pw, void* stream);
-/* "valid" conv over a window of x [Ti,Hi,Wi,Cin] starting at (off_t,off_h,off_w), T x H x W outputs stored bf16 with element
- * strides (ost_t, ost_h, ost_w): one phase of nearest-up-sample + CausalConv3d (UpsampleCausal3D, unet_causal_3d_blocks.py
- * :196-222) evaluated on the low-resolution tensor with pre-summed taps */
+/* conv over a window of x [Ti,Hi,Wi,Cin] starting at (off_t,off_h,off_w): output pixel (t,h,w), t<T, h<H, w<W, reads taps at
+ * x[off_t+t+dt, off_h+h+dh, off_w+w+dw] (zeros beyond the high end of x) and is stored bf16 with element strides (ost_t, ost_h,
+ * ost_w); residual (bf16, same addressing as out) may be null.  Uses: one phase of nearest-up-sample + CausalConv3d
+ * (UpsampleCausal3D, unet_causal_3d_blocks.py:196-222) on the low-resolution tensor with pre-summed taps; the stride-2 convs of
+ * the Wan VAE encoder (Resample down-sampling, vae.py:134-143, 190-212) over space-to-depth / frame-pair views */
 int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int off_h, int off_w, const void* w, const float* bias,
-                        void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t, long long ost_h,
-                        long long ost_w, void* stream);
+                        const void* residual, void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t,
+                        long long ost_h, long long ost_w, void* stream);
+
+/* ---- Wan VAE encode helpers (models/wan/modules/vae.py Encoder3d :318-427, Resample :134-143) ---- */
+/* planar fp32 [C,P] -> channels-last bf16 [P,Cpad] with zero channels C..Cpad-1 (Cpad % 8 == 0): video [3,T,H,W] -> conv operand */
+int b200_planar_to_cl_pad(const float* x, void* y_bf16, int C, long long P, int Cpad, void* stream);
+/* space-to-depth 2x2 of a channels-last bf16 tensor: [T,H,W,C] -> [T,H/2,W/2,4C], channel (2p+q)*C+c = x[t,2i+p,2j+q,c] */
+int b200_space_to_depth_cl(const void* x, void* y, int T, int H, int W, int C, void* stream);
 
 /* Fused quantise + all-gather of decoded frames (the one collective of the schedule): x fp32 [n] (this
  * rank's frames) -> uint8 written into slot `rank` (byte offset rank*n) of EVERY peer's gather buffer.  peer_bufs: HOST array

@@ -94,6 +94,27 @@ def run_vae(name):
                         seconds=np.float32(dt), threads=np.int32(torch.get_num_threads()))
 
 
+VAE_ENC_CASES = {"vae_enc_tiny": (synth.VAE_CFG_TINY, (3, 9, 32, 48), 0), "vae_enc_small": (synth.VAE_CFG, (3, 5, 48, 64), 1),
+                 "vae_enc_1f": (synth.VAE_CFG_TINY, (3, 1, 16, 24), 2)}
+
+
+def run_vae_enc(name):
+    """Reference WanVAE_.encode (vae.py:586-625: chunked 1,4,4,... with feature caches), un-tiled."""
+    ref = load_reference()
+    cfg, xshape, seed = VAE_ENC_CASES[name]
+    vae = ref.WanVAE_(dim=cfg["dim"], z_dim=cfg["z_dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], attn_scales=[],
+                      temperal_downsample=[False, True, True], dropout=0.0).eval().requires_grad_(False)
+    sd = synth.make_vae_state_dict(cfg, seed, encoder=True)
+    assert set(sd) == set(vae.state_dict()), set(sd) ^ set(vae.state_dict())
+    vae.load_state_dict(sd)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+    scale = [torch.tensor(synth.VAE_MEAN), 1.0 / torch.tensor(synth.VAE_STD)]
+    with torch.no_grad():
+        mu = vae.encode(x, scale)
+    print(f"{name}: reference encode out {tuple(mu.shape)} absmean {mu.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=mu.numpy().astype(np.float32))
+
+
 HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0), "hy10_tiny": ("hy10_tiny", (2, 8, 12), 1)}
 
 
@@ -178,4 +199,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_vae)(n)

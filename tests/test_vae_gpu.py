@@ -126,3 +126,42 @@ def test_upconv_subpixel_vs_torch():
         ref = F.conv2d(up.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
         assert out.shape == (T, 2 * H, 2 * W, co)
         assert rel_l2(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("name", ["vae_enc_tiny", "vae_enc_small", "vae_enc_1f"])
+def test_vae_encode(name):
+    """Wan VAE encode through the reference-shaped WanVAE.encode: whole-sequence causal convs, stride-2 convs as
+    space-to-depth / frame-pair window convs, folded head.  vs the reference's chunked encode (fixture) and the bf16-emulating
+    oracle: rel-L2 <= 2.5e-2 (the emulating oracle is 5e-3 from the fp32 reference)."""
+    from oracle import vae_oracle
+    from tests.test_vae_enc_cpu import enc_case
+    from wan2gp_b200.wan import WanVAE
+    cfg, sd, x = enc_case(name)
+    vae = WanVAE(state_dict=sd, cfg=cfg)
+    got = vae.encode([x[0].cuda()], tile_size=0)[0].cpu()
+    g = load_golden(name)["out"][0]
+    emu = vae_oracle.vae_encode(sd, x[0], synth.VAE_MEAN, synth.VAE_STD, cfg, emulate_bf16=True)
+    print(f"{name}: vs reference {rel_l2(got, g):.3e}; vs bf16-emulating oracle {rel_l2(got, emu):.3e}")
+    assert got.shape == g.shape and got.dtype == torch.float32
+    assert rel_l2(got, g) < 2.5e-2 and rel_l2(got, emu) < 2.5e-2
+
+
+def test_vae_encode_wide_rows_and_roundtrip():
+    """Rows wide enough for the row-tiled conv kernel at the first two levels (W = 416 -> 208 -> 104), vs the bf16-emulating oracle;
+    then decode(encode(x)) runs end to end with the expected shapes (1 + 4k frames -> 1 + k latent frames -> 1 + 4k frames)."""
+    from oracle import vae_oracle
+    from wan2gp_b200.wan import WanVAE
+    cfg = synth.VAE_CFG_TINY
+    sd = synth.make_vae_state_dict(cfg, 3, encoder=True)
+    x = synth._normal((3, 5, 16, 416), 0.5, 3, "input.video", "cpu").clamp_(-1, 1)
+    vae = WanVAE(state_dict=sd, cfg=cfg)
+    mu = vae.encode([x.cuda()], tile_size=0)[0]
+    emu = vae_oracle.vae_encode(sd, x, synth.VAE_MEAN, synth.VAE_STD, cfg, emulate_bf16=True)
+    print(f"wide encode: vs bf16-emulating oracle {rel_l2(mu.cpu(), emu):.3e}")
+    assert mu.shape == (16, 2, 2, 52) and rel_l2(mu.cpu(), emu) < 2.5e-2
+    rec = vae.decode([mu])[0]
+    assert rec.shape == (3, 5, 16, 416) and torch.isfinite(rec).all()
+    with pytest.raises(NotImplementedError):
+        vae.encode([x.cuda()], tile_size=256)
+    with pytest.raises(ValueError):
+        vae.encode([x[:, :4].cuda()], tile_size=0)

@@ -318,6 +318,48 @@ extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_
 }
 
 // ---------------------------------------------------------------------------------------------
+// VAE encode helpers
+// planar fp32 [C, P] -> channels-last bf16 [P, Cpad], channels >= C zero (video [3,T,H,W] -> 8-channel TMA-legal operand)
+__global__ void planar_to_cl_pad_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, long long P, int Cpad8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * Cpad8) return;
+    const long long p = i / Cpad8;
+    const int c0 = (int)(i - p * Cpad8) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? __ldg(x + (long long)(c0 + j) * P + p) : 0.f;
+    y[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+extern "C" int b200_planar_to_cl_pad(const float* x, void* y, int C, long long P, int Cpad, void* stream) {
+    if (!x || !y || C <= 0 || P <= 0 || Cpad < C || Cpad % 8) return b200_set_error(B200_ERR_ARG, "planar_to_cl_pad: bad argument");
+    const long long n = P * (Cpad / 8);
+    planar_to_cl_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint4*>(y), C, P, Cpad / 8);
+    CHECK_LAUNCH("planar_to_cl_pad");
+    return B200_OK;
+}
+// space-to-depth 2x2: x [T,H,W,C] -> y [T,H/2,W/2,4C], channel (2p+q)*C + c = x[t, 2i+p, 2j+q, c]  (H, W even).  A stride-2
+// 3x3 conv with ZeroPad2d((0,1,0,1)) (Resample 'downsample2d/3d', vae.py:134-143) becomes a stride-1 2x2 conv over y.
+__global__ void space_to_depth_cl_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8) {
+    // grid: x = 16-byte chunks of one OUTPUT row (W/2 * 4 * C8), y = output row, z = frame
+    const int Wo = W >> 1, n = Wo * 4 * C8;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    const int j = idx / (4 * C8), r = idx - j * 4 * C8;
+    const int pq = r / C8, c = r - pq * C8;
+    const int i = blockIdx.y, t = blockIdx.z;
+    y[(((long long)t * (H >> 1) + i) * Wo) * 4 * C8 + idx] =
+        __ldg(x + (((long long)t * H + 2 * i + (pq >> 1)) * W + 2 * j + (pq & 1)) * C8 + c);
+}
+extern "C" int b200_space_to_depth_cl(const void* x, void* y, int T, int H, int W, int C, void* stream) {
+    if (!x || !y || T <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C % 8 || H / 2 > 65535 || T > 65535)
+        return b200_set_error(B200_ERR_ARG, "space_to_depth_cl: bad argument (H, W even; C %% 8 == 0)");
+    const dim3 grid((unsigned)(((long long)(W / 2) * 4 * (C / 8) + 255) / 256), (unsigned)(H / 2), (unsigned)T);
+    space_to_depth_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C / 8);
+    CHECK_LAUNCH("space_to_depth_cl");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // HunyuanVideo 1.0 VAE helpers: GroupNorm over the WHOLE clip (torch.nn.GroupNorm on [B,C,T,H,W], unet_causal_3d_blocks.py
 // :378/:399, vae.py:292) on channels-last bf16.  Pass 1: per-group sum / sum-of-squares (fp32 per thread and block, fp64
 // across blocks, fixed summation order).  Pass 2 (apply) normalises, optionally applies SiLU and writes straight into the replicate-PADDED layout
@@ -495,12 +537,14 @@ extern "C" int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const f
 // One launch per phase of a nearest-up-sample + conv pair (UpsampleCausal3D, unet_causal_3d_blocks.py:196-222): the conv
 // over the 2x (x2x2) up-sampled tensor equals 4 (8) small convs with pre-summed taps over the LOW-resolution tensor.
 extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int off_h, int off_w, const void* w, const float* bias,
-                                   void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t,
-                                   long long ost_h, long long ost_w, void* stream) {
-    if (off_t < 0 || off_h < 0 || off_w < 0 || off_t + T + kt - 1 > Ti || off_h + H + kh - 1 > Hi || off_w + W + kw - 1 > Wi)
-        return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: window outside the input");
+                                   const void* residual, void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw,
+                                   long long ost_t, long long ost_h, long long ost_w, void* stream) {
+    // taps that fall beyond the high end of the input read zeros (TMA out-of-bounds fill): that is the ZeroPad2d((0,1,0,1)) of the
+    // encoder's stride-2 convs; the window must START inside the input
+    if (off_t < 0 || off_h < 0 || off_w < 0 || off_t >= Ti || off_h >= Hi || off_w >= Wi)
+        return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: window origin outside the input");
     ConvView v{Ti, Hi, Wi, off_t, off_h, off_w, ost_t, ost_h, ost_w};
-    return conv_cl_impl(x, w, bias, nullptr, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, 0, 0, -1, -1, stream, 1, &v);
+    return conv_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, 0, 0, -1, -1, stream, 1, &v);
 }
 
 // ---- row-tiled conv kernel (conv_sm100.cuh): instances and selection
@@ -606,7 +650,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     if (view) {
-        if (out_mode != 0 || residual) return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: bf16 output without residual only");
+        if (out_mode != 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl_view: bf16 output only");
         p.pad_t = -view->off_t; p.pad_h = -view->off_h; p.pad_w = -view->off_w;
         p.out = out;
         p.st_t = view->ost_t; p.st_h = view->ost_h; p.st_w = view->ost_w;

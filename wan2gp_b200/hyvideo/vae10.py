@@ -89,7 +89,7 @@ class _UpConvNearest:
             if n_t <= 0:
                 continue
             base = out.data_ptr() + 2 * ((o_t * 2 * H + py) * 2 * W + px) * Co
-            _lib.call("b200_conv3d_cl_view", xp.data_ptr(), T + ptf, H + 2, W + 2, off_t, py, px, w.data_ptr(), self.b.data_ptr(), base,
+            _lib.call("b200_conv3d_cl_view", xp.data_ptr(), T + ptf, H + 2, W + 2, off_t, py, px, w.data_ptr(), self.b.data_ptr(), 0, base,
                       n_t, H, W, self.cin, Co, kt, 2, 2, st_t, 4 * W * Co, 2 * Co, _s())
         return out
 

@@ -178,6 +178,63 @@ def vae_param_shapes(cfg=VAE_CFG):
     return s
 
 
+def vae_encoder_layout(cfg=VAE_CFG):
+    """Encoder3d (vae.py:318-372): list of ("res", cin, cout) | ("down2d", c) | ("down3d", c) for `downsamples`, plus the
+    channel count of conv1 and of the middle/head; temperal_downsample = [False, True, True] (vae.py:911-918)."""
+    dim, mult = cfg["dim"], cfg["dim_mult"]
+    dims = [dim * u for u in [1] + mult]
+    temporal = [False, True, True]
+    downs = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(cfg["num_res_blocks"]):
+            downs.append(("res", cin, cout))
+            cin = cout
+        if i != len(mult) - 1:
+            downs.append(("down3d" if temporal[i] else "down2d", cout))
+    return dims[0], downs, dims[-1]
+
+
+def vae_encoder_param_shapes(cfg=VAE_CFG):
+    """encoder.* and conv1.* of WanVAE_ (vae.py:318-372, 582)."""
+    z = cfg["z_dim"]
+    c0, downs, c_mid = vae_encoder_layout(cfg)
+    s = {"conv1.weight": (2 * z, 2 * z, 1, 1, 1), "conv1.bias": (2 * z,),
+         "encoder.conv1.weight": (c0, 3, 3, 3, 3), "encoder.conv1.bias": (c0,)}
+
+    def res(p, ci, co):
+        s[p + "residual.0.gamma"] = (ci, 1, 1, 1)
+        s[p + "residual.2.weight"] = (co, ci, 3, 3, 3)
+        s[p + "residual.2.bias"] = (co,)
+        s[p + "residual.3.gamma"] = (co, 1, 1, 1)
+        s[p + "residual.6.weight"] = (co, co, 3, 3, 3)
+        s[p + "residual.6.bias"] = (co,)
+        if ci != co:
+            s[p + "shortcut.weight"] = (co, ci, 1, 1, 1)
+            s[p + "shortcut.bias"] = (co,)
+    for j, u in enumerate(downs):
+        p = f"encoder.downsamples.{j}."
+        if u[0] == "res":
+            res(p, u[1], u[2])
+        else:
+            c = u[1]
+            s[p + "resample.1.weight"] = (c, c, 3, 3)
+            s[p + "resample.1.bias"] = (c,)
+            if u[0] == "down3d":
+                s[p + "time_conv.weight"] = (c, c, 3, 1, 1)
+                s[p + "time_conv.bias"] = (c,)
+    res("encoder.middle.0.", c_mid, c_mid)
+    s["encoder.middle.1.norm.gamma"] = (c_mid, 1, 1)
+    s["encoder.middle.1.to_qkv.weight"] = (3 * c_mid, c_mid, 1, 1)
+    s["encoder.middle.1.to_qkv.bias"] = (3 * c_mid,)
+    s["encoder.middle.1.proj.weight"] = (c_mid, c_mid, 1, 1)
+    s["encoder.middle.1.proj.bias"] = (c_mid,)
+    res("encoder.middle.2.", c_mid, c_mid)
+    s["encoder.head.0.gamma"] = (c_mid, 1, 1, 1)
+    s["encoder.head.2.weight"] = (2 * z, c_mid, 3, 3, 3)
+    s["encoder.head.2.bias"] = (2 * z,)
+    return s
+
+
 def make_vae_tensor(name, shape, seed=0, device="cpu"):
     if name.endswith("gamma"):
         return 1.0 + _normal(shape, 0.1, seed, name, device)
@@ -192,8 +249,11 @@ def make_vae_tensor(name, shape, seed=0, device="cpu"):
     return t
 
 
-def make_vae_state_dict(cfg=VAE_CFG, seed=0, device="cpu", dtype=torch.float32):
-    return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in vae_param_shapes(cfg).items()}
+def make_vae_state_dict(cfg=VAE_CFG, seed=0, device="cpu", dtype=torch.float32, encoder=False):
+    shapes = dict(vae_param_shapes(cfg))
+    if encoder:
+        shapes.update(vae_encoder_param_shapes(cfg))
+    return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in shapes.items()}
 
 
 # ------------------------------------------------------------------------ inputs

@@ -92,6 +92,70 @@ def upsample2x(x):
     return y
 
 
+class _DownConv:
+    """Resample down-sampling (vae.py:134-143): ZeroPad2d((0,1,0,1)) + Conv2d(C, C, 3, stride 2), computed as a stride-1 2x2 conv
+    over the space-to-depth tensor [T,H/2,W/2,4C]: kernel row a = 2*da + p (da = s2d tap, p = sub-pixel row), a = 3 gets zero
+    weight; the pad row/column on the bottom/right is the TMA zero fill beyond the tensor."""
+
+    def __init__(self, w, b, device, dtype=bf16):
+        co, ci = w.shape[:2]
+        w = w.detach().to(device, f32)                                      # [Co, Ci, 3, 3]
+        w2 = torch.zeros(co, 2, 2, 2, 2, ci, device=device, dtype=f32)      # [Co, da, db, p, q, Ci]
+        for da in range(2):
+            for p in range(2):
+                for db in range(2):
+                    for q in range(2):
+                        if 2 * da + p < 3 and 2 * db + q < 3:
+                            w2[:, da, db, p, q] = w[:, :, 2 * da + p, 2 * db + q]
+        self.cout, self.cin = co, ci
+        self.w = w2.reshape(co, 4, 4 * ci).to(dtype).contiguous()          # [Co][tap (da,db)][(p,q,c)]
+        self.b = b.detach().to(device, f32).contiguous()
+
+    def __call__(self, x, spare_frame=False):
+        """x [T,H,W,C] -> [T(+1),H/2,W/2,Co]; spare_frame allocates one extra (unwritten) frame so the result can be viewed as
+        frame pairs by _TimeDownConv."""
+        T, H, W, C = x.shape
+        if H % 2 or W % 2:
+            raise ValueError("VAE encode: frame height and width must be even at every level (multiples of 8)")
+        s2d = torch.empty(T, H // 2, W // 2, 4 * C, device=x.device, dtype=bf16)
+        _lib.call("b200_space_to_depth_cl", x.data_ptr(), s2d.data_ptr(), T, H, W, C, _s())
+        out = torch.empty(T + int(spare_frame), H // 2, W // 2, self.cout, device=x.device, dtype=bf16)
+        h, w = H // 2, W // 2
+        _lib.call("b200_conv3d_cl_view", s2d.data_ptr(), T, h, w, 0, 0, 0, self.w.data_ptr(), self.b.data_ptr(), 0, out.data_ptr(),
+                  T, h, w, 4 * C, self.cout, 1, 2, 2, h * w * self.cout, w * self.cout, self.cout, _s())
+        return out
+
+
+class _TimeDownConv:
+    """'downsample3d' time_conv (vae.py:141-143, 190-212): CausalConv3d(C, C, (3,1,1), stride (2,1,1), no padding) run chunk by
+    chunk with a one-frame cache.  Over the whole sequence: out[0] = y[0]; out[j] = w0 y[2j-2] + w1 y[2j-1] + w2 y[2j].  With y
+    viewed as frame PAIRS stacked along H ([m+1, 2h, w, C]) the even frames and the odd frames are two windows of one tensor:
+    launch 1 = 2-tap conv (w0, w2) over the even window, launch 2 = 1-tap conv (w1) over the odd window accumulated through the
+    residual input."""
+
+    def __init__(self, w, b, device, dtype=bf16):
+        w = w.detach().to(device, f32)[:, :, :, 0, 0]                        # [Co, Ci, 3]
+        self.cout, self.cin = w.shape[:2]
+        self.w_even = torch.stack([w[:, :, 0], w[:, :, 2]], 1).to(dtype).contiguous()      # [Co, 2, Ci]
+        self.w_odd = w[:, :, 1].unsqueeze(1).to(dtype).contiguous()                        # [Co, 1, Ci]
+        self.b = b.detach().to(device, f32).contiguous()
+
+    def __call__(self, y, T):
+        """y: buffer of T+1 frames [T+1,h,w,C] whose first T frames are valid (T odd)."""
+        _, h, w, C = y.shape
+        m = (T - 1) // 2
+        out = torch.empty(1 + m, h, w, self.cout, device=y.device, dtype=bf16)
+        out[0].copy_(y[0])                                                   # the first chunk's frame bypasses time_conv (:196-198)
+        if m > 0:
+            o1 = out[1:]
+            st = (h * w * self.cout, w * self.cout, self.cout)
+            _lib.call("b200_conv3d_cl_view", y.data_ptr(), m + 1, 2 * h, w, 0, 0, 0, self.w_even.data_ptr(), self.b.data_ptr(), 0,
+                      o1.data_ptr(), m, h, w, C, self.cout, 2, 1, 1, *st, _s())
+            _lib.call("b200_conv3d_cl_view", y.data_ptr(), m + 1, 2 * h, w, 0, h, 0, self.w_odd.data_ptr(), 0, o1.data_ptr(),
+                      o1.data_ptr(), m, h, w, C, self.cout, 1, 1, 1, *st, _s())
+        return out
+
+
 class WanVAEDecoder(torch.nn.Module):
     """Decoder half of WanVAE_ (vae.py:549-662); `decode(z, scale)` mirrors WanVAE_.decode."""
 
@@ -196,6 +260,108 @@ class WanVAEDecoder(torch.nn.Module):
         return torch.stack([self.decode_frames(zi, mean, std) for zi in z], 0)
 
 
+class WanVAEEncoder(torch.nn.Module):
+    """Encoder half of WanVAE_ (vae.py:318-427, 586-625), whole-sequence: `encode(x, scale)` mirrors WanVAE_.encode.  The reference
+    feeds the encoder chunks of 1, 4, 4, ... frames with per-conv feature caches; that equals causal convs over the whole
+    sequence plus the frame-pair rule of _TimeDownConv (pinned at 4e-7 by oracle/vae_oracle.py::vae_encode against the
+    reference).  conv1 (1x1x1), the mu half of `chunk(2)` and the latent normalisation are folded into the head conv."""
+
+    def __init__(self, cfg=None, device="cuda"):
+        super().__init__()
+        self.cfg = dict(cfg or synth.VAE_CFG)
+        self.z_dim = self.cfg["z_dim"]
+        self.device = torch.device(device)
+        self._ready, self._head = False, {}
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        dev = self.device
+        g = lambda k: sd[k].detach().to(dev, f32).contiguous()  # noqa: E731
+        w1 = sd["encoder.conv1.weight"].detach().to(dev, f32)
+        self.conv1 = _Conv(torch.cat([w1, w1.new_zeros(w1.shape[0], 5, *w1.shape[2:])], 1), sd["encoder.conv1.bias"], dev)   # Cin 3 -> 8
+
+        def res(p):
+            d = {"g0": g(p + "residual.0.gamma").reshape(-1), "c0": _Conv(sd[p + "residual.2.weight"], sd[p + "residual.2.bias"], dev),
+                 "g1": g(p + "residual.3.gamma").reshape(-1), "c1": _Conv(sd[p + "residual.6.weight"], sd[p + "residual.6.bias"], dev)}
+            if p + "shortcut.weight" in sd:
+                d["sc"] = _Conv(sd[p + "shortcut.weight"], sd[p + "shortcut.bias"], dev)
+            return d
+        _, downs, _ = synth.vae_encoder_layout(self.cfg)
+        self.downs = []
+        for j, u in enumerate(downs):
+            p = f"encoder.downsamples.{j}."
+            if u[0] == "res":
+                self.downs.append(("res", res(p)))
+            else:
+                d = {"conv": _DownConv(sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], dev)}
+                if u[0] == "down3d":
+                    d["time"] = _TimeDownConv(sd[p + "time_conv.weight"], sd[p + "time_conv.bias"], dev)
+                self.downs.append((u[0], d))
+        self.mid0, self.mid2 = res("encoder.middle.0."), res("encoder.middle.2.")
+        a = "encoder.middle.1."
+        c0 = sd[a + "proj.weight"].shape[0]
+        self.attn = {"g": g(a + "norm.gamma").reshape(-1), "wqkv": sd[a + "to_qkv.weight"].detach().to(dev, bf16).reshape(3 * c0, c0).contiguous(),
+                     "bqkv": g(a + "to_qkv.bias"), "wproj": sd[a + "proj.weight"].detach().to(dev, bf16).reshape(c0, c0).contiguous(),
+                     "bproj": g(a + "proj.bias")}
+        self.head_g = g("encoder.head.0.gamma").reshape(-1)
+        self.head_w, self.head_b = g("encoder.head.2.weight"), g("encoder.head.2.bias")
+        self.c1_w, self.c1_b = g("conv1.weight").reshape(2 * self.z_dim, 2 * self.z_dim), g("conv1.bias")
+        self._ready, self._head = True, {}
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    def _head_conv(self, mean, inv_std):
+        """head conv3d -> conv1 1x1x1 -> mu = chunk(2)[0] -> (mu - mean) * inv_std (vae.py:612-619) as ONE conv with fp32 planar output:
+        W = diag(inv_std) W1[:z] Wh,  b = inv_std * (W1[:z] bh + b1[:z] - mean)."""
+        key = (tuple(mean.tolist()), tuple(inv_std.tolist()))
+        if key not in self._head:
+            z = self.z_dim
+            m = inv_std[:, None] * self.c1_w[:z]                              # [z, 2z]
+            w = torch.einsum("om,mctyx->octyx", m, self.head_w)
+            b = inv_std * (self.c1_w[:z] @ self.head_b + self.c1_b[:z] - mean)
+            self._head = {key: _Conv(w, b, self.device)}
+        return self._head[key]
+
+    _res = staticmethod(WanVAEDecoder._res)
+    _attn = WanVAEDecoder._attn
+
+    @torch.no_grad()
+    def encode_frames(self, x, mean, inv_std):
+        """x [3, 1+4k, H, W] fp32 in [-1,1] on device -> normalised latent mean [16, 1+k, H/8, W/8] fp32."""
+        if not self._ready:
+            raise RuntimeError("WanVAE: load_state_dict() must be called before encode")
+        C, T, H, W = x.shape
+        if (T - 1) % 4:
+            raise ValueError("VAE encode takes 1 + 4k frames (vae.py:590-594)")
+        if H % 8 or W % 8:
+            raise ValueError("VAE encode: frame height and width must be multiples of 8")
+        x = x.to(self.device, f32).contiguous()
+        h = torch.empty(T, H, W, 8, device=self.device, dtype=bf16)
+        _lib.call("b200_planar_to_cl_pad", x.data_ptr(), h.data_ptr(), C, T * H * W, 8, _s())
+        h = self.conv1(h)
+        for kind, d in self.downs:
+            if kind == "res":
+                h = self._res(d, h)
+            else:
+                t = h.shape[0]
+                temporal = kind == "down3d" and t > 1
+                h = d["conv"](h, spare_frame=temporal)
+                if temporal:
+                    h = d["time"](h, t)
+        h = self._res(self.mid0, h)
+        h = self._attn(h)
+        h = self._res(self.mid2, h)
+        return self._head_conv(mean, inv_std)(rms_silu(h, self.head_g), out_mode=2)
+
+    def encode(self, x, scale=None, any_end_frame=False):
+        """WanVAE_.encode contract (vae.py:586-625): x [1,3,T,H,W]; scale = [mean, 1/std] -> mu [1,16,1+(T-1)/4,H/8,W/8] fp32."""
+        if any_end_frame:
+            raise NotImplementedError("any_end_frame encode is outside the t2v/i2v2_2 hot path")
+        z = self.z_dim
+        mean = torch.zeros(z) if scale is None else torch.as_tensor(scale[0], dtype=f32).reshape(-1).cpu()
+        inv_std = torch.ones(z) if scale is None else torch.as_tensor(scale[1], dtype=f32).reshape(-1).cpu()
+        mean, inv_std = mean.expand(z).to(self.device, f32).contiguous(), inv_std.expand(z).to(self.device, f32).contiguous()
+        return torch.stack([self.encode_frames(xi, mean, inv_std) for xi in x], 0)
+
+
 class WanVAE:
     """Mirror of models/wan/modules/vae.py::WanVAE (:935-1027)."""
 
@@ -208,12 +374,15 @@ class WanVAE:
         self.std = torch.tensor(synth.VAE_STD, dtype=f32, device=device)            # vae.py:952-955
         self.scale = [self.mean, 1.0 / self.std]
         self.model = WanVAEDecoder(cfg, device)
+        self.encoder_model = WanVAEEncoder(cfg, device)
         if state_dict is None and vae_pth is not None:
             state_dict = torch.load(vae_pth, map_location="cpu")
             if preprocess_sd is not None:
                 state_dict = preprocess_sd(state_dict)
         if state_dict is not None:
             self.model.load_state_dict(state_dict)
+            if "encoder.conv1.weight" in state_dict:           # decode-only checkpoints / synthetic decoders carry no encoder
+                self.encoder_model.load_state_dict(state_dict)
 
     @staticmethod
     def get_VAE_tile_size(vae_config, device_mem_capacity, mixed_precision, output_height=None, output_width=None):
@@ -243,5 +412,10 @@ class WanVAE:
             outs.append(u8.cpu())
         return outs
 
-    def encode(self, videos, tile_size=256, any_end_frame=False):
-        raise NotImplementedError("VAE encode is a 'next' row (SURVEY.md 8f.2)")
+    def encode(self, videos, tile_size=0, any_end_frame=False):
+        """list of [3,T,H,W] videos in [-1,1] -> list of normalised latents fp32 [16,1+(T-1)/4,H/8,W/8] (vae.py:1002-1010), un-tiled:
+        the reference's default tile_size=256 selects spatial_tiled_encode (tile + blend to fit small GPUs); here the whole clip is
+        encoded at once, which is the reference's tile_size=0 branch."""
+        if tile_size and tile_size > 0:
+            raise NotImplementedError("tiled encode is a 'next' row (SURVEY.md 8f.3); B200 encodes untiled (pass tile_size=0)")
+        return [self.encoder_model.encode(u.unsqueeze(0), self.scale, any_end_frame)[0] for u in videos]
