@@ -93,6 +93,14 @@ int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, vo
 int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt, float* pred_out,
                         float* star_dots, long long n, void* stream);
 
+/* One FlowUniPCMultistepScheduler.step (shared/utils/fm_solvers_unipc.py:655-740: solver_order 2, bh2, predict_x0,
+ * flow_prediction -- WanGP's default sample_solver, any2video.py:518-522) fused with the CFG combine (any2video.py:1701-1722).
+ * coef_host8 (HOST pointer) = {sigma_i, ca, cb, cc, cd, pp, pq, pr} from wan2gp_b200/pipeline.py::UniPCSchedule:
+ *   v = u + g (c - u);  x0 = x - sigma_i v;  xc = use_corrector ? ca x_last + cb m0 + cc m1 + cd x0 : x;  xn = pp xc + pq x0 + pr m0
+ * stores lat <- xn, x_last <- xc, m1 <- x0 (the caller swaps the roles of m0 and m1).  All fp32, n % 4 == 0; star_dots as above. */
+int b200_cfg_unipc_step(float* lat, const float* cond, const float* uncond, float guide, float* x_last, const float* m0, float* m1,
+                        const float* coef_host8, int use_corrector, float* star_dots, long long n, void* stream);
+
 /* ---- WanVAE decode (channels-last bf16 activations [T,H,W,C]) ---- */
 
 /* Causal 3-D / 2-D convolution as implicit GEMM (vae.py:43-63 CausalConv3d, :127-133 Conv2d):

@@ -194,9 +194,26 @@ def run_hyvae10(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
 
 
+def run_unipc(name):
+    """Trajectory of the reference FlowUniPCMultistepScheduler on seeded fp64 inputs (same generator as tests/test_unipc_cpu.py)."""
+    from oracle.refshim import load_reference_unipc
+    steps, shift = 20, 3.0
+    ref = load_reference_unipc().FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    ref.set_timesteps(steps, device="cpu", shift=shift)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64)
+    vs = [torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64) for _ in range(steps)]
+    traj = []
+    for i, t in enumerate(ref.timesteps):
+        x = ref.step(vs[i], t, x, return_dict=False)[0]
+        traj.append(x.numpy().copy())
+    np.savez_compressed(os.path.join(GOLDEN, "unipc.npz"), steps=steps, shift=shift, timesteps=ref.timesteps.numpy(), traj=np.stack(traj))
+    print(f"unipc: {steps} steps, final absmean {np.abs(traj[-1]).mean():.6f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae)(n)

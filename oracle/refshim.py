@@ -305,3 +305,52 @@ def load_reference_hyvae10():
     from models.hyvideo.vae.autoencoder_kl_causal_3d import AutoencoderKLCausal3D
     _loaded_hyvae10 = types.SimpleNamespace(DecoderCausal3D=DecoderCausal3D, AutoencoderKLCausal3D=AutoencoderKLCausal3D)
     return _loaded_hyvae10
+
+
+_loaded_unipc = None
+
+
+def load_reference_unipc():
+    """Reference FlowUniPCMultistepScheduler (shared/utils/fm_solvers_unipc.py), the default Wan sample solver (any2video.py:518-522).
+    diffusers' SchedulerMixin / ConfigMixin only provide config plumbing; register_to_config must populate self.config."""
+    global _loaded_unipc
+    if _loaded_unipc is not None:
+        return _loaded_unipc
+    import enum
+    import functools
+    import importlib.util
+    import inspect
+
+    def mod(name, **attrs):
+        m = sys.modules.setdefault(name, types.ModuleType(name))
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def wrapped(self, *a, **kw):
+            sig = inspect.signature(init)
+            bound = sig.bind(self, *a, **kw)
+            bound.apply_defaults()
+            cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+            self.config = types.SimpleNamespace(**cfg)
+            self.register_to_config = lambda **u: self.config.__dict__.update(u)
+            init(self, *a, **kw)
+        return wrapped
+
+    class Karras(enum.Enum):
+        UniPCMultistepScheduler = 1
+    mod("diffusers")
+    mod("diffusers.configuration_utils", ConfigMixin=type("ConfigMixin", (), {}), register_to_config=register_to_config)
+    mod("diffusers.schedulers")
+    mod("diffusers.schedulers.scheduling_utils", KarrasDiffusionSchedulers=Karras, SchedulerMixin=type("SchedulerMixin", (), {}),
+        SchedulerOutput=lambda prev_sample: types.SimpleNamespace(prev_sample=prev_sample))
+    du = mod("diffusers.utils")
+    du.deprecate = lambda *a, **k: None
+    du.is_scipy_available = lambda: False
+    spec = importlib.util.spec_from_file_location("_ref_fm_solvers_unipc", os.path.join(REFERENCE_ROOT, "shared/utils/fm_solvers_unipc.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    _loaded_unipc = types.SimpleNamespace(FlowUniPCMultistepScheduler=m.FlowUniPCMultistepScheduler)
+    return _loaded_unipc

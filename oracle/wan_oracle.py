@@ -213,3 +213,13 @@ def cfg_combine(cond, uncond, guide_scale, cfg_star=False, step_no=0, cfg_zero_s
 def euler_step(latents, noise_pred, sigma, sigma_next):
     """shared/utils/euler_scheduler.py:67-86 -- x <- x + (sigma_next - sigma) * v."""
     return latents + (sigma_next - sigma) * noise_pred
+
+
+def unipc_step(x, v, x_last, m0, m1, coef):
+    """CPU restatement of the fused UniPC update (csrc/elementwise.cuh::cfg_unipc_kernel) for given scalar coefficients
+    (wan2gp_b200/pipeline.py::UniPCSchedule.coefficients): returns (x_next, x_corrected, x0).  Pinned end to end against the reference
+    FlowUniPCMultistepScheduler.step (shared/utils/fm_solvers_unipc.py:655-740) in tests/test_unipc_cpu.py."""
+    x0 = x - coef["sigma"] * v
+    xc = coef["ca"] * x_last + coef["cb"] * m0 + coef["cc"] * m1 + coef["cd"] * x0 if coef["use_corrector"] else x
+    xn = (coef["pp"] * xc if coef["pp"] != 0 else 0) + coef["pq"] * x0 + (coef["pr"] * m0 if coef["pr"] != 0 else 0)
+    return xn, xc, x0

@@ -53,3 +53,66 @@ def test_denoise_loop_and_decode_match_oracle():
         if len(calls) == 3:
             den._interrupt = True
     assert den.generate(ctx, ctx_null, (16,) + thw, seed=11, callback=cb) is None
+
+
+def test_unipc_fused_step_kernel():
+    """b200_cfg_unipc_step over a whole 8-step schedule (CFG pair, CFG-Zero* on from step 2): one fused kernel per step against the
+    CPU restatement with the same host coefficients (which tests/test_unipc_cpu.py pins to the reference scheduler)."""
+    from oracle import wan_oracle
+    from wan2gp_b200 import ops
+    from wan2gp_b200.pipeline import UniPCSchedule
+    steps, shift, g = 8, 5.0, 4.0
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 16, 3, 8, 10, generator=gen)
+    conds = [torch.randn_like(x) for _ in range(steps)]
+    unconds = [c * 0.7 + 0.3 * torch.randn(x.shape, generator=gen) for c in conds]
+    sch_g, sch_c = UniPCSchedule(steps, shift), UniPCSchedule(steps, shift)
+    xg = x.cuda()
+    hist = [torch.zeros_like(xg) for _ in range(3)]
+    xc_, xl, m0, m1 = x.double(), torch.zeros_like(x).double(), torch.zeros_like(x).double(), torch.zeros_like(x).double()
+    for i in range(steps):
+        star = i >= 2
+        c, u = conds[i].double(), unconds[i].double()
+        if star:
+            u = u * ((c * u).sum() / ((u * u).sum() + 1e-8))
+        v = wan_oracle.cfg_combine(c, u, g)
+        xc_, corr, x0 = wan_oracle.unipc_step(xc_, v, xl, m0, m1, sch_c.coefficients(i))
+        xl, m0, m1 = corr, x0, m0
+        ops.cfg_unipc_step_(xg, conds[i].cuda(), unconds[i].cuda(), g, hist[0], hist[1], hist[2], sch_g.coefficients(i), cfg_star=star)
+        hist = [hist[0], hist[2], hist[1]]
+        assert rel_l2(xg.cpu(), xc_) < 2e-5, i
+        assert rel_l2(hist[1].cpu(), x0) < 2e-5 and (i == 0 or rel_l2(hist[0].cpu(), corr) < 2e-5)
+    # no-CFG variant (uncond = None) takes the same path
+    y = torch.randn(1, 16, 3, 8, 10, generator=gen)
+    yg, h2 = y.cuda(), [torch.zeros(1, 16, 3, 8, 10, device="cuda") for _ in range(3)]
+    s2 = UniPCSchedule(2, 3.0)
+    co = s2.coefficients(0)
+    ops.cfg_unipc_step_(yg, conds[0].cuda(), None, 1.0, h2[0], h2[1], h2[2], co)
+    want, _, _ = wan_oracle.unipc_step(y.double(), conds[0].double(), 0, 0, 0, co)
+    assert rel_l2(yg.cpu(), want) < 2e-6
+
+
+def test_denoise_loop_unipc_matches_oracle():
+    """WanDenoiser(sample_solver="unipc"): WanGP's default solver through the fused step, vs the oracle loop."""
+    from oracle import wan_oracle
+    from wan2gp_b200.pipeline import UniPCSchedule, WanDenoiser
+    from wan2gp_b200.wan import WanModel
+    cfg, thw, sd, x, t, ctx, _ = wan_case("tiny")
+    m1 = WanModel(**cfg)
+    m1.load_state_dict(sd)
+    steps, shift, g1 = 4, 5.0, 4.0
+    den = WanDenoiser(m1, num_steps=steps, shift=shift, guide_scale=g1, sample_solver="unipc")
+    ctx_null = torch.zeros_like(ctx)
+    got = den.generate(ctx, ctx_null, (16,) + thw, seed=11, decode=False)["latents"].cpu()
+    sch = UniPCSchedule(steps, shift)
+    lat = torch.randn(1, 16, *thw, generator=torch.Generator().manual_seed(11))
+    xl, m0, m1_ = torch.zeros_like(lat), torch.zeros_like(lat), torch.zeros_like(lat)
+    for i in range(steps):
+        tt = torch.tensor([float(sch.timesteps[i])])
+        c = wan_oracle.wan_forward(sd, cfg, lat, tt, ctx, emulate_bf16=True)
+        u = wan_oracle.wan_forward(sd, cfg, lat, tt, ctx_null, emulate_bf16=True)
+        lat, corr, x0 = wan_oracle.unipc_step(lat, wan_oracle.cfg_combine(c, u, g1), xl, m0, m1_, sch.coefficients(i))
+        xl, m0, m1_ = corr, x0, m0
+    r = rel_l2(got, lat)
+    print(f"4-step UniPC denoise loop: latents vs oracle loop rel-L2 {r:.3e}")
+    assert r < 1e-2

@@ -1,0 +1,70 @@
+"""CPU: the UniPC sampling-loop glue -- host coefficients of wan2gp_b200.pipeline.UniPCSchedule + the linear update
+the fused kernel applies -- against the UNMODIFIED reference FlowUniPCMultistepScheduler run in this container through
+oracle/refshim.py, and against the committed fixture (the reference does not exist on the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wan_oracle
+from tests.helpers import GOLDEN, rel_l2
+from wan2gp_b200.pipeline import UniPCSchedule
+
+CASES = [(6, 5.0), (20, 3.0), (30, 12.0), (2, 1.0), (1, 5.0)]
+
+
+def run_ours(steps, shift, x, vs):
+    sch = UniPCSchedule(steps, shift)
+    x = x.clone()
+    x_last, m0, m1 = torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+    traj = []
+    for i in range(steps):
+        x, xc, x0 = wan_oracle.unipc_step(x, vs[i], x_last, m0, m1, sch.coefficients(i))
+        x_last, m0, m1 = xc, x0, m0
+        traj.append(x.clone())
+    return sch, traj
+
+
+def inputs(steps, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64), [torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64) for _ in range(steps)]
+
+
+@pytest.mark.parametrize("steps,shift", CASES)
+def test_unipc_matches_reference_scheduler(steps, shift):
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is only present in the build container; the committed fixture covers this elsewhere")
+    from oracle.refshim import load_reference_unipc
+    ref = load_reference_unipc().FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    ref.set_timesteps(steps, device="cpu", shift=shift)                      # any2video.py:519-520
+    x, vs = inputs(steps)
+    sch, traj = run_ours(steps, shift, x, vs)
+    assert sch.timesteps == [int(t) for t in ref.timesteps]
+    assert np.allclose(sch.sigmas, ref.sigmas.numpy().astype(np.float64), rtol=0, atol=0)
+    xr = x.clone()
+    for i, t in enumerate(ref.timesteps):
+        xr = ref.step(vs[i], t, xr, return_dict=False)[0]
+        # the reference keeps its scalars in fp32; ours are fp64
+        assert rel_l2(traj[i], xr) < 2e-5, (i, rel_l2(traj[i], xr))
+
+
+def test_unipc_matches_fixture():
+    """tests/golden/unipc.npz = trajectory of the reference scheduler (oracle/gen_golden.py unipc): 20 steps, shift 3."""
+    g = np.load(os.path.join(GOLDEN, "unipc.npz"))
+    steps, shift = int(g["steps"]), float(g["shift"])
+    x, vs = inputs(steps)
+    sch, traj = run_ours(steps, shift, x, vs)
+    assert sch.timesteps == [int(t) for t in g["timesteps"]]
+    for i in range(steps):
+        assert rel_l2(traj[i], torch.from_numpy(g["traj"][i])) < 2e-5
+
+
+def test_unipc_orders():
+    """order 1 on the first step, order 2 afterwards, order 1 again on the last step (lower_order_final); last step returns x0."""
+    sch = UniPCSchedule(5, 5.0)
+    cs = [sch.coefficients(i) for i in range(5)]
+    assert cs[0]["pr"] == 0 and not cs[0]["use_corrector"] and all(c["use_corrector"] for c in cs[1:])
+    assert all(c["pr"] != 0 for c in cs[1:4]) and cs[4]["pr"] == 0
+    assert cs[4]["pp"] == 0 and abs(cs[4]["pq"] - 1.0) < 1e-12            # sigma_next = 0: x_next = x0
+    assert all(np.isfinite(list(c.values())).all() for c in cs)

@@ -90,3 +90,22 @@ def test_wan_forward_cuda_graphs():
     m.use_cuda_graphs = False
     e2 = m([x.clone() * 0.5], torch.tensor([300.0]), [ctx], pipeline=Pipe())[0]
     assert torch.equal(eager, g1) and torch.equal(e2, g2)
+
+
+def test_wan_context_projection_cache():
+    """cache_context: the text embedding and every block's cross-attention K/V are computed once per prompt and
+    reused across steps -- bit-identical to recomputing them; an in-place edit of the context tensor invalidates the cache."""
+    cfg, thw, sd, x, t, ctx, y = wan_case("small")
+    m = _build(cfg, sd)
+    ctx = ctx.cuda()
+    ref1 = m([x.clone()], t, [ctx], pipeline=Pipe())[0]
+    ref2 = m([x.clone() * 0.5], torch.tensor([300.0]), [ctx], pipeline=Pipe())[0]
+    m.cache_context = True
+    c1 = m([x.clone()], t, [ctx], pipeline=Pipe())[0]                                    # fills the cache
+    assert len(m._ckv_cache) == len(m.blocks)
+    c2 = m([x.clone() * 0.5], torch.tensor([300.0]), [ctx], pipeline=Pipe())[0]         # served from the cache
+    assert torch.equal(ref1, c1) and torch.equal(ref2, c2)
+    ctx.mul_(0.5)                                                                         # new prompt in the same buffer
+    c3 = m([x.clone()], t, [ctx], pipeline=Pipe())[0]
+    m.cache_context = False
+    assert torch.equal(c3, m([x.clone()], t, [ctx], pipeline=Pipe())[0]) and not torch.equal(c3, c1)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200_col_mean_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_add_vec": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_ll, c_void_p],
+    "b200_cfg_unipc_step": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p],
     "b200_conv3d_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_int, c_int, c_int, c_int, c_void_p],
     "b200_upconv2x_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

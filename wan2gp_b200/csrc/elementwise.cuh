@@ -306,4 +306,41 @@ __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restric
     if (pred_out) reinterpret_cast<float4*>(pred_out)[i] = p;
 }
 
+// One FlowUniPCMultistepScheduler.step (order <= 2, bh2, predict_x0, flow prediction) fused with the CFG combine; the scalar
+// coefficients come from the host (pipeline.py::UniPCSchedule).  Everything fp32, one pass: 5 reads + 3 writes per element.
+struct UniPCCoef { float sigma, ca, cb, cc, cd, pp, pq, pr; };
+__global__ void cfg_unipc_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond, float g,
+                                 float* __restrict__ x_last, const float* __restrict__ m0, float* __restrict__ m1, UniPCCoef k,
+                                 int use_corrector, const float* __restrict__ star_dots, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
+    float4 u = uncond ? __ldg(reinterpret_cast<const float4*>(uncond) + i) : c;
+    if (star_dots) {
+        const float alpha = __ldg(star_dots) / (__ldg(star_dots + 1) + 1e-8f);
+        u.x *= alpha; u.y *= alpha; u.z *= alpha; u.w *= alpha;
+    }
+    const float v[4] = {u.x + g * (c.x - u.x), u.y + g * (c.y - u.y), u.z + g * (c.z - u.z), u.w + g * (c.w - u.w)};
+    const float4 x4 = reinterpret_cast<const float4*>(lat)[i];
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(m0) + i);
+    const float x[4] = {x4.x, x4.y, x4.z, x4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+    float xl[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (use_corrector) {
+        const float4 l4 = reinterpret_cast<const float4*>(x_last)[i], b4 = reinterpret_cast<const float4*>(m1)[i];
+        xl[0] = l4.x; xl[1] = l4.y; xl[2] = l4.z; xl[3] = l4.w;
+        b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+    }
+    float x0[4], xc[4], xn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        x0[j] = x[j] - k.sigma * v[j];
+        xc[j] = use_corrector ? k.ca * xl[j] + k.cb * a[j] + k.cc * b[j] + k.cd * x0[j] : x[j];
+        // pp = sigma_next / sigma_i is exactly 0 on the last step: skip the product so a non-finite xc cannot leak into x0
+        xn[j] = (k.pp != 0.f ? k.pp * xc[j] : 0.f) + k.pq * x0[j] + (k.pr != 0.f ? k.pr * a[j] : 0.f);
+    }
+    reinterpret_cast<float4*>(lat)[i] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    reinterpret_cast<float4*>(x_last)[i] = make_float4(xc[0], xc[1], xc[2], xc[3]);
+    reinterpret_cast<float4*>(m1)[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+}
+
 }  // namespace b200

@@ -3,6 +3,8 @@ every function checks dtype/layout, passes raw device pointers + the current CUD
 B200Error on failure (no eager fallback)."""
 import math
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -169,4 +171,18 @@ def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None, cfg_star=False)
     dots = torch.empty(2, device=lat.device, dtype=f32) if cfg_star else None
     _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
               _p(dots), lat.numel(), _stream())
+    return lat
+
+
+def cfg_unipc_step_(lat, cond, uncond, guide, x_last, m0, m1, coef, cfg_star=False):
+    """One FlowUniPCMultistepScheduler.step fused with the CFG combine (pipeline.UniPCSchedule.coefficients gives `coef`):
+    lat <- x_next, x_last <- corrected sample, m1 <- x0 of this step (the caller swaps m0/m1)."""
+    for t_, n_ in ((lat, "lat"), (cond, "cond"), (x_last, "x_last"), (m0, "m0"), (m1, "m1")):
+        _chk(t_, f32, n_)
+        assert t_.is_contiguous() and t_.numel() == lat.numel()
+    assert uncond is None or (uncond.is_contiguous() and uncond.numel() == lat.numel())
+    dots = torch.empty(2, device=lat.device, dtype=f32) if cfg_star else None
+    c = (ctypes.c_float * 8)(coef["sigma"], coef["ca"], coef["cb"], coef["cc"], coef["cd"], coef["pp"], coef["pq"], coef["pr"])
+    _lib.call("b200_cfg_unipc_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), x_last.data_ptr(), m0.data_ptr(),
+              m1.data_ptr(), ctypes.addressof(c), int(coef["use_corrector"]), _p(dots), lat.numel(), _stream())
     return lat

@@ -25,12 +25,87 @@ def euler_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
     return [float(v) for v in t]
 
 
+class UniPCSchedule:
+    """Host side of FlowUniPCMultistepScheduler (shared/utils/fm_solvers_unipc.py), WanGP's default `sample_solver="unipc"`
+    (any2video.py:518-522): solver_order 2, bh2, predict_x0, flow_prediction, lower_order_final, corrector on every step > 0.
+    Every tensor update of one `step()` is a linear combination of {x, v, last_sample, x0_{i-1}, x0_{i-2}}; this class computes
+    the scalar coefficients (float64) and `ops.cfg_unipc_step_` applies them in ONE kernel fused with the CFG combine:
+        x0 = x - sigma_i v                                                   convert_model_output (:300-333)
+        xc = ca x_last + cb m0 + cc m1 + cd x0      (steps > 0, else xc = x)  multistep_uni_c_bh_update (:500-640)
+        xn = pp xc + pq x0 + pr m0                                            multistep_uni_p_bh_update (:345-470)
+    with m0 = x0_{i-1}, m1 = x0_{i-2}."""
+
+    def __init__(self, num_steps, shift=5.0, num_train_timesteps=1000):
+        # __init__ (:108-138): sigma_max/min of the training schedule with shift 1; set_timesteps (:158-225)
+        train = 1.0 - np.linspace(1, 1 / num_train_timesteps, num_train_timesteps)[::-1]
+        sig = np.linspace(float(np.float32(train[0])), float(np.float32(train[-1])), num_steps + 1)[:-1]
+        sig = shift * sig / (1 + (shift - 1) * sig)
+        self.timesteps = [int(v) for v in (sig * num_train_timesteps).astype(np.int64)]      # int64 truncation, as the reference
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32).astype(np.float64)
+        self.num_steps, self.solver_order = num_steps, 2
+        self.reset()
+
+    def reset(self):
+        self.lower_order_nums, self.this_order = 0, 1
+
+    @staticmethod
+    def _lam(sigma):
+        with np.errstate(divide="ignore"):
+            return np.log(1.0 - sigma) - np.log(sigma)
+
+    def _bh(self, i_t, i_s0, i_prev, order):
+        """Common part of UniP / UniC for the update from sigma[i_s0] to sigma[i_t]: (sigma ratio, alpha_t*h_phi_1, alpha_t*B_h, rk,
+        R, b) -- :392-447 / :571-612."""
+        sg = self.sigmas
+        sigma_t, sigma_s0 = sg[i_t], sg[i_s0]
+        alpha_t = 1.0 - sigma_t
+        h = self._lam(sigma_t) - self._lam(sigma_s0)
+        hh = -h
+        with np.errstate(invalid="ignore", over="ignore"):
+            h_phi_1 = np.expm1(hh)
+            B_h = np.expm1(hh)
+            rks = []
+            if order == 2:
+                rks.append((self._lam(sg[i_prev]) - self._lam(sigma_s0)) / h)
+            rks.append(1.0)
+            rks = np.array(rks)
+            R, b, h_phi_k, fact = [], [], h_phi_1 / hh - 1, 1
+            for k in range(1, order + 1):
+                R.append(rks ** (k - 1))
+                b.append(h_phi_k * fact / B_h)
+                fact *= k + 1
+                h_phi_k = h_phi_k / hh - 1 / fact
+        return sigma_t / sigma_s0, alpha_t * h_phi_1, alpha_t * B_h, rks[0], np.stack(R), np.array(b)
+
+    def coefficients(self, i):
+        """Scalars of step i (call in order i = 0, 1, ...): dict(sigma, use_corrector, ca, cb, cc, cd, pp, pq, pr)."""
+        c = dict(sigma=float(self.sigmas[i]), use_corrector=i > 0, ca=0.0, cb=0.0, cc=0.0, cd=0.0)
+        if i > 0:                                                     # UniC over sigma[i-1] -> sigma[i] with the PREVIOUS step's order
+            order = self.this_order
+            ratio, a_phi, a_bh, rk, R, b = self._bh(i, i - 1, i - 2, order)
+            rhos = np.array([0.5]) if order == 1 else np.linalg.solve(R, b)
+            k1 = rhos[0] / rk if order == 2 else 0.0
+            c.update(ca=ratio, cb=-a_phi + a_bh * (k1 + rhos[-1]), cc=-a_bh * k1, cd=-a_bh * rhos[-1])
+        # order of this step's predictor (:707-716): lower_order_final + multistep warm-up
+        self.this_order = min(min(self.solver_order, self.num_steps - i), self.lower_order_nums + 1)
+        ratio, a_phi, a_bh, rk, _, _ = self._bh(i + 1, i, i - 1, self.this_order)
+        k1 = 0.5 / rk if self.this_order == 2 else 0.0                # rhos_p = [0.5] for order 2 (:453-455)
+        c.update(pp=ratio, pq=-a_phi + a_bh * k1, pr=-a_bh * k1)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        return {k: (v if isinstance(v, bool) else float(v)) for k, v in c.items()}
+
+
 class WanDenoiser:
     """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
 
     def __init__(self, model, model2=None, vae=None, num_steps=50, shift=12.0, guide_scale=4.0, guide2_scale=3.0,
-                 switch_threshold=875, device="cuda", cfg_star_switch=False, cfg_zero_step=-1, cfg_group=None, cfg_rank=0):
+                 switch_threshold=875, device="cuda", cfg_star_switch=False, cfg_zero_step=-1, cfg_group=None, cfg_rank=0,
+                 sample_solver="euler"):
         self.model, self.model2, self.vae = model, model2, vae
+        for m in (model, model2):
+            if m is not None and hasattr(m, "cache_context"):
+                m.cache_context = True           # prompts are fixed for the whole schedule: project the text once (SURVEY.md 8f.4)
         # CFG-pair split (SURVEY.md section 8e, BASELINE configs[2]): the two ranks of `cfg_group` each run ONE branch
         # (cfg_rank 0 = cond, 1 = uncond) and exchange the fp32 prediction (19 MB at 720p x 81f) once per step; both then
         # apply the identical combine + scheduler update, so the latents stay replicated without a second collective.
@@ -38,10 +113,13 @@ class WanDenoiser:
         self.cfg_star_switch, self.cfg_zero_step = cfg_star_switch, cfg_zero_step      # CFG-Zero* (any2video.py:1701-1722)
         self.device = torch.device(device)
         self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
-        self.timesteps = euler_timesteps(num_steps, shift)
+        if sample_solver not in ("euler", "unipc", ""):
+            raise NotImplementedError(f"sample_solver {sample_solver!r}: euler and unipc (the WanGP default) are built")
+        self.unipc = None if sample_solver == "euler" else UniPCSchedule(num_steps, shift)
+        self.timesteps = euler_timesteps(num_steps, shift) if self.unipc is None else [float(t) for t in self.unipc.timesteps] + [0.0]
         self.num_steps = num_steps
         self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
-        self._pred = None
+        self._pred, self._hist = None, None
 
     def expert(self, t):
         """(model, guidance scale) for timestep t (any2video.py:1437-1443: switch when t <= switch_threshold)."""
@@ -74,7 +152,16 @@ class WanDenoiser:
         if cond is None:
             return None
         # NB any2video.py:1719 is overwritten by :1722, so steps <= cfg_zero_step are ordinary un-rescaled CFG
-        self._combine_step(latents, cond, uncond, g, dt, self.cfg_star_switch and uncond is not None and i > self.cfg_zero_step)
+        star = self.cfg_star_switch and uncond is not None and i > self.cfg_zero_step
+        if self.unipc is None:
+            self._combine_step(latents, cond, uncond, g, dt, star)
+        else:
+            if i == 0 or self._hist is None or self._hist[0].shape != latents.shape:
+                self.unipc.reset()
+                self._hist = [torch.zeros_like(latents) for _ in range(3)]          # last_sample, x0_{i-1}, x0_{i-2}
+            x_last, m0, m1 = self._hist
+            ops.cfg_unipc_step_(latents, cond, uncond, g, x_last, m0, m1, self.unipc.coefficients(i), cfg_star=star)
+            self._hist = [x_last, m1, m0]                                           # the kernel stored x0_i into m1
         return latents
 
     @staticmethod

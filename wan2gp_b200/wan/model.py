@@ -63,7 +63,8 @@ class WanModel(torch.nn.Module):
         self._g = {}                            # global (non-block) packed weights
         self._freqs_cache = {}
         self._ctx_cache = None
-        self.cache_context = False              # optional: reuse step-invariant text projections
+        self.cache_context = False              # reuse step-invariant text projections across steps: the text
+        self._ckv_cache = {}                    # embedding (model.py:1856) and every block's cross-attention K/V (model.py:255-258)
         # optional: one CUDA graph per transformer block (launch-bound small configs); the per-block
         # interrupt poll of the reference stays between graph replays
         self.use_cuda_graphs = False
@@ -124,6 +125,7 @@ class WanModel(torch.nn.Module):
         self._pack_globals(sd)
         self.blocks = [self._pack_block(sd, f"blocks.{i}.") for i in range(self.num_layers)]
         self._ready = True
+        self._graphs, self._ctx_cache, self._ckv_cache = {}, None, {}          # captured graphs / cached projections used the old weights
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
     def init_synthetic(self, seed=0):
@@ -279,16 +281,20 @@ class WanModel(torch.nn.Module):
         e, e0 = self._time(t)
         yd = None if y is None else y.to(self.device, f32).contiguous()
         # text embedding per entry (model.py:1856); optionally cached across steps
-        ctx_emb = []
+        ctx_emb, ctx_keys = [], []
         for c in ctx_list:
             key = (c.data_ptr(), c._version, tuple(c.shape)) if self.cache_context else None
+            ctx_keys.append(key)
             if key is not None and self._ctx_cache is not None and key in self._ctx_cache:
                 ctx_emb.append(self._ctx_cache[key])
                 continue
             emb = self._text(c[0] if c.dim() == 3 else c)
             if key is not None:
+                if self._ctx_cache is not None and len(self._ctx_cache) >= 8:          # a new prompt: drop the old projections
+                    self._ctx_cache, self._ckv_cache = None, {}
                 self._ctx_cache = dict(self._ctx_cache or {})
                 self._ctx_cache[key] = emb
+                self._ctx_cache[("ref",) + key] = c    # keeps the prompt tensor alive: its address cannot be recycled while cached
             ctx_emb.append(emb)
         # patch embedding: one fp32 residual stream per (entry, batch item)
         streams = []
@@ -307,7 +313,11 @@ class WanModel(torch.nn.Module):
                 graphs["g"][idx].replay()
                 continue
             for i in range(n):
-                ckv = self._cross_kv(blk, ctx_emb[i])
+                ckv = self._ckv_cache.get((ctx_keys[i], idx)) if ctx_keys[i] is not None else None
+                if ckv is None:
+                    ckv = self._cross_kv(blk, ctx_emb[i])
+                    if ctx_keys[i] is not None:
+                        self._ckv_cache[(ctx_keys[i], idx)] = ckv            # 2 * L_text * D bf16 per block (10 MB at 14B)
                 for s in streams[i]:
                     self._block(blk, s, e0, ctx_emb[i], cos, sin, ckv)
         if graphs is not None:
