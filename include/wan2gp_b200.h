@@ -182,6 +182,11 @@ int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int of
                         const void* residual, void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t,
                         long long ost_h, long long ost_w, void* stream);
 
+/* seam cross-fade of the tiled VAE decode / encode (vae.py:664-674 blend_v / blend_h, used by spatial_tiled_decode :676-723 and
+ * spatial_tiled_encode :841-881): the first min(extent, ...) rows (vertical=1) or columns (vertical=0) of fp32 planar tile
+ * b [planes,hb,wb] become a (1 - k/ext) + b (k/ext) with a = the last rows / columns of the neighbour tile a [planes,ha,wa] */
+int b200_blend_edge_f32(const float* a, float* b, long long planes, int ha, int wa, int hb, int wb, int extent, int vertical, void* stream);
+
 /* ---- Wan VAE encode helpers (models/wan/modules/vae.py Encoder3d :318-427, Resample :134-143) ---- */
 /* planar fp32 [C,P] -> channels-last bf16 [P,Cpad] with zero channels C..Cpad-1 (Cpad % 8 == 0): video [3,T,H,W] -> conv operand */
 int b200_planar_to_cl_pad(const float* x, void* y_bf16, int C, long long P, int Cpad, void* stream);

@@ -194,6 +194,37 @@ def run_hyvae10(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
 
 
+TILED_CASES = {"vae_tiled_dec": ("dec", (16, 2, 12, 14), 64, 4), "vae_tiled_enc": ("enc", (3, 5, 96, 112), 64, 5)}
+
+
+def run_vae_tiled(name):
+    """Reference WanVAE_.spatial_tiled_decode / spatial_tiled_encode (vae.py:676-723, 841-881) and the streaming tiled uint8 writer
+    decode_to_cpu_uint8 (:741-839) on the tiny config."""
+    ref = load_reference()
+    kind, shape, tile, seed = TILED_CASES[name]
+    cfg = synth.VAE_CFG_TINY
+    vae = ref.WanVAE_(dim=cfg["dim"], z_dim=cfg["z_dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], attn_scales=[],
+                      temperal_downsample=[False, True, True], dropout=0.0).eval().requires_grad_(False)
+    vae.load_state_dict(synth.make_vae_state_dict(cfg, seed, encoder=True))
+    scale = [torch.tensor(synth.VAE_MEAN), 1.0 / torch.tensor(synth.VAE_STD)]
+    with torch.no_grad():
+        if kind == "dec":
+            z = synth._normal((1,) + shape, 1.0, seed, "input.z", "cpu")
+            out = vae.spatial_tiled_decode(z.clone(), scale, tile)
+            # decode_to_cpu_uint8 un-normalises each latent tile IN PLACE on `latent_source[...].to(device, dtype)` (vae.py:796-799); on a
+            # GPU the latents were moved to the CPU first (:746-747) so .to() copies, but in this all-CPU fp32 run .to() returns the
+            # VIEW and overlapping tiles would be un-normalised twice.  Feeding fp64 latents with _model_dtype = fp32 restores the copy
+            # (= the production behaviour) without touching reference code.
+            vae._model_dtype = torch.float32
+            u8 = vae.decode_to_cpu_uint8(z.double(), scale, tile_size=tile)
+            np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), u8=u8.numpy(), tile=tile)
+        else:
+            x = synth._normal((1,) + shape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+            out = vae.spatial_tiled_encode(x, scale, tile)
+            np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), tile=tile)
+    print(f"{name}: reference tiled {kind} out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+
+
 def run_unipc(name):
     """Trajectory of the reference FlowUniPCMultistepScheduler on seeded fp64 inputs (same generator as tests/test_unipc_cpu.py)."""
     from oracle.refshim import load_reference_unipc
@@ -216,4 +247,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_vae)(n)

@@ -72,8 +72,10 @@ def test_error_behaviour():
         m([x.clone()], torch.tensor([1.0, 2.0, 3.0]), [ctx], pipeline=Pipe())
     with pytest.raises(_lib.B200Error):
         ops.gemm(torch.zeros(4, 12, device="cuda", dtype=bf16), torch.zeros(8, 12, device="cuda", dtype=bf16))     # K % 8
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                                   # no weights loaded: loud failure, no fallback
         WanVAE(device="cuda").decode([torch.zeros(16, 1, 2, 2)], tile_size=256)
+    with pytest.raises(NotImplementedError):
+        WanVAE(device="cuda").decode([torch.zeros(16, 1, 2, 2)], tile_size=0, any_end_frame=True)
 
 
 @pytest.mark.parametrize("C", [16, 96, 384, 1024])

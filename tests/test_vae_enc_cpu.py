@@ -104,3 +104,21 @@ def test_head_fold():
     m = inv_std[:, None] * w1[:z]
     wf, bf = torch.einsum("om,mctyx->octyx", m, wh), inv_std * (w1[:z] @ bh + b1[:z] - mean)
     assert rel_l2(F.conv3d(pad(x), wf, bf), want) < 1e-5
+
+
+def test_tiled_oracle_matches_reference():
+    """Tiled decode / encode: the tiling + seam cross-fade restatement == WanVAE_.spatial_tiled_decode /
+    spatial_tiled_encode, and uint8 of the blended fp32 frames == the reference's streaming tiled writer decode_to_cpu_uint8."""
+    from oracle import vae_oracle
+    cfg = synth.VAE_CFG_TINY
+    g = load_golden("vae_tiled_dec")
+    sd = synth.make_vae_state_dict(cfg, 4, encoder=True)
+    z = synth._normal((1, 16, 2, 12, 14), 1.0, 4, "input.z", "cpu")[0]
+    out = vae_oracle.vae_decode_tiled(sd, z, synth.VAE_MEAN, synth.VAE_STD, int(g["tile"]), cfg)
+    assert rel_l2(out, g["out"][0]) < 5e-6
+    d = (vae_oracle.frames_to_uint8(out).int() - torch.from_numpy(g["u8"][0]).int()).abs()
+    assert d.max() <= 1 and (d > 0).float().mean() < 1e-3
+    g = load_golden("vae_tiled_enc")
+    sd = synth.make_vae_state_dict(cfg, 5, encoder=True)
+    x = synth._normal((1, 3, 5, 96, 112), 0.5, 5, "input.video", "cpu").clamp_(-1, 1)[0]
+    assert rel_l2(vae_oracle.vae_encode_tiled(sd, x, synth.VAE_MEAN, synth.VAE_STD, int(g["tile"]), cfg), g["out"][0]) < 5e-6

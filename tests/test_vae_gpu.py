@@ -161,7 +161,36 @@ def test_vae_encode_wide_rows_and_roundtrip():
     assert mu.shape == (16, 2, 2, 52) and rel_l2(mu.cpu(), emu) < 2.5e-2
     rec = vae.decode([mu])[0]
     assert rec.shape == (3, 5, 16, 416) and torch.isfinite(rec).all()
-    with pytest.raises(NotImplementedError):
-        vae.encode([x.cuda()], tile_size=256)
+    with pytest.raises(ValueError):
+        vae.encode([x.cuda()], tile_size=20)
     with pytest.raises(ValueError):
         vae.encode([x[:, :4].cuda()], tile_size=0)
+
+
+def test_vae_tiled_decode_encode():
+    """tile_size > 0: latent / video tiles with 25 % overlap, each run through the whole-clip decoder / encoder, seams
+    cross-faded by b200_blend_edge_f32 -- vs the reference's spatial_tiled_decode, its streaming tiled uint8 writer and
+    spatial_tiled_encode (fixtures)."""
+    from wan2gp_b200.wan import WanVAE
+    cfg = synth.VAE_CFG_TINY
+    g = load_golden("vae_tiled_dec")
+    tile = int(g["tile"])
+    vae = WanVAE(state_dict=synth.make_vae_state_dict(cfg, 4, encoder=True), cfg=cfg)
+    z = synth._normal((1, 16, 2, 12, 14), 1.0, 4, "input.z", "cpu")[0]
+    got = vae.decode([z.cuda()], tile_size=tile)[0].cpu()
+    ref = g["out"][0].clamp(-1, 1)
+    print(f"tiled decode: vs reference rel-L2 {rel_l2(got, ref):.3e}, PSNR {psnr(got, ref, 2.0):.1f} dB")
+    assert got.shape == ref.shape and psnr(got, ref, 2.0) > 35.0 and rel_l2(got, ref) < 2.5e-2
+    u8 = vae.decode_to_cpu_uint8([z.cuda()], tile_size=tile, target_frames=4, target_height=90, target_width=100, frame_start=1)[0]
+    want = torch.from_numpy(g["u8"][0])[:, 1:5, :90, :100]
+    d = (u8.int() - want.int()).abs().float()
+    print(f"tiled uint8: mean |d| {d.mean():.3f} max {d.max():.0f}")
+    assert u8.shape == want.shape and d.mean() < 1.5
+    # a single tile (tile_size >= frame) must equal the un-tiled decode bit for bit
+    assert torch.equal(vae.decode([z.cuda()], tile_size=128)[0], vae.decode([z.cuda()], tile_size=0)[0])
+    g = load_golden("vae_tiled_enc")
+    vae = WanVAE(state_dict=synth.make_vae_state_dict(cfg, 5, encoder=True), cfg=cfg)
+    x = synth._normal((1, 3, 5, 96, 112), 0.5, 5, "input.video", "cpu").clamp_(-1, 1)[0]
+    mu = vae.encode([x.cuda()], tile_size=int(g["tile"]))[0].cpu()
+    print(f"tiled encode: vs reference rel-L2 {rel_l2(mu, g['out'][0]):.3e}")
+    assert mu.shape == g["out"][0].shape and rel_l2(mu, g["out"][0]) < 2.5e-2

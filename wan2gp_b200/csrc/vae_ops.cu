@@ -318,6 +318,36 @@ extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tile seams of the tiled VAE decode / encode (vae.py:664-674 blend_v / blend_h): the first `ext` rows (columns) of tile b become a
+// linear cross-fade from the last `ext` rows (columns) of its upper (left) neighbour a:  b = a (1 - k/ext) + b (k/ext).
+// a [planes, ha, wa], b [planes, hb, wb] fp32 planar; vertical: wa == wb, horizontal: ha == hb.
+__global__ void blend_edge_kernel(const float* __restrict__ a, float* __restrict__ b, long long planes, int ha, int wa, int hb, int wb,
+                                  int ext, int vertical) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = vertical ? ext : hb, cols = vertical ? wb : ext;
+    if (i >= planes * rows * cols) return;
+    const int x = (int)(i % cols), y = (int)((i / cols) % rows);
+    const long long pl = i / ((long long)cols * rows);
+    const int k = vertical ? y : x;
+    const float wgt = (float)k / (float)ext;
+    const float av = vertical ? a[(pl * ha + (ha - ext + y)) * wa + x] : a[(pl * ha + y) * wa + (wa - ext + x)];
+    float* bp = b + (pl * hb + y) * wb + x;
+    *bp = av * (1.f - wgt) + *bp * wgt;
+}
+extern "C" int b200_blend_edge_f32(const float* a, float* b, long long planes, int ha, int wa, int hb, int wb, int extent, int vertical,
+                                   void* stream) {
+    if (!a || !b || planes <= 0 || ha <= 0 || wa <= 0 || hb <= 0 || wb <= 0 || (vertical ? wa != wb : ha != hb))
+        return b200_set_error(B200_ERR_ARG, "blend_edge_f32: bad argument");
+    int ext = extent;
+    if (vertical) { if (ext > ha) ext = ha; if (ext > hb) ext = hb; } else { if (ext > wa) ext = wa; if (ext > wb) ext = wb; }
+    if (ext <= 0) return B200_OK;
+    const long long n = planes * (vertical ? (long long)ext * wb : (long long)hb * ext);
+    blend_edge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, planes, ha, wa, hb, wb, ext, vertical);
+    CHECK_LAUNCH("blend_edge_f32");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // VAE encode helpers
 // planar fp32 [C, P] -> channels-last bf16 [P, Cpad], channels >= C zero (video [3,T,H,W] -> 8-channel TMA-legal operand)
 __global__ void planar_to_cl_pad_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, long long P, int Cpad8) {

@@ -362,6 +362,32 @@ class WanVAEEncoder(torch.nn.Module):
         return torch.stack([self.encode_frames(xi, mean, inv_std) for xi in x], 0)
 
 
+def _blend(a, b, extent, vertical):
+    """blend_v / blend_h (vae.py:664-674) in place on tile b; a, b fp32 planar [C,F,h,w]."""
+    _lib.call("b200_blend_edge_f32", a.data_ptr(), b.data_ptr(), a.shape[0] * a.shape[1], a.shape[2], a.shape[3], b.shape[2], b.shape[3],
+              int(extent), int(vertical), _s())
+    return b
+
+
+def spatial_tiles(x, tile, stride, fn, blend_extent, row_limit):
+    """The tiling loop shared by spatial_tiled_decode (vae.py:676-723) and spatial_tiled_encode (:841-881): `fn` maps the crop
+    x[..., i:i+tile, j:j+tile] to a contiguous fp32 [C,F,h',w'] tile; each tile is cross-faded with its (already blended) upper
+    and left neighbours over `blend_extent` rows / columns, cropped to `row_limit` and written into the result."""
+    H, W = x.shape[-2:]
+    rows = [[fn(x[..., i:i + tile, j:j + tile].contiguous()) for j in range(0, W, stride)] for i in range(0, H, stride)]
+    out_rows = []
+    for i, row in enumerate(rows):
+        out = []
+        for j, t in enumerate(row):
+            if i > 0:
+                _blend(rows[i - 1][j], t, blend_extent, True)
+            if j > 0:
+                _blend(row[j - 1], t, blend_extent, False)
+            out.append(t[:, :, :row_limit, :row_limit])
+        out_rows.append(torch.cat(out, -1))
+    return torch.cat(out_rows, -2)
+
+
 class WanVAE:
     """Mirror of models/wan/modules/vae.py::WanVAE (:935-1027)."""
 
@@ -389,20 +415,33 @@ class WanVAE:
         """vae.py:968-1000 picks a tile size from free VRAM; on a 180 GB B200 the whole clip is decoded untiled."""
         return 0
 
+    def _tiled_decode(self, u, tile_size):
+        """WanVAE_.spatial_tiled_decode (vae.py:676-723): latent tiles of tile_size/8 with 25 % overlap, each decoded as a whole clip,
+        seams cross-faded.  get_VAE_tile_size() returns 0 on a B200 (whole clip un-tiled); an explicit tile_size > 0 (outputs beyond
+        1080p, vae.py:975-978) reproduces the reference's tiled result."""
+        tile_size = int(tile_size)
+        if tile_size < 16:
+            raise ValueError("VAE tile_size must be >= 16 pixels")
+        tl = int(tile_size / 8)
+        mean, std = self.mean, self.std
+        fn = lambda z: self.model.decode_frames(z, mean, std)                                        # noqa: E731
+        return spatial_tiles(u.to(self.device, f32), tl, int(tl * 0.75), fn, int(tile_size * 0.25), tile_size - int(tile_size * 0.25))
+
     def decode(self, zs, tile_size=0, any_end_frame=False):
         """list of [16,Tl,h,w] -> list of fp32 [3,F,H,W] clamped to [-1,1] (vae.py:1012-1017)."""
         if tile_size and tile_size > 0:
-            raise NotImplementedError("tiled decode is a 'next' row (SURVEY.md 8f.3); B200 decodes untiled")
+            if any_end_frame:
+                raise NotImplementedError("any_end_frame decode is outside the t2v/i2v2_2 hot path")
+            return [self._tiled_decode(u, tile_size).clamp_(-1, 1) for u in zs]
         return [self.model.decode(u.unsqueeze(0), self.scale, any_end_frame)[0].clamp_(-1, 1) for u in zs]
 
     def decode_to_cpu_uint8(self, zs, tile_size=0, target_frames=None, target_height=None, target_width=None,
                             any_end_frame=False, frame_start=0):
         """vae.py:1021-1027 -> :741-767: uint8 CPU frames, round(clamp((clamp(x,-1,1)+1)*127.5, 0, 255))."""
-        if tile_size and tile_size > 0:
-            raise NotImplementedError("tiled decode is a 'next' row (SURVEY.md 8f.3); B200 decodes untiled")
         outs = []
         for u in zs:
-            fr = self.model.decode(u.unsqueeze(0), self.scale, any_end_frame)[0]
+            # tile_size > 0: same tiles / seams as the reference's streaming tiled writer (vae.py:741-839), blended in fp32 first
+            fr = self._tiled_decode(u, tile_size) if tile_size and tile_size > 0 else self.model.decode(u.unsqueeze(0), self.scale, any_end_frame)[0]
             n = fr.shape[1]
             fs = min(max(0, int(frame_start or 0)), n)
             fe = n if target_frames is None else min(n, fs + int(target_frames))
@@ -414,8 +453,19 @@ class WanVAE:
 
     def encode(self, videos, tile_size=0, any_end_frame=False):
         """list of [3,T,H,W] videos in [-1,1] -> list of normalised latents fp32 [16,1+(T-1)/4,H/8,W/8] (vae.py:1002-1010), un-tiled:
-        the reference's default tile_size=256 selects spatial_tiled_encode (tile + blend to fit small GPUs); here the whole clip is
-        encoded at once, which is the reference's tile_size=0 branch."""
+        the reference's default tile_size=256 selects spatial_tiled_encode (tile + blend to fit small GPUs); the default here is the
+        whole clip at once = the reference's tile_size=0 branch; tile_size > 0 reproduces the tiled branch."""
         if tile_size and tile_size > 0:
-            raise NotImplementedError("tiled encode is a 'next' row (SURVEY.md 8f.3); B200 encodes untiled (pass tile_size=0)")
+            # WanVAE_.spatial_tiled_encode (vae.py:841-881): video tiles of tile_size with 25 % overlap, latents cross-faded.  The
+            # latent normalisation is affine and the cross-fade weights sum to 1, so normalising each tile first is the same map.
+            if any_end_frame:
+                raise NotImplementedError("any_end_frame encode is outside the t2v/i2v2_2 hot path")
+            tile_size = int(tile_size)
+            if tile_size < 32 or tile_size % 8:
+                raise ValueError("VAE encode tile_size must be a multiple of 8, >= 32")
+            tl = tile_size // 8
+            mean, inv_std = self.mean.to(self.device), (1.0 / self.std).to(self.device)
+            fn = lambda x: self.encoder_model.encode_frames(x, mean, inv_std)                        # noqa: E731
+            return [spatial_tiles(u.to(self.device, f32), tile_size, int(tile_size * 0.75), fn, int(tl * 0.25), tl - int(tl * 0.25))
+                    for u in videos]
         return [self.encoder_model.encode(u.unsqueeze(0), self.scale, any_end_frame)[0] for u in videos]
