@@ -187,7 +187,7 @@ def test_vae_tiled_decode_encode():
     print(f"tiled uint8: mean |d| {d.mean():.3f} max {d.max():.0f}")
     assert u8.shape == want.shape and d.mean() < 1.5
     # a single tile (tile_size >= frame) must equal the un-tiled decode bit for bit
-    assert torch.equal(vae.decode([z.cuda()], tile_size=128)[0], vae.decode([z.cuda()], tile_size=0)[0])
+    assert torch.equal(vae.decode([z.cuda()], tile_size=256)[0], vae.decode([z.cuda()], tile_size=0)[0])
     g = load_golden("vae_tiled_enc")
     vae = WanVAE(state_dict=synth.make_vae_state_dict(cfg, 5, encoder=True), cfg=cfg)
     x = synth._normal((1, 3, 5, 96, 112), 0.5, 5, "input.video", "cpu").clamp_(-1, 1)[0]
