@@ -151,7 +151,7 @@ int b200_pad_replicate_cl(const void* x, void* y, int T, int H, int W, int C, in
 int b200_rms_silu_pad_cl(const void* x, const float* gamma, void* y, int T, int H, int W, int C, int silu, int t0, int Tc, int pt,
                          int ph, int pw, void* stream);
 /* "valid" conv over an explicitly padded input xpad [T+kt-1, H+kh-1, W+kw-1, Cin]; T,H,W = output dims; other arguments as
- * b200_conv3d_cl (out_mode 0 or 2) */
+ * b200_conv3d_cl (out_mode 0, 2, or 3 = fp32 channels-last [T,H,W,Cout] with the optional bf16 residual) */
 int b200_conv3d_cl_prepadded(const void* xpad, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                              int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, void* stream);
 /* planar fp32 [C,P] -> channels-last bf16 [P, C*rep] with each channel repeated rep times (z.repeat_interleave, :489-490) */
@@ -181,6 +181,13 @@ int b200_group_norm_apply_cl(const void* x, const float* scale_shift, void* y, i
 int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int off_t, int off_h, int off_w, const void* w, const float* bias,
                         const void* residual, void* out, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, long long ost_t,
                         long long ost_h, long long ost_w, void* stream);
+
+/* ---- Hunyuan 1.5 VAE encode helpers (hyvideo/vae/hunyuanvideo_15_vae.py Downsample :253-296, Encoder :342-430) ---- */
+/* Downsample tail: space(-time) -> channel shuffle of the conv output h [T,H,W,Co/F] plus the group-mean shortcut of the shuffled
+ * input x [T,H,W,Ci] -> out bf16 [1+(T-1)/2 | T, H/2, W/2, Co]; F = 8 (temporal) or 4; ldh = channel pitch of h (>= Co/F) */
+int b200_hy_downsample_cl(const void* h, int ldh, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal, void* stream);
+/* y[p,c] = mean over g < r of x[p, c*r+g]: bf16 [P,C] -> bf16 [P,C/r] (Encoder.forward shortcut, :424-425) */
+int b200_group_mean_cl(const void* x, void* y, long long P, int C, int r, void* stream);
 
 /* seam cross-fade of the tiled VAE decode / encode (vae.py:664-674 blend_v / blend_h, used by spatial_tiled_decode :676-723 and
  * spatial_tiled_encode :841-881): the first min(extent, ...) rows (vertical=1) or columns (vertical=0) of fp32 planar tile

@@ -225,6 +225,25 @@ def run_vae_tiled(name):
     print(f"{name}: reference tiled {kind} out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
 
 
+HYVAE_ENC_CASES = {"hyvae_enc_tiny": ("hyvae_tiny", (3, 5, 16, 24), 2), "hyvae_enc_small": ("hyvae_small", (3, 5, 32, 48), 3)}
+
+
+def run_hyvae_enc(name):
+    """Reference Hunyuan 1.5 VAE Encoder (hunyuanvideo_15_vae.py:342-430) = AutoencoderKLConv3D.encode with tiling off (:866-887)."""
+    from oracle.refshim import load_reference_hyvae
+    hv = load_reference_hyvae()
+    cfg_name, xshape, seed = HYVAE_ENC_CASES[name]
+    cfg = synth.HYVAE_CONFIGS[cfg_name]
+    enc = hv.Encoder(in_channels=3, z_channels=cfg["z_channels"], block_out_channels=list(reversed(cfg["block_out_channels"])),
+                     num_res_blocks=cfg["num_res_blocks"], ffactor_spatial=cfg["ffactor_spatial"], ffactor_temporal=cfg["ffactor_temporal"]).eval().requires_grad_(False)
+    enc.load_state_dict(synth.make_hyvae_state_dict(cfg, seed, encoder=True))
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+    with torch.no_grad():
+        out = enc(x)
+    print(f"{name}: reference HY-1.5 VAE Encoder out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
+
+
 def run_unipc(name):
     """Trajectory of the reference FlowUniPCMultistepScheduler on seeded fp64 inputs (same generator as tests/test_unipc_cpu.py)."""
     from oracle.refshim import load_reference_unipc
@@ -247,4 +266,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_vae)(n)

@@ -9,7 +9,7 @@ external download (hunyuan.py:329-336); fixtures use reduced configs and the ups
 import torch
 import torch.nn.functional as F
 
-from wan2gp_b200.synth import hyvae_layout
+from wan2gp_b200.synth import hyvae_encoder_layout, hyvae_layout
 
 
 def _q(t, on):
@@ -95,3 +95,45 @@ def hyvae_decode(sd, cfg, z, emulate_bf16=False):
             h = upsample(sd, f"up.{i}.upsample.", h, up[1], up[2], em)
     h = _q(F.silu(rms_norm_c(h, sd["norm_out.gamma"])), em)
     return causal_conv3d_rep(h, sd["conv_out.conv.weight"], sd["conv_out.conv.bias"], em)
+
+
+def downsample(sd, p, x, cout, temporal, em):
+    """Downsample (:253-296): conv to cout/factor channels, space(-time) -> channel shuffle, group-mean shortcut of the shuffled input."""
+    Cin, T, H, W = x.shape
+    h = _q(causal_conv3d_rep(x, sd[p + "conv.conv.weight"], sd[p + "conv.conv.bias"], em), em)
+
+    def shuf(t, r1):            # "c (f r1) (h r2) (w r3) -> (r1 r2 r3 c) f h w"
+        c, f = t.shape[0], t.shape[1] // r1
+        return t.reshape(c, f, r1, H // 2, 2, W // 2, 2).permute(2, 4, 6, 0, 1, 3, 5).reshape(r1 * 4 * c, f, H // 2, W // 2)
+
+    def gmean(t, g):
+        return t.reshape(cout, g, *t.shape[1:]).mean(1)
+    factor = 8 if temporal else 4
+    gs = factor * Cin // cout
+    if temporal:
+        hf = shuf(h[:, :1], 1)
+        hh = torch.cat([torch.cat([hf, hf], 0), shuf(h[:, 1:], 2)], 1) if T > 1 else torch.cat([hf, hf], 0)
+        xf = gmean(shuf(x[:, :1], 1), gs // 2)
+        sc = torch.cat([xf, gmean(shuf(x[:, 1:], 2), gs)], 1) if T > 1 else xf
+    else:
+        hh, sc = shuf(h, 1), gmean(shuf(x, 1), gs)
+    return _q(hh + sc, em)
+
+
+def hyvae_encode(sd, cfg, x, emulate_bf16=False):
+    """x [3, 1+4k, H, W] fp32 -> moments [2 zc, 1+k, H/fs, W/fs] fp32 = (mean, logvar) of the posterior (Encoder.forward, :395-430)."""
+    em = emulate_bf16
+    h = _q(causal_conv3d_rep(_q(x.float(), em), sd["conv_in.conv.weight"], sd["conv_in.conv.bias"], em), em)
+    levels, c_mid = hyvae_encoder_layout(cfg)
+    for i, (blocks, down) in enumerate(levels):
+        for j in range(len(blocks)):
+            h = resnet(sd, f"down.{i}.block.{j}.", h, em)
+        if down is not None:
+            h = downsample(sd, f"down.{i}.downsample.", h, down[1], down[2], em)
+    h = resnet(sd, "mid.block_1.", h, em)
+    h = attn_block(sd, "mid.attn_1.", h, em)
+    h = resnet(sd, "mid.block_2.", h, em)
+    zc2 = 2 * cfg["z_channels"]
+    sc = h.reshape(zc2, c_mid // zc2, *h.shape[1:]).mean(1)                    # "b (c r) f h w -> b c r f h w" mean over r
+    y = _q(F.silu(rms_norm_c(h, sd["norm_out.gamma"])), em)
+    return causal_conv3d_rep(y, sd["conv_out.conv.weight"], sd["conv_out.conv.bias"], em) + _q(sc, em)

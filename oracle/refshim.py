@@ -235,8 +235,8 @@ def load_reference_hyvae():
     m = types.ModuleType("models.hyvideo.vae")
     m.__path__ = [os.path.join(REFERENCE_ROOT, "models/hyvideo/vae")]
     sys.modules["models.hyvideo.vae"] = m
-    from models.hyvideo.vae.hunyuanvideo_15_vae import Decoder
-    _loaded_hyvae = types.SimpleNamespace(Decoder=Decoder)
+    from models.hyvideo.vae.hunyuanvideo_15_vae import Decoder, Encoder
+    _loaded_hyvae = types.SimpleNamespace(Decoder=Decoder, Encoder=Encoder)
     return _loaded_hyvae
 
 

@@ -185,3 +185,28 @@ def test_hyvae10_time_slicing_and_surface():
     emu = hyvae10_oracle.hyvae10_decode(sd, cfg2, z[0].cpu(), emulate_bf16=True)
     print(f"hyvae10 full-attention: vs bf16-emulating oracle {rel_l2(got, emu):.3e}")
     assert rel_l2(got, emu) < 6e-2
+
+
+@pytest.mark.parametrize("name,cfg_name,xshape,seed", [("hyvae_enc_tiny", "hyvae_tiny", (3, 5, 16, 24), 2), ("hyvae_enc_small", "hyvae_small", (3, 5, 32, 48), 3)])
+def test_hyvae15_encode(name, cfg_name, xshape, seed):
+    """Hunyuan 1.5 VAE encode through the AutoencoderKLConv3D surface (`.encode(x).latent_dist.mode()`): vs the reference Encoder
+    (fixture) and the bf16-emulating oracle, rel-L2 <= 2.5e-2."""
+    from oracle import hyvae_oracle
+    from wan2gp_b200.hyvideo import AutoencoderKLConv3D
+    cfg = synth.HYVAE_CONFIGS[cfg_name]
+    sd = synth.make_hyvae_state_dict(cfg, seed, encoder=True)
+    full = {"encoder." + k: v for k, v in sd.items()}
+    full.update({"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, seed).items()})
+    vae = AutoencoderKLConv3D(latent_channels=cfg["z_channels"], block_out_channels=list(reversed(cfg["block_out_channels"])),
+                              layers_per_block=cfg["num_res_blocks"], ffactor_spatial=cfg["ffactor_spatial"], ffactor_temporal=cfg["ffactor_temporal"])
+    vae.load_state_dict(full)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+    post = vae.encode(x.cuda()).latent_dist
+    got = torch.cat([post.mean, post.logvar], 1)[0].cpu()
+    g = load_golden(name)["out"][0]
+    emu = hyvae_oracle.hyvae_encode(sd, cfg, x[0], emulate_bf16=True)
+    print(f"{name}: vs reference {rel_l2(got, g):.3e}; vs bf16-emulating oracle {rel_l2(got, emu):.3e}")
+    assert got.shape == g.shape and rel_l2(got, g) < 2.5e-2 and rel_l2(got, emu) < 2.5e-2
+    assert torch.equal(post.mode(), post.mean) and post.sample(torch.Generator().manual_seed(0)).shape == post.mean.shape
+    rec = vae.decode(post.mode(), return_dict=False)[0]                    # encode -> decode round trip runs end to end
+    assert rec.shape == (1,) + xshape and torch.isfinite(rec).all()

@@ -76,3 +76,15 @@ def test_post_quant_fold():
     want = F.conv3d(pad(F.conv3d(z, wq, bq)), wi, bi)
     wf, bf = torch.einsum("omtyx,mi->oityx", wi, wq.reshape(zc, zc)), bi + torch.einsum("omtyx,m->o", wi, bq)
     assert rel_l2(F.conv3d(pad(z), wf, bf), want) < 1e-5
+
+
+@pytest.mark.parametrize("name,cfg_name,xshape,seed", [("hyvae_enc_tiny", "hyvae_tiny", (3, 5, 16, 24), 2), ("hyvae_enc_small", "hyvae_small", (3, 5, 32, 48), 3)])
+def test_hyvae15_encode_oracle_matches_reference(name, cfg_name, xshape, seed):
+    """Hunyuan 1.5 VAE Encoder ('HY encode'): fp32 oracle == reference Encoder.forward on the committed fixture."""
+    from oracle import hyvae_oracle
+    cfg = synth.HYVAE_CONFIGS[cfg_name]
+    sd = synth.make_hyvae_state_dict(cfg, seed, encoder=True)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)[0]
+    g = load_golden(name)["out"][0]
+    out = hyvae_oracle.hyvae_encode(sd, cfg, x)
+    assert out.shape == g.shape and rel_l2(out, g) < 5e-6

@@ -46,6 +46,8 @@ SIGNATURES = {
     "b200_group_norm_apply_cl": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_conv3d_cl_view": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p],
+    "b200_hy_downsample_cl": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "b200_group_mean_cl": [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     "b200_blend_edge_f32": [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_planar_to_cl_pad": [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
     "b200_space_to_depth_cl": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -237,6 +237,12 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                     }
                                 }
                             }
+                            if (p.out_fp32) {                   // fp32 channels-last (latent moments of the Hunyuan VAE encoder)
+                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+                                #pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    if (j < ncols) op[j / 4] = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            } else {
                             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
                             #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -246,6 +252,7 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                     o.z = pack_bf16x2(f[j + 4], f[j + 5]); o.w = pack_bf16x2(f[j + 6], f[j + 7]);
                                     op[j / 8] = o;
                                 }
+                            }
                             }
                         }
                     }

@@ -318,6 +318,82 @@ extern "C" int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hunyuan 1.5 VAE encoder helpers (hunyuanvideo_15_vae.py Downsample :253-296, Encoder tail :423-430)
+// Downsample tail: space(-time) -> channel shuffle of the conv output h [T,H,W,Ch] (Ch = Co/F) plus the group-mean shortcut of the
+// same shuffle of x [T,H,W,Ci]  ->  out [To, H/2, W/2, Co];  F = 8 (temporal: To = 1 + (T-1)/2, first frame spatial-only and
+// duplicated over the two channel halves) or 4.  One thread = 8 consecutive output channels of one output pixel.
+__global__ void hy_downsample_cl_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                        int T, int H, int W, int Ci, int Co, int temporal, int ldh) {
+    const int C8 = Co >> 3, Ho = H >> 1, Wo = W >> 1;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Wo * C8) return;
+    const int wo = idx / C8, o0 = (idx - wo * C8) * 8;
+    const int ho = blockIdx.y, to = blockIdx.z;
+    const int F = temporal ? 8 : 4;                                      // ldh: channel pitch of h (>= Co/F; conv outputs are padded to 16)
+    const int Ch = Co / F;
+    const bool first = temporal && to == 0;
+    const int gs = first ? (F * Ci / Co) / 2 : F * Ci / Co;            // shortcut group size (:273, :279, :285)
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int oc = o0 + k;
+        // conv branch: which (r1, r2, r3, c) of h lands in output channel oc
+        int r, c;
+        if (first) { const int o2 = oc % (4 * Ch); r = o2 / Ch; c = o2 - r * Ch; }       // cat([h_first, h_first]) (:270)
+        else { r = oc / Ch; c = oc - r * Ch; }
+        const int r1 = (temporal && !first) ? (r >> 2) : 0, r2 = (r >> 1) & 1, r3 = r & 1;
+        const int tf = temporal ? (first ? 0 : 1 + 2 * (to - 1) + r1) : to;
+        float v = __bfloat162float(h[(((long long)tf * H + 2 * ho + r2) * W + 2 * wo + r3) * ldh + c]);
+        // shortcut: mean over gs consecutive channels of the shuffled x (channel j = r * Ci + c)
+        float acc = 0.f;
+        for (int g = 0; g < gs; ++g) {
+            const int j = oc * gs + g;
+            const int rr = j / Ci, cc = j - rr * Ci;
+            const int q1 = (temporal && !first) ? (rr >> 2) : 0, q2 = (rr >> 1) & 1, q3 = rr & 1;
+            const int tx = temporal ? (first ? 0 : 1 + 2 * (to - 1) + q1) : to;
+            acc += __bfloat162float(x[(((long long)tx * H + 2 * ho + q2) * W + 2 * wo + q3) * Ci + cc]);
+        }
+        o[k] = v + acc / (float)gs;
+    }
+    reinterpret_cast<uint4*>(out)[(((long long)to * Ho + ho) * Wo + wo) * C8 + (o0 >> 3)] =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+}
+extern "C" int b200_hy_downsample_cl(const void* h, int ldh, const void* x, void* out, int T, int H, int W, int Ci, int Co, int temporal,
+                                     void* stream) {
+    const int F = temporal ? 8 : 4;
+    if (ldh < Co / F) return b200_set_error(B200_ERR_ARG, "hy_downsample_cl: ldh < Co / F");
+    if (!h || !x || !out || T <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || Co % 8 || Co % F || (F * Ci) % Co || (temporal && ((T - 1) & 1)) ||
+        (temporal && (F * Ci / Co) % 2))
+        return b200_set_error(B200_ERR_ARG, "hy_downsample_cl: bad argument");
+    const int To = temporal ? 1 + (T - 1) / 2 : T;
+    if (H / 2 > 65535 || To > 65535) return b200_set_error(B200_ERR_ARG, "hy_downsample_cl: bad extent");
+    const dim3 grid((unsigned)(((long long)(W / 2) * (Co / 8) + 255) / 256), (unsigned)(H / 2), (unsigned)To);
+    hy_downsample_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), T, H, W, Ci, Co, temporal, ldh);
+    CHECK_LAUNCH("hy_downsample_cl");
+    return B200_OK;
+}
+// y[p, c] = mean_g x[p, c*r + g]  (Encoder.forward shortcut "b (c r) f h w -> b c r f h w".mean(r), :424-425); bf16 [P,C] -> bf16 [P,C/r]
+__global__ void group_mean_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long P, int C, int r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Co = C / r;
+    if (i >= P * Co) return;
+    const long long p = i / Co;
+    const int c = (int)(i - p * Co);
+    float acc = 0.f;
+    for (int g = 0; g < r; ++g) acc += __bfloat162float(x[p * C + c * r + g]);
+    y[i] = __float2bfloat16_rn(acc / (float)r);
+}
+extern "C" int b200_group_mean_cl(const void* x, void* y, long long P, int C, int r, void* stream) {
+    if (!x || !y || P <= 0 || C <= 0 || r <= 0 || C % r) return b200_set_error(B200_ERR_ARG, "group_mean_cl: bad argument");
+    const long long n = P * (C / r);
+    group_mean_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), P, C, r);
+    CHECK_LAUNCH("group_mean_cl");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tile seams of the tiled VAE decode / encode (vae.py:664-674 blend_v / blend_h): the first `ext` rows (columns) of tile b become a
 // linear cross-fade from the last `ext` rows (columns) of its upper (left) neighbour a:  b = a (1 - k/ext) + b (k/ext).
 // a [planes, ha, wa], b [planes, hb, wb] fp32 planar; vertical: wa == wb, horizontal: ha == hb.
@@ -696,6 +772,9 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         p.out = reinterpret_cast<__nv_bfloat16*>(out) + (long long)t_off * H * W * C;
         p.st_w = C; p.st_h = (long long)W * C; p.st_t = 2LL * H * W * C;
         p.csplit = C; p.st_split = (long long)H * W * C;
+    } else if (out_mode == 3) {
+        p.out = out; p.out_fp32 = 1;                                       // fp32 channels-last [T,H,W,Cout] (+ bf16 residual)
+        p.st_w = Cout; p.st_h = (long long)W * Cout; p.st_t = (long long)H * W * Cout;
     } else if (out_mode == 2) {
         p.out = out; p.out_fp32 = 1; p.planar = 1;
         p.st_w = 1; p.st_h = W; p.st_t = (long long)H * W; p.st_split = (long long)T * H * W;

@@ -76,7 +76,7 @@ def norm_act_conv(x, norm, conv, residual=None, out_mode=0, out=None):
     tc_max = max(1, min(T, PAD_SLICE_BYTES // frame_bytes - (kt - 1)))
     if out is None:
         out = (torch.empty(conv.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
-               else torch.empty(T, H, W, conv.cout, device=x.device, dtype=bf16))
+               else torch.empty(T, H, W, conv.cout, device=x.device, dtype=f32 if out_mode == 3 else bf16))
     for t0 in range(0, T, tc_max):
         tc = min(tc_max, T - t0)
         xp = norm.apply(x, st, True, t0, tc, (kt - 1, kh // 2, kw // 2))
@@ -186,6 +186,109 @@ class HYVAEDecoder(torch.nn.Module):
         return torch.stack(outs, 0)
 
 
+class HYVAEEncoder(torch.nn.Module):
+    """Hunyuan Video 1.5 VAE Encoder.forward (hunyuanvideo_15_vae.py:395-430), un-tiled: x [B,3,1+4k,H,W] -> posterior moments
+    [B, 2 zc, 1+k, H/fs, W/fs] fp32 (mean | logvar).  Same kernels as the decoder; Downsample (:253-296) = causal conv + one
+    shuffle / group-mean pass (`b200_hy_downsample_cl`), no strided convolution anywhere."""
+
+    def __init__(self, cfg, device="cuda"):
+        super().__init__()
+        self.cfg, self.device = dict(cfg), torch.device(device)
+        self._ready = False
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        dev = self.device
+        gam = lambda k: sd[k].detach().to(dev, f32).reshape(-1).contiguous()                      # noqa: E731
+        rms = lambda k: _RMSNorm(gam(k))                                                           # noqa: E731
+        rc = lambda p: _RepConv(sd[p + ".weight"], sd[p + ".bias"], dev)                           # noqa: E731
+        lin = lambda p: (sd[p + ".weight"].detach().to(dev, bf16).reshape(sd[p + ".weight"].shape[0], -1).contiguous(),  # noqa: E731
+                         sd[p + ".bias"].detach().to(dev, f32).contiguous())
+
+        def res(p):
+            d = {"g1": rms(p + "norm1.gamma"), "c1": rc(p + "conv1.conv"), "g2": rms(p + "norm2.gamma"), "c2": rc(p + "conv2.conv")}
+            if p + "nin_shortcut.weight" in sd:
+                d["nin"] = lin(p + "nin_shortcut")
+            return d
+        w_in = sd["conv_in.conv.weight"].detach().to(dev, f32)
+        self.cin = w_in.shape[1]
+        self.conv_in = _RepConv(torch.cat([w_in, w_in.new_zeros(w_in.shape[0], 8 - self.cin, *w_in.shape[2:])], 1), sd["conv_in.conv.bias"], dev)
+        levels, self.c_mid = synth.hyvae_encoder_layout(self.cfg)
+        self.levels = []
+        for i, (blocks, down) in enumerate(levels):
+            dn = None
+            if down is not None:                   # conv output channels padded to a multiple of 16 (zero weights); the shuffle reads the real ones
+                w, b = sd[f"down.{i}.downsample.conv.conv.weight"].detach().to(dev, f32), sd[f"down.{i}.downsample.conv.conv.bias"].detach().to(dev, f32)
+                padc = (-w.shape[0]) % 16
+                dn = (_RepConv(torch.cat([w, w.new_zeros(padc, *w.shape[1:])], 0), torch.cat([b, b.new_zeros(padc)]), dev), down[1], down[2])
+            self.levels.append(([res(f"down.{i}.block.{j}.") for j in range(len(blocks))], dn))
+        self.mid1, self.mid2 = res("mid.block_1."), res("mid.block_2.")
+        a = "mid.attn_1."
+        self.attn = {"g": gam(a + "norm.gamma"),
+                     "wqkv": torch.cat([lin(a + n)[0] for n in "qkv"], 0).contiguous(), "bqkv": torch.cat([lin(a + n)[1] for n in "qkv"], 0).contiguous(),
+                     "proj": lin(a + "proj_out")}
+        self.g_out = rms("norm_out.gamma")
+        self.conv_out = rc("conv_out.conv")
+        self._ready = True
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    _res = staticmethod(HYVAEDecoder._res)
+    _attn = HYVAEDecoder._attn
+
+    @torch.no_grad()
+    def forward(self, x):
+        if not self._ready:
+            raise RuntimeError("HYVAEEncoder: load_state_dict() must be called before encode")
+        outs = []
+        zc2 = 2 * self.cfg["z_channels"]
+        for xi in x:
+            xi = xi.to(self.device, f32).contiguous()
+            C, T, H, W = xi.shape
+            fs, ft = self.cfg["ffactor_spatial"], self.cfg["ffactor_temporal"]
+            if C != self.cin or (T - 1) % ft or H % fs or W % fs:
+                raise ValueError(f"Hunyuan VAE encode: expected [{self.cin}, 1+{ft}k, {fs}m, {fs}n] frames, got {tuple(xi.shape)}")
+            xcl = torch.empty(T, H, W, 8, device=self.device, dtype=bf16)
+            _lib.call("b200_planar_to_cl_pad", xi.data_ptr(), xcl.data_ptr(), C, T * H * W, 8, _s())
+            hold = [self.conv_in(xcl)]
+            del xcl
+            for blocks, down in self.levels:
+                for d in blocks:
+                    hold.append(self._res(d, hold))
+                if down is not None:
+                    conv, cout, temporal = down
+                    h = hold.pop()
+                    t, hh, ww, ci = h.shape
+                    hc = conv(h)
+                    out = torch.empty(1 + (t - 1) // 2 if temporal else t, hh // 2, ww // 2, cout, device=self.device, dtype=bf16)
+                    _lib.call("b200_hy_downsample_cl", hc.data_ptr(), hc.shape[-1], h.data_ptr(), out.data_ptr(), t, hh, ww, ci, cout, int(temporal), _s())
+                    del h, hc
+                    hold.append(out)
+            hold.append(self._res(self.mid1, hold))
+            hold.append(self._attn(hold.pop()))
+            hold.append(self._res(self.mid2, hold))
+            h = hold.pop()
+            t, hh, ww, c = h.shape
+            sc = torch.empty(t, hh, ww, zc2, device=self.device, dtype=bf16)                    # channel-group mean shortcut (:424-425)
+            _lib.call("b200_group_mean_cl", h.data_ptr(), sc.data_ptr(), t * hh * ww, c, c // zc2, _s())
+            mom = norm_act_conv(h, self.g_out, self.conv_out, residual=sc, out_mode=3)           # fp32 [T,h,w,2zc]
+            outs.append(mom.permute(3, 0, 1, 2).contiguous())
+        return torch.stack(outs, 0)
+
+
+class _Posterior:
+    """diffusers' DiagonalGaussianDistribution surface the callers use (`.mode()`, `.sample()`, `.mean`, `.logvar`)."""
+
+    def __init__(self, moments):
+        self.mean, self.logvar = moments.chunk(2, dim=1)
+        self.logvar = self.logvar.clamp(-30.0, 20.0)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        eps = torch.randn(self.mean.shape, generator=generator, device=self.mean.device if generator is None else generator.device, dtype=f32)
+        return self.mean + torch.exp(0.5 * self.logvar) * eps.to(self.mean.device)
+
+
 class AutoencoderKLConv3D(torch.nn.Module):
     """Decode surface of models/hyvideo/vae/hunyuanvideo_15_vae.py::AutoencoderKLConv3D (:523-907)."""
 
@@ -196,11 +299,15 @@ class AutoencoderKLConv3D(torch.nn.Module):
         self.ffactor_spatial, self.ffactor_temporal = ffactor_spatial, ffactor_temporal
         self.scaling_factor, self.shift_factor = scaling_factor, shift_factor
         self.config = types.SimpleNamespace(scaling_factor=scaling_factor, shift_factor=shift_factor, latent_channels=latent_channels)
-        self.decoder = HYVAEDecoder(dict(z_channels=latent_channels, out_channels=out_channels,
-                                         block_out_channels=list(reversed(list(block_out_channels))), num_res_blocks=layers_per_block,
-                                         ffactor_spatial=ffactor_spatial, ffactor_temporal=ffactor_temporal), device)
+        cfg = dict(z_channels=latent_channels, out_channels=out_channels, block_out_channels=list(reversed(list(block_out_channels))),
+                   num_res_blocks=layers_per_block, ffactor_spatial=ffactor_spatial, ffactor_temporal=ffactor_temporal)
+        self.decoder = HYVAEDecoder(cfg, device)
+        self.encoder = HYVAEEncoder(cfg, device)
 
     def load_state_dict(self, sd, strict=True, assign=False):
+        enc = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+        if enc:                                    # decode-only checkpoints carry no encoder
+            self.encoder.load_state_dict(enc)
         return self.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
 
     def enable_tiling(self, *a, **k):          # un-tiled whole-clip decode on a 180 GB GPU
@@ -216,5 +323,7 @@ class AutoencoderKLConv3D(torch.nn.Module):
         out = self.decoder(z)
         return types.SimpleNamespace(sample=out) if return_dict else (out,)
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("Hunyuan VAE encode is outside the decode hot path")
+    def encode(self, x, return_dict=True):
+        """AutoencoderKLConv3D.encode (:866-887), tiling off: posterior over the encoder's moments."""
+        post = _Posterior(self.encoder(x))
+        return types.SimpleNamespace(latent_dist=post) if return_dict else (post,)

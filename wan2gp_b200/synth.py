@@ -437,8 +437,59 @@ def hyvae_param_shapes(cfg):
     return s
 
 
-def make_hyvae_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
-    return {n: make_vae_tensor(n, s, seed, device).to(dtype) for n, s in hyvae_param_shapes(cfg).items()}
+def hyvae_encoder_layout(cfg):
+    """Encoder.__init__ (hunyuanvideo_15_vae.py:345-393): per level (list of (cin, cout) resnets, downsample (cin, cout, temporal) or
+    None), plus the channel count of the middle block.  HYVAE_CONFIGS hold block_out_channels in DECODER order."""
+    boc = list(reversed(cfg["block_out_channels"]))
+    n_sp, n_t0 = math.log2(cfg["ffactor_spatial"]), math.log2(cfg["ffactor_spatial"] // cfg["ffactor_temporal"])
+    levels, cin = [], boc[0]
+    for i, ch in enumerate(boc):
+        blocks = []
+        for _ in range(cfg["num_res_blocks"]):
+            blocks.append((cin, ch))
+            cin = ch
+        down = None
+        if i < n_sp:
+            down = (cin, boc[i + 1], i >= n_t0)
+            cin = boc[i + 1]
+        levels.append((blocks, down))
+    return levels, cin
+
+
+def hyvae_encoder_param_shapes(cfg, in_channels=3):
+    s = {}
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k, k)
+        s[name + ".bias"] = (co,)
+
+    def res(p, ci, co):
+        s[p + "norm1.gamma"] = (ci, 1, 1, 1)
+        conv(p + "conv1.conv", co, ci, 3)
+        s[p + "norm2.gamma"] = (co, 1, 1, 1)
+        conv(p + "conv2.conv", co, co, 3)
+        if ci != co:
+            conv(p + "nin_shortcut", co, ci, 1)
+    levels, c_mid = hyvae_encoder_layout(cfg)
+    conv("conv_in.conv", levels[0][0][0][0], in_channels, 3)
+    for i, (blocks, down) in enumerate(levels):
+        for j, (ci, co) in enumerate(blocks):
+            res(f"down.{i}.block.{j}.", ci, co)
+        if down is not None:
+            conv(f"down.{i}.downsample.conv.conv", down[1] // (8 if down[2] else 4), down[0], 3)
+    res("mid.block_1.", c_mid, c_mid)
+    s["mid.attn_1.norm.gamma"] = (c_mid, 1, 1, 1)
+    for n in ("q", "k", "v", "proj_out"):
+        conv("mid.attn_1." + n, c_mid, c_mid, 1)
+    res("mid.block_2.", c_mid, c_mid)
+    s["norm_out.gamma"] = (c_mid, 1, 1, 1)
+    conv("conv_out.conv", 2 * cfg["z_channels"], c_mid, 3)
+    return s
+
+
+def make_hyvae_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, encoder=False):
+    shapes = hyvae_encoder_param_shapes(cfg) if encoder else hyvae_param_shapes(cfg)
+    return {n: make_vae_tensor(("enc." if encoder else "") + n, s, seed, device).to(dtype) for n, s in shapes.items()}
 
 
 # --------------------------------------------------------------------------- HunyuanVideo 1.0 VAE decoder (AutoencoderKLCausal3D)
