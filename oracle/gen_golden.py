@@ -244,6 +244,27 @@ def run_hyvae_enc(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
 
 
+HYVAE10_ENC_CASES = {"hyvae10_enc_tiny": ("hyvae10_tiny", (3, 5, 16, 24), 2), "hyvae10_enc_small": ("hyvae10_small", (3, 9, 16, 16), 3)}
+
+
+def run_hyvae10_enc(name):
+    """Reference AutoencoderKLCausal3D.encode, un-tiled (autoencoder_kl_causal_3d.py:435-472): encoder -> quant_conv -> moments."""
+    from oracle.refshim import load_reference_hyvae10
+    hv = load_reference_hyvae10()
+    cfg_name, xshape, seed = HYVAE10_ENC_CASES[name]
+    cfg = synth.HYVAE10_CONFIGS[cfg_name]
+    vae = hv.AutoencoderKLCausal3D(in_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4,
+                                   up_block_types=("UpDecoderBlockCausal3D",) * 4, **cfg).eval().requires_grad_(False)
+    sd = synth.make_hyvae10_state_dict(cfg, seed, encoder=True)
+    assert set(sd) == set(vae.state_dict()), set(sd) ^ set(vae.state_dict())
+    vae.load_state_dict(sd)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+    with torch.no_grad():
+        out = vae.encode(x, return_dict=False)[0].parameters
+    print(f"{name}: reference HY-1.0 VAE encode moments {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
+
+
 def run_unipc(name):
     """Trajectory of the reference FlowUniPCMultistepScheduler on seeded fp64 inputs (same generator as tests/test_unipc_cpu.py)."""
     from oracle.refshim import load_reference_unipc
@@ -266,4 +287,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_vae)(n)

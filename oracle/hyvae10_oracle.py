@@ -15,7 +15,7 @@ Pinned by tests/golden/hyvae10_*.npz = outputs of the reference AutoencoderKLCau
 import torch
 import torch.nn.functional as F
 
-from wan2gp_b200.synth import hyvae10_layout
+from wan2gp_b200.synth import hyvae10_encoder_layout, hyvae10_layout
 from .hyvae_oracle import _q, causal_conv3d_rep
 
 
@@ -77,3 +77,30 @@ def hyvae10_decode(sd, cfg, z, emulate_bf16=False):
             h = upsample(sd, d + f"up_blocks.{i}.upsamplers.0.", h, up[0], up[1], em)
     h = _q(F.silu(group_norm(h, sd[d + "conv_norm_out.weight"], sd[d + "conv_norm_out.bias"], G)), em)
     return causal_conv3d_rep(h, sd[d + "conv_out.conv.weight"], sd[d + "conv_out.conv.bias"], em)
+
+
+def downsample(sd, p, x, st_t, st_s, em):
+    """DownsampleCausal3D (unet_causal_3d_blocks.py:226-298): replicate-padded causal 3x3x3 conv with stride (1|2, 2, 2)."""
+    xp = F.pad(_q(x, em)[None], (1, 1, 1, 1, 2, 0), mode="replicate")
+    y = F.conv3d(xp, _q(sd[p + "conv.conv.weight"].float(), em), sd[p + "conv.conv.bias"].float(), stride=(2 if st_t else 1, 2 if st_s else 1, 2 if st_s else 1))[0]
+    return _q(y, em)
+
+
+def hyvae10_encode(sd, cfg, x, emulate_bf16=False):
+    """x [3, 1+4k, H, W] fp32 -> moments [2 zc, 1+k, H/8, W/8] fp32: EncoderCausal3D.forward (vae/vae.py:135-184) then quant_conv
+    (autoencoder_kl_causal_3d.py:464-467, un-tiled branch)."""
+    em, G = emulate_bf16, cfg["norm_num_groups"]
+    e = "encoder."
+    h = _q(causal_conv3d_rep(_q(x.float(), em), sd[e + "conv_in.conv.weight"], sd[e + "conv_in.conv.bias"], em), em)
+    blocks, _ = hyvae10_encoder_layout(cfg)
+    for i, (rs, down) in enumerate(blocks):
+        for j in range(len(rs)):
+            h = resnet(sd, e + f"down_blocks.{i}.resnets.{j}.", h, G, em)
+        if down is not None:
+            h = downsample(sd, e + f"down_blocks.{i}.downsamplers.0.", h, down[0], down[1], em)
+    h = resnet(sd, e + "mid_block.resnets.0.", h, G, em)
+    h = attention(sd, e + "mid_block.attentions.0.", h, G, cfg["mid_block_causal_attn"], em)
+    h = resnet(sd, e + "mid_block.resnets.1.", h, G, em)
+    h = _q(F.silu(group_norm(h, sd[e + "conv_norm_out.weight"], sd[e + "conv_norm_out.bias"], G)), em)
+    h = causal_conv3d_rep(h, sd[e + "conv_out.conv.weight"], sd[e + "conv_out.conv.bias"], em)
+    return F.conv3d(h[None], sd["quant_conv.weight"].float(), sd["quant_conv.bias"].float())[0]

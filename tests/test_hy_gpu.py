@@ -210,3 +210,25 @@ def test_hyvae15_encode(name, cfg_name, xshape, seed):
     assert torch.equal(post.mode(), post.mean) and post.sample(torch.Generator().manual_seed(0)).shape == post.mean.shape
     rec = vae.decode(post.mode(), return_dict=False)[0]                    # encode -> decode round trip runs end to end
     assert rec.shape == (1,) + xshape and torch.isfinite(rec).all()
+
+
+@pytest.mark.parametrize("name,cfg_name,xshape,seed", [("hyvae10_enc_tiny", "hyvae10_tiny", (3, 5, 16, 24), 2), ("hyvae10_enc_small", "hyvae10_small", (3, 9, 16, 16), 3)])
+def test_hyvae10_encode(name, cfg_name, xshape, seed):
+    """HunyuanVideo 1.0 VAE encode through the AutoencoderKLCausal3D surface: stride-2 replicate-padded convs as window convs over the
+    space-to-depth / frame-pair views, quant_conv folded into conv_out.  vs the reference moments (fixture) and the bf16-emulating
+    oracle: rel-L2 <= 6e-2 (GroupNorm net, same bound as the decoder; the emulating oracle is 1.4e-2 from fp32)."""
+    from oracle import hyvae10_oracle
+    from wan2gp_b200.hyvideo import AutoencoderKLCausal3D
+    cfg = synth.HYVAE10_CONFIGS[cfg_name]
+    sd = synth.make_hyvae10_state_dict(cfg, seed, encoder=True)
+    vae = AutoencoderKLCausal3D(**cfg)
+    vae.load_state_dict(sd)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
+    post = vae.encode(x.cuda()).latent_dist
+    got = torch.cat([post.mean, post.logvar], 1)[0].cpu()
+    g = load_golden(name)["out"][0]
+    emu = hyvae10_oracle.hyvae10_encode(sd, cfg, x[0], emulate_bf16=True)
+    print(f"{name}: vs reference {rel_l2(got, g):.3e}; vs bf16-emulating oracle {rel_l2(got, emu):.3e}")
+    assert got.shape == g.shape and rel_l2(got, g) < 6e-2 and rel_l2(got, emu) < 6e-2
+    rec = vae.decode(post.mode(), return_dict=False)[0]                    # encode -> decode round trip runs end to end
+    assert rec.shape == (1,) + xshape and torch.isfinite(rec).all()

@@ -88,3 +88,44 @@ def test_hyvae15_encode_oracle_matches_reference(name, cfg_name, xshape, seed):
     g = load_golden(name)["out"][0]
     out = hyvae_oracle.hyvae_encode(sd, cfg, x)
     assert out.shape == g.shape and rel_l2(out, g) < 5e-6
+
+
+@pytest.mark.parametrize("name,cfg_name,xshape,seed", [("hyvae10_enc_tiny", "hyvae10_tiny", (3, 5, 16, 24), 2), ("hyvae10_enc_small", "hyvae10_small", (3, 9, 16, 16), 3)])
+def test_hyvae10_encode_oracle_matches_reference(name, cfg_name, xshape, seed):
+    """HunyuanVideo 1.0 VAE encode: fp32 oracle == reference AutoencoderKLCausal3D.encode (moments) on the committed fixture."""
+    from oracle import hyvae10_oracle
+    cfg = synth.HYVAE10_CONFIGS[cfg_name]
+    sd = synth.make_hyvae10_state_dict(cfg, seed, encoder=True)
+    x = synth._normal((1,) + xshape, 0.5, seed, "input.video", "cpu").clamp_(-1, 1)[0]
+    g = load_golden(name)["out"][0]
+    out = hyvae10_oracle.hyvae10_encode(sd, cfg, x)
+    assert out.shape == g.shape and rel_l2(out, g) < 5e-6
+
+
+@pytest.mark.parametrize("st_t", [False, True])
+@pytest.mark.parametrize("T", [1, 5])
+def test_strided_downsample_as_window_convs(st_t, T):
+    """DownsampleCausal3D's stride-(1|2,2,2) replicate-padded conv == stride-1 window convs over the space-to-depth (and frame-pair)
+    view of the padded tensor (_DownConvRep), restated with F.conv3d."""
+    from tests.test_vae_enc_cpu import _view_conv_cpu
+    from wan2gp_b200.hyvideo.vae10 import _DownConvRep
+    g = torch.Generator().manual_seed(10 * T + st_t)
+    H, W, C, Co = 4, 6, 8, 16
+    x = torch.randn(T, H, W, C, generator=g)
+    w, b = torch.randn(Co, C, 3, 3, 3, generator=g) * 0.2, torch.randn(Co, generator=g)
+    dc = _DownConvRep(w, b, st_t, "cpu", dtype=torch.float32)
+    xp = F.pad(x.permute(3, 0, 1, 2)[None], (1, 1, 1, 1, 2, 0), mode="replicate")
+    ref = F.conv3d(xp, w, b, stride=(2 if st_t else 1, 2, 2))[0].permute(1, 2, 3, 0)
+    xpc = xp[0].permute(1, 2, 3, 0)                                                     # [T+2, H+2, W+2, C]
+    hs, ws = (H + 2) // 2, (W + 2) // 2
+    s2d = xpc.reshape(T + 2, hs, 2, ws, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(T + 2, hs, ws, 4 * C)
+    if not st_t:
+        got = _view_conv_cpu(s2d, (0, 0, 0), dc.w_all, dc.b, T, H // 2, W // 2, (3, 2, 2))
+    else:
+        if (T + 2) % 2:
+            s2d = torch.cat([s2d, torch.full((1, hs, ws, 4 * C), float("nan"))], 0)     # spare frame, never read
+        pairs = s2d.reshape(s2d.shape[0] // 2, 2 * hs, ws, 4 * C)
+        to = (T - 1) // 2 + 1
+        got = (_view_conv_cpu(pairs, (0, 0, 0), dc.w_even, dc.b, to, H // 2, W // 2, (2, 2, 2))
+               + _view_conv_cpu(pairs, (0, hs, 0), dc.w_odd, None, to, H // 2, W // 2, (1, 2, 2)))
+    assert got.shape == ref.shape and torch.isfinite(got).all() and rel_l2(got, ref) < 1e-5

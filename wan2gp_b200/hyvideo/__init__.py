@@ -1,3 +1,3 @@
 from .model import HYVideoDiffusionTransformer, get_rotary_pos_embed  # noqa: F401
 from .vae import AutoencoderKLConv3D, HYVAEDecoder, HYVAEEncoder  # noqa: F401
-from .vae10 import AutoencoderKLCausal3D, HYVAE10Decoder  # noqa: F401
+from .vae10 import AutoencoderKLCausal3D, HYVAE10Decoder, HYVAE10Encoder  # noqa: F401

@@ -19,7 +19,7 @@ import types
 import torch
 
 from .. import _lib, ops, synth
-from .vae import _RepConv, norm_act_conv
+from .vae import _Posterior, _RepConv, norm_act_conv
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -92,6 +92,133 @@ class _UpConvNearest:
             _lib.call("b200_conv3d_cl_view", xp.data_ptr(), T + ptf, H + 2, W + 2, off_t, py, px, w.data_ptr(), self.b.data_ptr(), 0, base,
                       n_t, H, W, self.cin, Co, kt, 2, 2, st_t, 4 * W * Co, 2 * Co, _s())
         return out
+
+
+class _DownConvRep:
+    """DownsampleCausal3D (unet_causal_3d_blocks.py:226-298): replicate-padded causal 3x3x3 conv with stride (1|2, 2, 2), on the
+    stride-1 conv kernels.  Space: the PADDED tensor goes through space-to-depth ([.., (H+2)/2, (W+2)/2, 4C]) and the 3x3 taps become
+    2x2 taps (kernel row a = 2*da + p, row 3 gets zero weight).  Time (stride 2): output t reads padded frames 2t, 2t+1, 2t+2 -- with
+    the frames viewed as PAIRS stacked along H, taps (w0, w2) are a 2-frame conv over the even window and w1 a 1-frame conv over the
+    odd window, accumulated through the conv's residual input."""
+
+    def __init__(self, w, b, st_t, device, dtype=bf16):
+        co, ci = w.shape[:2]
+        w = w.detach().to(device, f32)                                      # [Co, Ci, 3, 3, 3]
+        w2 = torch.zeros(co, 3, 2, 2, 2, 2, ci, device=device, dtype=f32)   # [Co, dt, da, db, p, q, Ci]
+        for da in range(2):
+            for p in range(2):
+                for db in range(2):
+                    for q in range(2):
+                        if 2 * da + p < 3 and 2 * db + q < 3:
+                            w2[:, :, da, db, p, q] = w[:, :, :, 2 * da + p, 2 * db + q].permute(0, 2, 1)
+        w2 = w2.reshape(co, 3, 4, 4 * ci)                                    # [Co][dt][(da,db)][(p,q,c)]
+        self.cout, self.cin, self.st_t = co, ci, st_t
+        self.b = b.detach().to(device, f32).contiguous()
+        if st_t:
+            self.w_even = w2[:, [0, 2]].reshape(co, 8, 4 * ci).to(dtype).contiguous()
+            self.w_odd = w2[:, 1].reshape(co, 4, 4 * ci).to(dtype).contiguous()
+        else:
+            self.w_all = w2.reshape(co, 12, 4 * ci).to(dtype).contiguous()
+
+    def __call__(self, x):
+        T, H, W, C = x.shape
+        if H % 2 or W % 2:
+            raise ValueError("Hunyuan VAE encode: frame height and width must be even at every level")
+        xp = torch.empty(T + 2, H + 2, W + 2, C, device=x.device, dtype=bf16)
+        _lib.call("b200_pad_replicate_cl", x.data_ptr(), xp.data_ptr(), T, H, W, C, 2, 1, 1, _s())
+        hs, ws, h, w, co = (H + 2) // 2, (W + 2) // 2, H // 2, W // 2, self.cout
+        s2d = torch.empty(T + 2 + (T + 2) % 2, hs, ws, 4 * C, device=x.device, dtype=bf16)          # even frame count for the pair view
+        _lib.call("b200_space_to_depth_cl", xp.data_ptr(), s2d.data_ptr(), T + 2, H + 2, W + 2, C, _s())
+        del xp
+        st = (h * w * co, w * co, co)
+        if not self.st_t:
+            out = torch.empty(T, h, w, co, device=x.device, dtype=bf16)
+            _lib.call("b200_conv3d_cl_view", s2d.data_ptr(), T + 2, hs, ws, 0, 0, 0, self.w_all.data_ptr(), self.b.data_ptr(), 0, out.data_ptr(),
+                      T, h, w, 4 * C, co, 3, 2, 2, *st, _s())
+            return out
+        to, ns = (T - 1) // 2 + 1, s2d.shape[0] // 2
+        out = torch.empty(to, h, w, co, device=x.device, dtype=bf16)
+        _lib.call("b200_conv3d_cl_view", s2d.data_ptr(), ns, 2 * hs, ws, 0, 0, 0, self.w_even.data_ptr(), self.b.data_ptr(), 0, out.data_ptr(),
+                  to, h, w, 4 * C, co, 2, 2, 2, *st, _s())
+        _lib.call("b200_conv3d_cl_view", s2d.data_ptr(), ns, 2 * hs, ws, 0, hs, 0, self.w_odd.data_ptr(), 0, out.data_ptr(), out.data_ptr(),
+                  to, h, w, 4 * C, co, 1, 2, 2, *st, _s())
+        return out
+
+
+class HYVAE10Encoder(torch.nn.Module):
+    """EncoderCausal3D.forward + quant_conv (vae/vae.py:135-184, autoencoder_kl_causal_3d.py:464-467), un-tiled:
+    x [B,3,1+4k,H,W] -> posterior moments [B, 2 zc, 1+k, H/8, W/8] fp32.  quant_conv (1x1x1) is folded into conv_out."""
+
+    def __init__(self, cfg, device="cuda"):
+        super().__init__()
+        self.cfg, self.device = dict(cfg), torch.device(device)
+        self._ready = False
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        dev, G = self.device, self.cfg["norm_num_groups"]
+        gn = lambda p: _GroupNorm(sd[p + ".weight"], sd[p + ".bias"], G, dev)                        # noqa: E731
+        rc = lambda p: _RepConv(sd[p + ".weight"], sd[p + ".bias"], dev)                             # noqa: E731
+        lin = lambda p: (sd[p + ".weight"].detach().to(dev, bf16).reshape(sd[p + ".weight"].shape[0], -1).contiguous(),  # noqa: E731
+                         sd[p + ".bias"].detach().to(dev, f32).contiguous())
+
+        def res(p):
+            d = {"n1": gn(p + "norm1"), "c1": rc(p + "conv1.conv"), "n2": gn(p + "norm2"), "c2": rc(p + "conv2.conv")}
+            if p + "conv_shortcut.conv.weight" in sd:
+                d["sc"] = lin(p + "conv_shortcut.conv")
+            return d
+        e = "encoder."
+        w_in = sd[e + "conv_in.conv.weight"].detach().to(dev, f32)
+        self.cin = w_in.shape[1]
+        self.conv_in = _RepConv(torch.cat([w_in, w_in.new_zeros(w_in.shape[0], 8 - self.cin, *w_in.shape[2:])], 1), sd[e + "conv_in.conv.bias"], dev)
+        blocks, _ = synth.hyvae10_encoder_layout(self.cfg)
+        self.blocks = []
+        for i, (rs, down) in enumerate(blocks):
+            dn = None
+            if down is not None:
+                if not down[1]:
+                    raise NotImplementedError("time-only down-sampling block (not produced by the 884 layout)")
+                p = e + f"down_blocks.{i}.downsamplers.0.conv.conv"
+                dn = _DownConvRep(sd[p + ".weight"], sd[p + ".bias"], down[0], dev)
+            self.blocks.append(([res(e + f"down_blocks.{i}.resnets.{j}.") for j in range(len(rs))], dn))
+        self.mid1, self.mid2 = res(e + "mid_block.resnets.0."), res(e + "mid_block.resnets.1.")
+        a = e + "mid_block.attentions.0."
+        self.attn = {"gn": gn(a + "group_norm"),
+                     "wqkv": torch.cat([lin(a + n)[0] for n in ("to_q", "to_k", "to_v")], 0).contiguous(),
+                     "bqkv": torch.cat([lin(a + n)[1] for n in ("to_q", "to_k", "to_v")], 0).contiguous(), "proj": lin(a + "to_out.0")}
+        self.norm_out = gn(e + "conv_norm_out")
+        # quant_conv o conv_out: W' = Wq Wo, b' = Wq bo + bq
+        wo, bo = sd[e + "conv_out.conv.weight"].detach().to(dev, f32), sd[e + "conv_out.conv.bias"].detach().to(dev, f32)
+        wq, bq = sd["quant_conv.weight"].detach().to(dev, f32), sd["quant_conv.bias"].detach().to(dev, f32)
+        wq = wq.reshape(wq.shape[0], wq.shape[1])
+        self.conv_out = _RepConv(torch.einsum("om,mctyx->octyx", wq, wo), wq @ bo + bq, dev)
+        self._ready = True
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    @torch.no_grad()
+    def forward(self, x):
+        if not self._ready:
+            raise RuntimeError("HYVAE10Encoder: load_state_dict() must be called before encode")
+        outs = []
+        for xi in x:
+            xi = xi.to(self.device, f32).contiguous()
+            C, T, H, W = xi.shape
+            if C != self.cin or (T - 1) % 4 or H % 8 or W % 8:
+                raise ValueError(f"Hunyuan VAE encode: expected [{self.cin}, 1+4k, 8m, 8n] frames, got {tuple(xi.shape)}")
+            xcl = torch.empty(T, H, W, 8, device=self.device, dtype=bf16)
+            _lib.call("b200_planar_to_cl_pad", xi.data_ptr(), xcl.data_ptr(), C, T * H * W, 8, _s())
+            hold = [self.conv_in(xcl)]
+            del xcl
+            for rs, dn in self.blocks:
+                for d in rs:
+                    hold.append(self._res(d, hold))
+                if dn is not None:
+                    hold.append(dn(hold.pop()))
+            hold.append(self._res(self.mid1, hold))
+            hold.append(self._attn(hold.pop()))
+            hold.append(self._res(self.mid2, hold))
+            mom = norm_act_conv(hold.pop(), self.norm_out, self.conv_out, out_mode=3)               # fp32 [T,h,w,2zc]
+            outs.append(mom.permute(3, 0, 1, 2).contiguous())
+        return torch.stack(outs, 0)
 
 
 class HYVAE10Decoder(torch.nn.Module):
@@ -192,6 +319,10 @@ class HYVAE10Decoder(torch.nn.Module):
         return torch.stack(outs, 0)
 
 
+HYVAE10Encoder._res = staticmethod(HYVAE10Decoder._res)
+HYVAE10Encoder._attn = HYVAE10Decoder._attn
+
+
 class AutoencoderKLCausal3D(torch.nn.Module):
     """Decode surface of models/hyvideo/vae/autoencoder_kl_causal_3d.py::AutoencoderKLCausal3D."""
 
@@ -203,13 +334,15 @@ class AutoencoderKLCausal3D(torch.nn.Module):
         self.time_compression_ratio, self.spatial_compression_ratio = time_compression_ratio, spatial_compression_ratio
         self.config = types.SimpleNamespace(scaling_factor=scaling_factor, latent_channels=latent_channels,
                                             block_out_channels=tuple(block_out_channels))
-        self.decoder = HYVAE10Decoder(dict(latent_channels=latent_channels, out_channels=out_channels,
-                                           block_out_channels=list(block_out_channels), layers_per_block=layers_per_block,
-                                           norm_num_groups=norm_num_groups, time_compression_ratio=time_compression_ratio,
-                                           spatial_compression_ratio=spatial_compression_ratio,
-                                           mid_block_causal_attn=mid_block_causal_attn), device)
+        cfg = dict(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=list(block_out_channels),
+                   layers_per_block=layers_per_block, norm_num_groups=norm_num_groups, time_compression_ratio=time_compression_ratio,
+                   spatial_compression_ratio=spatial_compression_ratio, mid_block_causal_attn=mid_block_causal_attn)
+        self.decoder = HYVAE10Decoder(cfg, device)
+        self.encoder = HYVAE10Encoder(cfg, device)
 
     def load_state_dict(self, sd, strict=True, assign=False):
+        if "encoder.conv_in.conv.weight" in sd:                 # decode-only checkpoints carry no encoder
+            self.encoder.load_state_dict({k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))})
         return self.decoder.load_state_dict({k: v for k, v in sd.items() if k.startswith(("decoder.", "post_quant_conv."))})
 
     def enable_tiling(self, *a, **k):            # un-tiled whole-clip decode on a 180 GB GPU
@@ -221,5 +354,7 @@ class AutoencoderKLCausal3D(torch.nn.Module):
         out = self.decoder(z)
         return types.SimpleNamespace(sample=out) if return_dict else (out,)
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("Hunyuan VAE encode is outside the decode hot path")
+    def encode(self, x, return_dict=True):
+        """AutoencoderKLCausal3D.encode (autoencoder_kl_causal_3d.py:435-472), tiling off: posterior over quant_conv(encoder(x))."""
+        post = _Posterior(self.encoder(x))
+        return types.SimpleNamespace(latent_dist=post) if return_dict else (post,)

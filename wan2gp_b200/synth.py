@@ -557,9 +557,63 @@ def hyvae10_param_shapes(cfg):
     return s
 
 
-def make_hyvae10_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+def hyvae10_encoder_layout(cfg):
+    """Per down block: (list of (cin, cout) resnets, (stride_t, stride_s) or None) -- EncoderCausal3D.__init__ (vae/vae.py:75-118),
+    time_compression_ratio 4 rule."""
+    boc = list(cfg["block_out_channels"])
+    assert cfg["time_compression_ratio"] == 4
+    n_sp, n_t = int(math.log2(cfg["spatial_compression_ratio"])), int(math.log2(cfg["time_compression_ratio"]))
+    blocks, cin = [], boc[0]
+    for i, ch in enumerate(boc):
+        res = []
+        for _ in range(cfg["layers_per_block"]):
+            res.append((cin, ch))
+            cin = ch
+        sp, tm = i < n_sp, (i >= len(boc) - 1 - n_t and i != len(boc) - 1)
+        blocks.append((res, (tm, sp) if (sp or tm) else None))
+    return blocks, cin
+
+
+def hyvae10_encoder_param_shapes(cfg, in_channels=3):
+    """State-dict names of AutoencoderKLCausal3D's encode half: encoder.* + quant_conv (vae/vae.py:48-184, autoencoder_kl_causal_3d.py:243)."""
+    s = {}
+
+    def conv(name, co, ci, k):
+        s[name + ".weight"] = (co, ci, k, k, k)
+        s[name + ".bias"] = (co,)
+
+    def norm(name, c):
+        s[name + ".weight"] = s[name + ".bias"] = (c,)
+
+    def res(p, ci, co):
+        norm(p + "norm1", ci), conv(p + "conv1.conv", co, ci, 3), norm(p + "norm2", co), conv(p + "conv2.conv", co, co, 3)
+        if ci != co:
+            conv(p + "conv_shortcut.conv", co, ci, 1)
+    zc = cfg["latent_channels"]
+    blocks, c_mid = hyvae10_encoder_layout(cfg)
+    conv("encoder.conv_in.conv", cfg["block_out_channels"][0], in_channels, 3)
+    for i, (rs, down) in enumerate(blocks):
+        for j, (ci, co) in enumerate(rs):
+            res(f"encoder.down_blocks.{i}.resnets.{j}.", ci, co)
+        if down is not None:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv.conv", rs[-1][1], rs[-1][1], 3)
+    res("encoder.mid_block.resnets.0.", c_mid, c_mid), res("encoder.mid_block.resnets.1.", c_mid, c_mid)
+    a = "encoder.mid_block.attentions.0."
+    norm(a + "group_norm", c_mid)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[a + n + ".weight"], s[a + n + ".bias"] = (c_mid, c_mid), (c_mid,)
+    norm("encoder.conv_norm_out", c_mid)
+    conv("encoder.conv_out.conv", 2 * zc, c_mid, 3)
+    conv("quant_conv", 2 * zc, 2 * zc, 1)
+    return s
+
+
+def make_hyvae10_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, encoder=False):
     out = {}
-    for n, s in hyvae10_param_shapes(cfg).items():
+    shapes = dict(hyvae10_param_shapes(cfg))
+    if encoder:
+        shapes.update(hyvae10_encoder_param_shapes(cfg))
+    for n, s in shapes.items():
         if "norm" in n and n.endswith(".weight"):
             out[n] = (1.0 + _normal(s, 0.1, seed, n, device)).to(dtype)
         else:
