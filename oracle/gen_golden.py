@@ -265,6 +265,38 @@ def run_hyvae10_enc(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32))
 
 
+HY_TILED_CASES = {"hyvae_tiled": ("1.5", "hyvae_tiny", (8, 7, 6, 10), 16, 8, 6), "hyvae10_tiled": ("1.0", "hyvae10_tiny", (8, 7, 5, 7), 32, 16, 7)}
+
+
+def run_hy_tiled(name):
+    """Reference Hunyuan VAE decode with enable_tiling() (what the pipelines always do: hunyuan.py:772, pipeline_hunyuan_video.py:695),
+    small tile sizes so the tiny clip is cut into several temporal and spatial tiles."""
+    from oracle.refshim import load_reference_hy, load_reference_hyvae, load_reference_hyvae10
+    import importlib
+    fam, cfg_name, zshape, sample_size, sample_tsize, seed = HY_TILED_CASES[name]
+    if fam == "1.5":
+        load_reference_hy(), load_reference_hyvae()
+        m = importlib.import_module("models.hyvideo.vae.hunyuanvideo_15_vae")
+        cfg = synth.HYVAE_CONFIGS[cfg_name]
+        vae = m.AutoencoderKLConv3D(in_channels=3, out_channels=3, latent_channels=cfg["z_channels"], block_out_channels=tuple(reversed(cfg["block_out_channels"])),
+                                    layers_per_block=cfg["num_res_blocks"], ffactor_spatial=cfg["ffactor_spatial"], ffactor_temporal=cfg["ffactor_temporal"],
+                                    sample_size=sample_size, sample_tsize=sample_tsize).eval().requires_grad_(False)
+        vae.decoder.load_state_dict(synth.make_hyvae_state_dict(cfg, seed))
+    else:
+        hv = load_reference_hyvae10()
+        cfg = synth.HYVAE10_CONFIGS[cfg_name]
+        vae = hv.AutoencoderKLCausal3D(in_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4, up_block_types=("UpDecoderBlockCausal3D",) * 4,
+                                       sample_size=sample_size, sample_tsize=sample_tsize, **cfg).eval().requires_grad_(False)
+        vae.load_state_dict(synth.make_hyvae10_state_dict(cfg, seed, encoder=True))
+    vae.enable_tiling()
+    z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    with torch.no_grad():
+        out = vae.decode(z, return_dict=False)[0]
+    print(f"{name}: reference tiled decode out {tuple(out.shape)} absmean {out.abs().mean():.6f}; latent tile {vae.tile_latent_min_size} x {vae.tile_latent_min_tsize}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), sample_size=sample_size, sample_tsize=sample_tsize,
+                        lat_size=vae.tile_latent_min_size, lat_tsize=vae.tile_latent_min_tsize)
+
+
 def run_unipc(name):
     """Trajectory of the reference FlowUniPCMultistepScheduler on seeded fp64 inputs (same generator as tests/test_unipc_cpu.py)."""
     from oracle.refshim import load_reference_unipc
@@ -287,4 +319,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_vae)(n)
+        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)

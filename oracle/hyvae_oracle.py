@@ -137,3 +137,36 @@ def hyvae_encode(sd, cfg, x, emulate_bf16=False):
     sc = h.reshape(zc2, c_mid // zc2, *h.shape[1:]).mean(1)                    # "b (c r) f h w -> b c r f h w" mean over r
     y = _q(F.silu(rms_norm_c(h, sd["norm_out.gamma"])), em)
     return causal_conv3d_rep(y, sd["conv_out.conv.weight"], sd["conv_out.conv.bias"], em) + _q(sc, em)
+
+
+def tiled_decode(decode_fn, z, lat_size, lat_tsize, sample_size, sample_tsize, overlap=0.25, spatial=True, temporal=True):
+    """The tiling dispatch shared by both Hunyuan VAEs (hunyuanvideo_15_vae.py:806-864, 889-896; autoencoder_kl_causal_3d.py:474-482,
+    638-855): temporal tiles of lat_tsize+1 latent frames with stride int(lat_tsize*(1-overlap)) (first decoded frame of every tile
+    but the first dropped, blend_t over int(sample_tsize*overlap) frames), each decoded through spatial tiles of lat_size with
+    stride int(lat_size*(1-overlap)) (blend_v / blend_h over int(sample_size*overlap) pixels).  decode_fn: [zc,T,h,w] -> [3,F,H,W]."""
+    from .vae_oracle import spatial_tiles
+
+    def sp(t):
+        if spatial and (t.shape[-1] > lat_size or t.shape[-2] > lat_size):
+            blend = int(sample_size * overlap)
+            return spatial_tiles(t, lat_size, int(lat_size * (1 - overlap)), decode_fn, blend, sample_size - blend)
+        return decode_fn(t)
+    if not (temporal and z.shape[1] > lat_tsize):
+        return sp(z)
+    stride, blend = int(lat_tsize * (1 - overlap)), int(sample_tsize * overlap)
+    t_limit = sample_tsize - blend
+    row = []
+    for i in range(0, z.shape[1], stride):
+        d = sp(z[:, i:i + lat_tsize + 1]).clone()
+        row.append(d[:, 1:] if i > 0 else d)
+    out = []
+    for i, t in enumerate(row):
+        if i > 0:
+            a = row[i - 1]
+            e = min(a.shape[1], t.shape[1], blend)
+            for k in range(e):
+                t[:, k] = a[:, -e + k] * (1 - k / e) + t[:, k] * (k / e)
+            out.append(t[:, :t_limit])
+        else:
+            out.append(t[:, :t_limit + 1])
+    return torch.cat(out, 1)

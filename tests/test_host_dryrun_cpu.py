@@ -42,6 +42,21 @@ def test_hunyuan_vae_host_paths(stub_abi):
     assert enc(torch.randn(1, 3, 5, 16, 24)).shape == (1, 16, 3, 4, 6)
     assert dec(torch.randn(1, 8, 3, 4, 6)).shape == (1, 3, 5, 16, 24)
     assert {"b200_hy_downsample_cl", "b200_group_mean_cl", "b200_hy_upsample_cl", "b200_rms_silu_pad_cl"} <= set(stub_abi)
+    # tiled dispatch (enable_tiling): 7 latent frames -> temporal tiles of 4(+1) with stride 3, spatial tiles of 4 with stride 3
+    from wan2gp_b200.hyvideo import AutoencoderKLCausal3D, AutoencoderKLConv3D
+    vae = AutoencoderKLConv3D(latent_channels=8, block_out_channels=[32, 64, 64], layers_per_block=1, ffactor_spatial=4, ffactor_temporal=2,
+                              sample_size=16, sample_tsize=8, device="cpu")
+    vae.load_state_dict({"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 0).items()})
+    vae.enable_tiling()
+    assert vae.decode(torch.randn(1, 8, 7, 6, 10), return_dict=False)[0].shape == (1, 3, 13, 24, 40)
+    cfg10 = synth.HYVAE10_CONFIGS["hyvae10_tiny"]
+    vae = AutoencoderKLCausal3D(sample_size=32, sample_tsize=16, device="cpu", **cfg10)
+    vae.load_state_dict(synth.make_hyvae10_state_dict(cfg10, 0, encoder=True))
+    vae.enable_tiling()
+    assert vae.decode(torch.randn(1, 8, 7, 5, 7), return_dict=False)[0].shape == (1, 3, 25, 40, 56)
+    assert "b200_blend_edge_f32" in stub_abi
+    vae.disable_tiling()
+    assert vae.decode(torch.randn(1, 8, 2, 2, 3), return_dict=True).sample.shape == (1, 3, 5, 16, 24)
 
 
 def test_wan_vae_host_paths(stub_abi):

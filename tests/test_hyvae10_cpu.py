@@ -129,3 +129,23 @@ def test_strided_downsample_as_window_convs(st_t, T):
         got = (_view_conv_cpu(pairs, (0, 0, 0), dc.w_even, dc.b, to, H // 2, W // 2, (2, 2, 2))
                + _view_conv_cpu(pairs, (0, hs, 0), dc.w_odd, None, to, H // 2, W // 2, (1, 2, 2)))
     assert got.shape == ref.shape and torch.isfinite(got).all() and rel_l2(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["hyvae_tiled", "hyvae10_tiled"])
+def test_hunyuan_tiled_decode_oracle_matches_reference(name):
+    """Temporal + spatial tiling with cross-faded seams (what the reference pipelines always enable): restatement == the reference's
+    AutoencoderKLConv3D / AutoencoderKLCausal3D .decode after enable_tiling()."""
+    from oracle import hyvae10_oracle, hyvae_oracle
+    g = load_golden(name)
+    if name == "hyvae_tiled":
+        cfg = synth.HYVAE_CONFIGS["hyvae_tiny"]
+        sd = synth.make_hyvae_state_dict(cfg, 6)
+        z = synth._normal((1, 8, 7, 6, 10), 1.0, 6, "input.z", "cpu")[0]
+        fn = lambda t: hyvae_oracle.hyvae_decode(sd, cfg, t)                                          # noqa: E731
+    else:
+        cfg = synth.HYVAE10_CONFIGS["hyvae10_tiny"]
+        sd = synth.make_hyvae10_state_dict(cfg, 7, encoder=True)
+        z = synth._normal((1, 8, 7, 5, 7), 1.0, 7, "input.z", "cpu")[0]
+        fn = lambda t: hyvae10_oracle.hyvae10_decode(sd, cfg, t)                                      # noqa: E731
+    out = hyvae_oracle.tiled_decode(fn, z, int(g["lat_size"]), int(g["lat_tsize"]), int(g["sample_size"]), int(g["sample_tsize"]))
+    assert out.shape == g["out"][0].shape and rel_l2(out, g["out"][0]) < 5e-6

@@ -1,8 +1,8 @@
 """B200-native Hunyuan Video 1.5 VAE decode (hot-path row H6 of SURVEY.md section 8a): the `AutoencoderKLConv3D` surface the
 pipeline uses (`.decode(z, return_dict=False)[0]`, `.enable_tiling()`, `.config.scaling_factor / .shift_factor`,
 models/hyvideo/diffusion/pipelines/pipeline_hunyuan_video.py:1790-1812) over the reference Decoder
-(models/hyvideo/vae/hunyuanvideo_15_vae.py:432-520), UN-TILED: one B200 holds the whole clip, so `enable_tiling()` is a
-no-op (the reference tiles only to fit small GPUs; tiled + blended output differs from the plain decoder near tile seams).
+(models/hyvideo/vae/hunyuanvideo_15_vae.py:432-520).  Un-tiled by default (one B200 holds the whole clip); `enable_tiling()`
+switches to the reference's temporal + spatial tiling with cross-faded seams (`_TiledDecode`), which is what its pipelines use.
 
 Channels-last bf16 activations [T,H,W,C].  Replicate-padded causal convs (CausalConv3d :124-158) = one `pad_replicate` pass +
 the tcgen05 implicit-GEMM conv over the padded tensor (TMA zero fill cannot replicate); 1x1x1 convs are plain GEMMs over
@@ -289,7 +289,82 @@ class _Posterior:
         return self.mean + torch.exp(0.5 * self.logvar) * eps.to(self.mean.device)
 
 
-class AutoencoderKLConv3D(torch.nn.Module):
+class _TiledDecode:
+    """The tiling switches and dispatch both Hunyuan VAE classes share (hunyuanvideo_15_vae.py:582-625, 806-864, 889-896;
+    autoencoder_kl_causal_3d.py:297-330, 474-482, 638-855).  The pipelines call enable_tiling() before every decode (hunyuan.py:772,
+    pipeline_hunyuan_video.py:695) and get_VAE_tile_size() picks 256 px x 64 frames even on a large GPU, so the reference's ACTUAL output is
+    the tiled + cross-faded one; this reproduces it tile for tile (each tile = one whole-clip decode on the B200 kernels, seams blended
+    by b200_blend_edge_f32).  disable_tiling() gives the un-tiled whole-clip decode (one pass, no seams, ~2x fewer FLOPs)."""
+
+    tile_overlap_factor = 0.25
+    use_spatial_tiling = use_temporal_tiling = False
+
+    def _init_tiles(self, sample_size, sample_tsize, lat_size, lat_tsize):
+        self.tile_sample_min_size, self.tile_sample_min_tsize = sample_size, sample_tsize
+        self.tile_latent_min_size, self.tile_latent_min_tsize = lat_size, lat_tsize
+
+    def enable_spatial_tiling(self, use_tiling=True):
+        self.use_spatial_tiling = use_tiling
+
+    def enable_temporal_tiling(self, use_tiling=True):
+        self.use_temporal_tiling = use_tiling
+
+    def enable_tiling(self, use_tiling=True):
+        self.enable_spatial_tiling(use_tiling), self.enable_temporal_tiling(use_tiling)
+
+    def disable_spatial_tiling(self):
+        self.enable_spatial_tiling(False)
+
+    def disable_temporal_tiling(self):
+        self.enable_temporal_tiling(False)
+
+    def disable_tiling(self):
+        self.enable_tiling(False)
+
+    def enable_slicing(self):
+        return None                              # batch items are decoded one at a time anyway
+
+    disable_slicing = enable_slicing
+
+    def _decode_clip(self, z):
+        """z [zc,T,h,w] -> frames fp32 [3,F,H,W] with the reference's tiling dispatch."""
+        from ..wan.vae import _lib as lib, spatial_tiles
+        ov = self.tile_overlap_factor
+        one = lambda t: self.decoder(t[None])[0]                                                       # noqa: E731
+
+        def sp(t):
+            ls = self.tile_latent_min_size
+            if self.use_spatial_tiling and (t.shape[-1] > ls or t.shape[-2] > ls):
+                blend = int(self.tile_sample_min_size * ov)
+                return spatial_tiles(t, ls, int(ls * (1 - ov)), one, blend, self.tile_sample_min_size - blend)
+            return one(t.contiguous())
+        lt = self.tile_latent_min_tsize
+        if not (self.use_temporal_tiling and z.shape[1] > lt):
+            return sp(z)
+        stride, blend = int(lt * (1 - ov)), int(self.tile_sample_min_tsize * ov)
+        if not 0 < stride < lt:
+            raise ValueError("temporal tile stride must be in (0, tile_latent_min_tsize)")
+        t_limit = self.tile_sample_min_tsize - blend
+        row = []
+        for i in range(0, z.shape[1], stride):
+            d = sp(z[:, i:i + lt + 1])
+            row.append(d[:, 1:].contiguous() if i > 0 else d)
+        out = []
+        for i, t in enumerate(row):
+            if i > 0 and t.shape[1] > 0:
+                a = row[i - 1]                     # blend_t: frames are the "rows" of a [C, F, H*W] tile
+                lib.call("b200_blend_edge_f32", a.data_ptr(), t.data_ptr(), a.shape[0], a.shape[1], a.shape[2] * a.shape[3], t.shape[1],
+                         t.shape[2] * t.shape[3], blend, 1, _s())
+            out.append(t[:, :t_limit + (1 if i == 0 else 0)])
+        return torch.cat(out, 1)
+
+    def _decode_batch(self, z):
+        if not (self.use_spatial_tiling or self.use_temporal_tiling):
+            return self.decoder(z)
+        return torch.stack([self._decode_clip(zi.to(self.decoder.device, f32)) for zi in z], 0)
+
+
+class AutoencoderKLConv3D(_TiledDecode, torch.nn.Module):
     """Decode surface of models/hyvideo/vae/hunyuanvideo_15_vae.py::AutoencoderKLConv3D (:523-907)."""
 
     def __init__(self, in_channels=3, out_channels=3, latent_channels=32, block_out_channels=(128, 256, 512, 1024, 1024),
@@ -303,6 +378,7 @@ class AutoencoderKLConv3D(torch.nn.Module):
                    num_res_blocks=layers_per_block, ffactor_spatial=ffactor_spatial, ffactor_temporal=ffactor_temporal)
         self.decoder = HYVAEDecoder(cfg, device)
         self.encoder = HYVAEEncoder(cfg, device)
+        self._init_tiles(sample_size, sample_tsize, sample_size // ffactor_spatial, sample_tsize // ffactor_temporal)     # :568-575
 
     def load_state_dict(self, sd, strict=True, assign=False):
         enc = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
@@ -310,17 +386,15 @@ class AutoencoderKLConv3D(torch.nn.Module):
             self.encoder.load_state_dict(enc)
         return self.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
 
-    def enable_tiling(self, *a, **k):          # un-tiled whole-clip decode on a 180 GB GPU
-        return None
-
-    def enable_spatial_tiling(self, *a, **k):
-        return None
-
-    def enable_temporal_tiling(self, *a, **k):
-        return None
+    def set_tile_sample_min_size(self, sample_size, tile_overlap_factor=0.25, sample_tsize=None):
+        """hunyuanvideo_15_vae.py:582-594."""
+        self.tile_sample_min_size, self.tile_latent_min_size = sample_size, sample_size // self.ffactor_spatial
+        self.tile_overlap_factor = tile_overlap_factor
+        if sample_tsize is not None:
+            self.tile_sample_min_tsize, self.tile_latent_min_tsize = sample_tsize, sample_tsize // self.ffactor_temporal
 
     def decode(self, z, return_dict=True, generator=None):
-        out = self.decoder(z)
+        out = self._decode_batch(z)
         return types.SimpleNamespace(sample=out) if return_dict else (out,)
 
     def encode(self, x, return_dict=True):

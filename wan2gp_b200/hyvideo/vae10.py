@@ -1,9 +1,9 @@
 """B200-native HunyuanVideo 1.0 VAE decode (hot-path row H5 of SURVEY.md section 8a): the `AutoencoderKLCausal3D` surface the
 pipeline uses (`.decode(z, return_dict=False)[0]`, `.enable_tiling()`, `.config.scaling_factor`,
 models/hyvideo/diffusion/pipelines/pipeline_hunyuan_video.py:1790-1812) over post_quant_conv + DecoderCausal3D
-(models/hyvideo/vae/autoencoder_kl_causal_3d.py:474-493, vae/vae.py:186-365, vae/unet_causal_3d_blocks.py), UN-TILED: one
-B200 holds the whole clip, so the tiling switches are no-ops (the reference tiles to fit small GPUs; tiled + blended output
-differs from the plain decoder near tile seams).
+(models/hyvideo/vae/autoencoder_kl_causal_3d.py:474-493, vae/vae.py:186-365, vae/unet_causal_3d_blocks.py).  Un-tiled by default
+(one B200 holds the whole clip); `enable_tiling()` switches to the reference's temporal + spatial tiling with cross-faded seams
+(hyvideo/vae.py::_TiledDecode), which is what its pipelines use.
 
 Channels-last bf16 activations [T,H,W,C].
   * GroupNorm (clip-wide statistics) -> SiLU -> replicate pad is ONE elementwise pass after a statistics pass: it writes the
@@ -19,7 +19,7 @@ import types
 import torch
 
 from .. import _lib, ops, synth
-from .vae import _Posterior, _RepConv, norm_act_conv
+from .vae import _Posterior, _RepConv, _TiledDecode, norm_act_conv
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -323,7 +323,7 @@ HYVAE10Encoder._res = staticmethod(HYVAE10Decoder._res)
 HYVAE10Encoder._attn = HYVAE10Decoder._attn
 
 
-class AutoencoderKLCausal3D(torch.nn.Module):
+class AutoencoderKLCausal3D(_TiledDecode, torch.nn.Module):
     """Decode surface of models/hyvideo/vae/autoencoder_kl_causal_3d.py::AutoencoderKLCausal3D."""
 
     def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None, block_out_channels=(128, 256, 512, 512),
@@ -339,19 +339,16 @@ class AutoencoderKLCausal3D(torch.nn.Module):
                    spatial_compression_ratio=spatial_compression_ratio, mid_block_causal_attn=mid_block_causal_attn)
         self.decoder = HYVAE10Decoder(cfg, device)
         self.encoder = HYVAE10Encoder(cfg, device)
+        ss = sample_size[0] if isinstance(sample_size, (list, tuple)) else sample_size                    # autoencoder_kl_causal_3d.py:251-262
+        self._init_tiles(ss, sample_tsize, int(ss / (2 ** (len(block_out_channels) - 1))), sample_tsize // time_compression_ratio)
 
     def load_state_dict(self, sd, strict=True, assign=False):
         if "encoder.conv_in.conv.weight" in sd:                 # decode-only checkpoints carry no encoder
             self.encoder.load_state_dict({k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))})
         return self.decoder.load_state_dict({k: v for k, v in sd.items() if k.startswith(("decoder.", "post_quant_conv."))})
 
-    def enable_tiling(self, *a, **k):            # un-tiled whole-clip decode on a 180 GB GPU
-        return None
-
-    enable_spatial_tiling = enable_temporal_tiling = disable_tiling = enable_slicing = disable_slicing = enable_tiling
-
     def decode(self, z, return_dict=True, generator=None):
-        out = self.decoder(z)
+        out = self._decode_batch(z)
         return types.SimpleNamespace(sample=out) if return_dict else (out,)
 
     def encode(self, x, return_dict=True):
