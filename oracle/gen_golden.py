@@ -312,6 +312,18 @@ def run_unipc(name):
         traj.append(x.numpy().copy())
     np.savez_compressed(os.path.join(GOLDEN, "unipc.npz"), steps=steps, shift=shift, timesteps=ref.timesteps.numpy(), traj=np.stack(traj))
     print(f"unipc: {steps} steps, final absmean {np.abs(traj[-1]).mean():.6f}")
+    # dpm++ (any2video.py:523-532): FlowDPMSolverMultistepScheduler fed with get_sampling_sigmas through retrieve_timesteps
+    R = load_reference_unipc()
+    ref = R.FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    ts, _ = R.retrieve_timesteps(ref, device="cpu", sigmas=R.get_sampling_sigmas(steps, shift))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64)
+    traj = []
+    for i, t in enumerate(ts):
+        x = ref.step(torch.randn(1, 4, 2, 3, 5, generator=g, dtype=torch.float64), t, x, return_dict=False)[0]
+        traj.append(x.numpy().copy())
+    np.savez_compressed(os.path.join(GOLDEN, "dpmpp.npz"), steps=steps, shift=shift, timesteps=ts.numpy(), traj=np.stack(traj))
+    print(f"dpm++: {steps} steps, final absmean {np.abs(traj[-1]).mean():.6f}")
 
 
 if __name__ == "__main__":

@@ -352,5 +352,12 @@ def load_reference_unipc():
     spec = importlib.util.spec_from_file_location("_ref_fm_solvers_unipc", os.path.join(REFERENCE_ROOT, "shared/utils/fm_solvers_unipc.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    _loaded_unipc = types.SimpleNamespace(FlowUniPCMultistepScheduler=m.FlowUniPCMultistepScheduler)
+    du.BaseOutput = dict
+    mod("diffusers.utils.torch_utils", randn_tensor=lambda *a, **k: None)
+    spec2 = importlib.util.spec_from_file_location("_ref_fm_solvers", os.path.join(REFERENCE_ROOT, "shared/utils/fm_solvers.py"))
+    m2 = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(m2)
+    _loaded_unipc = types.SimpleNamespace(FlowUniPCMultistepScheduler=m.FlowUniPCMultistepScheduler,
+                                          FlowDPMSolverMultistepScheduler=m2.FlowDPMSolverMultistepScheduler,
+                                          get_sampling_sigmas=m2.get_sampling_sigmas, retrieve_timesteps=m2.retrieve_timesteps)
     return _loaded_unipc

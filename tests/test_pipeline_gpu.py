@@ -116,3 +116,24 @@ def test_denoise_loop_unipc_matches_oracle():
     r = rel_l2(got, lat)
     print(f"4-step UniPC denoise loop: latents vs oracle loop rel-L2 {r:.3e}")
     assert r < 1e-2
+
+
+def test_dpmpp_through_fused_kernel():
+    """sample_solver="dpm++": the same fused kernel with DPMppSchedule's coefficients, vs the fp64 restatement."""
+    from oracle import wan_oracle
+    from wan2gp_b200 import ops
+    from wan2gp_b200.pipeline import DPMppSchedule, WanDenoiser
+    steps, shift, g = 6, 5.0, 3.0
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 16, 2, 6, 8, generator=gen)
+    sch_g, sch_c = DPMppSchedule(steps, shift), DPMppSchedule(steps, shift)
+    xg, hist = x.cuda(), [torch.zeros(1, 16, 2, 6, 8, device="cuda") for _ in range(3)]
+    xc, xl, m0, m1 = x.double(), 0, torch.zeros_like(x).double(), torch.zeros_like(x).double()
+    for i in range(steps):
+        c, u = torch.randn(x.shape, generator=gen), torch.randn(x.shape, generator=gen)
+        xc, _, x0 = wan_oracle.unipc_step(xc, wan_oracle.cfg_combine(c.double(), u.double(), g), xl, m0, m1, sch_c.coefficients(i))
+        m0, m1 = x0, m0
+        ops.cfg_unipc_step_(xg, c.cuda(), u.cuda(), g, hist[0], hist[1], hist[2], sch_g.coefficients(i))
+        hist = [hist[0], hist[2], hist[1]]
+        assert rel_l2(xg.cpu(), xc) < 2e-5, i
+    assert WanDenoiser(None, num_steps=4, shift=5.0, sample_solver="dpm++").timesteps[:4] == [float(t) for t in DPMppSchedule(4, 5.0).timesteps]

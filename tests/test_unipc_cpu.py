@@ -9,13 +9,13 @@ import torch
 
 from oracle import wan_oracle
 from tests.helpers import GOLDEN, rel_l2
-from wan2gp_b200.pipeline import UniPCSchedule
+from wan2gp_b200.pipeline import DPMppSchedule, UniPCSchedule
 
 CASES = [(6, 5.0), (20, 3.0), (30, 12.0), (2, 1.0), (1, 5.0)]
 
 
-def run_ours(steps, shift, x, vs):
-    sch = UniPCSchedule(steps, shift)
+def run_ours(steps, shift, x, vs, cls=UniPCSchedule):
+    sch = cls(steps, shift)
     x = x.clone()
     x_last, m0, m1 = torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
     traj = []
@@ -68,3 +68,31 @@ def test_unipc_orders():
     assert all(c["pr"] != 0 for c in cs[1:4]) and cs[4]["pr"] == 0
     assert cs[4]["pp"] == 0 and abs(cs[4]["pq"] - 1.0) < 1e-12            # sigma_next = 0: x_next = x0
     assert all(np.isfinite(list(c.values())).all() for c in cs)
+
+
+@pytest.mark.parametrize("steps,shift", CASES)
+def test_dpmpp_matches_reference_scheduler(steps, shift):
+    """sample_solver="dpm++" (any2video.py:523-532): host coefficients + the same fused update vs FlowDPMSolverMultistepScheduler."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is only present in the build container; the committed fixture covers this elsewhere")
+    from oracle.refshim import load_reference_unipc
+    R = load_reference_unipc()
+    ref = R.FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    ts, _ = R.retrieve_timesteps(ref, device="cpu", sigmas=R.get_sampling_sigmas(steps, shift))
+    x, vs = inputs(steps)
+    sch, traj = run_ours(steps, shift, x, vs, DPMppSchedule)
+    assert sch.timesteps == [int(t) for t in ts]
+    xr = x.clone()
+    for i, t in enumerate(ts):
+        xr = ref.step(vs[i], t, xr, return_dict=False)[0]
+        assert rel_l2(traj[i], xr) < 2e-5, (i, rel_l2(traj[i], xr))
+
+
+def test_dpmpp_matches_fixture():
+    g = np.load(os.path.join(GOLDEN, "dpmpp.npz"))
+    steps, shift = int(g["steps"]), float(g["shift"])
+    x, vs = inputs(steps)
+    sch, traj = run_ours(steps, shift, x, vs, DPMppSchedule)
+    assert sch.timesteps == [int(t) for t in g["timesteps"]]
+    for i in range(steps):
+        assert rel_l2(traj[i], torch.from_numpy(g["traj"][i])) < 2e-5

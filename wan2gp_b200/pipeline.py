@@ -96,6 +96,40 @@ class UniPCSchedule:
         return {k: (v if isinstance(v, bool) else float(v)) for k, v in c.items()}
 
 
+class DPMppSchedule:
+    """Host side of FlowDPMSolverMultistepScheduler (shared/utils/fm_solvers.py; `sample_solver="dpm++"`, any2video.py:523-532):
+    dpmsolver++ order 2, midpoint, final_sigmas_type "zero" (last step first order), sigmas = get_sampling_sigmas(steps, shift).
+    Its update is the same linear form the UniPC kernel applies, without a corrector (fm_solvers.py:459-478, 529-560):
+        x0 = x - sigma_i v;   xn = pp x + pq x0 + pr x0_{i-1}
+    first order:  pp = sigma_t/sigma_s, pq = -alpha_t (e^{-h} - 1);   second:  pq *= (1 + 1/(2 r0)), pr = alpha_t (e^{-h} - 1) / (2 r0)."""
+
+    def __init__(self, num_steps, shift=5.0, num_train_timesteps=1000):
+        sig = np.linspace(1, 0, num_steps + 1)[:num_steps]                       # get_sampling_sigmas (fm_solvers.py:22-26)
+        sig = shift * sig / (1 + (shift - 1) * sig)
+        self.timesteps = [int(v) for v in (sig * num_train_timesteps).astype(np.int64)]
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32).astype(np.float64)
+        self.num_steps = num_steps
+        self.reset()
+
+    def reset(self):
+        self.lower_order_nums = 0
+
+    def coefficients(self, i):
+        sg, lam = self.sigmas, UniPCSchedule._lam
+        sigma_t, sigma_s0 = sg[i + 1], sg[i]
+        alpha_t = 1.0 - sigma_t
+        with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
+            h = lam(sigma_t) - lam(sigma_s0)
+            coef = -alpha_t * np.expm1(-h)
+            first = self.lower_order_nums < 1 or i == self.num_steps - 1         # lower_order_final with final sigma zero (:745-749)
+            k1 = 0.0 if first else 0.5 / ((lam(sigma_s0) - lam(sg[i - 1])) / h)
+        c = dict(sigma=float(sg[i]), use_corrector=False, ca=0.0, cb=0.0, cc=0.0, cd=0.0,
+                 pp=float(sigma_t / sigma_s0), pq=float(coef * (1 + k1)), pr=float(-coef * k1))
+        if self.lower_order_nums < 2:
+            self.lower_order_nums += 1
+        return c
+
+
 class WanDenoiser:
     """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
 
@@ -113,9 +147,9 @@ class WanDenoiser:
         self.cfg_star_switch, self.cfg_zero_step = cfg_star_switch, cfg_zero_step      # CFG-Zero* (any2video.py:1701-1722)
         self.device = torch.device(device)
         self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
-        if sample_solver not in ("euler", "unipc", ""):
-            raise NotImplementedError(f"sample_solver {sample_solver!r}: euler and unipc (the WanGP default) are built")
-        self.unipc = None if sample_solver == "euler" else UniPCSchedule(num_steps, shift)
+        if sample_solver not in ("euler", "unipc", "", "dpm++"):
+            raise NotImplementedError(f"sample_solver {sample_solver!r}: euler, unipc (the WanGP default) and dpm++ are built")
+        self.unipc = None if sample_solver == "euler" else (DPMppSchedule if sample_solver == "dpm++" else UniPCSchedule)(num_steps, shift)
         self.timesteps = euler_timesteps(num_steps, shift) if self.unipc is None else [float(t) for t in self.unipc.timesteps] + [0.0]
         self.num_steps = num_steps
         self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
