@@ -288,13 +288,18 @@ def run_hy_tiled(name):
         vae = hv.AutoencoderKLCausal3D(in_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4, up_block_types=("UpDecoderBlockCausal3D",) * 4,
                                        sample_size=sample_size, sample_tsize=sample_tsize, **cfg).eval().requires_grad_(False)
         vae.load_state_dict(synth.make_hyvae10_state_dict(cfg, seed, encoder=True))
+    if fam == "1.5":
+        vae.encoder.load_state_dict(synth.make_hyvae_state_dict(cfg, seed, encoder=True))
     vae.enable_tiling()
     z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")
+    fs, ft = (cfg["ffactor_spatial"], cfg["ffactor_temporal"]) if fam == "1.5" else (8, 4)
+    xv = synth._normal((1, 3, ft * (zshape[1] - 1) + 1, fs * zshape[2], fs * zshape[3]), 0.5, seed, "input.video", "cpu").clamp_(-1, 1)
     with torch.no_grad():
         out = vae.decode(z, return_dict=False)[0]
+        enc = vae.encode(xv, return_dict=False)[0].parameters          # moments of the tiled encode of a clip of the decoded size
     print(f"{name}: reference tiled decode out {tuple(out.shape)} absmean {out.abs().mean():.6f}; latent tile {vae.tile_latent_min_size} x {vae.tile_latent_min_tsize}")
-    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), sample_size=sample_size, sample_tsize=sample_tsize,
-                        lat_size=vae.tile_latent_min_size, lat_tsize=vae.tile_latent_min_tsize)
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), enc=enc.numpy().astype(np.float32),
+                        sample_size=sample_size, sample_tsize=sample_tsize, lat_size=vae.tile_latent_min_size, lat_tsize=vae.tile_latent_min_tsize)
 
 
 def run_unipc(name):

@@ -139,25 +139,26 @@ def hyvae_encode(sd, cfg, x, emulate_bf16=False):
     return causal_conv3d_rep(y, sd["conv_out.conv.weight"], sd["conv_out.conv.bias"], em) + _q(sc, em)
 
 
-def tiled_decode(decode_fn, z, lat_size, lat_tsize, sample_size, sample_tsize, overlap=0.25, spatial=True, temporal=True):
-    """The tiling dispatch shared by both Hunyuan VAEs (hunyuanvideo_15_vae.py:806-864, 889-896; autoencoder_kl_causal_3d.py:474-482,
-    638-855): temporal tiles of lat_tsize+1 latent frames with stride int(lat_tsize*(1-overlap)) (first decoded frame of every tile
-    but the first dropped, blend_t over int(sample_tsize*overlap) frames), each decoded through spatial tiles of lat_size with
-    stride int(lat_size*(1-overlap)) (blend_v / blend_h over int(sample_size*overlap) pixels).  decode_fn: [zc,T,h,w] -> [3,F,H,W]."""
+def tiled(fn, x, in_s, in_t, out_s, out_t, overlap=0.25, spatial=True, temporal=True):
+    """The tiling dispatch shared by both Hunyuan VAEs, decode and encode (hunyuanvideo_15_vae.py:650-703, 806-864, 866-896;
+    autoencoder_kl_causal_3d.py:435-482, 597-855): temporal tiles of in_t+1 frames with stride int(in_t*(1-overlap)) (first output frame
+    of every tile but the first dropped, blend_t over int(out_t*overlap) frames), each mapped through spatial tiles of in_s with stride
+    int(in_s*(1-overlap)) (blend_v / blend_h over int(out_s*overlap)).  Decode: in = latent tile sizes, out = sample tile sizes; encode:
+    the other way round.  fn: [C,T,h,w] -> [C',T',h',w']."""
     from .vae_oracle import spatial_tiles
 
     def sp(t):
-        if spatial and (t.shape[-1] > lat_size or t.shape[-2] > lat_size):
-            blend = int(sample_size * overlap)
-            return spatial_tiles(t, lat_size, int(lat_size * (1 - overlap)), decode_fn, blend, sample_size - blend)
-        return decode_fn(t)
-    if not (temporal and z.shape[1] > lat_tsize):
-        return sp(z)
-    stride, blend = int(lat_tsize * (1 - overlap)), int(sample_tsize * overlap)
-    t_limit = sample_tsize - blend
+        if spatial and (t.shape[-1] > in_s or t.shape[-2] > in_s):
+            blend = int(out_s * overlap)
+            return spatial_tiles(t, in_s, int(in_s * (1 - overlap)), fn, blend, out_s - blend)
+        return fn(t)
+    if not (temporal and x.shape[1] > in_t):
+        return sp(x)
+    stride, blend = int(in_t * (1 - overlap)), int(out_t * overlap)
+    t_limit = out_t - blend
     row = []
-    for i in range(0, z.shape[1], stride):
-        d = sp(z[:, i:i + lat_tsize + 1]).clone()
+    for i in range(0, x.shape[1], stride):
+        d = sp(x[:, i:i + in_t + 1]).clone()
         row.append(d[:, 1:] if i > 0 else d)
     out = []
     for i, t in enumerate(row):
@@ -170,3 +171,11 @@ def tiled_decode(decode_fn, z, lat_size, lat_tsize, sample_size, sample_tsize, o
         else:
             out.append(t[:, :t_limit + 1])
     return torch.cat(out, 1)
+
+
+def tiled_decode(decode_fn, z, lat_size, lat_tsize, sample_size, sample_tsize, **kw):
+    return tiled(decode_fn, z, lat_size, lat_tsize, sample_size, sample_tsize, **kw)
+
+
+def tiled_encode(encode_fn, x, lat_size, lat_tsize, sample_size, sample_tsize, **kw):
+    return tiled(encode_fn, x, sample_size, sample_tsize, lat_size, lat_tsize, **kw)

@@ -230,7 +230,10 @@ def load_reference_hyvae():
     class BaseOutput(dict):
         pass
     sys.modules["diffusers.models.autoencoders.vae"].BaseOutput = BaseOutput
-    sys.modules["diffusers.models.autoencoders.vae"].DiagonalGaussianDistribution = type("DiagonalGaussianDistribution", (), {})
+    class DiagonalGaussianDistribution:          # diffusers' posterior container: only `.parameters` (the encoder's moments) is read here
+        def __init__(self, parameters, deterministic=False):
+            self.parameters = parameters
+    sys.modules["diffusers.models.autoencoders.vae"].DiagonalGaussianDistribution = DiagonalGaussianDistribution
     sys.modules["diffusers.models.modeling_outputs"].AutoencoderKLOutput = type("AutoencoderKLOutput", (BaseOutput,), {})
     m = types.ModuleType("models.hyvideo.vae")
     m.__path__ = [os.path.join(REFERENCE_ROOT, "models/hyvideo/vae")]

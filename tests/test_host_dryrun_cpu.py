@@ -46,14 +46,18 @@ def test_hunyuan_vae_host_paths(stub_abi):
     from wan2gp_b200.hyvideo import AutoencoderKLCausal3D, AutoencoderKLConv3D
     vae = AutoencoderKLConv3D(latent_channels=8, block_out_channels=[32, 64, 64], layers_per_block=1, ffactor_spatial=4, ffactor_temporal=2,
                               sample_size=16, sample_tsize=8, device="cpu")
-    vae.load_state_dict({"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 0).items()})
+    full = {"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 0).items()}
+    full.update({"encoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 0, encoder=True).items()})
+    vae.load_state_dict(full)
     vae.enable_tiling()
     assert vae.decode(torch.randn(1, 8, 7, 6, 10), return_dict=False)[0].shape == (1, 3, 13, 24, 40)
+    assert vae.encode(torch.randn(1, 3, 13, 24, 40)).latent_dist.mean.shape == (1, 8, 7, 6, 10)
     cfg10 = synth.HYVAE10_CONFIGS["hyvae10_tiny"]
     vae = AutoencoderKLCausal3D(sample_size=32, sample_tsize=16, device="cpu", **cfg10)
     vae.load_state_dict(synth.make_hyvae10_state_dict(cfg10, 0, encoder=True))
     vae.enable_tiling()
     assert vae.decode(torch.randn(1, 8, 7, 5, 7), return_dict=False)[0].shape == (1, 3, 25, 40, 56)
+    assert vae.encode(torch.randn(1, 3, 25, 40, 56)).latent_dist.mean.shape == (1, 8, 7, 5, 7)
     assert "b200_blend_edge_f32" in stub_abi
     vae.disable_tiling()
     assert vae.decode(torch.randn(1, 8, 2, 2, 3), return_dict=True).sample.shape == (1, 3, 5, 16, 24)

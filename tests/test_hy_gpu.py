@@ -246,13 +246,17 @@ def test_hunyuan_tiled_decode(name):
         vae = AutoencoderKLConv3D(latent_channels=cfg["z_channels"], block_out_channels=list(reversed(cfg["block_out_channels"])),
                                   layers_per_block=cfg["num_res_blocks"], ffactor_spatial=cfg["ffactor_spatial"],
                                   ffactor_temporal=cfg["ffactor_temporal"], sample_size=ss, sample_tsize=st)
-        vae.load_state_dict({"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 6).items()})
+        full = {"decoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 6).items()}
+        full.update({"encoder." + k: v for k, v in synth.make_hyvae_state_dict(cfg, 6, encoder=True).items()})
+        vae.load_state_dict(full)
         z = synth._normal((1, 8, 7, 6, 10), 1.0, 6, "input.z", "cpu")
+        xv = synth._normal((1, 3, 13, 24, 40), 0.5, 6, "input.video", "cpu").clamp_(-1, 1)
     else:
         cfg = synth.HYVAE10_CONFIGS["hyvae10_tiny"]
         vae = AutoencoderKLCausal3D(sample_size=ss, sample_tsize=st, **cfg)
         vae.load_state_dict(synth.make_hyvae10_state_dict(cfg, 7, encoder=True))
         z = synth._normal((1, 8, 7, 5, 7), 1.0, 7, "input.z", "cpu")
+        xv = synth._normal((1, 3, 25, 40, 56), 0.5, 7, "input.video", "cpu").clamp_(-1, 1)
     assert (vae.tile_latent_min_size, vae.tile_latent_min_tsize) == (int(g["lat_size"]), int(g["lat_tsize"]))
     untiled = vae.decode(z.cuda(), return_dict=False)[0]
     vae.enable_tiling()
@@ -260,5 +264,9 @@ def test_hunyuan_tiled_decode(name):
     ref = g["out"][0]
     print(f"{name}: vs reference tiled decode rel-L2 {rel_l2(got, ref):.3e}, PSNR {psnr(got.clamp(-1, 1), ref.clamp(-1, 1), 2.0):.1f} dB")
     assert got.shape == ref.shape and rel_l2(got, ref) < 6e-2 and psnr(got.clamp(-1, 1), ref.clamp(-1, 1), 2.0) > 35.0
+    post = vae.encode(xv.cuda()).latent_dist                                            # tiled encode (same switches)
+    mom = torch.cat([post.mean, post.logvar], 1)[0].cpu()
+    print(f"{name}: tiled encode vs reference rel-L2 {rel_l2(mom, g['enc'][0]):.3e}")
+    assert mom.shape == g["enc"][0].shape and rel_l2(mom, g["enc"][0]) < 6e-2
     vae.disable_tiling()
     assert torch.equal(vae.decode(z.cuda(), return_dict=False)[0], untiled)

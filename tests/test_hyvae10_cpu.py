@@ -139,13 +139,20 @@ def test_hunyuan_tiled_decode_oracle_matches_reference(name):
     g = load_golden(name)
     if name == "hyvae_tiled":
         cfg = synth.HYVAE_CONFIGS["hyvae_tiny"]
-        sd = synth.make_hyvae_state_dict(cfg, 6)
+        sd, sde = synth.make_hyvae_state_dict(cfg, 6), synth.make_hyvae_state_dict(cfg, 6, encoder=True)
         z = synth._normal((1, 8, 7, 6, 10), 1.0, 6, "input.z", "cpu")[0]
+        xv = synth._normal((1, 3, 13, 24, 40), 0.5, 6, "input.video", "cpu").clamp_(-1, 1)[0]
         fn = lambda t: hyvae_oracle.hyvae_decode(sd, cfg, t)                                          # noqa: E731
+        fe = lambda t: hyvae_oracle.hyvae_encode(sde, cfg, t)                                         # noqa: E731
     else:
         cfg = synth.HYVAE10_CONFIGS["hyvae10_tiny"]
         sd = synth.make_hyvae10_state_dict(cfg, 7, encoder=True)
         z = synth._normal((1, 8, 7, 5, 7), 1.0, 7, "input.z", "cpu")[0]
+        xv = synth._normal((1, 3, 25, 40, 56), 0.5, 7, "input.video", "cpu").clamp_(-1, 1)[0]
         fn = lambda t: hyvae10_oracle.hyvae10_decode(sd, cfg, t)                                      # noqa: E731
-    out = hyvae_oracle.tiled_decode(fn, z, int(g["lat_size"]), int(g["lat_tsize"]), int(g["sample_size"]), int(g["sample_tsize"]))
+        fe = lambda t: hyvae10_oracle.hyvae10_encode(sd, cfg, t)                                      # noqa: E731
+    tiles = (int(g["lat_size"]), int(g["lat_tsize"]), int(g["sample_size"]), int(g["sample_tsize"]))
+    out = hyvae_oracle.tiled_decode(fn, z, *tiles)
     assert out.shape == g["out"][0].shape and rel_l2(out, g["out"][0]) < 5e-6
+    enc = hyvae_oracle.tiled_encode(fe, xv, *tiles)                                                     # tiled encode -> posterior moments
+    assert enc.shape == g["enc"][0].shape and rel_l2(enc, g["enc"][0]) < 5e-6

@@ -326,28 +326,28 @@ class _TiledDecode:
 
     disable_slicing = enable_slicing
 
-    def _decode_clip(self, z):
-        """z [zc,T,h,w] -> frames fp32 [3,F,H,W] with the reference's tiling dispatch."""
+    def _tiled_clip(self, x, fn, in_s, in_t, out_s, out_t):
+        """x [C,T,h,w] -> fn applied tile by tile with the reference's dispatch.  Decode: in = latent tile sizes, out = sample tile sizes
+        (temporal_tiled_decode / spatial_tiled_decode); encode: the other way round (temporal_tiled_encode / spatial_tiled_encode).
+        Strides come from the INPUT tile, blend extents and crop limits from the OUTPUT tile."""
         from ..wan.vae import _lib as lib, spatial_tiles
         ov = self.tile_overlap_factor
-        one = lambda t: self.decoder(t[None])[0]                                                       # noqa: E731
+        one = lambda t: fn(t[None])[0]                                                                # noqa: E731
 
         def sp(t):
-            ls = self.tile_latent_min_size
-            if self.use_spatial_tiling and (t.shape[-1] > ls or t.shape[-2] > ls):
-                blend = int(self.tile_sample_min_size * ov)
-                return spatial_tiles(t, ls, int(ls * (1 - ov)), one, blend, self.tile_sample_min_size - blend)
+            if self.use_spatial_tiling and (t.shape[-1] > in_s or t.shape[-2] > in_s):
+                blend = int(out_s * ov)
+                return spatial_tiles(t, in_s, int(in_s * (1 - ov)), one, blend, out_s - blend)
             return one(t.contiguous())
-        lt = self.tile_latent_min_tsize
-        if not (self.use_temporal_tiling and z.shape[1] > lt):
-            return sp(z)
-        stride, blend = int(lt * (1 - ov)), int(self.tile_sample_min_tsize * ov)
-        if not 0 < stride < lt:
-            raise ValueError("temporal tile stride must be in (0, tile_latent_min_tsize)")
-        t_limit = self.tile_sample_min_tsize - blend
+        if not (self.use_temporal_tiling and x.shape[1] > in_t):
+            return sp(x)
+        stride, blend = int(in_t * (1 - ov)), int(out_t * ov)
+        if not 0 < stride < in_t:
+            raise ValueError("temporal tile stride must be in (0, tile size)")
+        t_limit = out_t - blend
         row = []
-        for i in range(0, z.shape[1], stride):
-            d = sp(z[:, i:i + lt + 1])
+        for i in range(0, x.shape[1], stride):
+            d = sp(x[:, i:i + in_t + 1])
             row.append(d[:, 1:].contiguous() if i > 0 else d)
         out = []
         for i, t in enumerate(row):
@@ -361,7 +361,14 @@ class _TiledDecode:
     def _decode_batch(self, z):
         if not (self.use_spatial_tiling or self.use_temporal_tiling):
             return self.decoder(z)
-        return torch.stack([self._decode_clip(zi.to(self.decoder.device, f32)) for zi in z], 0)
+        args = (self.tile_latent_min_size, self.tile_latent_min_tsize, self.tile_sample_min_size, self.tile_sample_min_tsize)
+        return torch.stack([self._tiled_clip(zi.to(self.decoder.device, f32), self.decoder, *args) for zi in z], 0)
+
+    def _encode_batch(self, x):
+        if not (self.use_spatial_tiling or self.use_temporal_tiling):
+            return self.encoder(x)
+        args = (self.tile_sample_min_size, self.tile_sample_min_tsize, self.tile_latent_min_size, self.tile_latent_min_tsize)
+        return torch.stack([self._tiled_clip(xi.to(self.encoder.device, f32), self.encoder, *args) for xi in x], 0)
 
 
 class AutoencoderKLConv3D(_TiledDecode, torch.nn.Module):
@@ -399,5 +406,5 @@ class AutoencoderKLConv3D(_TiledDecode, torch.nn.Module):
 
     def encode(self, x, return_dict=True):
         """AutoencoderKLConv3D.encode (:866-887), tiling off: posterior over the encoder's moments."""
-        post = _Posterior(self.encoder(x))
+        post = _Posterior(self._encode_batch(x))
         return types.SimpleNamespace(latent_dist=post) if return_dict else (post,)

@@ -353,5 +353,5 @@ class AutoencoderKLCausal3D(_TiledDecode, torch.nn.Module):
 
     def encode(self, x, return_dict=True):
         """AutoencoderKLCausal3D.encode (autoencoder_kl_causal_3d.py:435-472), tiling off: posterior over quant_conv(encoder(x))."""
-        post = _Posterior(self.encoder(x))
+        post = _Posterior(self._encode_batch(x))
         return types.SimpleNamespace(latent_dist=post) if return_dict else (post,)
