@@ -360,7 +360,13 @@ def load_reference_unipc():
     spec2 = importlib.util.spec_from_file_location("_ref_fm_solvers", os.path.join(REFERENCE_ROOT, "shared/utils/fm_solvers.py"))
     m2 = importlib.util.module_from_spec(spec2)
     spec2.loader.exec_module(m2)
+    mods = {}
+    for nm in ("lcm_scheduler", "basic_flowmatch"):
+        sp = importlib.util.spec_from_file_location("_ref_" + nm, os.path.join(REFERENCE_ROOT, "shared/utils", nm + ".py"))
+        mods[nm] = importlib.util.module_from_spec(sp)
+        sp.loader.exec_module(mods[nm])
     _loaded_unipc = types.SimpleNamespace(FlowUniPCMultistepScheduler=m.FlowUniPCMultistepScheduler,
+                                          LCMScheduler=mods["lcm_scheduler"].LCMScheduler, FlowMatchScheduler=mods["basic_flowmatch"].FlowMatchScheduler,
                                           FlowDPMSolverMultistepScheduler=m2.FlowDPMSolverMultistepScheduler,
                                           get_sampling_sigmas=m2.get_sampling_sigmas, retrieve_timesteps=m2.retrieve_timesteps)
     return _loaded_unipc

@@ -9,7 +9,7 @@ import torch
 
 from oracle import wan_oracle
 from tests.helpers import GOLDEN, rel_l2
-from wan2gp_b200.pipeline import DPMppSchedule, UniPCSchedule
+from wan2gp_b200.pipeline import DPMppSchedule, UniPCSchedule, causvid_timesteps, euler_timesteps, lcm_timesteps
 
 CASES = [(6, 5.0), (20, 3.0), (30, 12.0), (2, 1.0), (1, 5.0)]
 
@@ -96,3 +96,43 @@ def test_dpmpp_matches_fixture():
     assert sch.timesteps == [int(t) for t in g["timesteps"]]
     for i in range(steps):
         assert rel_l2(traj[i], torch.from_numpy(g["traj"][i])) < 2e-5
+
+
+def test_single_step_solver_tables_match_reference():
+    """euler / lcm / causvid are the same Euler kernel with different sigma tables: tables and whole trajectories vs the reference
+    EulerScheduler-free restatement, LCMScheduler and FlowMatchScheduler (any2video.py:506-517, 533-543)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is only present in the build container")
+    from oracle.refshim import load_reference_unipc
+    R = load_reference_unipc()
+    for steps, shift in ((4, 5.0), (8, 3.0), (12, 7.0)):
+        ref = R.LCMScheduler(num_train_timesteps=1000, num_inference_steps=min(steps, 8), shift=shift)
+        ref.set_timesteps(min(steps, 8), device="cpu", shift=shift)
+        ts = lcm_timesteps(steps, shift)
+        assert len(ts) == min(steps, 8) + 1 and np.allclose(ts[:-1], ref.timesteps.numpy(), rtol=1e-6)
+        x, vs = inputs(len(ts) - 1)
+        xr, xo = x.clone().float(), x.clone()
+        for i, t in enumerate(ref.timesteps):
+            xr = ref.step(vs[i].float(), t, xr).prev_sample
+            xo = wan_oracle.euler_step(xo, vs[i], ts[i] / 1000.0, ts[i + 1] / 1000.0)
+        assert rel_l2(xo, xr.double()) < 1e-5
+    for steps in (4, 9):
+        ref = R.FlowMatchScheduler(num_inference_steps=steps, shift=5.0, sigma_min=0, extra_one_step=True)
+        ref.timesteps = torch.tensor([1000, 934, 862, 756, 603, 410, 250, 140, 74])[:steps]
+        ref.sigmas = torch.cat([ref.timesteps / 1000, torch.tensor([0.])])
+        ts = causvid_timesteps(steps)
+        x, vs = inputs(steps)
+        xr, xo = x.clone().float(), x.clone()
+        for i, t in enumerate(ref.timesteps):
+            xr = ref.step(vs[i].float(), t, xr)[0]
+            xo = wan_oracle.euler_step(xo, vs[i], ts[i] / 1000.0, ts[i + 1] / 1000.0)
+        assert rel_l2(xo, xr.double()) < 1e-5
+    assert len(euler_timesteps(5, 3.0)) == 6
+
+
+def test_denoiser_solver_selection():
+    from wan2gp_b200.pipeline import WanDenoiser
+    n = {s: WanDenoiser(None, num_steps=12, shift=5.0, sample_solver=s, device="cpu").num_steps for s in ("euler", "unipc", "", "dpm++", "lcm", "causvid")}
+    assert n == {"euler": 12, "unipc": 12, "": 12, "dpm++": 12, "lcm": 8, "causvid": 9}      # lcm caps at 8 steps, causvid's table has 9
+    with pytest.raises(NotImplementedError):
+        WanDenoiser(None, sample_solver="heun", device="cpu")

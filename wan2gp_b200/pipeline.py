@@ -25,6 +25,23 @@ def euler_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
     return [float(v) for v in t]
 
 
+def lcm_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
+    """LCMScheduler.set_timesteps (shared/utils/lcm_scheduler.py:26-57; `sample_solver="lcm"`, any2video.py:533-543): at most 8 steps, sigmas
+    from 1 down to sigma_min = 0.003/1.002 (NOT 0), shifted; its step (:59-87) is the Euler update x += v (sigma_next - sigma)."""
+    n = min(int(num_steps), 8)
+    t = np.linspace(0, 1, n + 1, dtype=np.float32)
+    smin = np.float32(0.003 / 1.002)
+    sig = (smin + (np.float32(1.0) - smin) * (1 - t)).astype(np.float32)
+    sig = (np.float32(shift) * sig / (1 + (np.float32(shift) - 1) * sig)).astype(np.float32)
+    return [float(v) for v in sig.astype(np.float64) * num_train_timesteps]
+
+
+def causvid_timesteps(num_steps):
+    """`sample_solver="causvid"` (any2video.py:513-517): fixed table, sigmas = t/1000 ++ [0], FlowMatchScheduler.step (basic_flowmatch.py:45-57)
+    = Euler."""
+    return [float(v) for v in [1000, 934, 862, 756, 603, 410, 250, 140, 74][:num_steps]] + [0.0]
+
+
 class UniPCSchedule:
     """Host side of FlowUniPCMultistepScheduler (shared/utils/fm_solvers_unipc.py), WanGP's default `sample_solver="unipc"`
     (any2video.py:518-522): solver_order 2, bh2, predict_x0, flow_prediction, lower_order_final, corrector on every step > 0.
@@ -147,10 +164,16 @@ class WanDenoiser:
         self.cfg_star_switch, self.cfg_zero_step = cfg_star_switch, cfg_zero_step      # CFG-Zero* (any2video.py:1701-1722)
         self.device = torch.device(device)
         self.guide_scale, self.guide2_scale, self.switch_threshold = guide_scale, guide2_scale, switch_threshold
-        if sample_solver not in ("euler", "unipc", "", "dpm++"):
-            raise NotImplementedError(f"sample_solver {sample_solver!r}: euler, unipc (the WanGP default) and dpm++ are built")
-        self.unipc = None if sample_solver == "euler" else (DPMppSchedule if sample_solver == "dpm++" else UniPCSchedule)(num_steps, shift)
-        self.timesteps = euler_timesteps(num_steps, shift) if self.unipc is None else [float(t) for t in self.unipc.timesteps] + [0.0]
+        if sample_solver not in ("euler", "unipc", "", "dpm++", "lcm", "causvid"):
+            raise NotImplementedError(f"sample_solver {sample_solver!r}: euler, unipc (the WanGP default), dpm++, lcm and causvid are built")
+        multistep = {"unipc": UniPCSchedule, "": UniPCSchedule, "dpm++": DPMppSchedule}.get(sample_solver)
+        self.unipc = None if multistep is None else multistep(num_steps, shift)
+        if self.unipc is not None:
+            self.timesteps = [float(t) for t in self.unipc.timesteps] + [0.0]
+        else:                                     # single-step solvers: one Euler kernel, different sigma tables
+            self.timesteps = {"euler": lambda: euler_timesteps(num_steps, shift), "lcm": lambda: lcm_timesteps(num_steps, shift),
+                              "causvid": lambda: causvid_timesteps(num_steps)}[sample_solver]()
+        num_steps = len(self.timesteps) - 1
         self.num_steps = num_steps
         self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
         self._pred, self._hist = None, None
