@@ -360,13 +360,15 @@ def load_reference_unipc():
     spec2 = importlib.util.spec_from_file_location("_ref_fm_solvers", os.path.join(REFERENCE_ROOT, "shared/utils/fm_solvers.py"))
     m2 = importlib.util.module_from_spec(spec2)
     spec2.loader.exec_module(m2)
+    du.logging = types.SimpleNamespace(get_logger=lambda *a, **k: types.SimpleNamespace(warning=print, info=print, warn=print))
     mods = {}
-    for nm in ("lcm_scheduler", "basic_flowmatch"):
-        sp = importlib.util.spec_from_file_location("_ref_" + nm, os.path.join(REFERENCE_ROOT, "shared/utils", nm + ".py"))
+    for nm in ("lcm_scheduler", "basic_flowmatch", "../../models/hyvideo/diffusion/schedulers/scheduling_flow_match_discrete"):
+        sp = importlib.util.spec_from_file_location("_ref_" + os.path.basename(nm), os.path.normpath(os.path.join(REFERENCE_ROOT, "shared/utils", nm + ".py")))
         mods[nm] = importlib.util.module_from_spec(sp)
         sp.loader.exec_module(mods[nm])
     _loaded_unipc = types.SimpleNamespace(FlowUniPCMultistepScheduler=m.FlowUniPCMultistepScheduler,
                                           LCMScheduler=mods["lcm_scheduler"].LCMScheduler, FlowMatchScheduler=mods["basic_flowmatch"].FlowMatchScheduler,
+                                          FlowMatchDiscreteScheduler=mods["../../models/hyvideo/diffusion/schedulers/scheduling_flow_match_discrete"].FlowMatchDiscreteScheduler,
                                           FlowDPMSolverMultistepScheduler=m2.FlowDPMSolverMultistepScheduler,
                                           get_sampling_sigmas=m2.get_sampling_sigmas, retrieve_timesteps=m2.retrieve_timesteps)
     return _loaded_unipc

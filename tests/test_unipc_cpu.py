@@ -9,7 +9,7 @@ import torch
 
 from oracle import wan_oracle
 from tests.helpers import GOLDEN, rel_l2
-from wan2gp_b200.pipeline import DPMppSchedule, UniPCSchedule, causvid_timesteps, euler_timesteps, lcm_timesteps
+from wan2gp_b200.pipeline import DPMppSchedule, UniPCSchedule, causvid_timesteps, euler_timesteps, flow_match_timesteps, lcm_timesteps
 
 CASES = [(6, 5.0), (20, 3.0), (30, 12.0), (2, 1.0), (1, 5.0)]
 
@@ -136,3 +136,22 @@ def test_denoiser_solver_selection():
     assert n == {"euler": 12, "unipc": 12, "": 12, "dpm++": 12, "lcm": 8, "causvid": 9}      # lcm caps at 8 steps, causvid's table has 9
     with pytest.raises(NotImplementedError):
         WanDenoiser(None, sample_solver="heun", device="cpu")
+
+
+def test_hunyuan_flow_match_table_matches_reference():
+    """HunyuanDenoiser's sigma grid == FlowMatchDiscreteScheduler(shift, reverse=True, solver="euler") and its step is the Euler update."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is only present in the build container")
+    from oracle.refshim import load_reference_unipc
+    R = load_reference_unipc()
+    for steps, shift in ((30, 7.0), (50, 9.0), (4, 6.0)):
+        ref = R.FlowMatchDiscreteScheduler(shift=shift, reverse=True, solver="euler")
+        ref.set_timesteps(steps, device="cpu")
+        ts = flow_match_timesteps(steps, shift)
+        assert len(ts) == steps + 1 and ts[-1] == 0.0 and np.allclose(ts[:-1], ref.timesteps.numpy(), rtol=1e-6)
+        x, vs = inputs(steps)
+        xr, xo = x.clone().float(), x.clone()
+        for i, t in enumerate(ref.timesteps):
+            xr = ref.step(vs[i].float(), t, xr, return_dict=False)[0]
+            xo = wan_oracle.euler_step(xo, vs[i], ts[i] / 1000.0, ts[i + 1] / 1000.0)
+        assert rel_l2(xo, xr.double()) < 1e-5

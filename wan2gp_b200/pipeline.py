@@ -25,6 +25,15 @@ def euler_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
     return [float(v) for v in t]
 
 
+def flow_match_timesteps(num_steps, shift=7.0, num_train_timesteps=1000):
+    """FlowMatchDiscreteScheduler.set_timesteps with reverse=True, solver="euler" (models/hyvideo/diffusion/schedulers/
+    scheduling_flow_match_discrete.py:123-151, 183-184; built at hunyuan.py:864-868): sigmas = shift(linspace(1, 0, n+1)) in fp32; returns
+    the n+1 values * 1000 (the last is 0).  NB the grid differs from the Wan EulerScheduler's (linspace(1000, 1, n) ++ [0])."""
+    sig = np.linspace(1, 0, num_steps + 1, dtype=np.float32)
+    sig = (np.float32(shift) * sig / (1 + (np.float32(shift) - 1) * sig)).astype(np.float32)
+    return [float(v) for v in sig.astype(np.float64) * num_train_timesteps]
+
+
 def lcm_timesteps(num_steps, shift=5.0, num_train_timesteps=1000):
     """LCMScheduler.set_timesteps (shared/utils/lcm_scheduler.py:26-57; `sample_solver="lcm"`, any2video.py:533-543): at most 8 steps, sigmas
     from 1 down to sigma_min = 0.003/1.002 (NOT 0), shifted; its step (:59-87) is the Euler update x += v (sigma_next - sigma)."""
@@ -256,12 +265,12 @@ class WanDenoiser:
 class HunyuanDenoiser:
     """Denoise-loop call site of the Hunyuan Video 1.5 pipeline (models/hyvideo/diffusion/pipelines/pipeline_hunyuan_video.py
     :1597-1763): latent_model_input = cat(latents, cond_latents) (:1640-1650), transformer(cond) / transformer(uncond)
-    (:1655/:1687), CFG combine (:1719-1743) and the flow-matching scheduler step (:1755), here the Euler update fused with
-    the combine.  guidance 6.0 / shift 9 are defaults/hunyuan_1_5_t2v.json."""
+    (:1655/:1687), CFG combine (:1719-1743) and the flow-matching scheduler step (:1755; FlowMatchDiscreteScheduler, reverse=True, euler), here the
+    Euler update fused with the combine.  guidance 6.0 / shift 9 are defaults/hunyuan_1_5_t2v.json."""
 
     def __init__(self, model, num_steps=30, shift=9.0, guide_scale=6.0, device="cuda"):
         self.model, self.device, self.guide_scale = model, torch.device(device), guide_scale
-        self.timesteps = euler_timesteps(num_steps, shift)
+        self.timesteps = flow_match_timesteps(num_steps, shift)              # scheduler.step = x + v (sigma_next - sigma) (:237-240)
         self.num_steps = num_steps
         self._interrupt = False
 
