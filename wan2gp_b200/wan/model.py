@@ -290,9 +290,12 @@ class WanModel(torch.nn.Module):
                 continue
             emb = self._text(c[0] if c.dim() == 3 else c)
             if key is not None:
-                if self._ctx_cache is not None and len(self._ctx_cache) >= 8:          # a new prompt: drop the old projections
-                    self._ctx_cache, self._ckv_cache = None, {}
                 self._ctx_cache = dict(self._ctx_cache or {})
+                live = [k for k in self._ctx_cache if k[0] != "ref"]
+                if len(live) >= 2:                     # room for one CFG pair: evict the oldest prompt with its 40 x 10 MB of K/V
+                    old = live[0]
+                    self._ctx_cache.pop(old), self._ctx_cache.pop(("ref",) + old, None)
+                    self._ckv_cache = {k: v for k, v in self._ckv_cache.items() if k[0] != old}
                 self._ctx_cache[key] = emb
                 self._ctx_cache[("ref",) + key] = c    # keeps the prompt tensor alive: its address cannot be recycled while cached
             ctx_emb.append(emb)
