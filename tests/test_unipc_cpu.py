@@ -127,7 +127,22 @@ def test_single_step_solver_tables_match_reference():
             xr = ref.step(vs[i].float(), t, xr)[0]
             xo = wan_oracle.euler_step(xo, vs[i], ts[i] / 1000.0, ts[i + 1] / 1000.0)
         assert rel_l2(xo, xr.double()) < 1e-5
-    assert len(euler_timesteps(5, 3.0)) == 6
+    # Wan EulerScheduler (shared/utils/euler_scheduler.py: no third-party imports, loaded straight from the reference tree)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_euler", "/root/reference/shared/utils/euler_scheduler.py")
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    for steps, shift in ((50, 12.0), (20, 5.0), (1, 3.0)):
+        ref = em.EulerScheduler(num_train_timesteps=1000, use_timestep_transform=True)
+        rts = ref.set_timesteps(steps, device=None, shift=shift)
+        ts = euler_timesteps(steps, shift)
+        assert len(ts) == steps + 1 and ts[-1] == 0.0 and np.allclose(ts[:-1], rts.numpy(), rtol=1e-6)
+        x, vs = inputs(steps)
+        xr, xo = x.clone(), x.clone()
+        for i, t in enumerate(rts):
+            xr = ref.step(vs[i], t, xr, return_dict=False)[0]
+            xo = wan_oracle.euler_step(xo, vs[i], ts[i] / 1000.0, ts[i + 1] / 1000.0)
+        assert rel_l2(xo, xr) < 1e-6
 
 
 def test_denoiser_solver_selection():
