@@ -79,3 +79,17 @@ def test_product_never_imports_the_oracle():
             if (s.startswith("import ") or s.startswith("from ")) and "oracle" in s:
                 bad.append(f"{f}:{i}: {s}")
     assert not bad, bad
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    import pathlib
+    import re
+    root = pathlib.Path(__file__).resolve().parents[1]
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = [str(p.relative_to(root)) for p in (root / "wan2gp_b200").rglob("*.py") if pat.search(p.read_text())]
+    assert offenders == []
+    # and nothing the GPU box runs may open the reference tree at run time (docstrings cite it as "/root/reference/" text only)
+    opens = re.compile(r"(open|load|listdir|isdir|exists|sys\.path\.\w+)\([^)]*/root/reference")
+    assert [str(p.relative_to(root)) for p in list((root / "wan2gp_b200").rglob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]
+            if opens.search(p.read_text())] == []
