@@ -81,7 +81,7 @@ def test_product_never_imports_the_oracle():
     assert not bad, bad
 
 
-def test_product_never_imports_the_oracle():
+def test_product_does_not_open_the_reference_tree():
     """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
     import pathlib
     import re
