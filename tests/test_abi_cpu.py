@@ -93,3 +93,26 @@ def test_product_does_not_open_the_reference_tree():
     opens = re.compile(r"(open|load|listdir|isdir|exists|sys\.path\.\w+)\([^)]*/root/reference")
     assert [str(p.relative_to(root)) for p in list((root / "wan2gp_b200").rglob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]
             if opens.search(p.read_text())] == []
+
+
+def test_prompt_cache_eviction():
+    """wan/model.py::_PromptCache: at most one CFG pair is kept; evicting a prompt drops its per-block K/V; the prompt tensor is held."""
+    import torch
+    from wan2gp_b200.wan.model import _PromptCache
+    pc = _PromptCache()
+    ts = [torch.zeros(3, 4) for _ in range(4)]
+    keys = [pc.key(t) for t in ts]
+    assert len(set(keys)) == 4 and pc.key(ts[0]) == keys[0]
+    for k, t in zip(keys[:2], ts[:2]):
+        pc.put_emb(k, ("emb", k), t)
+        for i in range(3):
+            pc.put_ckv(k, i, ("ckv", k, i))
+    assert pc.get_emb(keys[0]) == ("emb", keys[0]) and pc.get_ckv(keys[1], 2) == ("ckv", keys[1], 2) and len(pc.ckv) == 6
+    pc.put_emb(keys[2], "e2", ts[2])                         # third prompt evicts the oldest
+    assert pc.get_emb(keys[0]) is None and pc.get_ckv(keys[0], 0) is None and len(pc.ckv) == 3 and pc.ref[keys[2]] is ts[2]
+    pc.put_ckv(keys[0], 0, "stale")                          # K/V of an evicted prompt is not stored
+    assert pc.get_ckv(keys[0], 0) is None
+    ts[1].add_(1)                                            # in-place edit = new prompt
+    assert pc.key(ts[1]) != keys[1]
+    pc.clear()
+    assert not pc.emb and not pc.ckv and not pc.ref

@@ -102,7 +102,7 @@ def test_wan_context_projection_cache():
     ref2 = m([x.clone() * 0.5], torch.tensor([300.0]), [ctx], pipeline=Pipe())[0]
     m.cache_context = True
     c1 = m([x.clone()], t, [ctx], pipeline=Pipe())[0]                                    # fills the cache
-    assert len(m._ckv_cache) == len(m.blocks)
+    assert len(m._prompts.ckv) == len(m.blocks)
     c2 = m([x.clone() * 0.5], torch.tensor([300.0]), [ctx], pipeline=Pipe())[0]         # served from the cache
     assert torch.equal(ref1, c1) and torch.equal(ref2, c2)
     ctx.mul_(0.5)                                                                         # new prompt in the same buffer

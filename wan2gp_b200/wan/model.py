@@ -42,6 +42,40 @@ class _Block:
                  "cnk", "w_ckv", "b_ckv", "w_co", "b_co", "w1", "b1", "w2", "b2")
 
 
+class _PromptCache:
+    """Step-invariant text projections of at most `max_prompts` prompts (one CFG pair): the text embedding (model.py:1856) and every
+    block's cross-attention K/V (model.py:255-258).  A prompt is identified by (data_ptr, version, shape) of the tensor the caller
+    passes; the cache keeps a reference to that tensor so its address cannot be recycled while the entry lives.  Pure Python (unit-tested
+    on CPU); eviction is oldest-first."""
+
+    def __init__(self, max_prompts=2):
+        self.max_prompts, self.emb, self.ref, self.ckv = max_prompts, {}, {}, {}
+
+    @staticmethod
+    def key(t):
+        return (t.data_ptr(), t._version, tuple(t.shape))
+
+    def get_emb(self, key):
+        return self.emb.get(key)
+
+    def put_emb(self, key, emb, ref):
+        while len(self.emb) >= self.max_prompts:
+            old = next(iter(self.emb))
+            self.emb.pop(old), self.ref.pop(old, None)
+            self.ckv = {k: v for k, v in self.ckv.items() if k[0] != old}
+        self.emb[key], self.ref[key] = emb, ref
+
+    def get_ckv(self, key, idx):
+        return self.ckv.get((key, idx))
+
+    def put_ckv(self, key, idx, ckv):
+        if key in self.emb:
+            self.ckv[(key, idx)] = ckv
+
+    def clear(self):
+        self.emb, self.ref, self.ckv = {}, {}, {}
+
+
 class WanModel(torch.nn.Module):
     """Drop-in for the reference WanModel on the t2v / i2v2_2 path."""
 
@@ -62,9 +96,9 @@ class WanModel(torch.nn.Module):
         self.blocks = []                        # len(model.blocks) is read by callers
         self._g = {}                            # global (non-block) packed weights
         self._freqs_cache = {}
-        self._ctx_cache = None
+        self._prompts = _PromptCache()
         self.cache_context = False              # reuse step-invariant text projections across steps: the text
-        self._ckv_cache = {}                    # embedding (model.py:1856) and every block's cross-attention K/V (model.py:255-258)
+                                                # embedding (model.py:1856) and every block's cross-attention K/V (model.py:255-258)
         # optional: one CUDA graph per transformer block (launch-bound small configs); the per-block
         # interrupt poll of the reference stays between graph replays
         self.use_cuda_graphs = False
@@ -125,7 +159,8 @@ class WanModel(torch.nn.Module):
         self._pack_globals(sd)
         self.blocks = [self._pack_block(sd, f"blocks.{i}.") for i in range(self.num_layers)]
         self._ready = True
-        self._graphs, self._ctx_cache, self._ckv_cache = {}, None, {}          # captured graphs / cached projections used the old weights
+        self._graphs = {}                                                     # captured graphs / cached projections used the old weights
+        self._prompts.clear()
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
     def init_synthetic(self, seed=0):
@@ -283,21 +318,13 @@ class WanModel(torch.nn.Module):
         # text embedding per entry (model.py:1856); optionally cached across steps
         ctx_emb, ctx_keys = [], []
         for c in ctx_list:
-            key = (c.data_ptr(), c._version, tuple(c.shape)) if self.cache_context else None
+            key = _PromptCache.key(c) if self.cache_context else None
             ctx_keys.append(key)
-            if key is not None and self._ctx_cache is not None and key in self._ctx_cache:
-                ctx_emb.append(self._ctx_cache[key])
-                continue
-            emb = self._text(c[0] if c.dim() == 3 else c)
-            if key is not None:
-                self._ctx_cache = dict(self._ctx_cache or {})
-                live = [k for k in self._ctx_cache if k[0] != "ref"]
-                if len(live) >= 2:                     # room for one CFG pair: evict the oldest prompt with its 40 x 10 MB of K/V
-                    old = live[0]
-                    self._ctx_cache.pop(old), self._ctx_cache.pop(("ref",) + old, None)
-                    self._ckv_cache = {k: v for k, v in self._ckv_cache.items() if k[0] != old}
-                self._ctx_cache[key] = emb
-                self._ctx_cache[("ref",) + key] = c    # keeps the prompt tensor alive: its address cannot be recycled while cached
+            emb = self._prompts.get_emb(key) if key is not None else None
+            if emb is None:
+                emb = self._text(c[0] if c.dim() == 3 else c)
+                if key is not None:
+                    self._prompts.put_emb(key, emb, c)
             ctx_emb.append(emb)
         # patch embedding: one fp32 residual stream per (entry, batch item)
         streams = []
@@ -316,11 +343,11 @@ class WanModel(torch.nn.Module):
                 graphs["g"][idx].replay()
                 continue
             for i in range(n):
-                ckv = self._ckv_cache.get((ctx_keys[i], idx)) if ctx_keys[i] is not None else None
+                ckv = self._prompts.get_ckv(ctx_keys[i], idx) if ctx_keys[i] is not None else None
                 if ckv is None:
                     ckv = self._cross_kv(blk, ctx_emb[i])
                     if ctx_keys[i] is not None:
-                        self._ckv_cache[(ctx_keys[i], idx)] = ckv            # 2 * L_text * D bf16 per block (10 MB at 14B)
+                        self._prompts.put_ckv(ctx_keys[i], idx, ckv)         # 2 * L_text * D bf16 per block (10 MB at 14B)
                 for s in streams[i]:
                     self._block(blk, s, e0, ctx_emb[i], cos, sin, ckv)
         if graphs is not None:
