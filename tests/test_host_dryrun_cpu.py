@@ -72,3 +72,68 @@ def test_wan_vae_host_paths(stub_abi):
     assert vae.decode([torch.randn(16, 2, 12, 14)], tile_size=64)[0].shape == (3, 5, 96, 112)
     assert vae.decode([torch.randn(16, 2, 4, 6)], tile_size=0)[0].shape == (3, 5, 32, 48)
     assert {"b200_blend_edge_f32", "b200_planar_to_cl_pad", "b200_upconv2x_cl", "b200_vae_prologue"} <= set(stub_abi)
+
+
+class _Pipe:
+    _interrupt = False
+
+
+def test_dit_host_paths(stub_abi):
+    """WanModel (t2v, i2v joint CFG pair with the prompt cache) and HYVideoDiffusionTransformer (1.5 and 1.0 families): every launch of a
+    whole forward has a well-formed argument list and the host-side shape algebra closes."""
+    from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer
+    from wan2gp_b200.wan import WanModel
+    thw = (3, 8, 12)
+    cfg = synth.WAN_CONFIGS["tiny"]
+    m = WanModel(**cfg, device="cpu")
+    m.load_state_dict(synth.make_wan_state_dict(cfg, 0))
+    x, t, ctx, y = synth.make_wan_inputs(cfg, thw, 0)
+    assert m([x.clone()], t, [ctx], pipeline=_Pipe())[0].shape == (1, 16) + thw
+    cfg = synth.WAN_CONFIGS["tiny_i2v"]
+    m = WanModel(**cfg, device="cpu")
+    m.load_state_dict(synth.make_wan_state_dict(cfg, 0))
+    x, t, ctx, y = synth.make_wan_inputs(cfg, thw, 0)
+    m.cache_context = True
+    ctx0 = ctx * 0
+    for _ in range(2):                                        # second call is served from the prompt cache
+        outs = m([x.clone(), x.clone()], t, [ctx, ctx0], y=y, pipeline=_Pipe())
+        assert [o.shape for o in outs] == [(1, 16) + thw] * 2
+    assert len(m._prompts.emb) == 2 and len(m._prompts.ckv) == 2 * len(m.blocks)
+    n_kv = stub_abi.count("b200_rmsnorm_rope")
+    m([x.clone(), x.clone()], t, [ctx, ctx0], y=y, pipeline=_Pipe())
+    per_forward_cached = stub_abi.count("b200_rmsnorm_rope") - n_kv
+    m.cache_context = False
+    n_kv = stub_abi.count("b200_rmsnorm_rope")
+    m([x.clone(), x.clone()], t, [ctx, ctx0], y=y, pipeline=_Pipe())
+    assert stub_abi.count("b200_rmsnorm_rope") - n_kv == per_forward_cached + 2 * len(m.blocks)      # the cross-K norms come back
+    for name in ("hy_tiny", "hy10_tiny"):
+        cfg = synth.HY_CONFIGS[name]
+        v10 = cfg.get("family") == "1.0"
+        kw = dict(mm_single_blocks_depth=cfg["mm_single_blocks_depth"], text_states_dim_2=cfg["text_states_dim_2"], guidance_embed=True) if v10 else dict(mm_single_blocks_depth=0, text_pool_type=None, glyph_byT5_v2=True, use_cond_type_embedding=True, pre_split_qkv=True)
+        hm = HYVideoDiffusionTransformer(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"],
+                                         out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
+                                         mm_double_blocks_depth=cfg["mm_double_blocks_depth"], text_states_dim=cfg["text_states_dim"],
+                                         device="cpu", **kw)
+        hm.load_state_dict(synth.make_hy_state_dict(cfg, 0))
+        thw2 = (2, 8, 12) if v10 else (3, 6, 10)
+        xi, tt, txt, tm, b5, bm = synth.make_hy_inputs(cfg, thw2, seed=0)
+        extra = dict(text_states_2=torch.randn(1, cfg["text_states_dim_2"]), guidance=torch.tensor([6000.0])) if v10 else dict(byt5_text_states=b5, byt5_text_mask=bm)
+        out = hm(xi, tt, text_states=txt, text_mask=tm, pipeline=_Pipe(), **extra)
+        assert out.shape == (1, cfg["out_channels"]) + thw2
+
+
+@pytest.mark.parametrize("solver", ["euler", "unipc", "dpm++", "lcm", "causvid"])
+def test_denoiser_host_paths(stub_abi, solver):
+    """WanDenoiser.step for every sample solver: schedule bookkeeping, history rotation and the ctypes coefficient block of the fused step."""
+    from wan2gp_b200.pipeline import WanDenoiser
+    from wan2gp_b200.wan import WanModel
+    cfg = synth.WAN_CONFIGS["tiny"]
+    m = WanModel(**cfg, device="cpu")
+    m.load_state_dict(synth.make_wan_state_dict(cfg, 0))
+    den = WanDenoiser(m, num_steps=3, shift=5.0, guide_scale=4.0, device="cpu", sample_solver=solver, cfg_star_switch=True, cfg_zero_step=0)
+    x, t, ctx, _ = synth.make_wan_inputs(cfg, (3, 8, 12), 0)
+    lat = x.clone()
+    for i in range(den.num_steps):
+        assert den.step(lat, i, ctx, ctx * 0) is lat
+    kernel = "b200_cfg_euler_step" if solver in ("euler", "lcm", "causvid") else "b200_cfg_unipc_step"
+    assert stub_abi.count(kernel) == den.num_steps
