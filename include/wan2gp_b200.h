@@ -58,6 +58,12 @@ int b200_ln_modulate(const float* x, const float* shift, const float* scale, int
 int b200_rmsnorm_rope(void* x_bf16, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
                       const float* sin_t, int per_head, void* stream);
 
+/* the same for the q and k column blocks of one fused q|k|v buffer in ONE launch (two norm weights, shared RoPE tables):
+ * replaces norm_q / norm_k + the two apply_rotary_emb calls of WanSelfAttention.forward (model.py:343-344, 372-377) and of
+ * MMDoubleStreamBlock (hyvideo/modules/models.py:226-228, 254-255). */
+int b200_qk_rmsnorm_rope(void* q_bf16, void* k_bf16, long long ld, const float* wq, const float* wk, int L, int D, float eps,
+                         const float* cos_t, const float* sin_t, int per_head, void* stream);
+
 /* out[Lq, H*128] = softmax(q k^T / sqrt(128)) v per head; q/k/v/out bf16 with row strides ldq/ldk/ldv/ldo
  * (elements), head h at columns [128h, 128h+128).  Non-causal, no mask.
  * Replaces pay_attention -> sdpa_wrapper (shared/attention.py:208-225) at model.py:385 (self) and :265 (cross). */

@@ -125,22 +125,28 @@ def patch_embed(sd, x):
 
 
 # ---- W3-W10: one WanAttentionBlock -- model.py:631-711
-def block_forward(sd, cfg, i, x, e0, ctx, cos, sin, emulate, taps=None):
+def block_forward(sd, cfg, i, x, e0, ctx, cos, sin, emulate, taps=None, rows=None):
+    """rows (LongTensor or None): evaluate the block only for these token rows -- keys / values still come from ALL rows of x, every
+    other operation of the block is row-wise -- and return [len(rows), D].  Used by the production-shape parity tests (L = 75 600),
+    where the full L x L attention of the restatement would not fit."""
     D, H, eps = cfg["dim"], cfg["num_heads"], cfg["eps"]
     p = f"blocks.{i}."
     m = (sd[p + "modulation"].float() + e0).reshape(6, D)               # model.py:632
     # self-attention (model.py:634-660)
     a = _q(layer_norm(x, eps) * (1 + m[1]) + m[0], emulate)
-    q = _q(linear(a, sd, p + "self_attn.q", emulate), emulate)
+    q = _q(linear(a if rows is None else a[rows], sd, p + "self_attn.q", emulate), emulate)
     k = _q(linear(a, sd, p + "self_attn.k", emulate), emulate)
     v = _q(linear(a, sd, p + "self_attn.v", emulate), emulate)
     q = rms_norm_full(q, sd[p + "self_attn.norm_q.weight"].float(), eps).reshape(-1, H, D // H)
     k = rms_norm_full(k, sd[p + "self_attn.norm_k.weight"].float(), eps).reshape(-1, H, D // H)
-    q = _q(apply_rope(q, cos, sin), emulate)
+    q = _q(apply_rope(q, cos if rows is None else cos[rows], sin if rows is None else sin[rows]), emulate)
     k = _q(apply_rope(k, cos, sin), emulate)
     o = _q(attention(q, k, v.reshape(-1, H, D // H), emulate).reshape(-1, D), emulate)
     if taps is not None:
         taps[f"b{i}.a"], taps[f"b{i}.q"], taps[f"b{i}.k"], taps[f"b{i}.attn"] = a, q.reshape(-1, D), k.reshape(-1, D), o
+    del a, q, k, v
+    if rows is not None:
+        x = x[rows]
     x = x + linear(o, sd, p + "self_attn.o", emulate) * m[2]
     # text cross-attention (model.py:663-668, 245-265, 444)
     c = F.layer_norm(x, (D,), sd[p + "norm3.weight"].float(), sd[p + "norm3.bias"].float(), eps)

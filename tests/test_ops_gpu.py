@@ -97,6 +97,13 @@ def test_rmsnorm_rope(ops):
         ops.rmsnorm_rope_(x, w, 1e-6, cos.cuda(), sin.cuda())
         assert rel_l2(buf[:, D:2 * D].cpu(), ref_rope) < TOL_BF16
         assert torch.equal(buf[:, :D], keep[:, :D]) and torch.equal(buf[:, 2 * D:], keep[:, 2 * D:])
+        # q and k of the fused buffer in ONE launch (two weights): bit-identical to the two single-segment launches
+        w2 = 0.3 * (1 + _randn(D, seed=9, scale=0.1))
+        one, two = keep.clone(), keep.clone()
+        ops.rmsnorm_rope_(one[:, :D], w, 1e-6, cos.cuda(), sin.cuda())
+        ops.rmsnorm_rope_(one[:, D:2 * D], w2, 1e-6, cos.cuda(), sin.cuda())
+        ops.qk_rmsnorm_rope_(two[:, :D], two[:, D:2 * D], w, w2, 1e-6, cos.cuda(), sin.cuda())
+        assert torch.equal(one, two)
         y = keep[:, :D].contiguous()
         ops.rmsnorm_rope_(y, w, 1e-6)                        # no RoPE (cross-attention)
         assert rel_l2(y.cpu(), wan_oracle.rms_norm_full(keep[:, :D].float().cpu(), w.cpu(), 1e-6)) < TOL_BF16

@@ -1,0 +1,215 @@
+"""Parity at the shapes bench.py measures ("weak" item 1 / SURVEY.md section 8c: "14B shape parity per block is still checkable").
+
+The small-shape tests stop at L = 1000 / 4096 x 1536 x 1536; the benchmarked kernels run L = 75 600 (591 KV tiles, a partial last
+tile, 11 840 CTAs), N / K = 13 824 and [L, F] buffers of 2.09 GB (> 2^31 bytes) -- where 32-bit offset, phase-bit and rasterisation
+bugs live.  A full-size fp64 reference does not fit, so every check evaluates the reference on SAMPLED rows / crops (first tile,
+last partial tile, tile borders, random) with plain torch on the GPU (test infrastructure) or with the oracle restricted to rows:
+
+  (a) self-attention L = 75 600, H = 40 and the Hunyuan joint length 119 567, H = 16      vs fp64 softmax(QK^T)V
+  (b) the four Wan2.2-14B linear layers incl. the GELU and the TMA reduce-add epilogues     vs fp64
+  (c) one full Wan2.2-14B transformer block on the fp32 residual stream                     vs oracle.block_forward(emulate_bf16, rows)
+  (d) the 720p convolution layers of the three VAEs                                        vs F.conv3d fp64 on crops
+      and one whole 720p x 9-frame Wan VAE decode                                           vs oracle.vae_decode on the GPU
+
+Tolerances as everywhere: fp32-output kernels 1e-3, bf16-output kernels 4e-3, one DiT block 5e-3 vs the
+bf16-emulating oracle, VAE decode 2.5e-2 vs the bf16-emulating oracle and PSNR >= 35 dB vs the fp32 oracle.  Every test prints the
+measured error so GPUTEST logs carry the numbers."""
+import math
+
+import pytest
+import torch
+
+from tests.helpers import psnr, rel_l2
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+bf16, f32 = torch.bfloat16, torch.float32
+L14, D14, F14, H14 = 75600, 5120, 13824, 40
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from wan2gp_b200 import ops as o
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return o
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=f32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda", dtype=f32) * scale).to(dtype)
+
+
+def sample_rows(L, n_random=256, tile=128, seed=0):
+    """First tile, the tiles around the middle CTA boundary, the last full tile, the partial tail and random rows."""
+    fixed = list(range(0, 40)) + list(range(tile - 8, tile + 8)) + list(range(2 * tile - 4, 2 * tile + 4))
+    last_full = (L // tile) * tile
+    fixed += list(range(max(0, last_full - 16), L))                 # end of the last full tile + the whole partial tile
+    mid = (L // (2 * tile)) * tile
+    fixed += list(range(mid - 8, mid + 8))
+    g = torch.Generator().manual_seed(seed)
+    rnd = torch.randint(0, L, (n_random,), generator=g).tolist()
+    rows = sorted(set(r for r in fixed + rnd if 0 <= r < L))
+    return torch.tensor(rows, device="cuda", dtype=torch.long)
+
+
+def attention_rows_fp64(q, k, v, rows, heads, H):
+    """softmax(q k^T / sqrt(128)) v for the sampled query rows of the given heads, fp64; q/k/v [L, H*128] bf16."""
+    outs = []
+    for h in heads:
+        sl = slice(h * 128, (h + 1) * 128)
+        qh, kh, vh = q[rows, sl].double(), k[:, sl].double(), v[:, sl].double()
+        outs.append(torch.softmax(qh @ kh.t() / math.sqrt(128.0), -1) @ vh)
+    return torch.stack(outs, 1)                                       # [rows, len(heads), 128]
+
+
+@pytest.mark.parametrize("L,H,heads", [(L14, H14, (0, 17, 39)), (119567, 16, (0, 7, 15))])
+def test_attention_production_length(ops, L, H, heads):
+    D = H * 128
+    qkv = _randn(L, 3 * D, seed=11, dtype=bf16)                       # fused [L, 3D] buffer, strided head views as in the model
+    qkv[:, :D] *= 1.5                                                 # logits with a few-sigma spread: rescale path taken
+    out = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
+    rows = sample_rows(L, 256, seed=L)
+    ref = attention_rows_fp64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], rows, heads, H)
+    got = torch.stack([out[rows, h * 128:(h + 1) * 128] for h in heads], 1)
+    err = rel_l2(got, ref)
+    worst = float((got.double() - ref).abs().max())
+    print(f"attention L={L} H={H}: {len(rows)} rows x {len(heads)} heads, rel-L2 {err:.3e}, max|d| {worst:.3e}")
+    assert err < 4e-3
+    # per-row check (a wrong tile would be averaged away by the global norm)
+    per_row = ((got.double() - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).max()
+    assert float(per_row) < 2e-2, float(per_row)
+
+
+@pytest.mark.parametrize("name,N,K,mode", [("qkv", 3 * D14, D14, "bf16"), ("ffn.0", F14, D14, "gelu"),
+                                           ("o-proj", D14, D14, "acc"), ("ffn.2", D14, F14, "acc")])
+def test_gemm_production_shapes(ops, name, N, K, mode):
+    a = _randn(L14, K, seed=21, dtype=bf16)
+    w = _randn(N, K, seed=22, scale=K ** -0.5, dtype=bf16)
+    bias, gate = _randn(N, seed=23), _randn(N, seed=24)
+    rows = sample_rows(L14, 200, seed=N + K)
+    lin = a[rows].double() @ w.double().t() + bias.double()
+    if mode == "acc":                                                 # x += (a w^T + b) * gate on the fp32 residual stream (TMA reduce-add)
+        x0 = _randn(L14, N, seed=25)
+        keep = x0[rows].double()
+        ops.gemm(a, w, out=x0, bias=bias, gate=gate, accumulate=True)
+        err = rel_l2(x0[rows], keep + lin * gate.double())
+        tol = 1e-3
+        assert bool(torch.isfinite(x0).all())
+    else:
+        out = ops.gemm(a, w, bias=bias, act=1 if mode == "gelu" else 0)
+        ref = torch.nn.functional.gelu(lin.float(), approximate="tanh") if mode == "gelu" else lin
+        err = rel_l2(out[rows], ref)
+        tol = 4e-3
+        assert bool(torch.isfinite(out.float()).all())
+        # columns of the last N tile and of a tile in the middle, all rows of two row tiles (rasterisation / 64-bit offsets)
+        for r0 in (0, 75520):
+            blk = out[r0:r0 + 80, N - 256:].double()
+            refb = a[r0:r0 + 80].double() @ w[N - 256:].double().t() + bias[N - 256:].double()
+            refb = torch.nn.functional.gelu(refb.float(), approximate="tanh") if mode == "gelu" else refb
+            assert rel_l2(blk, refb) < tol
+    print(f"gemm {name} {L14} x {N} x {K} ({mode}): {len(rows)} rows, rel-L2 {err:.3e}")
+    assert err < tol
+
+
+def test_wan14b_block_vs_oracle(ops):
+    """One WanAttentionBlock of the Wan2.2-14B architecture on an L = 75 600 residual stream (latent [1,16,21,90,160]) through the
+    product's block driver, against the oracle restricted to sampled tokens (keys / values from all tokens)."""
+    from oracle import wan_oracle
+    from wan2gp_b200 import synth
+    from wan2gp_b200.wan import WanModel
+    cfg = dict(synth.WAN_CONFIGS["t2v_2_2"], num_layers=1)
+    thw = (21, 90, 160)
+    shapes = synth.wan_param_shapes(cfg)
+    sd = {n: synth.make_wan_tensor(n, s, cfg, 3, "cuda") for n, s in shapes.items() if n.startswith("blocks.0.")}
+    model = WanModel(**cfg, device="cuda")
+    blk = model._pack_block(sd, "blocks.0.")
+    cos, sin = wan_oracle.rope_tables(thw)
+    cos, sin = cos.cuda(), sin.cuda()
+    x = _randn(L14, D14, seed=31)
+    e0 = _randn(6, D14, seed=32, scale=0.1)
+    ctx = _randn(512, D14, seed=33, dtype=bf16)
+    rows = sample_rows(L14, 128, seed=5)
+    with torch.no_grad():
+        ref = wan_oracle.block_forward(sd, cfg, 0, x, e0, ctx.float(), cos, sin, True, rows=rows)
+        xp = x.clone()
+        model._block(blk, xp, e0.reshape(-1).contiguous(), ctx, cos, sin)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(xp).all())
+    err = rel_l2(xp[rows], ref)
+    delta = rel_l2(xp[rows] - x[rows], ref - x[rows])                  # error of the block's UPDATE (the residual passes through exactly)
+    print(f"Wan2.2-14B block, L={L14}: {len(rows)} tokens, rel-L2 {err:.3e} on x_out, {delta:.3e} on the update")
+    assert err < 5e-3 and delta < 2e-2
+
+
+def _conv_crop_ref(x_cl, w, b, k, crop, mode):
+    """F.conv3d fp64 of a crop (t0,t1,h0,h1,w0,w1) of the output; x_cl [T,H,W,C] bf16; causal in time, centred in space."""
+    t0, t1, h0, h1, w0, w1 = crop
+    T, H, W, C = x_cl.shape
+    kt, kh, kw = k
+    ts = torch.arange(t0 - (kt - 1), t1)
+    hs = torch.arange(h0 - kh // 2, h1 + kh // 2)
+    ws = torch.arange(w0 - kw // 2, w1 + kw // 2)
+    if mode == "replicate":
+        win = x_cl[ts.clamp(0, T - 1).cuda()][:, hs.clamp(0, H - 1).cuda()][:, :, ws.clamp(0, W - 1).cuda()].double()
+    else:
+        win = x_cl[ts.clamp(0, T - 1).cuda()][:, hs.clamp(0, H - 1).cuda()][:, :, ws.clamp(0, W - 1).cuda()].double()
+        win = win * ((ts >= 0) & (ts < T)).cuda().double().reshape(-1, 1, 1, 1)
+        win = win * ((hs >= 0) & (hs < H)).cuda().double().reshape(1, -1, 1, 1)
+        win = win * ((ws >= 0) & (ws < W)).cuda().double().reshape(1, 1, -1, 1)
+    return torch.nn.functional.conv3d(win.permute(3, 0, 1, 2)[None], w.to(bf16).double(), b.double())[0]      # [co, t, h, w]
+
+
+@pytest.mark.parametrize("name,T,H,W,ci,co,k,cls", [
+    ("wan s3 96->96", 9, 720, 1280, 96, 96, (3, 3, 3), "wan"), ("wan head 96->3", 9, 720, 1280, 96, 3, (3, 3, 3), "wan"),
+    ("wan s2 192->192", 9, 360, 640, 192, 192, (3, 3, 3), "wan"), ("wan s1 384->384", 11, 180, 320, 384, 384, (3, 3, 3), "wan"),
+    ("wan time_conv 384->768", 10, 180, 320, 384, 768, (3, 1, 1), "wan"), ("wan conv2d 192->96 (as 3x3)", 5, 720, 1280, 192, 96, (1, 3, 3), "wan"),
+    ("hy 128->128 replicate", 5, 720, 1280, 128, 128, (3, 3, 3), "hy"), ("hy head 128->3 replicate", 5, 720, 1280, 128, 3, (3, 3, 3), "hy"),
+    ("hy 256->256 replicate", 9, 360, 640, 256, 256, (3, 3, 3), "hy")])
+def test_vae_convs_720p(ops, name, T, H, W, ci, co, k, cls):
+    from wan2gp_b200.hyvideo.vae import _RepConv
+    from wan2gp_b200.wan.vae import _Conv
+    x = _randn(T, H, W, ci, seed=41, dtype=bf16)
+    w = _randn(co, ci, *k, seed=42, scale=(ci * k[0] * k[1] * k[2]) ** -0.5)
+    b = _randn(co, seed=43)
+    conv = (_Conv if cls == "wan" else _RepConv)(w, b, "cuda")
+    planar = co == 3
+    out = conv(x, out_mode=2) if planar else conv(x)                  # planar fp32 [3,T,H,W] head / channels-last bf16
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
+    hs, ws = min(48, H), min(72, W)
+    crops = [(0, min(3, T), 0, hs, 0, ws), (T - 2, T, H - hs, H, W - ws, W), (T // 2, T // 2 + 2, H // 2 - 24, H // 2 + 24, W // 2 - 36, W // 2 + 36),
+             (0, 2, H - hs, H, 0, ws), (T - 1, T, 0, hs, W - ws, W), (1, 3, 100, 148, 120, 260)]
+    worst = 0.0
+    for c in crops:
+        if c[3] > H or c[5] > W:
+            continue
+        ref = _conv_crop_ref(x, w, b, k, c, "replicate" if cls == "hy" else "zeros")
+        got = out[:, c[0]:c[1], c[2]:c[3], c[4]:c[5]] if planar else out[c[0]:c[1], c[2]:c[3], c[4]:c[5]].permute(3, 0, 1, 2)
+        worst = max(worst, rel_l2(got, ref))
+    print(f"conv {name} @ {T}x{H}x{W}: worst crop rel-L2 {worst:.3e}")
+    assert worst < (1e-3 if planar else 4e-3)
+
+
+def test_wanvae_decode_720p_9frames(ops):
+    """Whole Wan VAE decode of a [16,3,90,160] latent (9 frames at 720 x 1280) vs the oracle evaluated on the GPU."""
+    from oracle import vae_oracle
+    from wan2gp_b200 import synth
+    from wan2gp_b200.wan import WanVAE
+    sd = synth.make_vae_state_dict(synth.VAE_CFG, 0)
+    z = synth._normal((16, 3, 90, 160), 1.0, 7, "input.z720", "cpu")
+    vae = WanVAE(device="cuda", state_dict=sd)
+    got = vae.model.decode_frames(z.cuda(), vae.mean, vae.std)
+    got = got[0] if got.dim() == 5 else got
+    torch.cuda.synchronize()
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref_bf = vae_oracle.vae_decode(sdg, z.cuda(), synth.VAE_MEAN, synth.VAE_STD, emulate_bf16=True)
+        ref_32 = vae_oracle.vae_decode(sdg, z.cuda(), synth.VAE_MEAN, synth.VAE_STD, emulate_bf16=False)
+    assert got.shape == ref_32.shape == (3, 9, 720, 1280)
+    e_bf, p32 = rel_l2(got, ref_bf), psnr(got.clamp(-1, 1), ref_32.clamp(-1, 1), 2.0)
+    u8 = (vae_oracle.frames_to_uint8(got).int() - vae_oracle.frames_to_uint8(ref_32).int()).abs()
+    print(f"WanVAE decode 720p x 9f: rel-L2 vs bf16-emulating oracle {e_bf:.3e}, PSNR vs fp32 oracle {p32:.1f} dB, mean |d uint8| {float(u8.float().mean()):.3f}, max {int(u8.max())}")
+    assert e_bf < 2.5e-2 and p32 > 35.0 and float(u8.float().mean()) < 1.5

@@ -82,6 +82,82 @@ if "rows" in which:
     qkv = torch.randn(L, 3 * D, device="cuda").to(bf16); w = torch.ones(D, device="cuda")
     cos = torch.randn(L, 128, device="cuda"); sin = torch.randn(L, 128, device="cuda")
     rec("rmsnorm_rope L x D (strided in qkv)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6, cos, sin)), bytes_=L * D * 4 + L * 128 * 8)
+if "lib" in which:
+    # ---- the library bar: what the UNMODIFIED reference would run on this GPU for the same shapes --
+    # F.scaled_dot_product_attention (shared/attention.py:208-225; cuDNN / flash backends), torch.matmul -> cuBLASLt
+    # (models/wan/modules/model.py:322,337,405) and cuDNN conv3d (models/wan/modules/vae.py:43-63), timed the same way, next to
+    # our kernel at the same shape in the same process.  Test/measurement infrastructure only: nothing here is on the product path.
+    import torch.nn.functional as Fn
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    lib = []
+
+    def lrec(name, ours_ms, lib_ms, flops, note=""):
+        r = {"shape": name, "ours_ms": ours_ms, "lib_ms": lib_ms, "ours_tflops": flops / ours_ms / 1e9 if ours_ms else None,
+             "lib_tflops": flops / lib_ms / 1e9 if lib_ms else None, "ours_over_lib": (lib_ms / ours_ms) if (ours_ms and lib_ms) else None, "lib": note}
+        lib.append(r); print(json.dumps(r), flush=True)
+
+    for Lq, tag in [(L, "self-attention L=75600 H=40 d=128"), (32760, "self-attention L=32760 (480p) H=40 d=128")]:
+        qkv = torch.randn(Lq, 3 * D, device="cuda").to(bf16)
+        out = torch.empty(Lq, D, device="cuda", dtype=bf16)
+        ours = timeit(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, out=out), iters=3, warm=1)
+        q4, k4, v4 = (qkv[:, i * D:(i + 1) * D].reshape(1, Lq, H, 128).transpose(1, 2) for i in range(3))   # what sdpa_wrapper passes
+        for be, nm in [(SDPBackend.CUDNN_ATTENTION, "cuDNN SDPA"), (SDPBackend.FLASH_ATTENTION, "torch flash SDPA"), (None, "SDPA default dispatch")]:
+            try:
+                if be is None:
+                    fn = lambda: Fn.scaled_dot_product_attention(q4, k4, v4)
+                else:
+                    def fn(be=be):
+                        with sdpa_kernel(be):
+                            return Fn.scaled_dot_product_attention(q4, k4, v4)
+                ms = timeit(fn, iters=3, warm=1)
+                err = float((fn().transpose(1, 2).reshape(Lq, D).float() - out.float()).abs().max())
+                lrec(tag, ours, ms, 4.0 * Lq * Lq * D, f"{nm}; max|ours-lib| = {err:.3e}")
+            except Exception as e:   # noqa: BLE001
+                lrec(tag, ours, None, 4.0 * Lq * Lq * D, f"{nm}: unavailable ({repr(e)[:120]})")
+        del qkv, out, q4, k4, v4
+    a = torch.randn(L, D, device="cuda").to(bf16)
+    for name, N, K in [("qkv 75600 x 15360 x 5120", 3 * D, D), ("o-proj 75600 x 5120 x 5120", D, D), ("ffn.0 75600 x 13824 x 5120", F, D),
+                       ("ffn.2 75600 x 5120 x 13824", D, F), ("cuBLAS reference 8192^3", 8192, 8192)]:
+        Mm = 8192 if N == 8192 else L
+        A = torch.randn(Mm, K, device="cuda").to(bf16) if (K != D or Mm != L) else a
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(bf16)
+        bias = torch.randn(N, device="cuda")
+        o = torch.empty(Mm, N, device="cuda", dtype=bf16)
+        ours = timeit(lambda: ops.gemm(A, w, out=o, bias=bias))
+        lb = timeit(lambda: Fn.linear(A, w, bias.to(bf16)))          # cuBLASLt with bias epilogue, as nn.Linear does
+        lm = timeit(lambda: torch.matmul(A, w.t(), out=o))
+        lrec("gemm " + name, ours, min(lb, lm), 2.0 * Mm * N * K, f"cuBLASLt: F.linear+bias {lb:.3f} ms, matmul {lm:.3f} ms")
+        del w, o, A
+    del a
+    if "libconv" in which:
+        from wan2gp_b200.wan.vae import _Conv
+        for name, T, Hh, Ww, ci, co, k in [("s0 384->384 3x3x3 @21x90x160", 21, 90, 160, 384, 384, (3, 3, 3)), ("s1 384->384 3x3x3 @41x180x320", 41, 180, 320, 384, 384, (3, 3, 3)),
+                                            ("s2 192->192 3x3x3 @81x360x640", 81, 360, 640, 192, 192, (3, 3, 3)), ("s3 96->96 3x3x3 @81x720x1280", 81, 720, 1280, 96, 96, (3, 3, 3)),
+                                            ("up3 conv2d 192->96 3x3 @81x720x1280", 81, 720, 1280, 192, 96, (1, 3, 3)), ("head 96->3 3x3x3 @81x720x1280", 81, 720, 1280, 96, 3, (3, 3, 3))]:
+            x = torch.randn(T, Hh, Ww, ci, device="cuda", dtype=bf16)
+            wt = torch.randn(co, ci, *k, device="cuda") * 0.02
+            conv = _Conv(wt, torch.randn(co, device="cuda"), "cuda")
+            mode = 2 if co == 3 else 0
+            out = conv(x, out_mode=mode)
+            fl = 2.0 * T * Hh * Ww * ci * co * k[0] * k[1] * k[2]
+            ours = timeit(lambda: conv(x, out=out, out_mode=mode), iters=3, warm=1)
+            del out
+            try:
+                # cuDNN conv3d the way the reference calls it: NCDHW logical layout; channels_last_3d memory so cuDNN can pick its NDHWC tensor-core kernels
+                xn = x.permute(3, 0, 1, 2)[None].contiguous(memory_format=torch.channels_last_3d)
+                xp = Fn.pad(xn, (k[2] // 2, k[2] // 2, k[1] // 2, k[1] // 2, k[0] - 1, 0))
+                wn = wt.to(bf16).contiguous(memory_format=torch.channels_last_3d)
+                bb = torch.randn(co, device="cuda").to(bf16)
+                torch.backends.cudnn.benchmark = True
+                lms = timeit(lambda: Fn.conv3d(xp, wn, bb), iters=3, warm=2)
+                lms_pad = timeit(lambda: Fn.conv3d(Fn.pad(xn, (k[2] // 2, k[2] // 2, k[1] // 2, k[1] // 2, k[0] - 1, 0)), wn, bb), iters=3, warm=1)
+                lrec("conv " + name, ours, lms, fl, f"cuDNN conv3d bf16 channels_last_3d on a pre-padded input; with the reference's F.pad copy {lms_pad:.3f} ms")
+                del xn, xp, wn
+            except Exception as e:   # noqa: BLE001
+                lrec("conv " + name, ours, None, fl, f"cuDNN conv3d unavailable ({repr(e)[:120]})")
+            del x, conv, wt
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"peaks": {"bf16_tflops_burst": PEAK_TF, "hbm_gbs": PEAK_HBM}, "rows": lib}, open("gpurun_out/lib_bar.json", "w"), indent=1)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/kernel_bench.json", "w"), indent=1)
 if "conv" in which:

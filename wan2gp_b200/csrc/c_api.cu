@@ -16,6 +16,7 @@
 #include "../../include/wan2gp_b200.h"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
+#include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -114,6 +115,19 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
     return B200_OK;
 }
 
+// CTA-pair (cta_group::2) kernel: 256 x 256 tiles, one cluster of 2 CTAs per tile, grid = 2 * min(#tiles, #SMs / 2)
+template <bool EPI_TMA>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st, const CUtensorMap* tc = nullptr) {
+    auto kern = gemm_pair_tcgen05_kernel<EPI_TMA>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<EPI_TMA>::kBytes);
+    if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "gemm pair smem attr: %s", cudaGetErrorString(e));
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int pairs = tiles < b200_num_sms() / 2 ? tiles : b200_num_sms() / 2;
+    kern<<<2 * pairs, 256, Gemm2Smem<EPI_TMA>::kBytes, st>>>(ta, tb, tc ? *tc : ta, p);
+    CHECK_LAUNCH("gemm_pair_tcgen05");
+    return B200_OK;
+}
+
 // conv layers with Cin = 96: three 32-channel boxes (64B swizzle) per tap => K = 96 exactly, no zero-padded MMAs
 int b200_launch_gemm_k96(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     switch (BN) {
@@ -169,6 +183,40 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
     if (b_mn_major && N % 64) return b200_set_error(B200_ERR_ARG, "gemm: MN-major B needs N%%64==0");
     const bool mn = b_mn_major != 0;
     const int BN = b200_pick_bn(N, mn);
+    // large K-major linear layers: CTA-pair kernel (B200_GEMM_PAIR=0 selects the single-CTA 128 x 256 kernel for A/B runs)
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* ev = getenv("B200_GEMM_PAIR"); use_pair = ev ? atoi(ev) : 1; }
+    if (use_pair && !mn && BN == 256 && N % 256 == 0 && M >= 512) {
+        CUtensorMap ta2, tb2, tc2;
+        uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};
+        uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldb * 2};
+        uint32_t box[2] = {GEMM_BK, GEMM_BM};                 // A: 64 x 128 rows per CTA; B: 64 x 128 weight rows per CTA
+        int r = b200_make_tmap_bf16(&ta2, A, 2, da, sa, box, 128);
+        if (r) return r;
+        r = b200_make_tmap_bf16(&tb2, B, 2, db, sb, box, 128);
+        if (r) return r;
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.M = M; p.N = N; p.K = K;
+        p.mode = MODE_LINEAR;
+        p.num_k_iters = (K + GEMM_BK - 1) / GEMM_BK;
+        p.m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
+        p.n_tiles = N / GEMM2_BN;
+        p.n_group = 16;
+        p.out = out; p.out_fp32 = out_fp32; p.accumulate = accumulate; p.ldc = ldc;
+        p.bias = bias; p.gate = gate; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16); p.act = act;
+        static int pair_tma_reduce = -1;
+        if (pair_tma_reduce < 0) { const char* ev = getenv("B200_GEMM_TMA_REDUCE"); pair_tma_reduce = ev ? atoi(ev) : 1; }
+        if (pair_tma_reduce && accumulate && out_fp32 && !residual_bf16 && act == 0 && ldc % 4 == 0) {
+            uint64_t dc[2] = {(uint64_t)N, (uint64_t)M}, sc[1] = {(uint64_t)ldc * 4};
+            uint32_t boxc[2] = {32, GEMM_BM};
+            r = b200_make_tmap(&tc2, out, 2, dc, sc, boxc, 128, 1);
+            if (r) return r;
+            p.tma_reduce = 1;
+            return launch_gemm_pair<true>(ta2, tb2, p, (cudaStream_t)stream, &tc2);
+        }
+        return launch_gemm_pair<false>(ta2, tb2, p, (cudaStream_t)stream);
+    }
     CUtensorMap ta, tb;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -281,9 +329,23 @@ extern "C" int b200_rmsnorm_rope(void* x, long long ld, const float* w, int L, i
     if (!x || !w || L <= 0) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: null/empty argument");
     if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
     if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: cos/sin must both be given");
-    if (per_head) rmsnorm_rope_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
-    else rmsnorm_rope_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, w, D, eps, cos_t, sin_t);
+    auto xb = reinterpret_cast<__nv_bfloat16*>(x);
+    if (per_head) rmsnorm_rope_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(xb, xb, ld, w, w, D, eps, cos_t, sin_t);
+    else rmsnorm_rope_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(xb, xb, ld, w, w, D, eps, cos_t, sin_t);
     CHECK_LAUNCH("rmsnorm_rope");
+    return B200_OK;
+}
+
+extern "C" int b200_qk_rmsnorm_rope(void* q, void* k, long long ld, const float* wq, const float* wk, int L, int D, float eps,
+                                    const float* cos_t, const float* sin_t, int per_head, void* stream) {
+    if (!q || !k || !wq || !wk || L <= 0) return b200_set_error(B200_ERR_ARG, "qk_rmsnorm_rope: null/empty argument");
+    if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "qk_rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
+    if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "qk_rmsnorm_rope: cos/sin must both be given");
+    auto qb = reinterpret_cast<__nv_bfloat16*>(q), kb = reinterpret_cast<__nv_bfloat16*>(k);
+    const dim3 grid(L, 2);
+    if (per_head) rmsnorm_rope_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(qb, kb, ld, wq, wk, D, eps, cos_t, sin_t);
+    else rmsnorm_rope_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(qb, kb, ld, wq, wk, D, eps, cos_t, sin_t);
+    CHECK_LAUNCH("qk_rmsnorm_rope");
     return B200_OK;
 }
 

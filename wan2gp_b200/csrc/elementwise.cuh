@@ -68,10 +68,13 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
 constexpr int RN_MAXV = 4;    // uint4 (8 bf16) per thread, D <= 256*8*4 = 8192
 template <bool PER_HEAD>
 __global__ void __launch_bounds__(256)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __restrict__ w, int D, float eps,
-                    const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ x2, long long ld, const float* __restrict__ w,
+                    const float* __restrict__ w2, int D, float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
     __shared__ float red[8];
     const long long row = blockIdx.x;
+    // blockIdx.y = 1: the second segment (k of a fused q|k|v buffer) with its own norm weight -- q and k of one token in ONE launch,
+    // their CTAs adjacent in the grid so the token's cos/sin row is fetched from HBM once
+    if (blockIdx.y) { x = x2; w = w2; }
     uint4* xr = reinterpret_cast<uint4*>(x + row * ld);
     const int nv = D >> 3;
     uint4 v[RN_MAXV];
@@ -99,6 +102,19 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __
     }
     float r = 0.f;
     if (!PER_HEAD) r = rsqrtf(block_sum_256(s, red) / D + eps);
+    // every element this thread owns sits at the same position d inside its head (the stride 256 * 8 is a multiple of 128): the
+    // 16 table values are loaded ONCE per thread instead of once per 16-byte chunk (4 table LDG.128 per data LDG.128 made the
+    // kernel load-issue bound at 45 % of HBM)
+    float cv[8], sv[8];
+    if (cos_t) {
+        const int d = (threadIdx.x << 3) & 127;
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d + 4));
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d + 4));
+        cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+        sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+    }
     #pragma unroll
     for (int i = 0; i < RN_MAXV; ++i) {
         const int idx = threadIdx.x + i * 256;
@@ -117,13 +133,6 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const float* __
                 f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * r * wv[2 * k + 1];
             }
             if (cos_t) {
-                const int d = col & 127;        // position inside the 128-wide head
-                const float4 c0 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d));
-                const float4 c1 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d + 4));
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d + 4));
-                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float x0 = f[2 * k], x1 = f[2 * k + 1];

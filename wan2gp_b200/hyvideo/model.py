@@ -209,8 +209,7 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
             a = ops.ln_modulate(x, m[0:D], m[D:2 * D], pre_round=True)     # norm1 -> bf16 -> modulate_ (models.py:210-216)
             ops.gemm(a, s.w_qkv, out=qkv[rows], bias=s.b_qkv)
             rope = (cos, sin) if s is blk[0] else (None, None)             # RoPE on the image stream only (:232-235)
-            ops.rmsnorm_rope_(qkv[rows, :D], s.qn, 1e-6, *rope, per_head=True)
-            ops.rmsnorm_rope_(qkv[rows, D:2 * D], s.kn, 1e-6, *rope, per_head=True)
+            ops.qk_rmsnorm_rope_(qkv[rows, :D], qkv[rows, D:2 * D], s.qn, s.kn, 1e-6, *rope, per_head=True)
         n = L + n_valid                                                    # q_lens = k_lens = img_len + text_len (:1086-1088)
         ops.attention(qkv[:n, :D], qkv[:n, D:2 * D], qkv[:n, 2 * D:], H, out=attn[:n])
         for s, x, rows, m in ((blk[0], img, slice(0, L), mods[0]), (blk[1], txt, slice(L, None), mods[1])):
@@ -228,8 +227,7 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
             a = ops.ln_modulate(x, m[0:D], m[D:2 * D], pre_round=True)
             ops.gemm(a, b.w1[:3 * D], out=qkv[rows], bias=b.b1[:3 * D])
             ops.gemm(a, b.w1[3 * D:], out=cat[rows, D:], bias=b.b1[3 * D:], act=ACT_GELU_TANH)
-            ops.rmsnorm_rope_(qkv[rows, :D], b.qn, 1e-6, *rope, per_head=True)
-            ops.rmsnorm_rope_(qkv[rows, D:2 * D], b.kn, 1e-6, *rope, per_head=True)
+            ops.qk_rmsnorm_rope_(qkv[rows, :D], qkv[rows, D:2 * D], b.qn, b.kn, 1e-6, *rope, per_head=True)
         n = L + n_valid
         ops.attention(qkv[:n, :D], qkv[:n, D:2 * D], qkv[:n, 2 * D:], H, out=cat[:n, :D])
         for x, rows in ((img, slice(0, L)), (txt, slice(L, None))):

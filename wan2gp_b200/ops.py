@@ -90,6 +90,20 @@ def rmsnorm_rope_(x, w, eps=1e-6, cos=None, sin=None, per_head=False):
     return x
 
 
+def qk_rmsnorm_rope_(q, k, wq, wk, eps=1e-6, cos=None, sin=None, per_head=False):
+    """rmsnorm_rope_ of the q and the k column block of one fused buffer in a single launch (same row stride)."""
+    _chk(q, bf16, "q"), _chk(k, bf16, "k"), _chk(wq, f32, "wq"), _chk(wk, f32, "wk")
+    L, D = q.shape
+    assert k.shape == q.shape and q.stride(1) == 1 and k.stride(1) == 1 and q.stride(0) == k.stride(0)
+    assert wq.numel() == (128 if per_head else D) and wk.numel() == wq.numel()
+    if cos is not None:
+        _chk(cos, f32, "cos"), _chk(sin, f32, "sin")
+        assert cos.shape == (L, 128) and sin.shape == (L, 128) and cos.is_contiguous() and sin.is_contiguous()
+    _lib.call("b200_qk_rmsnorm_rope", q.data_ptr(), k.data_ptr(), q.stride(0), wq.data_ptr(), wk.data_ptr(), L, D, float(eps), _p(cos), _p(sin),
+              int(per_head), _stream())
+    return q, k
+
+
 def attention(q, k, v, num_heads, out=None, scale=None):
     """q [Lq, H*128], k/v [Lk, H*128] bf16 (row-strided views allowed) -> [Lq, H*128] bf16."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):

@@ -10,7 +10,7 @@ Data layout in HBM (one sample):
   biases / norms / modulation / RoPE tables   fp32
 
 Per block (reference model.py:631-711) the launches are:
-  add_vec (modulation + e0) -> ln_modulate -> GEMM qkv -> rmsnorm_rope(q) -> rmsnorm_rope(k) -> attention ->
+  add_vec (modulation + e0) -> ln_modulate -> GEMM qkv -> qk_rmsnorm_rope(q, k) -> attention ->
   GEMM o (+bias, *gate, += x) -> ln_modulate(affine) -> GEMM q' -> rmsnorm -> GEMM kv'(ctx) -> rmsnorm ->
   attention(512 keys) -> GEMM o' (+= x) -> ln_modulate -> GEMM ffn.0 (+GELU) -> GEMM ffn.2 (*gate, += x)
 """
@@ -221,8 +221,7 @@ class WanModel(torch.nn.Module):
         # ---- self attention
         a = ops.ln_modulate(x, m[0:D], m[D:2 * D], eps=eps)
         qkv = ops.gemm(a, b.w_qkv, bias=b.b_qkv)
-        ops.rmsnorm_rope_(qkv[:, :D], b.nq, eps, cos, sin)
-        ops.rmsnorm_rope_(qkv[:, D:2 * D], b.nk, eps, cos, sin)
+        ops.qk_rmsnorm_rope_(qkv[:, :D], qkv[:, D:2 * D], b.nq, b.nk, eps, cos, sin)
         att = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, out=a)
         del qkv
         ops.gemm(att, b.w_o, out=x, bias=b.b_o, gate=m[2 * D:3 * D], accumulate=True)
