@@ -31,6 +31,10 @@ extern "C" {
 
 const char* b200_last_error(void);
 int b200_version(void);
+
+/* size (floats) of the CFG-Zero* scratch buffer: {<c,u>, <u,u>, per-CTA partial sums, completion ticket}.  The reduction is
+ * evaluated in a fixed order, so identical inputs give bit-identical alpha on every launch and every rank. */
+#define B200_CFG_DOTS_FLOATS (2 + 2 * 1184 + 2)
 /* number of kernels this library has launched in the calling process (bench.py reports it as gpu_launches) */
 long long b200_launch_count(void);
 
@@ -94,7 +98,7 @@ int b200_col_mean_f32(const float* x, float* out, int rows, int cols, void* stre
 int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, void* stream);
 
 /* lat -= dt * (u + g (c - u)); uncond may be NULL (no CFG); pred_out optional.  any2video.py:1701-1722 +
- * euler_scheduler.py:67-86.  n % 4 == 0.  star_dots (device float[2] scratch, or NULL): CFG-Zero* -- u is first rescaled by
+ * euler_scheduler.py:67-86.  n % 4 == 0.  star_dots (device float[B200_CFG_DOTS_FLOATS] scratch, or NULL): CFG-Zero* -- u is first rescaled by
  * alpha = <c,u> / (||u||^2 + 1e-8) computed over the whole sample (any2video.py:1706-1714, steps > cfg_zero_step). */
 int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt, float* pred_out,
                         float* star_dots, long long n, void* stream);

@@ -10,10 +10,23 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _have(tool):
+    import shutil
+    return shutil.which(tool) is not None or os.path.exists(os.path.join("/usr/local/cuda/bin", tool))
+
+
 @pytest.fixture(scope="module")
 def lib():
+    """The prebuilt library if it is current; rebuilding needs nvcc (skip, not error, on a box without the CUDA toolkit)."""
     from wan2gp_b200 import build
-    return ctypes.CDLL(build.build())
+    if not os.path.exists(build.LIB) and not _have("nvcc"):
+        pytest.skip("no prebuilt libwan2gp_b200.so and no nvcc on this box")
+    try:
+        return ctypes.CDLL(build.build())
+    except (RuntimeError, FileNotFoundError):
+        if not _have("nvcc"):
+            pytest.skip("nvcc not available to rebuild libwan2gp_b200.so")
+        raise
 
 
 def test_header_symbols_exported(lib):
@@ -33,7 +46,10 @@ def test_sass_is_blackwell_native():
     """tcgen05.mma / tcgen05.ld / TMA appear as UTCHMMA / LDTM / UTMALDG in the SASS (B200_PROFILING.md)."""
     import subprocess
     from wan2gp_b200 import build
-    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    if not _have("cuobjdump") or (not os.path.exists(build.LIB) and not _have("nvcc")):
+        pytest.skip("cuobjdump / nvcc not available on this box")
+    cuobjdump = "cuobjdump" if __import__("shutil").which("cuobjdump") else "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
     assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path

@@ -92,3 +92,50 @@ def test_cfg_pair_split_gloo():
     [p.join(timeout=60) for p in procs]
     assert [r[1] for r in res] == [0, 0, 1, 1] and all(r[2] == 2 and r[3] for r in res)
     assert res[0][4] == res[1][4] and res[2][4] == res[3][4] and res[0][4] != res[2][4]
+
+
+class _AbortingModel(_FakeModel):
+    """Returns [None] (the reference's abort contract, model.py:1995-1998) from step `at` on -- on ONE rank only."""
+
+    def __init__(self, abort):
+        self.abort, self.calls = abort, 0
+
+    def __call__(self, x, t, context, **kw):
+        self.calls += 1
+        if self.abort and self.calls >= 2:
+            return [None] * len(list(x))
+        return super().__call__(x, t, context, **kw)
+
+
+def _abort_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from wan2gp_b200.pipeline import WanDenoiser
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    wd.init(backend="gloo")
+    group, cfg_rank, sample, _ = wd.make_cfg_pairs()
+    lat = torch.randn(1, 16, 2, 4, 4, generator=torch.Generator().manual_seed(7))
+    ctx, ctxn = torch.randn(1, 8, 16), torch.zeros(1, 8, 16)
+    den = WanDenoiser(_AbortingModel(abort=(rank == 1)), num_steps=4, shift=5.0, device="cpu", cfg_group=group, cfg_rank=cfg_rank)
+    den._combine_step = lambda latents, c, u, gs, dt, star: latents.sub_(dt * (u + gs * (c - u)))
+    outcomes = [den.step(lat, i, ctx, ctxn) is None for i in range(3)]
+    # second part: generate_batch where only rank 1's denoiser aborts
+    class _Den:
+        def generate(self, context, context_null, latent_shape, seed=0, device_frames=False):
+            return None if rank == 1 else {"x": torch.zeros(3, 5, 16, 16, dtype=torch.uint8)}
+    res = wd.generate_batch(lambda: _Den(), [None, None], None, (16, 2, 2, 2), [0, 1], device="cpu", fused=False)
+    q.put((rank, outcomes, res is None))
+    dist.destroy_process_group()
+
+
+def test_interrupt_is_agreed_collectively_gloo():
+    """`_interrupt` is per process.  The partner of an interrupted rank must not be left waiting in the pair's all-gather
+    (pipeline.WanDenoiser.step) nor in the final frame all-gather (dist.generate_batch): both ranks return None together."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_abort_worker, args=(r, 2, 29655, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    for rank, outcomes, batch_none in res:
+        assert outcomes == [False, True, True], (rank, outcomes)      # step 0 completes on both, step 1 aborts on BOTH
+        assert batch_none

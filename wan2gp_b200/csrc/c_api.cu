@@ -36,18 +36,36 @@ int b200_set_error(int code, const char* fmt, ...) {
 void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_version(void) { return 100; }
+extern "C" int b200_version(void) { return 200; }
+static_assert(CFG_DOTS_FLOATS == B200_CFG_DOTS_FLOATS, "header constant out of sync with the kernel");
 extern "C" long long b200_launch_count(void) { return g_launches.load(); }
 
+// Per-device caches (a process may drive several devices, one host thread each): SM count and "max dynamic shared memory
+// attribute already set for kernel X on device d" bit masks.  Relaxed atomics: the cached values are idempotent.
 int b200_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & 63;
+    int v = sms[slot].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[slot].store(v, std::memory_order_relaxed);
     }
-    return sms;
+    return v;
+}
+// true the first time it is called for (mask, current device): the caller then sets the per-device function attribute
+bool b200_first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return !(mask.load(std::memory_order_relaxed) & bit);
+}
+void b200_mark_used_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mask.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
 }
 
 // ------------------------------------------------------------------ tensor maps
@@ -102,11 +120,11 @@ template <int BN, bool MN, int BKC = 64, int NBOX = 1, bool EPI_TMA = false>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st,
                             const CUtensorMap* tc = nullptr) {
     auto kern = gemm_tcgen05_kernel<BN, MN, BKC, NBOX, EPI_TMA>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (b200_first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BKC, NBOX, EPI_TMA>::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
-        attr_done = true;
+        b200_mark_used_on_device(attr_done);
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
@@ -411,8 +429,9 @@ extern "C" int b200_cfg_unipc_step(float* lat, const float* cond, const float* u
         return b200_set_error(B200_ERR_ARG, "cfg_unipc_step: bad argument");
     const long long n4 = n / 4;
     if (star_dots) {
-        cudaMemsetAsync(star_dots, 0, 2 * sizeof(float), (cudaStream_t)stream);
-        const unsigned blocks = (unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+        // star_dots = float[B200_CFG_DOTS_FLOATS] scratch (include/wan2gp_b200.h): dots, per-CTA partials, ticket
+        cudaMemsetAsync(star_dots + 2 + 2 * CFG_DOTS_MAX_BLOCKS, 0, 2 * sizeof(float), (cudaStream_t)stream);
+        const unsigned blocks = (unsigned)((n4 + 255) / 256 < CFG_DOTS_MAX_BLOCKS ? (n4 + 255) / 256 : CFG_DOTS_MAX_BLOCKS);
         cfg_dots_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond, uncond, star_dots, n4);
         CHECK_LAUNCH("cfg_dots");
     }
@@ -428,8 +447,9 @@ extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* u
     if (!lat || !cond || n <= 0 || n % 4 || (star_dots && !uncond)) return b200_set_error(B200_ERR_ARG, "cfg_euler_step: bad argument");
     const long long n4 = n / 4;
     if (star_dots) {
-        cudaMemsetAsync(star_dots, 0, 2 * sizeof(float), (cudaStream_t)stream);
-        const unsigned blocks = (unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+        // star_dots = float[B200_CFG_DOTS_FLOATS] scratch (include/wan2gp_b200.h): dots, per-CTA partials, ticket
+        cudaMemsetAsync(star_dots + 2 + 2 * CFG_DOTS_MAX_BLOCKS, 0, 2 * sizeof(float), (cudaStream_t)stream);
+        const unsigned blocks = (unsigned)((n4 + 255) / 256 < CFG_DOTS_MAX_BLOCKS ? (n4 + 255) / 256 : CFG_DOTS_MAX_BLOCKS);
         cfg_dots_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond, uncond, star_dots, n4);
         CHECK_LAUNCH("cfg_dots");
     }

@@ -282,10 +282,17 @@ __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restr
 // CFG combine + flow-matching Euler update (any2video.py:1701-1722 plain CFG; euler_scheduler.py:67-86):
 // lat <- lat - dt * (u + g (c - u)); also writes the combined prediction (optional)
 // CFG-Zero* (any2video.py:1701-1722): alpha = <c,u> / (||u||^2 + 1e-8) over the whole sample, uncond *= alpha before the
-// combine.  dots[0] += sum c*u, dots[1] += sum u*u  (caller zeroes dots).
+// combine.  Bit-reproducible: every CTA writes its partial sums to scratch[2 + 2 b], the LAST CTA to finish (atomic ticket)
+// adds the partials in index order in double and publishes dots[0] = sum c*u, dots[1] = sum u*u.  The same inputs therefore give
+// the same alpha on every launch and on every rank of a CFG-pair split (float atomicAdd accumulation depended on CTA order).
+// scratch: float[CFG_DOTS_FLOATS] = {dots[2], partials[2 * CFG_DOTS_MAX_BLOCKS], ticket}; the ticket must be 0 on entry and is
+// reset on exit.
+constexpr int CFG_DOTS_MAX_BLOCKS = 1184;
+constexpr int CFG_DOTS_FLOATS = 2 + 2 * CFG_DOTS_MAX_BLOCKS + 2;
 __global__ void __launch_bounds__(256)
-cfg_dots_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float* __restrict__ dots, long long n4) {
+cfg_dots_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float* __restrict__ scratch, long long n4) {
     __shared__ float red[8];
+    __shared__ bool last;
     float cu = 0.f, uu = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
@@ -295,7 +302,26 @@ cfg_dots_kernel(const float* __restrict__ cond, const float* __restrict__ uncond
     }
     cu = block_sum_256(cu, red);
     uu = block_sum_256(uu, red);
-    if (threadIdx.x == 0) { atomicAdd(dots, cu); atomicAdd(dots + 1, uu); }
+    float* part = scratch + 2;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 2 + 2 * CFG_DOTS_MAX_BLOCKS);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = cu;
+        part[2 * blockIdx.x + 1] = uu;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (unsigned int j = 0; j < gridDim.x; ++j) {
+            a += (double)__ldcg(part + 2 * j);
+            b += (double)__ldcg(part + 2 * j + 1);
+        }
+        scratch[0] = (float)a;
+        scratch[1] = (float)b;
+        *ticket = 0u;
+    }
 }
 
 __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond,

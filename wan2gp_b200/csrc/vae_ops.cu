@@ -657,11 +657,11 @@ extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int of
 template <int BN, int ROWS, int BKC = 64>
 static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (b200_first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS, BKC>::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row smem attr: %s", cudaGetErrorString(e));
-        attr_done = true;
+        b200_mark_used_on_device(attr_done);
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
@@ -877,10 +877,10 @@ extern "C" int b200_attention_1head(const void* qkv, void* out, void* workspace,
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + (long long)N * Np);
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (b200_first_use_on_device(attr_done)) {
         cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        b200_mark_used_on_device(attr_done);
     }
 
     for (int f = 0; f < F; ++f) {

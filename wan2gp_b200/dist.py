@@ -63,22 +63,48 @@ def allgather_frames(frames, group=None):
     return torch.cat([out[r][: int(counts[r])] for r in range(world)], 0)
 
 
-def generate_batch(make_denoiser, contexts, context_null, latent_shape, seeds, device=None):
+def generate_batch(make_denoiser, contexts, context_null, latent_shape, seeds, device=None, fused=None):
     """Batch-split generation: rank r denoises + decodes samples shard(len(seeds), r, world) with its own denoiser
     (weights replicated; both Wan2.2 experts fit one 180 GB GPU), then all ranks all-gather the uint8 frames.
-    `make_denoiser()` returns a wan2gp_b200.pipeline.WanDenoiser with a VAE attached."""
+    `make_denoiser()` returns a wan2gp_b200.pipeline.WanDenoiser with a VAE attached.
+
+    fused (default: on for NCCL with one sample per rank): the decoded frames stay fp32 on the device and the quantisation to uint8 is
+    fused with the all-gather (`FusedFrameGather`: every rank stores its bytes straight into all peers' buffers over NVLink) --
+    no CPU round trip, no separate ncclAllGather.  Otherwise frames_to_u8 + allgather_frames (NCCL / gloo)."""
     rank, world = init(device=device)
+    if fused is None:
+        fused = world > 1 and dist.is_initialized() and dist.get_backend() == "nccl" and len(seeds) == world
     mine = shard(len(seeds), rank, world)
     den = make_denoiser()
-    outs = []
-    for i in mine:
-        res = den.generate(contexts[i], context_null, latent_shape, seed=seeds[i])
-        if res is None:
-            return None
-        outs.append(res["x"])
     dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
-    local = torch.stack(outs, 0).to(dev) if outs else torch.empty((0, 3, 4 * (latent_shape[1] - 1) + 1, 8 * latent_shape[2], 8 * latent_shape[3]), dtype=torch.uint8, device=dev)
+    frame_shape = (3, 4 * (latent_shape[1] - 1) + 1, 8 * latent_shape[2], 8 * latent_shape[3])
+    outs, aborted = [], False
+    for i in mine:
+        res = den.generate(contexts[i], context_null, latent_shape, seed=seeds[i], device_frames=fused)
+        if res is None:                              # this rank was interrupted: stop working, but still enter the collectives below
+            aborted = True
+            break
+        outs.append(res["x"])
+    # `_interrupt` is per process: agree on the abort collectively so that no rank is left waiting in the all-gather
+    if world > 1:
+        flag = torch.tensor([1.0 if aborted else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        aborted = bool(flag.item() > 0)
+    if aborted:
+        return None
+    if fused and world > 1 and len(seeds) == world:
+        # one sample per rank, frames still fp32 on the device: quantise + all-gather in ONE kernel over NVLink peer memory
+        fr = outs[0].contiguous()
+        key = (fr.numel(), str(dev))
+        fg = _FUSED.get(key)
+        if fg is None:
+            fg = _FUSED[key] = FusedFrameGather(fr.numel(), dev)
+        return fg.gather(fr).view(world, *frame_shape).clone()
+    local = torch.stack(outs, 0).to(dev) if outs else torch.empty((0,) + frame_shape, dtype=torch.uint8, device=dev)
     return allgather_frames(local)
+
+
+_FUSED = {}          # (bytes per rank, device) -> FusedFrameGather (symmetric buffers are expensive to rendezvous: keep them)
 
 
 class FusedFrameGather:

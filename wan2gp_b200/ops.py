@@ -10,6 +10,7 @@ import torch
 from . import _lib
 
 bf16, f32 = torch.bfloat16, torch.float32
+CFG_DOTS_FLOATS = 2 + 2 * 1184 + 2        # include/wan2gp_b200.h::B200_CFG_DOTS_FLOATS
 
 
 def _stream():
@@ -182,7 +183,7 @@ def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None, cfg_star=False)
     """lat -= dt * (u + g (c - u)); cfg_star=True applies the CFG-Zero* rescale of u (any2video.py:1706-1714)."""
     _chk(lat, f32, "lat"), _chk(cond, f32, "cond")
     assert lat.is_contiguous() and cond.is_contiguous() and (uncond is None or uncond.is_contiguous())
-    dots = torch.empty(2, device=lat.device, dtype=f32) if cfg_star else None
+    dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
     _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
               _p(dots), lat.numel(), _stream())
     return lat
@@ -195,7 +196,7 @@ def cfg_unipc_step_(lat, cond, uncond, guide, x_last, m0, m1, coef, cfg_star=Fal
         _chk(t_, f32, n_)
         assert t_.is_contiguous() and t_.numel() == lat.numel()
     assert uncond is None or (uncond.is_contiguous() and uncond.numel() == lat.numel())
-    dots = torch.empty(2, device=lat.device, dtype=f32) if cfg_star else None
+    dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
     c = (ctypes.c_float * 8)(coef["sigma"], coef["ca"], coef["cb"], coef["cc"], coef["cd"], coef["pp"], coef["pq"], coef["pr"])
     _lib.call("b200_cfg_unipc_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), x_last.data_ptr(), m0.data_ptr(),
               m1.data_ptr(), ctypes.addressof(c), int(coef["use_corrector"]), _p(dots), lat.numel(), _stream())

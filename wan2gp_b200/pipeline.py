@@ -207,11 +207,19 @@ class WanDenoiser:
         elif self.cfg_group is not None:
             import torch.distributed as dist
             mine = model([latents], tt, [context if self.cfg_rank == 0 else context_null], **kw)[0]
-            if mine is None:
+            # `_interrupt` is per process: the pair must AGREE on the abort before either rank skips the collective, otherwise the
+            # partner blocks in ncclAllGather forever.  The flag rides in front of the prediction (same collective, +1 float).
+            shape = tuple(latents.shape)
+            payload = torch.empty(1 + latents.numel(), device=latents.device, dtype=f32)
+            payload[0] = 1.0 if mine is None else 0.0
+            if mine is not None:
+                payload[1:].copy_(mine.reshape(-1))
+            both = [torch.empty_like(payload), torch.empty_like(payload)]
+            dist.all_gather(both, payload, group=self.cfg_group)                  # ncclAllGather inside the 2-rank pair
+            if float(both[0][0]) + float(both[1][0]) > 0:
+                self._interrupt = True                                            # both ranks leave the schedule together
                 return None
-            both = [torch.empty_like(mine), torch.empty_like(mine)]
-            dist.all_gather(both, mine.contiguous(), group=self.cfg_group)        # ncclAllGather inside the 2-rank pair
-            cond, uncond = both
+            cond, uncond = both[0][1:].reshape(shape), both[1][1:].reshape(shape)
         else:
             # joint pass: same blocks applied to each branch in turn (any2video.py:1634, model.py:2030-2037)
             cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
@@ -248,9 +256,10 @@ class WanDenoiser:
         return latents_host
 
     @torch.no_grad()
-    def generate(self, context, context_null, latent_shape, seed=0, y=None, callback=None, decode=True):
+    def generate(self, context, context_null, latent_shape, seed=0, y=None, callback=None, decode=True, device_frames=False):
         """Full schedule: noise -> denoise loop -> VAE decode; returns {"x": uint8 CPU [3,F,H,W]} or latents, None if aborted
-        (contract of WanAny2V.generate, any2video.py:1810-1826)."""
+        (contract of WanAny2V.generate, any2video.py:1810-1826).  device_frames: return the clamped fp32 frames on the device instead
+        (dist.generate_batch fuses their quantisation with the all-gather)."""
         g = torch.Generator(device="cpu").manual_seed(seed)
         latents = torch.randn(1, *latent_shape, dtype=f32, generator=g).to(self.device)      # any2video.py:1470
         context, context_null = context.to(self.device), (None if context_null is None else context_null.to(self.device))
@@ -259,6 +268,8 @@ class WanDenoiser:
                 return None
         if not decode or self.vae is None:
             return {"latents": latents}
+        if device_frames:
+            return {"x": self.vae.decode([latents[0]], 0)[0]}
         return {"x": self.vae.decode_to_cpu_uint8([latents[0]], 0)[0]}
 
 

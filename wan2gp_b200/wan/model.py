@@ -178,6 +178,8 @@ class WanModel(torch.nn.Module):
             self.blocks.append(self._pack_block({n: synth.make_wan_tensor(n, s, cfg, seed, self.device)
                                                  for n, s in shapes.items() if n.startswith(p)}, p))
         self._ready = True
+        self._graphs = {}                                                     # as load_state_dict: nothing captured / cached may
+        self._prompts.clear()                                                 # keep pointing at the previous weights
         return self
 
     def apply_post_init_changes(self):

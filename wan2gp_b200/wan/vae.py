@@ -445,10 +445,13 @@ class WanVAE:
             n = fr.shape[1]
             fs = min(max(0, int(frame_start or 0)), n)
             fe = n if target_frames is None else min(n, fs + int(target_frames))
-            fr = fr[:, fs:fe, :target_height, :target_width].contiguous()
+            # quantise the whole frame range (H = 8h, W = 8w: numel % 4 == 0 as the 16-byte kernel needs), crop the uint8 result
+            # afterwards: the reference accepts any target_height / target_width (vae.py:757-767)
+            fr = fr[:, fs:fe].contiguous()
             u8 = torch.empty(fr.shape, device=fr.device, dtype=torch.uint8)
-            _lib.call("b200_frames_to_u8", fr.data_ptr(), u8.data_ptr(), fr.numel(), _s())
-            outs.append(u8.cpu())
+            if fr.numel():
+                _lib.call("b200_frames_to_u8", fr.data_ptr(), u8.data_ptr(), fr.numel(), _s())
+            outs.append(u8[:, :, :target_height, :target_width].cpu())
         return outs
 
     def encode(self, videos, tile_size=0, any_end_frame=False):
