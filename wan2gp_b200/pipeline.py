@@ -185,6 +185,7 @@ class WanDenoiser:
         num_steps = len(self.timesteps) - 1
         self.num_steps = num_steps
         self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
+        self.interrupt_source = None                 # pipeline object that owns `_interrupt` when this denoiser is driven by WanAny2V
         self._pred, self._hist = None, None
 
     def expert(self, t):
@@ -200,7 +201,8 @@ class WanDenoiser:
         dt = (t - self.timesteps[i + 1]) / 1000.0
         model, g = self.expert(t)
         tt = torch.tensor([t], dtype=f32)
-        kw = dict(y=y, freqs=freqs, pipeline=self, current_step_no=i, max_steps=self.num_steps, callback=callback)
+        # the model polls `pipeline._interrupt` once per block: the object the UI thread writes to (WanAny2V) when one is attached
+        kw = dict(y=y, freqs=freqs, pipeline=self.interrupt_source or self, current_step_no=i, max_steps=self.num_steps, callback=callback)
         if context_null is None:
             cond = model([latents], tt, [context], **kw)[0]
             uncond = None
