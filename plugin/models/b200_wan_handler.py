@@ -96,10 +96,10 @@ class family_handler:
     def load_model(model_filename, model_type, base_model_type, model_def, quantizeTransformer=False, text_encoder_quantization=None,
                    dtype=torch.bfloat16, VAE_dtype=torch.float32, mixed_precision_transformer=False, save_quantized=False,
                    submodel_no_list=None, text_encoder_filename=None, VAE_upsampling=None, text_encoder=None, vae_state_dict=None,
-                   state_dicts=None, device="cuda", **kwargs):
+                   vae_cfg=None, state_dicts=None, device="cuda", **kwargs):
         """-> (pipeline_obj, pipe_dict).  `model_filename`: list of checkpoint paths (high-noise expert first, wan_handler.py /
         any2video.py:170-232).  Extra keyword-only hooks for tests / embedders: `state_dicts` (already loaded weights instead of
-        files), `vae_state_dict`, `text_encoder` (callable(prompts, device) -> list of [len, 4096] tensors)."""
+        files), `vae_state_dict` / `vae_cfg` (reduced VAE in tests), `text_encoder` (callable(prompts, device) -> list of [len, 4096] tensors)."""
         from wan2gp_b200 import synth
         from wan2gp_b200.wan import WanAny2V, WanModel, WanVAE
         if base_model_type not in ARCHS:
@@ -127,7 +127,7 @@ class family_handler:
             if vae_path is None:
                 raise FileNotFoundError("Wan2.1_VAE.safetensors not found (query_model_files lists it for download)")
             vae_state_dict = _read_state_dict(vae_path)
-        vae = WanVAE(device=device, state_dict=vae_state_dict)
+        vae = WanVAE(device=device, state_dict=vae_state_dict, cfg=vae_cfg)
         te_module = None
         if text_encoder is None:
             # WanGP's umT5 encoder (models/wan/modules/t5.py:270 T5EncoderModel), constructed as any2video.py:119-126 does

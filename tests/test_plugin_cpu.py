@@ -65,11 +65,10 @@ def pipeline(stub_abi, monkeypatch):  # noqa: F811
         cfg = synth.WAN_CONFIGS[h.ARCHS[arch][0]]
         sds = [synth.make_wan_state_dict(cfg, s) for s in (0, 1)]
         vsd = synth.make_vae_state_dict(synth.VAE_CFG_TINY, 0, encoder=True)
-        monkeypatch.setattr("wan2gp_b200.wan.vae.WanVAEDecoder.__init__.__defaults__", (synth.VAE_CFG_TINY, "cuda"), raising=False)
         model_def = json.load(open(os.path.join(ROOT, "plugin", "defaults", arch + ".json")))["model"]
         return fh.load_model(["hi", "lo"], arch, arch, model_def, dtype=torch.bfloat16, VAE_dtype=torch.float32, submodel_no_list=[1, 2],
                              text_encoder_filename=None, profile=1, lm_decoder_engine="legacy", text_encoder=fake_t5, state_dicts=sds,
-                             vae_state_dict=vsd, device="cpu")
+                             vae_state_dict=vsd, vae_cfg=synth.VAE_CFG_TINY, device="cpu")
     return fh, make
 
 
