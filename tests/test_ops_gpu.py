@@ -109,7 +109,10 @@ def test_rmsnorm_rope(ops):
         assert rel_l2(y.cpu(), wan_oracle.rms_norm_full(keep[:, :D].float().cpu(), w.cpu(), 1e-6)) < TOL_BF16
 
 
-@pytest.mark.parametrize("Lq,Lk,H", [(128, 128, 1), (128, 256, 2), (200, 333, 3), (1000, 1000, 2), (300, 512, 4), (64, 80, 1)])
+# Lq >= 1024 takes the CTA-pair kernel (attn2_sm100.cuh: 512 query rows per cluster): full / ragged pair blocks, a second CTA that is
+# entirely out of range (1100 = 2 x 512 + 76), partial last K/V tile, cross-attention length 512
+@pytest.mark.parametrize("Lq,Lk,H", [(128, 128, 1), (128, 256, 2), (200, 333, 3), (1000, 1000, 2), (300, 512, 4), (64, 80, 1),
+                                     (1024, 1024, 2), (2000, 1333, 3), (1100, 512, 2), (1536, 200, 1), (3510, 3510, 2)])
 def test_attention(ops, Lq, Lk, H):
     D = H * 128
     q, k, v = (_randn(L, D, seed=s, dtype=bf16) for L, s in ((Lq, 1), (Lk, 2), (Lk, 3)))

@@ -206,8 +206,9 @@ def test_wanvae_decode_720p_9frames(ops):
     torch.cuda.synchronize()
     sdg = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
-        ref_bf = vae_oracle.vae_decode(sdg, z.cuda(), synth.VAE_MEAN, synth.VAE_STD, emulate_bf16=True)
-        ref_32 = vae_oracle.vae_decode(sdg, z.cuda(), synth.VAE_MEAN, synth.VAE_STD, emulate_bf16=False)
+        mean, std = torch.tensor(synth.VAE_MEAN, device="cuda"), torch.tensor(synth.VAE_STD, device="cuda")
+        ref_bf = vae_oracle.vae_decode(sdg, z.cuda(), mean, std, emulate_bf16=True)
+        ref_32 = vae_oracle.vae_decode(sdg, z.cuda(), mean, std, emulate_bf16=False)
     assert got.shape == ref_32.shape == (3, 9, 720, 1280)
     e_bf, p32 = rel_l2(got, ref_bf), psnr(got.clamp(-1, 1), ref_32.clamp(-1, 1), 2.0)
     u8 = (vae_oracle.frames_to_uint8(got).int() - vae_oracle.frames_to_uint8(ref_32).int()).abs()

@@ -1,0 +1,65 @@
+"""Attention kernel variants A/B: parity (sampled rows vs fp64) + CUDA-event timing at the Wan 720p / 480p self-attention shapes.
+One subprocess per variant (the kernel choice is a process-wide env switch), each under a timeout so a hang cannot eat the lease.
+Writes gpurun_out/attn_ab.json.   Usage: python tools/attn_ab.py [variant ...]   (default: 0 1 2 4)"""
+import json
+import math
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+NAMES = {"0": "single-CTA (r01 kernel)", "1": "pair, packed-fp32 softmax", "2": "pair, scalar softmax", "4": "pair, packed + 1/4 exp2 on FMA pipe"}
+
+
+def leg():
+    import torch
+    from wan2gp_b200 import ops
+    bf16 = torch.bfloat16
+    out = {"variant": os.environ.get("B200_ATT_PAIR"), "parity": [], "timing": []}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for Lq, Lk, H in [(1024, 1024, 2), (2000, 1333, 3), (1100, 512, 2), (9000, 9000, 2)]:
+        D = H * 128
+        q, k, v = (torch.randn(n, D, device="cuda", generator=g).to(bf16) for n in (Lq, Lk, Lk))
+        o = ops.attention(q, k, v, H)
+        torch.cuda.synchronize()
+        qh, kh, vh = (t.double().reshape(-1, H, 128).permute(1, 0, 2) for t in (q, k, v))
+        ref = (torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128), -1) @ vh).permute(1, 0, 2).reshape(Lq, D)
+        rel = float((o.double() - ref).norm() / ref.norm())
+        out["parity"].append({"Lq": Lq, "Lk": Lk, "H": H, "rel_l2": rel, "ok": rel < 4e-3})
+        print(out["parity"][-1], flush=True)
+    if all(p["ok"] for p in out["parity"]):
+        for L, H in [(75600, 40), (32760, 40)]:
+            D = H * 128
+            qkv = torch.randn(L, 3 * D, device="cuda").to(bf16)
+            o = torch.empty(L, D, device="cuda", dtype=bf16)
+            fn = lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, out=o)
+            fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = sorted(ts)[len(ts) // 2]
+            out["timing"].append({"L": L, "H": H, "ms": ms, "tflops": 4.0 * L * L * D / ms / 1e9, "all_ms": ts})
+            print(out["timing"][-1], flush=True)
+            del qkv, o
+    print("LEG " + json.dumps(out))
+
+
+if __name__ == "__main__":
+    if os.environ.get("ATT_LEG"):
+        leg()
+        sys.exit(0)
+    res = {}
+    for var in (sys.argv[1:] or ["0", "1", "2", "4"]):
+        env = dict(os.environ, ATT_LEG="1", B200_ATT_PAIR=var)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=240)
+            line = [l for l in r.stdout.splitlines() if l.startswith("LEG ")]
+            res[var] = dict(json.loads(line[-1][4:]), name=NAMES.get(var, var)) if line else {"name": NAMES.get(var, var), "error": (r.stdout + r.stderr)[-1500:]}
+        except subprocess.TimeoutExpired:
+            res[var] = {"name": NAMES.get(var, var), "error": "timeout (hang)"}
+        print(var, json.dumps(res[var])[:600], flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "attn_ab.json"), "w"), indent=1)

@@ -14,6 +14,7 @@
 #include <mutex>
 
 #include "../../include/wan2gp_b200.h"
+#include "attn2_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
@@ -305,6 +306,29 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
     p.Lq = Lq; p.Lk = Lk; p.H = H;
     p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
+    // long query sequences: CTA-pair kernel (attn2_sm100.cuh): 512 query rows per cluster, each CTA stages half of every K/V tile.
+    // B200_ATT_PAIR=0 selects the single-CTA kernel (A/B runs); other values: see below.
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* ev = getenv("B200_ATT_PAIR"); use_pair = ev ? atoi(ev) : 1; }
+    if (use_pair && Lq >= 1024) {
+        CUtensorMap tk2;
+        uint32_t boxk[2] = {64, 64};                         // this CTA's 64 keys x one 64-wide d slab
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldk * 2};
+        int r = b200_make_tmap_bf16(&tk2, k, 2, dims, str, boxk, 128); if (r) return r;
+        dim3 grid2(2 * ((Lq + 2 * ATT_QTILES * ATT_BM - 1) / (2 * ATT_QTILES * ATT_BM)), H);
+        auto launch2 = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM_BYTES);
+            if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention pair smem attr: %s", cudaGetErrorString(e));
+            kern<<<grid2, ATT_THREADS, ATT2_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk2, tv, p);
+            return B200_OK;
+        };
+        // variants (B200_ATT_PAIR): 1 = packed-fp32 softmax (default), 2 = scalar softmax, 4 = packed + every 4th exp2 on the FMA pipe
+        int rc2 = use_pair == 4 ? launch2(attn_pair_fwd_d128_kernel<4, true>)
+                : use_pair == 2 ? launch2(attn_pair_fwd_d128_kernel<0, false>) : launch2(attn_pair_fwd_d128_kernel<0, true>);
+        if (rc2) return rc2;
+        CHECK_LAUNCH("attn_pair_fwd_d128");
+        return B200_OK;
+    }
     dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H);
     // tuning variants (B200_ATT_VARIANT = "<poly><split>", e.g. "41"); the default (1 = no poly, split P) is the measured best
     static int variant = -1;

@@ -283,6 +283,31 @@ __device__ __forceinline__ float ex2_poly3(float x) {
     const float p = fmaf(fmaf(fmaf(0.05517105758190155f, f, 0.2426096349954605f), f, 0.6932609677314758f), f, 0.9999281764030457f);
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // p * 2^round(x)
 }
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 process two fp32 lanes per instruction) and the 3-input max (FMNMX3): they cut the
+// issue slots -- and under the 1 kW cap the energy -- of the attention softmax (one FFMA + one FADD + one FMNMX per score otherwise).
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ float ex2_approx(float x) {
