@@ -122,6 +122,17 @@ int b200_cfg_unipc_step(float* lat, const float* cond, const float* uncond, floa
 int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                    int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream);
 
+/* Fused "conv -> next layer's RMS_norm + SiLU" (Wan VAE ResidualBlock, vae.py:246-273: norm -> SiLU -> CausalConv3d chains).  The
+ * epilogue of the producing conv owns all channels of a pixel when Cout is one N tile, so it writes silu(F.normalize(out) * sqrt(C) *
+ * gamma) (vae.py:85-103) to norm_out in addition to (out != NULL) or instead of (out == NULL) the raw tensor: the stand-alone norm pass
+ * (b200_rms_silu_cl: one read + one write of the activation) is not launched.  b200_conv_norm_fusable() says whether a layer qualifies
+ * (row-tiled kernel, Cout of 96 or 192); otherwise the caller uses b200_conv3d_cl + b200_rms_silu_cl. */
+int b200_conv_norm_fusable(int W, int Cin, int Cout, int kh, int kw);
+int b200_conv3d_cl_norm(const void* x, const void* w, const float* bias, const void* residual, void* out, void* norm_out,
+                        const float* gamma, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, void* stream);
+int b200_upconv2x_cl_norm(const void* x, const void* w4, const float* bias, void* out, void* norm_out, const float* gamma, int T, int H,
+                          int W, int Cin, int Cout, void* stream);
+
 /* Resample 'upsample2d/3d' spatial part (vae.py:124-133: nearest-exact 2x then Conv2d 3x3 pad 1) as four 2x2 sub-pixel
  * convolutions on the low-resolution input: x bf16 [T,H,W,Cin]; w4 bf16 [4][Cout][4][Cin] = per output parity (py,px) the 3x3
  * taps that hit the same source pixel summed; out bf16 [T,2H,2W,Cout]. */

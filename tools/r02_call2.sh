@@ -14,4 +14,6 @@ PY
 )
 echo "pair kernel usable: $PAIR_OK"; export B200_ATT_PAIR=$PAIR_OK
 echo "== ops + prod + plugin tests =="; timeout 1200 python -m pytest tests/test_ops_gpu.py tests/test_plugin_gpu.py tests/test_multigpu_gpu.py "tests/test_prod_shapes_gpu.py::test_wanvae_decode_720p_9frames" "tests/test_prod_shapes_gpu.py::test_attention_production_length" tests/test_wan_gpu.py tests/test_hy_gpu.py -q -s -x > gpurun_out/call2_tests.log 2>&1; echo "rc=$?"; grep -E "rel-L2|passed|failed|mean \|d" gpurun_out/call2_tests.log | tail -25
+echo "== vae tests + fused-norm A/B =="; timeout 900 python -m pytest tests/test_vae_gpu.py -q -x > gpurun_out/call2_vae.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/call2_vae.log
+for f in 1 0; do B200_VAE_FUSE_NORM=$f timeout 300 python tools/wanvae_bench.py 2>&1 | tail -2 | sed "s/^/fuse_norm=$f: /"; done | tee gpurun_out/call2_vae_ab.log
 echo "== bench =="; timeout 900 python bench.py --steps 3 --warmup 2 > gpurun_out/bench_r02_a.json 2> gpurun_out/bench_r02_a.err; echo "rc=$?"; tail -c 3000 gpurun_out/bench_r02_a.json; tail -5 gpurun_out/bench_r02_a.err

@@ -33,6 +33,10 @@ SIGNATURES = {
     "b200_cfg_unipc_step": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p],
     "b200_conv3d_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_int, c_int, c_int, c_int, c_void_p],
+    "b200_conv_norm_fusable": [c_int, c_int, c_int, c_int, c_int],
+    "b200_conv3d_cl_norm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_void_p],
+    "b200_upconv2x_cl_norm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_upconv2x_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_rms_silu_cl": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     "b200_upsample2x_cl": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -85,6 +89,11 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise B200Error(f"{name} failed ({rc}): {lib.b200_last_error().decode()}")
+
+
+def query(name, *args):
+    """Host-side query functions of the ABI (no launch, plain int result; no error convention)."""
+    return int(getattr(load(), name)(*args))
 
 
 def launch_count():

@@ -49,7 +49,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_rowoff(uint32_t smem_
     return d;
 }
 
-template <int BN, int ROWS, int BKC = 64>
+// NORM: the epilogue also applies the RMS_norm (+SiLU) of the layer that consumes this conv's output (models/wan/modules/vae.py:85-103,
+// 246-250: F.normalize over channels * sqrt(C) * gamma, then SiLU) -- every epilogue thread owns one pixel and, with a single N tile,
+// all of its channels, so the statistics need no exchange.  The separate norm pass (one read + one write of every activation,
+// 15 % of the Wan decode) disappears: a ResidualBlock's first conv writes ONLY the normalised tensor, its second conv (and the
+// up-sampling convs) write the raw tensor for the skip path plus the normalised one for the next block.
+template <int BN, int ROWS, int BKC = 64, bool NORM = false>
 __global__ void __launch_bounds__(256, 1)
 conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using S = ConvRowSmem<BN, ROWS, BKC>;
@@ -192,6 +197,74 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const bool row_ok = (h < p.H) && (w < p.W);
                 const long long row_off = t0 * p.st_t + h * p.st_h + w * p.st_w;
                 const uint32_t t_row = tmem_base + acc * 256 + r * BN + ((uint32_t)(wq * 32) << 16);
+                if constexpr (NORM) {
+                    // bf16 channels-last output, one N tile (BN == N, BN % 32 == 0): keep the rounded row packed in registers
+                    static_assert(BN % 32 == 0, "NORM epilogue: whole 32-column chunks");
+                    uint32_t pk[BN / 2];
+                    float ss = 0.f;
+                    #pragma unroll
+                    for (int c = 0; c < BN / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(t_row + c * 32, v);
+                        tmem_ld_wait();
+                        float f[32];
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias) {
+                            #pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
+                                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                            }
+                        }
+                        if (p.residual && row_ok) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c * 32);
+                            #pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 r4 = __ldg(rp + j / 8);
+                                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                                #pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    f[j + 2 * q] += __uint_as_float(rw[q] << 16);
+                                    f[j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                                }
+                            }
+                        }
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t w2 = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                            pk[c * 16 + j] = w2;
+                            const float a = __uint_as_float(w2 << 16), b = __uint_as_float(w2 & 0xffff0000u);   // the ROUNDED values, as the
+                            ss = fmaf(a, a, fmaf(b, b, ss));                                                    // separate norm pass saw them
+                        }
+                        if (!p.norm_only && row_ok) {
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + c * 32);
+                            #pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[c * 16 + 4 * j], pk[c * 16 + 4 * j + 1], pk[c * 16 + 4 * j + 2], pk[c * 16 + 4 * j + 3]);
+                        }
+                    }
+                    const float inv = sqrtf((float)BN) / fmaxf(sqrtf(ss), 1e-12f);
+                    if (row_ok) {
+                        uint4* np = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.norm_out) + row_off);
+                        #pragma unroll
+                        for (int q = 0; q < BN / 8; ++q) {
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.norm_gamma + q * 8));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.norm_gamma + q * 8 + 4));
+                            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                            uint32_t o[4];
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t w2 = pk[q * 4 + k];
+                                const float a = silu_fast(__uint_as_float(w2 << 16) * inv * g[2 * k]);
+                                const float b = silu_fast(__uint_as_float(w2 & 0xffff0000u) * inv * g[2 * k + 1]);
+                                o[k] = pack_bf16x2(a, b);
+                            }
+                            np[q] = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 #pragma unroll 1
                 for (int c = 0; c < BN / 32 + (BN % 32 ? 1 : 0); ++c) {
                     uint32_t v[32];

@@ -59,6 +59,12 @@ struct GemmParams {
     const __nv_bfloat16* residual;   // same mapping as out (bf16) or null : value += residual
     int act;
     int conv_base_offset;     // conv_sm100.cuh: put (addr >> 7) & 7 into the A descriptors' base-offset field
+    // ---- fused "next layer's norm" epilogue (conv_sm100.cuh, NORM instantiations; requires one N tile = all channels of a pixel):
+    // norm_out[pixel, :] = silu( bf16(value) / max(||bf16(value)||_2, 1e-12) * sqrt(N) * norm_gamma ), same pixel strides as out;
+    // norm_only: the raw tensor is not written (its only consumer was the norm)
+    const float* norm_gamma;
+    void* norm_out;
+    int norm_only;
 };
 
 // BKC = K elements per TMA box (64 -> 128B swizzle, 32 -> 64B swizzle); NBOX boxes of A and of B form one pipeline stage

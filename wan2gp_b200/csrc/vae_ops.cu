@@ -607,7 +607,8 @@ extern "C" int b200_group_norm_apply_cl(const void* x, const float* scale_shift,
 struct ConvView { int Ti, Hi, Wi, off_t, off_h, off_w; long long ost_t, ost_h, ost_w; };
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream, int prepadded = 0, const ConvView* view = nullptr);
+                        void* stream, int prepadded = 0, const ConvView* view = nullptr, const float* norm_gamma = nullptr,
+                        void* norm_out = nullptr);
 
 extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                               int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
@@ -625,6 +626,40 @@ extern "C" int b200_upconv2x_cl(const void* x, const void* w4, const float* bias
             const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w4) + (long long)(2 * py + px) * Cout * 4 * Cin;
             // parity 0 reads source rows (h-1, h); parity 1 reads (h, h+1)
             int r = conv_cl_impl(x, wp, bias, nullptr, out, T, H, W, Cin, Cout, 1, 2, 2, 0, 0, 1 - py, 1 - px, py, px, stream);
+            if (r) return r;
+        }
+    return B200_OK;
+}
+
+static bool conv_row_wanted(int W, int kh, int kw);
+static bool conv_norm_instance(int BN, int Cout);
+static int env_flag(const char* name, int dflt);
+// 1 if b200_conv3d_cl_norm / b200_upconv2x_cl_norm can serve a layer with these dimensions (row-tiled kernel, one N tile of 96 or 192
+// channels).  W is the INPUT width of the launch (the low-resolution width for the up-sampling conv).
+extern "C" int b200_conv_norm_fusable(int W, int Cin, int Cout, int kh, int kw) {
+    const int BN = b200_pick_bn(Cout, false);
+    if (!conv_row_wanted(W, kh, kw) || !conv_norm_instance(BN, Cout) || Cin % 8) return 0;
+    static const int row_k32n = env_flag("B200_CONV_ROW_K32", 1);
+    const bool k96 = (Cin == 96) && row_k32n;
+    return (BN == 192 && k96) ? 0 : 1;
+}
+
+// b200_conv3d_cl (out_mode 0) whose epilogue ALSO writes silu(RMS_norm(out) * gamma) -- the input of the next layer's conv -- to
+// norm_out (bf16 [T,H,W,Cout]); out may be NULL when the raw tensor has no other consumer.  Replaces CausalConv3d followed by
+// RMS_norm + SiLU of the next residual sub-layer (vae.py:246-250 inside ResidualBlock.forward :254-273).
+extern "C" int b200_conv3d_cl_norm(const void* x, const void* w, const float* bias, const void* residual, void* out, void* norm_out,
+                                   const float* gamma, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, void* stream) {
+    if (!norm_out || !gamma) return b200_set_error(B200_ERR_ARG, "conv3d_cl_norm: norm_out / gamma required");
+    return conv_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, kh >> 1, kw >> 1, -1, -1, stream, 0, nullptr, gamma, norm_out);
+}
+// b200_upconv2x_cl with the same fused norm: out and norm_out are [T, 2H, 2W, Cout].
+extern "C" int b200_upconv2x_cl_norm(const void* x, const void* w4, const float* bias, void* out, void* norm_out, const float* gamma, int T,
+                                     int H, int W, int Cin, int Cout, void* stream) {
+    if (!x || !w4 || !out || !norm_out || !gamma) return b200_set_error(B200_ERR_ARG, "upconv2x_cl_norm: null argument");
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w4) + (long long)(2 * py + px) * Cout * 4 * Cin;
+            int r = conv_cl_impl(x, wp, bias, nullptr, out, T, H, W, Cin, Cout, 1, 2, 2, 0, 0, 1 - py, 1 - px, py, px, stream, 0, nullptr, gamma, norm_out);
             if (r) return r;
         }
     return B200_OK;
@@ -654,9 +689,9 @@ extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int of
 }
 
 // ---- row-tiled conv kernel (conv_sm100.cuh): instances and selection
-template <int BN, int ROWS, int BKC = 64>
+template <int BN, int ROWS, int BKC = 64, bool NORM = false>
 static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC>;
+    auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC, NORM>;
     static std::atomic<unsigned long long> attr_done{0};
     if (b200_first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS, BKC>::kBytes);
@@ -670,6 +705,13 @@ static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, co
     return B200_OK;
 }
 static int conv_row_rows(int BN) { return BN <= 128 ? 2 : 1; }
+// instances with the fused next-layer norm epilogue: the single-N-tile layers of the Wan decoder's 96- and 192-channel stages
+static bool conv_norm_instance(int BN, int Cout) { return Cout == BN && (BN == 96 || BN == 192); }
+static int launch_conv_row_norm(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    if (BN == 96) return k32 ? launch_conv_row_inst<96, 2, 32, true>(ta, tb, p, st) : launch_conv_row_inst<96, 2, 64, true>(ta, tb, p, st);
+    if (BN == 192 && !k32) return launch_conv_row_inst<192, 1, 64, true>(ta, tb, p, st);
+    return b200_set_error(B200_ERR_ARG, "no fused-norm row-conv instance for BN=%d", BN);
+}
 static int launch_conv_row(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     if (k32) {                                    // Cin = 96: three 32-channel chunks (64B swizzle)
         switch (BN) {
@@ -707,8 +749,8 @@ static bool conv_row_wanted(int W, int kh, int kw) {
 
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream, int prepadded, const ConvView* view) {
-    if (!x || !w || !out || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
+                        void* stream, int prepadded, const ConvView* view, const float* norm_gamma, void* norm_out) {
+    if (!x || !w || (!out && !norm_out) || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
     if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
     if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
     if (out_mode == 1 && (Cout % 64 || residual)) return b200_set_error(B200_ERR_ARG, "conv3d_cl: bad interleave arguments");
@@ -780,6 +822,17 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         p.st_w = 1; p.st_h = W; p.st_t = (long long)H * W; p.st_split = (long long)T * H * W;
     } else {
         return b200_set_error(B200_ERR_ARG, "conv3d_cl: out_mode %d", out_mode);
+    }
+    if (norm_out) {
+        // fused RMS_norm + SiLU of the consuming layer: bf16 channels-last outputs of the row kernel with all channels in one N tile
+        if (!row || !conv_norm_instance(BN, Cout) || !norm_gamma || (out_mode != 0) || p.csplit || view)
+            return b200_set_error(B200_ERR_ARG, "conv3d_cl_norm: layer not fusable (W=%d Cout=%d mode=%d): ask b200_conv_norm_fusable first", W, Cout, out_mode);
+        p.norm_gamma = norm_gamma; p.norm_out = norm_out; p.norm_only = out ? 0 : 1;
+        if (up_py >= 0) p.norm_out = reinterpret_cast<__nv_bfloat16*>(norm_out) + ((long long)up_py * 2 * W + up_px) * Cout;
+        if (!out) p.out = p.norm_out;
+        static const int base_off_n = env_flag("B200_CONV_ROW_BASEOFF", 0);
+        p.conv_base_offset = base_off_n;
+        return launch_conv_row_norm(BN, k96, ta, tb, p, (cudaStream_t)stream);
     }
     if (row) {
         static const int base_off = env_flag("B200_CONV_ROW_BASEOFF", 0);

@@ -11,6 +11,8 @@ The reference decodes one latent frame per Python-loop iteration through per-con
                     its 2C channels are interleaved in time by the GEMM epilogue's store mapping
 Activations are channels-last bf16 [T,H,W,C]; every conv is a tcgen05 implicit GEMM (csrc/gemm_sm100.cuh).
 """
+import os
+
 import torch
 
 from .. import _lib, ops, synth
@@ -20,6 +22,11 @@ bf16, f32 = torch.bfloat16, torch.float32
 
 def _s():
     return torch.cuda.current_stream().cuda_stream
+
+
+# the consumer's RMS_norm + SiLU in the producing conv's epilogue where a pixel's channels sit in one CTA (B200_VAE_FUSE_NORM=0: the
+# separate norm pass everywhere, for A/B measurements)
+FUSE_NORM = os.environ.get("B200_VAE_FUSE_NORM", "1") != "0"
 
 
 class _Conv:
@@ -49,6 +56,24 @@ class _Conv:
         return out
 
 
+    # ---- fused "this conv -> the consumer's RMS_norm + SiLU" (csrc/conv_sm100.cuh NORM epilogue)
+    def fusable(self, W):
+        kt, kh, kw = self.k
+        return FUSE_NORM and _lib.query("b200_conv_norm_fusable", int(W), self.cin, self.cout, kh, kw) == 1
+
+    def with_norm(self, x, gamma, residual=None, raw=True):
+        """-> (conv(x) [+ residual] or None, silu(rms_norm(that) * gamma)): both bf16 [T,H,W,Cout]; raw=False skips the un-normalised
+        tensor (a ResidualBlock's first conv: its output is only ever read through the norm, vae.py:246-250)."""
+        T, H, W, C = x.shape
+        assert C == self.cin and x.is_contiguous() and x.dtype == bf16
+        kt, kh, kw = self.k
+        out = torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16) if raw else None
+        nrm = torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16)
+        _lib.call("b200_conv3d_cl_norm", x.data_ptr(), self.w.data_ptr(), self.b.data_ptr(), 0 if residual is None else residual.data_ptr(),
+                  0 if out is None else out.data_ptr(), nrm.data_ptr(), gamma.data_ptr(), T, H, W, self.cin, self.cout, kt, kh, kw, _s())
+        return out, nrm
+
+
 class _UpConv:
     """nearest-exact 2x + Conv2d 3x3 (vae.py:124-133) folded into four 2x2 sub-pixel convs (csrc/vae_ops.cu::b200_upconv2x_cl)."""
 
@@ -76,6 +101,19 @@ class _UpConv:
         _lib.call("b200_upconv2x_cl", x.data_ptr(), self.w4.data_ptr(), self.b.data_ptr(), out.data_ptr(), T, H, W, self.cin,
                   self.cout, _s())
         return out
+
+
+    def fusable(self, W):
+        return FUSE_NORM and _lib.query("b200_conv_norm_fusable", int(W), self.cin, self.cout, 2, 2) == 1
+
+    def with_norm(self, x, gamma):
+        T, H, W, C = x.shape
+        assert C == self.cin and x.is_contiguous() and x.dtype == bf16
+        out = torch.empty(T, 2 * H, 2 * W, self.cout, device=x.device, dtype=bf16)
+        nrm = torch.empty_like(out)
+        _lib.call("b200_upconv2x_cl_norm", x.data_ptr(), self.w4.data_ptr(), self.b.data_ptr(), out.data_ptr(), nrm.data_ptr(), gamma.data_ptr(),
+                  T, H, W, self.cin, self.cout, _s())
+        return out, nrm
 
 
 def rms_silu(x, gamma, silu=True):
@@ -204,10 +242,20 @@ class WanVAEDecoder(torch.nn.Module):
 
     # ---- blocks
     @staticmethod
-    def _res(d, x):
+    def _res(d, x, xn=None, next_gamma=None):
+        """ResidualBlock (vae.py:238-273) -> (x', silu(norm(x') * next_gamma) or None).  xn: silu(norm(x) * g0) if the producer of x
+        already wrote it; next_gamma: norm weight of the layer that consumes x' (the next block's residual.0, or the head's norm)."""
         h = d["sc"](x) if "sc" in d else x                                   # vae.py:255 shortcut
-        y = d["c0"](rms_silu(x, d["g0"]))
-        return d["c1"](rms_silu(y, d["g1"]), residual=h)                     # vae.py:273 x + h fused in the epilogue
+        if xn is None:
+            xn = rms_silu(x, d["g0"])
+        W = x.shape[2]
+        if d["c0"].fusable(W):
+            yn = d["c0"].with_norm(xn, d["g1"], raw=False)[1]                # the raw conv output is only read through the norm
+        else:
+            yn = rms_silu(d["c0"](xn), d["g1"])
+        if next_gamma is not None and d["c1"].fusable(W):
+            return d["c1"].with_norm(yn, next_gamma, residual=h)             # vae.py:273 x + h, plus the consumer's norm
+        return d["c1"](yn, residual=h), None
 
     def _attn(self, x):
         T, H, W, C = x.shape
@@ -223,14 +271,16 @@ class WanVAEDecoder(torch.nn.Module):
         return ops.gemm(o, a["wproj"], bias=a["bproj"], residual=x.reshape(T * N, C)).reshape(T, H, W, C)
 
     @staticmethod
-    def _up(kind, d, x):
+    def _up(kind, d, x, next_gamma=None):
         T, H, W, C = x.shape
         if kind == "up3d" and T > 1:
             y = torch.empty(2 * T - 1, H, W, C, device=x.device, dtype=bf16)
             y[0].copy_(x[0])                                                 # frame 0 bypasses time_conv (vae.py:155-158)
             d["time"](x[1:], out=y, out_mode=1, t_off=1)                     # causal over frames 1.., interleaved store
             x = y
-        return d["conv"](x)                                             # 2x nearest + 3x3 conv as sub-pixel convs
+        if next_gamma is not None and d["conv"].fusable(W):
+            return d["conv"].with_norm(x, next_gamma)
+        return d["conv"](x), None                                       # 2x nearest + 3x3 conv as sub-pixel convs
 
     @torch.no_grad()
     def decode_frames(self, z, mean, std):
@@ -243,12 +293,17 @@ class WanVAEDecoder(torch.nn.Module):
         _lib.call("b200_vae_prologue", z.data_ptr(), mean.data_ptr(), std.data_ptr(), self.conv2_w.data_ptr(),
                   self.conv2_b.data_ptr(), x.data_ptr(), T, H, W, _s())
         x = self.conv1(x)
-        x = self._res(self.mid0, x)
+        x = self._res(self.mid0, x)[0]
         x = self._attn(x)
-        x = self._res(self.mid2, x)
-        for kind, d in self.ups:
-            x = self._res(d, x) if kind == "res" else self._up(kind, d, x)
-        return self.head(rms_silu(x, self.head_g), out_mode=2)
+        x = self._res(self.mid2, x)[0]
+        xn = None                                       # silu(norm(x)) when the producer of x already wrote it
+        for idx, (kind, d) in enumerate(self.ups):
+            nxt = self.ups[idx + 1] if idx + 1 < len(self.ups) else None
+            next_gamma = self.head_g if nxt is None else (nxt[1]["g0"] if nxt[0] == "res" else None)
+            x, xn = self._res(d, x, xn, next_gamma) if kind == "res" else self._up(kind, d, x, next_gamma)
+        if xn is None:
+            xn = rms_silu(x, self.head_g)
+        return self.head(xn, out_mode=2)
 
     def decode(self, z, scale=None, any_end_frame=False):
         """WanVAE_.decode contract (vae.py:628-662): z [1,16,T,h,w]; scale = [mean, 1/std] -> [1,3,F,H,W] fp32."""
@@ -339,16 +394,16 @@ class WanVAEEncoder(torch.nn.Module):
         h = self.conv1(h)
         for kind, d in self.downs:
             if kind == "res":
-                h = self._res(d, h)
+                h = self._res(d, h)[0]
             else:
                 t = h.shape[0]
                 temporal = kind == "down3d" and t > 1
                 h = d["conv"](h, spare_frame=temporal)
                 if temporal:
                     h = d["time"](h, t)
-        h = self._res(self.mid0, h)
+        h = self._res(self.mid0, h)[0]
         h = self._attn(h)
-        h = self._res(self.mid2, h)
+        h = self._res(self.mid2, h)[0]
         return self._head_conv(mean, inv_std)(rms_silu(h, self.head_g), out_mode=2)
 
     def encode(self, x, scale=None, any_end_frame=False):
