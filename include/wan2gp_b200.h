@@ -133,6 +133,13 @@ int b200_conv3d_cl_norm(const void* x, const void* w, const float* bias, const v
 int b200_upconv2x_cl_norm(const void* x, const void* w4, const float* bias, void* out, void* norm_out, const float* gamma, int T, int H,
                           int W, int Cin, int Cout, void* stream);
 
+/* Decoder head conv Cin -> Cout <= 3, 3x3x3, planar fp32 output (vae.py:505-508 `head`; Hunyuan `conv_out`): the 9 spatial taps are
+ * stacked into the GEMM's N (a 3x1x1 conv with 27 -> 32 output channels into the fp32 workspace ws [T,Hg,Wg,32]) and a gather kernel
+ * adds the 9 shifted partial sums + bias.  w_stack: bf16 [32][3][Cin], row (dh*3+dw)*Cout + co.  prepadded = 1: x is the replicate-
+ * padded [T+2,H+2,W+2,Cin] tensor (Hunyuan), Hg/Wg = H+2/W+2; else zero padding, Hg/Wg = H/W.  ws_bytes >= T*Hg*Wg*128. */
+int b200_conv3d_head_cl(const void* x, const void* w_stack, const float* bias, void* ws, long long ws_bytes, float* out, int T, int H,
+                        int W, int Cin, int Cout, int prepadded, void* stream);
+
 /* Resample 'upsample2d/3d' spatial part (vae.py:124-133: nearest-exact 2x then Conv2d 3x3 pad 1) as four 2x2 sub-pixel
  * convolutions on the low-resolution input: x bf16 [T,H,W,Cin]; w4 bf16 [4][Cout][4][Cin] = per output parity (py,px) the 3x3
  * taps that hit the same source pixel summed; out bf16 [T,2H,2W,Cout]. */

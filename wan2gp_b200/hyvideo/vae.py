@@ -39,6 +39,8 @@ class _RepConv(_Conv):
     def prepadded(self, xp, T, H, W, residual, out, out_mode):
         """'valid' conv over an already padded operand xp [T+kt-1, H+kh-1, W+kw-1, Cin]."""
         kt, kh, kw = self.k
+        if out_mode == 2 and self.w_stack is not None and residual is None:
+            return self.head(xp, T, H, W, True, out)
         if out is None:
             out = (torch.empty(self.cout, T, H, W, device=xp.device, dtype=f32) if out_mode == 2
                    else torch.empty(T, H, W, self.cout, device=xp.device, dtype=bf16))

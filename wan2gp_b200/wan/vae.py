@@ -27,6 +27,8 @@ def _s():
 # the consumer's RMS_norm + SiLU in the producing conv's epilogue where a pixel's channels sit in one CTA (B200_VAE_FUSE_NORM=0: the
 # separate norm pass everywhere, for A/B measurements)
 FUSE_NORM = os.environ.get("B200_VAE_FUSE_NORM", "1") != "0"
+# decoder head conv with its 9 spatial taps stacked into N (B200_VAE_HEAD_STACK=0: the N=16 implicit-GEMM head, for A/B measurements)
+HEAD_STACK = os.environ.get("B200_VAE_HEAD_STACK", "1") != "0"
 
 
 class _Conv:
@@ -42,11 +44,29 @@ class _Conv:
         if co % 4:                                        # planar head (Cout=3): pad for safety of vector loads
             bias = torch.cat([bias, bias.new_zeros(16 - co)])
         self.b = bias.contiguous()
+        self.w_stack = None
+        if HEAD_STACK and co <= 3 and (kt, kh, kw) == (3, 3, 3):
+            # decoder head: the 9 spatial taps stacked into the GEMM's N (csrc/vae_ops.cu::b200_conv3d_head_cl):
+            # w_stack[(dh*3+dw)*co + c, dt, ci] = w[c, ci, dt, dh, dw], rows padded to 32
+            ws = w.detach().to(device, f32).permute(3, 4, 0, 2, 1).reshape(9 * co, kt, ci)
+            self.w_stack = torch.cat([ws, ws.new_zeros(32 - 9 * co, kt, ci)], 0).to(bf16).contiguous()
+
+    def head(self, x, T, H, W, prepadded, out=None):
+        """Planar fp32 [Cout,T,H,W] = conv(x) through the tap-stacked GEMM + gather; x [T,H,W,C] or the replicate-padded [T+2,H+2,W+2,C]."""
+        Hg, Wg = (H + 2, W + 2) if prepadded else (H, W)
+        ws = torch.empty(T * Hg * Wg * 32, device=x.device, dtype=f32)
+        if out is None:
+            out = torch.empty(self.cout, T, H, W, device=x.device, dtype=f32)
+        _lib.call("b200_conv3d_head_cl", x.data_ptr(), self.w_stack.data_ptr(), self.b.data_ptr(), ws.data_ptr(), ws.numel() * 4, out.data_ptr(),
+                  T, H, W, self.cin, self.cout, int(prepadded), _s())
+        return out
 
     def __call__(self, x, residual=None, out=None, out_mode=0, t_off=0):
         T, H, W, C = x.shape
         assert C == self.cin and x.is_contiguous() and x.dtype == bf16
         kt, kh, kw = self.k
+        if out_mode == 2 and self.w_stack is not None and residual is None:
+            return self.head(x, T, H, W, False, out)
         if out is None:
             out = (torch.empty(self.cout, T, H, W, device=x.device, dtype=f32) if out_mode == 2
                    else torch.empty(T, H, W, self.cout, device=x.device, dtype=bf16))
