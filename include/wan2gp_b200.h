@@ -133,6 +133,14 @@ int b200_conv3d_cl_norm(const void* x, const void* w, const float* bias, const v
 int b200_upconv2x_cl_norm(const void* x, const void* w4, const float* bias, void* out, void* norm_out, const float* gamma, int T, int H,
                           int W, int Cin, int Cout, void* stream);
 
+/* Streaming (time-sliced) causal conv: x_hist = [T + kt - 1, H, W, Cin] (kt-1 history frames of the previous slice, zeros for the first,
+ * then this slice's T frames); 'valid' in time, zero-padded in space.  Replaces CausalConv3d.forward with its feature cache
+ * (vae.py:55-61) inside the reference's chunked decode loop (vae.py:639-655).  out_mode 0 (+ optional residual, + optional fused
+ * norm_out/gamma) or 1 (time_conv interleave). */
+int b200_conv3d_cl_stream(const void* x_hist, const void* w, const float* bias, const void* residual, void* out, void* norm_out,
+                          const float* gamma, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off,
+                          void* stream);
+
 /* Decoder head conv Cin -> Cout <= 3, 3x3x3, planar fp32 output (vae.py:505-508 `head`; Hunyuan `conv_out`): the 9 spatial taps are
  * stacked into the GEMM's N (a 3x1x1 conv with 27 -> 32 output channels into the fp32 workspace ws [T,Hg,Wg,32]) and a gather kernel
  * adds the 9 shifted partial sums + bias.  w_stack: bf16 [32][3][Cin], row (dh*3+dw)*Cout + co.  prepadded = 1: x is the replicate-

@@ -29,7 +29,7 @@ def test_generate_t2v_matches_oracle_loop(monkeypatch):
     from oracle import vae_oracle, wan_oracle
     from wan2gp_b200.pipeline import UniPCSchedule
     pipe_obj, cfg, sds, vsd = _load("b200_t2v_2_2", "tiny", monkeypatch)
-    steps, shift, g1, g2, thr, seed = 4, 5.0, 4.0, 3.0, 600, 11
+    steps, shift, g1, g2, thr, seed = 4, 5.0, 4.0, 3.0, 900, 11     # UniPC timesteps 999, 937, 833, 624: two steps per expert
     kw = wgp_kwargs(sampling_steps=steps, shift=shift, guide_scale=g1, guide2_scale=g2, switch_threshold=thr, seed=seed, frame_num=9, height=64,
                     width=96, cfg_star_switch=1, cfg_zero_step=-1)
     out = pipe_obj.generate(**kw)

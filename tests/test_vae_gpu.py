@@ -194,3 +194,21 @@ def test_vae_tiled_decode_encode():
     mu = vae.encode([x.cuda()], tile_size=int(g["tile"]))[0].cpu()
     print(f"tiled encode: vs reference rel-L2 {rel_l2(mu, g['out'][0]):.3e}")
     assert mu.shape == g["out"][0].shape and rel_l2(mu, g["out"][0]) < 2.5e-2
+
+
+def test_streamed_decode_equals_whole_clip():
+    """Time-sliced decode (per-conv 2-frame history carried between slices = the reference's feature-cache decode, vae.py:639-655, for
+    slices of several latent frames) against the whole-clip decode: same kernels on the same operands, so bit-identical.  Exercises
+    the fused-norm epilogues, the tap-stacked head with history frames, time_conv across slice boundaries and ragged last slices."""
+    from wan2gp_b200.wan import WanVAE
+    sd = synth.make_vae_state_dict(synth.VAE_CFG, 3)
+    vae = WanVAE(device="cuda", state_dict=sd)
+    for (T, h, w), chunk in (((7, 16, 26), 3), ((10, 30, 52), 4), ((9, 16, 32), 8)):
+        z = synth._normal((16, T, h, w), 1.0, T, "input.zs", "cpu").cuda()
+        whole = vae.model.decode_frames(z, vae.mean, vae.std)
+        sliced = vae.model.decode_frames_streamed(z, vae.mean, vae.std, chunk=chunk)
+        assert whole.shape == sliced.shape == (3, 4 * (T - 1) + 1, 8 * h, 8 * w)
+        assert bool(torch.isfinite(whole).all())
+        d = (whole - sliced).abs().max()
+        print(f"streamed vs whole decode T={T} chunk={chunk}: max|d| = {float(d):.3e}")
+        assert float(d) == 0.0

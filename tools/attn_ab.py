@@ -1,6 +1,6 @@
 """Attention kernel variants A/B: parity (sampled rows vs fp64) + CUDA-event timing at the Wan 720p / 480p self-attention shapes.
 One subprocess per variant (the kernel choice is a process-wide env switch), each under a timeout so a hang cannot eat the lease.
-Writes gpurun_out/attn_ab.json.   Usage: python tools/attn_ab.py [variant ...]   (default: 0 1 2 4)"""
+Writes gpurun_out/attn_ab.json.   Usage: python tools/attn_ab.py [variant ...]   (default: v1 v100 v104 v103 v102; p0/p1/p2/p4 = the CTA-pair kernel family)"""
 import json
 import math
 import os
@@ -9,14 +9,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-NAMES = {"0": "single-CTA (r01 kernel)", "1": "pair, packed-fp32 softmax", "2": "pair, scalar softmax", "4": "pair, packed + 1/4 exp2 on FMA pipe"}
+NAMES = {"p0": "single-CTA (r01 kernel)", "p1": "pair, packed-fp32 softmax", "p2": "pair, scalar softmax", "p4": "pair, packed + 1/4 exp2 on FMA pipe",
+         "v1": "single-CTA r01 kernel (scalar softmax, all exp2 on MUFU)", "v100": "single-CTA, packed softmax", "v104": "single-CTA, packed + 1/4 of the exp2 pairs on the FMA pipe",
+         "v103": "single-CTA, packed + 1/3 on the FMA pipe", "v102": "single-CTA, packed + 1/2 on the FMA pipe"}
 
 
 def leg():
     import torch
     from wan2gp_b200 import ops
     bf16 = torch.bfloat16
-    out = {"variant": os.environ.get("B200_ATT_PAIR"), "parity": [], "timing": []}
+    out = {"variant": os.environ.get("ATT_LEG"), "parity": [], "timing": []}
     g = torch.Generator(device="cuda").manual_seed(0)
     for Lq, Lk, H in [(1024, 1024, 2), (2000, 1333, 3), (1100, 512, 2), (9000, 9000, 2)]:
         D = H * 128
@@ -52,8 +54,9 @@ if __name__ == "__main__":
         leg()
         sys.exit(0)
     res = {}
-    for var in (sys.argv[1:] or ["0", "1", "2", "4"]):
-        env = dict(os.environ, ATT_LEG="1", B200_ATT_PAIR=var)
+    for var in (sys.argv[1:] or ["v1", "v100", "v104", "v103", "v102"]):
+        # "pN": B200_ATT_PAIR=N (pair kernel family); "vN": single-CTA kernel, B200_ATT_VARIANT=N
+        env = dict(os.environ, ATT_LEG=var, B200_ATT_PAIR=var[1:] if var[0] == "p" else "0", B200_ATT_VARIANT=var[1:] if var[0] == "v" else "1")
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=240)
             line = [l for l in r.stdout.splitlines() if l.startswith("LEG ")]

@@ -38,6 +38,8 @@ SIGNATURES = {
                             c_int, c_void_p],
     "b200_upconv2x_cl_norm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_conv3d_head_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "b200_conv3d_cl_stream": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_int, c_void_p],
     "b200_upconv2x_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_rms_silu_cl": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     "b200_upsample2x_cl": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

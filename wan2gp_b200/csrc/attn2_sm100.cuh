@@ -238,10 +238,16 @@ attn_pair_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
                 for (int h = 0; h < 2; ++h) {
                     #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        float x0, x1;
-                        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[h * 64 + 2 * c]), __uint_as_float(v[h * 64 + 2 * c + 1])), sc2, nm2), x0, x1);
-                        const float e0 = (POLY > 0 && (2 * c) % (POLY > 0 ? POLY : 1) == POLY - 1) ? ex2_poly3(x0) : ex2_approx(x0);
-                        const float e1 = (POLY > 0 && (2 * c + 1) % (POLY > 0 ? POLY : 1) == POLY - 1) ? ex2_poly3(x1) : ex2_approx(x1);
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[h * 64 + 2 * c]), __uint_as_float(v[h * 64 + 2 * c + 1])), sc2, nm2);
+                        float e0, e1;
+                        if (POLY > 0 && c % (POLY > 0 ? POLY : 1) == POLY - 1) {
+                            ex2_poly3_x2(x2, e0, e1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
                         acc2[c & 3] = add_f32x2(acc2[c & 3], pack_f32x2(e0, e1));
                         v[h * 64 + c] = pack_bf16x2(e0, e1);
                     }

@@ -42,7 +42,11 @@ constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (ATT_QTILES + 2 * ATT_KV_STAGES)
 
 // POLY: every POLY-th column of a row takes its exp2 on the FMA pipe (0 = all on MUFU).
 // SPLIT: P is handed to the MMA warp in two 64-key halves so P*V starts while the second half is still being computed.
-template <int POLY, bool SPLIT>
+// PACK2: softmax arithmetic on packed fp32 pairs (FFMA2 / FADD2) with 3-input max (FMNMX3): 3 instead of 4.5 issue slots per score; POLY
+// then counts PAIRS (every POLY-th pair of a row takes both exponentials through ex2_poly3_x2 on the FMA pipe).  MUFU.EX2 runs at 16
+// results/clk/SM: the 2 x 16 384 exponentials of one K/V step need the same 2048 clocks as its four 128x128x128 MMAs, so with all of
+// them on MUFU the softmax of one Q tile cannot finish inside the MMA time of the other (ncu r01: tensor 68 %, MUFU 68 %).
+template <int POLY, bool SPLIT, bool PACK2 = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -76,7 +80,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); }
-        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 128);
+        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], PACK2 ? 4 : 128);     // PACK2: one arrival per softmax warp (lane 0 after __syncwarp)
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -198,7 +202,16 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             // row max with 8 independent partial maxima (ILP: at most two softmax warps share a scheduler)
             float mx;
-            {
+            if constexpr (PACK2) {
+                float mx4[4];
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) mx4[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+                #pragma unroll
+                for (int i = 12; i < 124; i += 2) mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                mx4[0] = fmax3(mx4[0], __uint_as_float(v[124]), __uint_as_float(v[125]));
+                mx4[1] = fmax3(mx4[1], __uint_as_float(v[126]), __uint_as_float(v[127]));
+                mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]) * p.scale_log2;
+            } else {
                 float mx8[8];
                 #pragma unroll
                 for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(v[i]);
@@ -234,14 +247,49 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             //      place (v[h*64 + c] <- keys h*64 + 2c, 2c+1) and published per 64-key half
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = -m_used;
+            if constexpr (PACK2) {
+                const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+                uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};          // four independent packed accumulators (+0.0f bit pattern)
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    #pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[h * 64 + 2 * c]), __uint_as_float(v[h * 64 + 2 * c + 1])), sc2, nm2);
+                        float e0, e1;
+                        if (POLY > 0 && c % (POLY > 0 ? POLY : 1) == POLY - 1) {
+                            ex2_poly3_x2(x2, e0, e1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        acc2[c & 3] = add_f32x2(acc2[c & 3], pack_f32x2(e0, e1));
+                        v[h * 64 + c] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st_32x32b_x32(tS + h * 32, v + h * 64);
+                    if (SPLIT || h == 1) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {                                  // 4 instead of 128 shared-memory barrier updates per hand-off
+                            if (SPLIT) mbar_arrive(&p_full[qi * 2 + h]);
+                            else { mbar_arrive(&p_full[qi * 2]); mbar_arrive(&p_full[qi * 2 + 1]); }
+                        }
+                    }
+                }
+                float a0, a1;
+                unpack_f32x2(add_f32x2(add_f32x2(acc2[0], acc2[1]), add_f32x2(acc2[2], acc2[3])), a0, a1);
+                ls[0] = a0 + a1;
+            } else {
             #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const float x0 = fmaf(__uint_as_float(v[h * 64 + 2 * c]), p.scale_log2, neg_m);
                     const float x1 = fmaf(__uint_as_float(v[h * 64 + 2 * c + 1]), p.scale_log2, neg_m);
-                    const float e0 = (POLY > 0 && (2 * c) % POLY == POLY - 1) ? ex2_poly3(x0) : ex2_approx(x0);
-                    const float e1 = (POLY > 0 && (2 * c + 1) % POLY == POLY - 1) ? ex2_poly3(x1) : ex2_approx(x1);
+                    const float e0 = (POLY > 0 && (2 * c) % (POLY > 0 ? POLY : 1) == POLY - 1) ? ex2_poly3(x0) : ex2_approx(x0);
+                    const float e1 = (POLY > 0 && (2 * c + 1) % (POLY > 0 ? POLY : 1) == POLY - 1) ? ex2_poly3(x1) : ex2_approx(x1);
                     ls[c & 3] += e0 + e1;
                     v[h * 64 + c] = pack_bf16x2(e0, e1);
                 }
@@ -252,6 +300,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (SPLIT) mbar_arrive(&p_full[qi * 2 + h]);
                     else { mbar_arrive(&p_full[qi * 2]); mbar_arrive(&p_full[qi * 2 + 1]); }
                 }
+            }
             }
             l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         }

@@ -309,7 +309,7 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
     // long query sequences: CTA-pair kernel (attn2_sm100.cuh): 512 query rows per cluster, each CTA stages half of every K/V tile.
     // B200_ATT_PAIR=0 selects the single-CTA kernel (A/B runs); other values: see below.
     static int use_pair = -1;
-    if (use_pair < 0) { const char* ev = getenv("B200_ATT_PAIR"); use_pair = ev ? atoi(ev) : 1; }
+    if (use_pair < 0) { const char* ev = getenv("B200_ATT_PAIR"); use_pair = ev ? atoi(ev) : 0; }
     if (use_pair && Lq >= 1024) {
         CUtensorMap tk2;
         uint32_t boxk[2] = {64, 64};                         // this CTA's 64 keys x one 64-wide d slab
@@ -349,6 +349,11 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
         case 0: rc = launch(attn_fwd_d128_kernel<0, false>); break;
         case 41: rc = launch(attn_fwd_d128_kernel<4, true>); break;
         case 21: rc = launch(attn_fwd_d128_kernel<2, true>); break;
+        // packed-fp32 softmax (FFMA2 / FADD2 / FMNMX3); 10x: every x-th PAIR of exponentials on the FMA pipe
+        case 100: rc = launch(attn_fwd_d128_kernel<0, true, true>); break;
+        case 104: rc = launch(attn_fwd_d128_kernel<4, true, true>); break;
+        case 103: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
+        case 102: rc = launch(attn_fwd_d128_kernel<2, true, true>); break;
         default: rc = launch(attn_fwd_d128_kernel<0, true>); break;
     }
     if (rc) return rc;

@@ -308,6 +308,25 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// two exp2 on the FMA / ALU pipes with packed fp32 arithmetic (the polynomial of ex2_poly3): 2 FMNMX + 3 packed range-reduction ops +
+// 3 FFMA2 + 2 IMAD for two results, i.e. 5 issue slots per exponential against 8 MUFU-pipe clocks for ex2.approx
+__device__ __forceinline__ void ex2_poly3_x2(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x2 = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+    const uint64_t t2 = add_f32x2(x2, magic);                                       // round-to-nearest integer in the low mantissa bits
+    const uint64_t r2 = add_f32x2(t2, nmagic);
+    const uint64_t f2 = fma_f32x2(r2, pack_f32x2(-1.0f, -1.0f), x2);                // f in [-0.5, 0.5]
+    uint64_t p2 = fma_f32x2(pack_f32x2(0.05517105758190155f, 0.05517105758190155f), f2, pack_f32x2(0.2426096349954605f, 0.2426096349954605f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999281764030457f, 0.9999281764030457f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));         // p * 2^round(x)
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -608,7 +608,7 @@ struct ConvView { int Ti, Hi, Wi, off_t, off_h, off_w; long long ost_t, ost_h, o
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
                         void* stream, int prepadded = 0, const ConvView* view = nullptr, const float* norm_gamma = nullptr,
-                        void* norm_out = nullptr);
+                        void* norm_out = nullptr, int t_valid = 0);
 
 extern "C" int b200_conv3d_cl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H,
                               int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, void* stream) {
@@ -652,6 +652,20 @@ extern "C" int b200_conv3d_cl_norm(const void* x, const void* w, const float* bi
     if (!norm_out || !gamma) return b200_set_error(B200_ERR_ARG, "conv3d_cl_norm: norm_out / gamma required");
     return conv_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, 0, 0, kh >> 1, kw >> 1, -1, -1, stream, 0, nullptr, gamma, norm_out);
 }
+// Streaming (time-sliced) form of b200_conv3d_cl / b200_conv3d_cl_norm: x is [T + kt - 1, H, W, Cin] = the kt-1 history frames of the
+// previous time slice (zeros for the first slice) followed by the T frames of this slice; the conv is 'valid' in time (no causal zero
+// fill) and zero-padded in space; T output frames.  This is the reference's chunked decode with per-conv feature caches
+// (vae.py:639-655, CausalConv3d.forward :55-61 cache_x) for slices of any length.  out_mode 0 (bf16 [T,H,W,Cout], optional residual and
+// fused norm_out / gamma as b200_conv3d_cl_norm) or 1 (time_conv interleave, t_off as b200_conv3d_cl).
+extern "C" int b200_conv3d_cl_stream(const void* x_hist, const void* w, const float* bias, const void* residual, void* out, void* norm_out,
+                                     const float* gamma, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off,
+                                     void* stream) {
+    if (out_mode != 0 && out_mode != 1) return b200_set_error(B200_ERR_ARG, "conv3d_cl_stream: out_mode 0 or 1");
+    if (norm_out && out_mode != 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl_stream: fused norm needs out_mode 0");
+    return conv_cl_impl(x_hist, w, bias, residual, out, T, H, W, Cin, Cout, kt, kh, kw, out_mode, t_off, kh >> 1, kw >> 1, -1, -1, stream, 0, nullptr,
+                        norm_out ? gamma : nullptr, norm_out, 1);
+}
+
 // b200_upconv2x_cl with the same fused norm: out and norm_out are [T, 2H, 2W, Cout].
 extern "C" int b200_upconv2x_cl_norm(const void* x, const void* w4, const float* bias, void* out, void* norm_out, const float* gamma, int T,
                                      int H, int W, int Cin, int Cout, void* stream) {
@@ -749,7 +763,7 @@ static bool conv_row_wanted(int W, int kh, int kw) {
 
 static int conv_cl_impl(const void* x, const void* w, const float* bias, const void* residual, void* out, int T, int H, int W,
                         int Cin, int Cout, int kt, int kh, int kw, int out_mode, int t_off, int pad_h, int pad_w, int up_py, int up_px,
-                        void* stream, int prepadded, const ConvView* view, const float* norm_gamma, void* norm_out) {
+                        void* stream, int prepadded, const ConvView* view, const float* norm_gamma, void* norm_out, int t_valid) {
     if (!x || !w || (!out && !norm_out) || T <= 0 || H <= 0 || W <= 0) return b200_set_error(B200_ERR_ARG, "conv3d_cl: null/empty argument");
     if (Cin % 8) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cin %% 8 != 0");
     if (out_mode != 2 && Cout % 16) return b200_set_error(B200_ERR_ARG, "conv3d_cl: Cout %% 16 != 0");
@@ -765,7 +779,8 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
-        uint64_t Ti = prepadded ? T + kt - 1 : T, Hi = prepadded ? H + kh - 1 : H, Wi = prepadded ? W + kw - 1 : W;
+        // t_valid: the input carries its kt-1 history frames explicitly ([T+kt-1,H,W,Cin], streaming decode) -- 'valid' in time, padded in space
+        uint64_t Ti = (prepadded || t_valid) ? T + kt - 1 : T, Hi = prepadded ? H + kh - 1 : H, Wi = prepadded ? W + kw - 1 : W;
         if (view) { Ti = view->Ti; Hi = view->Hi; Wi = view->Wi; }
         uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, Ti};
         uint64_t str[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
@@ -786,7 +801,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     p.mode = MODE_CONV;
     p.N = Cout;
     p.T = T; p.H = H; p.W = W; p.kt = kt; p.kh = kh; p.kw = kw;
-    p.pad_h = pad_h; p.pad_w = pad_w; p.pad_t = prepadded ? 0 : kt - 1;
+    p.pad_h = pad_h; p.pad_w = pad_w; p.pad_t = (prepadded || t_valid) ? 0 : kt - 1;
     p.cin_chunks = k96 ? (row ? 3 : 1) : (Cin + 63) / 64;      // row kernel: three 32-channel chunks; per-tap k96: one 3-box stage
     p.num_k_iters = taps * p.cin_chunks;
     p.tiles_h = row ? (H + ROWS - 1) / ROWS : (H + CONV_BH - 1) / CONV_BH;
@@ -884,13 +899,17 @@ extern "C" int b200_conv3d_head_cl(const void* x, const void* w_stack, const flo
                                    int W, int Cin, int Cout, int prepadded, void* stream) {
     if (!x || !w_stack || !bias || !ws || !out || Cout < 1 || Cout > 3 || T <= 0 || H <= 0 || W <= 0 || H > 65535 || T > 65535)
         return b200_set_error(B200_ERR_ARG, "conv3d_head_cl: bad argument");
-    const int Hg = prepadded ? H + 2 : H, Wg = prepadded ? W + 2 : W;
+    // prepadded: 0 = zero padding everywhere (whole clip); 1 = replicate-padded input [T+2,H+2,W+2]; 2 = streaming slice: 2 history frames
+    // in front ([T+2,H,W]), zero padding in space
+    const bool rep = prepadded == 1;
+    const int Hg = rep ? H + 2 : H, Wg = rep ? W + 2 : W;
     if (ws_bytes < (long long)T * Hg * Wg * 32 * 4) return b200_set_error(B200_ERR_ARG, "conv3d_head_cl: workspace too small");
-    // stacked 3x1x1 conv -> fp32 channels-last G (out_mode 3); prepadded: 'valid' in time over the T+2 padded frames
-    int r = conv_cl_impl(x, w_stack, nullptr, nullptr, ws, T, Hg, Wg, Cin, 32, 3, 1, 1, 3, 0, 0, 0, -1, -1, stream, prepadded ? 1 : 0);
+    // stacked 3x1x1 conv -> fp32 channels-last G (out_mode 3); 'valid' in time when the input carries its own front frames
+    int r = conv_cl_impl(x, w_stack, nullptr, nullptr, ws, T, Hg, Wg, Cin, 32, 3, 1, 1, 3, 0, 0, 0, -1, -1, stream, rep ? 1 : 0, nullptr, nullptr, nullptr,
+                         prepadded == 2 ? 1 : 0);
     if (r) return r;
     const dim3 grid((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)T);
-    head_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), bias, out, T, H, W, Hg, Wg, prepadded ? 0 : 1, Cout);
+    head_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), bias, out, T, H, W, Hg, Wg, rep ? 0 : 1, Cout);
     CHECK_LAUNCH("head_gather");
     return B200_OK;
 }

@@ -136,8 +136,9 @@ class _UpConv:
         return out, nrm
 
 
-def rms_silu(x, gamma, silu=True):
-    y = torch.empty_like(x)
+def rms_silu(x, gamma, silu=True, out=None):
+    y = torch.empty_like(x) if out is None else out
+    assert y.shape == x.shape and y.is_contiguous()
     C = x.shape[-1]
     _lib.call("b200_rms_silu_cl", x.data_ptr(), gamma.data_ptr(), y.data_ptr(), x.numel() // C, C, int(silu), _s())
     return y
@@ -324,6 +325,144 @@ class WanVAEDecoder(torch.nn.Module):
         if xn is None:
             xn = rms_silu(x, self.head_g)
         return self.head(xn, out_mode=2)
+
+    # ------------------------------------------------------------------ time-sliced (streaming) decode
+    # The whole-clip decode above keeps ~4 full-resolution activations live (0.7 GB per latent frame each at 720p): beyond ~40 latent
+    # frames at 720p (or ~16 at 1080p) that exceeds the 180 GB of a B200.  The streamed decode walks the latent frames in slices of
+    # `chunk` frames and carries, for every temporal conv, the last kt-1 = 2 frames of its input to the next slice -- the reference's
+    # chunked decode with per-conv feature caches (vae.py:639-655, CausalConv3d.forward :55-61), for slices of any length instead of one
+    # latent frame.  Every output value sees exactly the operands of the whole-clip decode, so the two are bit-identical.
+    class _Hist:
+        def __init__(self, dev):
+            self.h, self.dev = {}, dev
+
+        def ext(self, key, K, H, W, C):
+            """[2 + K, H, W, C] buffer whose first 2 frames are the history of conv `key` (zeros before the first slice)."""
+            xe = torch.empty(K + 2, H, W, C, device=self.dev, dtype=bf16)
+            prev = self.h.get(key)
+            if prev is None:
+                xe[:2].zero_()
+            else:
+                xe[:2].copy_(prev)
+            return xe
+
+        def keep(self, key, xe):
+            self.h[key] = xe[-2:].clone()
+
+    @staticmethod
+    def _sconv(conv, xe, K, residual=None, out=None, nrm=None, gamma=None, out_mode=0, t_off=0):
+        _, H, W, C = xe.shape
+        kt, kh, kw = conv.k
+        assert kt == 3 and xe.shape[0] == K + 2 and C == conv.cin
+        _lib.call("b200_conv3d_cl_stream", xe.data_ptr(), conv.w.data_ptr(), conv.b.data_ptr(), 0 if residual is None else residual.data_ptr(),
+                  0 if out is None else out.data_ptr(), 0 if nrm is None else nrm.data_ptr(), 0 if gamma is None else gamma.data_ptr(),
+                  K, H, W, conv.cin, conv.cout, kt, kh, kw, out_mode, t_off, _s())
+
+    def _res_s(self, st, key, d, x, xe0, nxt):
+        """Streaming ResidualBlock: x raw [K,H,W,C]; xe0 = history-extended normalised input if the producer wrote it; nxt = (key, gamma)
+        of the consumer's conv or None.  -> (x' raw, history-extended normalised x' or None)."""
+        K, H, W, C = x.shape
+        h = d["sc"](x) if "sc" in d else x
+        if xe0 is None:
+            xe0 = st.ext(key + ".c0", K, H, W, C)
+            rms_silu(x, d["g0"], out=xe0[2:])
+        st.keep(key + ".c0", xe0)
+        co = d["c0"].cout
+        xe1 = st.ext(key + ".c1", K, H, W, co)
+        if d["c0"].fusable(W):
+            self._sconv(d["c0"], xe0, K, nrm=xe1[2:], gamma=d["g1"])
+        else:
+            y = torch.empty(K, H, W, co, device=x.device, dtype=bf16)
+            self._sconv(d["c0"], xe0, K, out=y)
+            rms_silu(y, d["g1"], out=xe1[2:])
+        del xe0
+        st.keep(key + ".c1", xe1)
+        x2 = torch.empty(K, H, W, co, device=x.device, dtype=bf16)
+        xe_n = None
+        if nxt is not None and d["c1"].fusable(W):
+            xe_n = st.ext(nxt[0], K, H, W, co)
+            self._sconv(d["c1"], xe1, K, residual=h, out=x2, nrm=xe_n[2:], gamma=nxt[1])
+        else:
+            self._sconv(d["c1"], xe1, K, residual=h, out=x2)
+        return x2, xe_n
+
+    def _up_s(self, st, key, kind, d, x, first, nxt):
+        K, H, W, C = x.shape
+        if kind == "up3d":
+            if first:
+                y = torch.empty(2 * K - 1, H, W, C, device=x.device, dtype=bf16)
+                y[0].copy_(x[0])                                             # latent frame 0 bypasses time_conv (vae.py:155-158)
+                d["time"](x[1:], out=y, out_mode=1, t_off=1)                 # zero history: frame 0 is never seen (vae.py:179-180)
+                st.h[key + ".time"] = x[-2:].clone()
+            else:
+                xe = st.ext(key + ".time", K, H, W, C)
+                xe[2:].copy_(x)
+                st.keep(key + ".time", xe)
+                y = torch.empty(2 * K, H, W, C, device=x.device, dtype=bf16)
+                self._sconv(d["time"], xe, K, out=y, out_mode=1, t_off=0)
+            x = y
+        T2 = x.shape[0]
+        if nxt is not None and d["conv"].fusable(W):
+            co = d["conv"].cout
+            x2 = torch.empty(T2, 2 * H, 2 * W, co, device=x.device, dtype=bf16)
+            xe_n = st.ext(nxt[0], T2, 2 * H, 2 * W, co)
+            _lib.call("b200_upconv2x_cl_norm", x.data_ptr(), d["conv"].w4.data_ptr(), d["conv"].b.data_ptr(), x2.data_ptr(), xe_n[2:].data_ptr(),
+                      nxt[1].data_ptr(), T2, H, W, d["conv"].cin, co, _s())
+            return x2, xe_n
+        return d["conv"](x), None
+
+    @torch.no_grad()
+    def decode_frames_streamed(self, z, mean, std, chunk=8, out=None):
+        """Time-sliced decode_frames: same result (bit-identical), memory bounded by `chunk` latent frames per slice (>= 3)."""
+        if not self._ready:
+            raise RuntimeError("WanVAE: load_state_dict() must be called before decode")
+        C, T, H, W = z.shape
+        chunk = max(3, int(chunk))
+        if T <= chunk or self.head.w_stack is None:
+            return self.decode_frames(z, mean, std)
+        z = z.to(self.device, f32).contiguous()
+        F = 4 * (T - 1) + 1
+        if out is None:
+            out = torch.empty(3, F, 8 * H, 8 * W, device=self.device, dtype=f32)
+        st = self._Hist(self.device)
+        nups = len(self.ups)
+        f0, t0 = 0, 0
+        while t0 < T:
+            K = min(chunk, T - t0)
+            if T - (t0 + K) in (1, 2):          # never leave a tail of fewer than 3 latent frames
+                K = T - t0
+            first = t0 == 0
+            zc = z[:, t0:t0 + K].contiguous()
+            xe = st.ext("conv1", K, H, W, 16)
+            _lib.call("b200_vae_prologue", zc.data_ptr(), mean.data_ptr(), std.data_ptr(), self.conv2_w.data_ptr(),
+                      self.conv2_b.data_ptr(), xe[2:].data_ptr(), K, H, W, _s())
+            st.keep("conv1", xe)
+            x = torch.empty(K, H, W, self.conv1.cout, device=self.device, dtype=bf16)
+            self._sconv(self.conv1, xe, K, out=x)
+            x = self._res_s(st, "mid0", self.mid0, x, None, None)[0]
+            x = self._attn(x)                                                   # per frame: no history
+            x = self._res_s(st, "mid2", self.mid2, x, None, None)[0]
+            xe_n = None
+            for idx, (kind, d) in enumerate(self.ups):
+                nk = self.ups[idx + 1][0] if idx + 1 < nups else "head"
+                nxt = ("head", self.head_g) if nk == "head" else ((f"up{idx + 1}.c0", self.ups[idx + 1][1]["g0"]) if nk == "res" else None)
+                if kind == "res":
+                    x, xe_n = self._res_s(st, f"up{idx}", d, x, xe_n, nxt)
+                else:
+                    x, xe_n = self._up_s(st, f"up{idx}", kind, d, x, first, nxt)
+            n, Hf, Wf, Ch = x.shape
+            if xe_n is None:
+                xe_n = st.ext("head", n, Hf, Wf, Ch)
+                rms_silu(x, self.head_g, out=xe_n[2:])
+            st.keep("head", xe_n)
+            del x
+            fr = self.head.head(xe_n, n, Hf, Wf, 2)                            # streaming slice: 2 history frames in front
+            out[:, f0:f0 + n].copy_(fr)
+            del fr, xe_n
+            f0 += n
+            t0 += K
+        assert f0 == F
+        return out
 
     def decode(self, z, scale=None, any_end_frame=False):
         """WanVAE_.decode contract (vae.py:628-662): z [1,16,T,h,w]; scale = [mean, 1/std] -> [1,3,F,H,W] fp32."""
