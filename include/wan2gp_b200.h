@@ -74,6 +74,12 @@ int b200_qk_rmsnorm_rope(void* q_bf16, void* k_bf16, long long ld, const float* 
 int b200_attention_d128(const void* q, const void* k, const void* v, void* out, int Lq, int Lk, int H, long long ldq,
                         long long ldk, long long ldv, long long ldo, float scale, void* stream);
 
+/* The same for nseq equally long sequences stacked along the rows (q / out [nseq*Lq, H*128], k / v [nseq*Lk, H*128]); sequence z
+ * attends to its own keys only.  One launch for the cond / uncond forwards of a CFG pair, which the reference runs one after the other
+ * (any2video.py:1625-1646; model.py:2030-2037 joint pass). */
+int b200_attention_d128_batched(const void* q, const void* k, const void* v, void* out, int nseq, int Lq, int Lk, int H, long long ldq,
+                                long long ldk, long long ldv, long long ldo, float scale, void* stream);
+
 /* x fp32 -> bf16, n % 4 == 0 */
 int b200_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 

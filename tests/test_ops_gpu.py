@@ -164,3 +164,15 @@ def test_cfg_euler(ops):
     ref = wan_oracle.euler_step(lat0.cpu(), wan_oracle.cfg_combine(c.cpu(), u.cpu(), 4.0, cfg_star=True, step_no=3), 0.9, 0.85)
     ops.cfg_euler_step_(lat0, c, u, 4.0, 0.05, cfg_star=True)
     assert rel_l2(lat0.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("nseq,Lq,Lk,H", [(2, 300, 300, 2), (2, 1000, 512, 3), (3, 130, 77, 1), (2, 3510, 3510, 2)])
+def test_attention_batched_equals_separate(ops, nseq, Lq, Lk, H):
+    """nseq sequences stacked along the rows in ONE launch (CFG cond / uncond) == one launch per sequence, bit for bit: ragged last Q
+    tiles (rows of the next sequence are loaded but never stored) and ragged last K/V tiles (rows of the next sequence are masked)."""
+    D = H * 128
+    q, k, v = (_randn(nseq * n, D, seed=s, dtype=bf16) for n, s in ((Lq, 1), (Lk, 2), (Lk, 3)))
+    both = ops.attention(q, k, v, H, nseq=nseq)
+    for z in range(nseq):
+        one = ops.attention(q[z * Lq:(z + 1) * Lq], k[z * Lk:(z + 1) * Lk], v[z * Lk:(z + 1) * Lk], H)
+        assert torch.equal(both[z * Lq:(z + 1) * Lq], one), z

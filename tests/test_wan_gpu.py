@@ -109,3 +109,21 @@ def test_wan_context_projection_cache():
     c3 = m([x.clone()], t, [ctx], pipeline=Pipe())[0]
     m.cache_context = False
     assert torch.equal(c3, m([x.clone()], t, [ctx], pipeline=Pipe())[0]) and not torch.equal(c3, c1)
+
+
+def test_wan_forward_stacked_streams_equal_single():
+    """The streams of all list entries / batch items run STACKED along the rows (one launch of every row-wise kernel per block, the two
+    attentions with a sequence count): bit-identical to one stream at a time, eager, with the prompt cache and under graph replay."""
+    cfg, thw, sd, x, t, ctx, y = wan_case("small")
+    m = _build(cfg, sd)
+    ctx, ctx2 = ctx.cuda(), (ctx * 0.25).cuda()
+    x2 = torch.cat([x, x * 0.7], 0)                                                       # a batch of 2 in the second entry
+    single = [m([x.clone()], t, [ctx], pipeline=Pipe())[0], m([x2[:1].clone()], t, [ctx2], pipeline=Pipe())[0],
+              m([x2[1:].clone()], t, [ctx2], pipeline=Pipe())[0]]
+    for cache, graphs in ((False, False), (True, False), (True, True)):
+        m.cache_context, m.use_cuda_graphs = cache, graphs
+        for _ in range(2):                                                                # second pass: cache hits / graph replay
+            out = m([x.clone(), x2.clone()], t, [ctx, ctx2], pipeline=Pipe())
+            assert out[0].shape == (1, 16) + thw and out[1].shape == (2, 16) + thw
+            assert torch.equal(out[0], single[0]) and torch.equal(out[1][:1], single[1]) and torch.equal(out[1][1:], single[2]), (cache, graphs)
+    m.cache_context, m.use_cuda_graphs = False, False

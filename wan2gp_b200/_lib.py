@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200_qk_rmsnorm_rope": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "b200_attention_d128": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll,
                             c_float, c_void_p],
+    "b200_attention_d128_batched": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_float, c_void_p],
     "b200_cast_f32_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "b200_patch_embed": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                          c_int, c_void_p],

@@ -71,6 +71,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int q_blk = blockIdx.x;
     const int head = blockIdx.y;
     const int n_kv = (p.Lk + ATT_BN - 1) / ATT_BN;
+    // blockIdx.z = sequence of a batch of equally long sequences stacked along the rows (CFG cond / uncond branches in one launch):
+    // rows [z Lq, z Lq + Lq) of q / out and [z Lk, z Lk + Lk) of k / v.  A partial last K/V tile then reads rows of the NEXT sequence
+    // instead of TMA zero fill -- finite data whose scores are masked to -inf below, exactly like the zero-filled rows.
+    const int q_row0 = blockIdx.z * p.Lq, k_row0 = blockIdx.z * p.Lk;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_k); prefetch_tmap(&tmap_v); }
     if (warp == 1 && lane == 0) {
@@ -99,7 +103,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_arrive_expect_tx(q_full, ATT_QTILES * ATT_TILE_BYTES);
             #pragma unroll
             for (int i = 0; i < ATT_QTILES; ++i) {
-                const int r0 = (q_blk * ATT_QTILES + i) * ATT_BM;
+                const int r0 = q_row0 + (q_blk * ATT_QTILES + i) * ATT_BM;
                 tma_load_2d(sQ + i * ATT_TILE_BYTES, &tmap_q, q_full, col, r0);
                 tma_load_2d(sQ + i * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_q, q_full, col + 64, r0);
             }
@@ -108,12 +112,12 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint32_t ph = (j / ATT_KV_STAGES) & 1;
                 mbar_wait(&k_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
-                tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], col, j * ATT_BN);
-                tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_k, &k_full[st], col + 64, j * ATT_BN);
+                tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], col, k_row0 + j * ATT_BN);
+                tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_k, &k_full[st], col + 64, k_row0 + j * ATT_BN);
                 mbar_wait(&v_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
-                tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], col, j * ATT_BN);
-                tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_v, &v_full[st], col + 64, j * ATT_BN);
+                tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], col, k_row0 + j * ATT_BN);
+                tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_v, &v_full[st], col + 64, k_row0 + j * ATT_BN);
             }
         }
         __syncwarp();
@@ -308,8 +312,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(&pv_done[qi], (n_kv - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l;
-        const long long grow = ((long long)q_blk * ATT_QTILES + qi) * ATT_BM + row;
-        __nv_bfloat16* orow = p.out + grow * p.ldo + head * ATT_D;
+        const long long grow = ((long long)q_blk * ATT_QTILES + qi) * ATT_BM + row;          // row inside this sequence
+        __nv_bfloat16* orow = p.out + (q_row0 + grow) * p.ldo + head * ATT_D;
         #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t o[32];

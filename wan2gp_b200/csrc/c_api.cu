@@ -284,22 +284,35 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
 }
 
 // ------------------------------------------------------------------ attention
+static int attention_impl(const void* q, const void* k, const void* v, void* out, int nseq, int Lq, int Lk, int H,
+                          long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream);
 extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, void* out, int Lq, int Lk, int H,
                                    long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+    return attention_impl(q, k, v, out, 1, Lq, Lk, H, ldq, ldk, ldv, ldo, scale, stream);
+}
+// nseq equally long sequences stacked along the rows: q / out [nseq * Lq, H*128], k / v [nseq * Lk, H*128]; sequence z attends only to
+// its own keys.  One launch for the cond / uncond branches of a CFG pair (any2video.py:1625-1646 runs them as two forwards).
+extern "C" int b200_attention_d128_batched(const void* q, const void* k, const void* v, void* out, int nseq, int Lq, int Lk, int H,
+                                           long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+    if (nseq < 1 || nseq > 65535) return b200_set_error(B200_ERR_ARG, "attention_batched: nseq out of range");
+    return attention_impl(q, k, v, out, nseq, Lq, Lk, H, ldq, ldk, ldv, ldo, scale, stream);
+}
+static int attention_impl(const void* q, const void* k, const void* v, void* out, int nseq, int Lq, int Lk, int H,
+                          long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
     if (!q || !k || !v || !out || Lq <= 0 || Lk <= 0 || H <= 0) return b200_set_error(B200_ERR_ARG, "attention: null/empty argument");
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return b200_set_error(B200_ERR_ARG, "attention: row strides must be multiples of 8");
     CUtensorMap tq, tk, tv;
     uint32_t box[2] = {64, 128};
     {
-        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lq}; uint64_t str[1] = {(uint64_t)ldq * 2};
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lq * nseq}; uint64_t str[1] = {(uint64_t)ldq * 2};
         int r = b200_make_tmap_bf16(&tq, q, 2, dims, str, box, 128); if (r) return r;
     }
     {
-        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldk * 2};
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk * nseq}; uint64_t str[1] = {(uint64_t)ldk * 2};
         int r = b200_make_tmap_bf16(&tk, k, 2, dims, str, box, 128); if (r) return r;
     }
     {
-        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldv * 2};
+        uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk * nseq}; uint64_t str[1] = {(uint64_t)ldv * 2};
         int r = b200_make_tmap_bf16(&tv, v, 2, dims, str, box, 128); if (r) return r;
     }
     AttnParams p;
@@ -310,7 +323,7 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
     // B200_ATT_PAIR=0 selects the single-CTA kernel (A/B runs); other values: see below.
     static int use_pair = -1;
     if (use_pair < 0) { const char* ev = getenv("B200_ATT_PAIR"); use_pair = ev ? atoi(ev) : 0; }
-    if (use_pair && Lq >= 1024) {
+    if (use_pair && Lq >= 1024 && nseq == 1) {
         CUtensorMap tk2;
         uint32_t boxk[2] = {64, 64};                         // this CTA's 64 keys x one 64-wide d slab
         uint64_t dims[2] = {(uint64_t)H * 128, (uint64_t)Lk}; uint64_t str[1] = {(uint64_t)ldk * 2};
@@ -329,7 +342,7 @@ extern "C" int b200_attention_d128(const void* q, const void* k, const void* v, 
         CHECK_LAUNCH("attn_pair_fwd_d128");
         return B200_OK;
     }
-    dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H);
+    dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H, nseq);
     // tuning variants (B200_ATT_VARIANT = "<poly><split>", e.g. "41"); the default (1 = no poly, split P) is the measured best
     static int variant = -1;
     if (variant < 0) {

@@ -105,18 +105,24 @@ def qk_rmsnorm_rope_(q, k, wq, wk, eps=1e-6, cos=None, sin=None, per_head=False)
     return q, k
 
 
-def attention(q, k, v, num_heads, out=None, scale=None):
-    """q [Lq, H*128], k/v [Lk, H*128] bf16 (row-strided views allowed) -> [Lq, H*128] bf16."""
+def attention(q, k, v, num_heads, out=None, scale=None, nseq=1):
+    """q [Lq, H*128], k/v [Lk, H*128] bf16 (row-strided views allowed) -> [Lq, H*128] bf16.
+    nseq > 1: nseq equally long sequences stacked along the rows (q [nseq*Lq, .], k/v [nseq*Lk, .]), each attending to its own keys."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, bf16, n)
         assert t.dim() == 2 and t.stride(1) == 1 and t.shape[1] == num_heads * 128
-    Lq, Lk = q.shape[0], k.shape[0]
+    assert q.shape[0] % nseq == 0 and k.shape[0] % nseq == 0 and v.shape[0] == k.shape[0]
+    Lq, Lk = q.shape[0] // nseq, k.shape[0] // nseq
     if out is None:
-        out = torch.empty(Lq, num_heads * 128, device=q.device, dtype=bf16)
+        out = torch.empty(q.shape[0], num_heads * 128, device=q.device, dtype=bf16)
     scale = 1.0 / math.sqrt(128) if scale is None else scale
-    _timed("attention" if Lq == Lk else "cross_attention", 4.0 * Lq * Lk * num_heads * 128, lambda: _lib.call(
-        "b200_attention_d128", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Lq, Lk, num_heads,
-        q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream()))
+    if nseq == 1:
+        fn = lambda: _lib.call("b200_attention_d128", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Lq, Lk, num_heads,   # noqa: E731
+                               q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream())
+    else:
+        fn = lambda: _lib.call("b200_attention_d128_batched", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nseq, Lq, Lk,   # noqa: E731
+                               num_heads, q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale), _stream())
+    _timed("attention" if Lq == Lk else "cross_attention", 4.0 * nseq * Lq * Lk * num_heads * 128, fn)
     return out
 
 
@@ -128,13 +134,16 @@ def cast_bf16(x):
     return y
 
 
-def patch_embed(x, y, w, bias, D, patch=2):
+def patch_embed(x, y, w, bias, D, patch=2, out=None):
     """x [C0,T,H,W] fp32, y [C1,T,H,W] fp32 or None, w [D, (C0+C1)*patch^2] fp32 -> [L, D] fp32."""
     _chk(x, f32, "x"), _chk(w, f32, "w"), _chk(bias, f32, "bias")
     C0, T, H, W = x.shape
     C1 = 0 if y is None else y.shape[0]
     assert x.is_contiguous() and (y is None or y.is_contiguous()) and w.is_contiguous()
-    out = torch.empty(T * (H // patch) * (W // patch), D, device=x.device, dtype=f32)
+    L = T * (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty(L, D, device=x.device, dtype=f32)
+    assert out.shape == (L, D) and out.is_contiguous() and out.dtype == f32
     _lib.call("b200_patch_embed", x.data_ptr(), C0, _p(y), C1, w.data_ptr(), bias.data_ptr(), out.data_ptr(), T, H, W, D,
               int(patch), _stream())
     return out
