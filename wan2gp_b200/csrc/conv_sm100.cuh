@@ -26,14 +26,18 @@ constexpr int CONVR_BW = 128;                 // M tile = 128 consecutive pixels
 
 // BKC = channels per K chunk: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B: Cin = 96 = 3 x 32 exactly,
 // no zero-padded K is multiplied)
-template <int BN, int ROWS, int BKC = 64>
+// PAIR: two CTAs of a cluster work on two adjacent pixel tiles and SHARE every weight tile (tcgen05.mma.cta_group::2, M = 256): each
+// stages and reads half of the Cout rows of B.
+template <int BN, int ROWS, int BKC = 64, bool PAIR = false>
 struct ConvRowSmem {
     static_assert(ROWS * BN <= 256, "ROWS accumulators of BN columns per TMEM buffer");
     static_assert(BKC == 64 || BKC == 32, "K chunk");
+    static_assert(!PAIR || BN % 32 == 0, "pair: each CTA stages BN/2 weight rows, UMMA N % 16 == 0");
     static constexpr int kRowBytes = BKC * 2;
     static constexpr int kAStage = (((CONVR_BW + 2) * (ROWS + 2) * kRowBytes) + 1023) / 1024 * 1024;     // sized for 3x3 taps
-    static constexpr int kBStage = (BN * kRowBytes + 1023) / 1024 * 1024;
-    static constexpr int kBBytes = BN * kRowBytes;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;
+    static constexpr int kBStage = (kBRows * kRowBytes + 1023) / 1024 * 1024;
+    static constexpr int kBBytes = kBRows * kRowBytes;
     static constexpr int kAStages = 2;
     static constexpr int kBMax = (200 * 1024 - kAStages * kAStage) / kBStage;
     static constexpr int kBStages = kBMax > 8 ? 8 : kBMax;
@@ -54,10 +58,15 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_rowoff(uint32_t smem_
 // all of its channels, so the statistics need no exchange.  The separate norm pass (one read + one write of every activation,
 // 15 % of the Wan decode) disappears: a ResidualBlock's first conv writes ONLY the normalised tensor, its second conv (and the
 // up-sampling convs) write the raw tensor for the skip path plus the normalised one for the next block.
-template <int BN, int ROWS, int BKC = 64, bool NORM = false>
+// PAIR (launched with a cluster dimension of 2): CTA r of a pair owns pixel tile 2 * pair + r and weight rows [r BN/2, (r+1) BN/2); the
+// leader issues M = 256 MMAs that read the activation halo tile of each CTA at the same shared-memory offset and both halves of the
+// weight tile.  Why: at Cout = 96 / 192 the single-CTA kernel is bound by the shared-memory pipe, not the tensor pipe -- per
+// M128 x N192 x K16 MMA (96 clk) it reads 4 KB of A + 6 KB of B and the TMA refills ~7.5 KB (B is re-fetched for every tile), 187 B/clk
+// against 128 B/clk; with the weight tile shared the same MMA costs 4 + 3 KB of reads and ~4.5 KB of refills.
+template <int BN, int ROWS, int BKC = 64, bool NORM = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using S = ConvRowSmem<BN, ROWS, BKC>;
+    using S = ConvRowSmem<BN, ROWS, BKC, PAIR>;
     constexpr int RB = S::kRowBytes;                          // bytes per pixel row of the smem tiles
     constexpr int SA = S::kAStages, SB = S::kBStages;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
@@ -77,6 +86,8 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -85,22 +96,27 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        // PAIR: "accumulator empty" lives on the leader: one arrival per epilogue warp of each CTA
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 8 : 128); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    // PAIR: the persistent loop runs over PAIRS of pixel tiles (n_tiles == 1); this CTA's tile is 2 * pair + rank
+    const int num_tiles = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles * p.n_tiles;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int taps_hw = p.kh * p.kw;
     const int WB = CONVR_BW + p.kw - 1;                       // box width (pixels) = smem rows per image row
     // tile -> (n_blk fastest, then w tile, then frame, then h band): the frames a causal conv re-reads stay in L2
     auto tile_coords = [&](int tile, int& n_blk, int& t0, int& h0, int& w0) {
-        const int m_blk = tile / p.n_tiles;
+        int m_blk = tile / p.n_tiles;
         n_blk = tile - m_blk * p.n_tiles;
+        if constexpr (PAIR) { m_blk = 2 * tile + (int)cta_rank; n_blk = 0; }      // an odd tile count leaves one all-out-of-range tile (h0 >= H)
         const int per_band = p.T * p.tiles_w;
         const int band = m_blk / per_band;
         const int r = m_blk - band * per_band;
@@ -114,19 +130,31 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if (elect_one()) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             const uint32_t a_bytes = (uint32_t)WB * (ROWS + p.kh - 1) * RB;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int n_blk, t0, h0, w0; tile_coords(tile, n_blk, t0, h0, w0);
                 for (int dt = 0; dt < p.kt; ++dt) {
                     for (int cc = 0; cc < p.cin_chunks; ++cc) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
-                        mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                         // causal in time (all padding in front), centred in space; OOB -> zero fill
-                        tma_load_4d(smem_a + sa * S::kAStage, &tmap_a, &a_full[sa], cc * BKC, w0 - p.pad_w, h0 - p.pad_h, t0 + dt - p.pad_t);
+                        if constexpr (PAIR) {       // both CTAs' bytes are credited to the leader's barrier
+                            if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * a_bytes);
+                            tma_load_4d_pair(smem_a + sa * S::kAStage, &tmap_a, mapa_cluster(smem_u32(&a_full[sa]), 0), cc * BKC, w0 - p.pad_w,
+                                             h0 - p.pad_h, t0 + dt - p.pad_t);
+                        } else {
+                            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                            tma_load_4d(smem_a + sa * S::kAStage, &tmap_a, &a_full[sa], cc * BKC, w0 - p.pad_w, h0 - p.pad_h, t0 + dt - p.pad_t);
+                        }
                         if (++sa == SA) { sa = 0; pa ^= 1; }
                         for (int tap = 0; tap < taps_hw; ++tap) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
-                            mbar_arrive_expect_tx(&b_full[sb], S::kBBytes);
-                            tma_load_3d(smem_b + sb * S::kBStage, &tmap_b, &b_full[sb], cc * BKC, dt * taps_hw + tap, n_blk * BN);
+                            if constexpr (PAIR) {   // this CTA's half of the Cout rows
+                                if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * S::kBBytes);
+                                tma_load_3d_pair(smem_b + sb * S::kBStage, &tmap_b, mapa_cluster(smem_u32(&b_full[sb]), 0), cc * BKC, dt * taps_hw + tap,
+                                                 (int)cta_rank * (BN / 2));
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[sb], S::kBBytes);
+                                tma_load_3d(smem_b + sb * S::kBStage, &tmap_b, &b_full[sb], cc * BKC, dt * taps_hw + tap, n_blk * BN);
+                            }
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -136,12 +164,12 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         __syncwarp();
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, false);
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN, false);
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
             const int use_bo = p.conv_base_offset;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
@@ -164,19 +192,20 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                         const uint64_t da = BKC == 64 ? umma_desc_kmajor_sw128_rowoff(a_row + kk * 32, use_bo)
                                                                       : umma_desc_kmajor_sw64(a_row + kk * 32);
                                         const uint64_t db = BKC == 64 ? umma_desc_kmajor_sw128(b_base + kk * 32) : umma_desc_kmajor_sw64(b_base + kk * 32);
-                                        umma_bf16_ss(d_tmem + r * BN, da, db, idesc, !(first && kk == 0));
+                                        if constexpr (PAIR) umma_bf16_ss_pair(d_tmem + r * BN, da, db, idesc, !(first && kk == 0));
+                                        else umma_bf16_ss(d_tmem + r * BN, da, db, idesc, !(first && kk == 0));
                                     }
                                 }
                                 first = false;
-                                umma_commit(&b_empty[sb]);          // frees the weight slot when these MMAs retire
+                                if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 0b11); else umma_commit(&b_empty[sb]);   // frees the weight slot
                                 if (++sb == SB) { sb = 0; pb ^= 1; }
                             }
                         }
-                        umma_commit(&a_empty[sa]);                  // frees the activation halo tile
+                        if constexpr (PAIR) umma_commit_pair(&a_empty[sa], 0b11); else umma_commit(&a_empty[sa]);           // frees the halo tile
                         if (++sa == SA) { sa = 0; pa ^= 1; }
                     }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc], 0b11); else umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -186,7 +215,7 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const int wq = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = wq * 32 + lane;             // accumulator row = pixel of the row tile
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int n_blk, t0, h0, w0; tile_coords(tile, n_blk, t0, h0, w0);
             const int w = w0 + row;
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -333,16 +362,21 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if constexpr (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
+            } else {
+                mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 

@@ -703,28 +703,65 @@ extern "C" int b200_conv3d_cl_view(const void* x, int Ti, int Hi, int Wi, int of
 }
 
 // ---- row-tiled conv kernel (conv_sm100.cuh): instances and selection
-template <int BN, int ROWS, int BKC = 64, bool NORM = false>
+template <int BN, int ROWS, int BKC = 64, bool NORM = false, bool PAIR = false>
 static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC, NORM>;
+    auto kern = conv_row_tcgen05_kernel<BN, ROWS, BKC, NORM, PAIR>;
+    using S = ConvRowSmem<BN, ROWS, BKC, PAIR>;
     static std::atomic<unsigned long long> attr_done{0};
     if (b200_first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvRowSmem<BN, ROWS, BKC>::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row smem attr: %s", cudaGetErrorString(e));
         b200_mark_used_on_device(attr_done);
     }
+    if constexpr (PAIR) {
+        // one cluster of two CTAs per pair of pixel tiles; persistent over min(#pairs, #SMs / 2) clusters
+        const int pairs = (p.m_tiles + 1) / 2;
+        const int clusters = pairs < b200_num_sms() / 2 ? pairs : b200_num_sms() / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = S::kBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row pair launch: %s", cudaGetErrorString(e));
+        CHECK_LAUNCH("conv_row_pair_tcgen05");
+        return B200_OK;
+    }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < b200_num_sms() ? tiles : b200_num_sms();
-    kern<<<grid, 256, ConvRowSmem<BN, ROWS, BKC>::kBytes, st>>>(ta, tb, p);
+    kern<<<grid, 256, S::kBytes, st>>>(ta, tb, p);
     CHECK_LAUNCH("conv_row_tcgen05");
     return B200_OK;
 }
 static int conv_row_rows(int BN) { return BN <= 128 ? 2 : 1; }
 // instances with the fused next-layer norm epilogue: the single-N-tile layers of the Wan decoder's 96- and 192-channel stages
 static bool conv_norm_instance(int BN, int Cout) { return Cout == BN && (BN == 96 || BN == 192); }
-static int launch_conv_row_norm(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    if (BN == 96) return k32 ? launch_conv_row_inst<96, 2, 32, true>(ta, tb, p, st) : launch_conv_row_inst<96, 2, 64, true>(ta, tb, p, st);
-    if (BN == 192 && !k32) return launch_conv_row_inst<192, 1, 64, true>(ta, tb, p, st);
+static int launch_conv_row_norm(int BN, bool k32, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    if (pair) {
+        if (BN == 96) return k32 ? launch_conv_row_inst<96, 2, 32, true, true>(ta, tb, p, st) : launch_conv_row_inst<96, 2, 64, true, true>(ta, tb, p, st);
+        if (BN == 192 && !k32) return launch_conv_row_inst<192, 1, 64, true, true>(ta, tb, p, st);
+    } else {
+        if (BN == 96) return k32 ? launch_conv_row_inst<96, 2, 32, true>(ta, tb, p, st) : launch_conv_row_inst<96, 2, 64, true>(ta, tb, p, st);
+        if (BN == 192 && !k32) return launch_conv_row_inst<192, 1, 64, true>(ta, tb, p, st);
+    }
     return b200_set_error(B200_ERR_ARG, "no fused-norm row-conv instance for BN=%d", BN);
+}
+// CTA-pair instances (weights shared by two pixel tiles): the shared-memory-bound widths of the decoders' high-resolution stages
+static bool conv_pair_instance(int BN, bool k32) { return (BN == 96) || (!k32 && (BN == 192 || BN == 128 || BN == 256)); }
+static int launch_conv_row_pair(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    if (BN == 96) return k32 ? launch_conv_row_inst<96, 2, 32, false, true>(ta, tb, p, st) : launch_conv_row_inst<96, 2, 64, false, true>(ta, tb, p, st);
+    if (!k32) {
+        switch (BN) {
+            case 256: return launch_conv_row_inst<256, 1, 64, false, true>(ta, tb, p, st);
+            case 192: return launch_conv_row_inst<192, 1, 64, false, true>(ta, tb, p, st);
+            case 128: return launch_conv_row_inst<128, 2, 64, false, true>(ta, tb, p, st);
+        }
+    }
+    return b200_set_error(B200_ERR_ARG, "no pair row-conv instance for BN=%d", BN);
 }
 static int launch_conv_row(int BN, bool k32, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     if (k32) {                                    // Cin = 96: three 32-channel chunks (64B swizzle)
@@ -789,10 +826,15 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         int r = b200_make_tmap_bf16(&ta, x, 4, dims, str, box, k96 ? 64 : 128);
         if (r) return r;
     }
+    // CTA pairs sharing the weight tile (B200_CONV_PAIR=0: single-CTA kernels everywhere, for A/B measurements): one N tile, row kernel,
+    // enough tiles to fill the chip; outputs through the plain strided mapping (no interleave / planar modes)
+    static const int pair_on = env_flag("B200_CONV_PAIR", 1);
+    const bool pair = pair_on && row && Cout == BN && conv_pair_instance(BN, k96) && out_mode != 1 && out_mode != 2 &&
+                      (long long)T * ((H + ROWS - 1) / ROWS) * ((W + CONVR_BW - 1) / CONVR_BW) >= 2LL * b200_num_sms();
     {
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
         uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2};
-        uint32_t box[3] = {kbox, 1, (uint32_t)BN};
+        uint32_t box[3] = {kbox, 1, (uint32_t)(pair ? BN / 2 : BN)};
         int r = b200_make_tmap_bf16(&tb, w, 3, dims, str, box, k96 ? 64 : 128);
         if (r) return r;
     }
@@ -847,11 +889,12 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         if (!out) p.out = p.norm_out;
         static const int base_off_n = env_flag("B200_CONV_ROW_BASEOFF", 0);
         p.conv_base_offset = base_off_n;
-        return launch_conv_row_norm(BN, k96, ta, tb, p, (cudaStream_t)stream);
+        return launch_conv_row_norm(BN, k96, pair, ta, tb, p, (cudaStream_t)stream);
     }
     if (row) {
         static const int base_off = env_flag("B200_CONV_ROW_BASEOFF", 0);
         p.conv_base_offset = base_off;
+        if (pair) return launch_conv_row_pair(BN, k96, ta, tb, p, (cudaStream_t)stream);
         return launch_conv_row(BN, k96, ta, tb, p, (cudaStream_t)stream);
     }
     return k96 ? b200_launch_gemm_k96(BN, ta, tb, p, (cudaStream_t)stream) : b200_launch_gemm(BN, false, ta, tb, p, (cudaStream_t)stream);
