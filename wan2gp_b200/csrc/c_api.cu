@@ -15,6 +15,7 @@
 
 #include "../../include/wan2gp_b200.h"
 #include "attn2_sm100.cuh"
+#include "attn3_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
@@ -151,6 +152,7 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
 int b200_launch_gemm_k96(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     switch (BN) {
         case 96: return launch_gemm_inst<96, false, 32, 3>(ta, tb, p, st);
+        case 32: return launch_gemm_inst<32, false, 32, 3>(ta, tb, p, st);        // tap-stacked decoder head (27 -> 32 channels)
         case 16: return launch_gemm_inst<16, false, 32, 3>(ta, tb, p, st);
     }
     return b200_set_error(B200_ERR_ARG, "no K=96 GEMM instance for BN=%d", BN);
@@ -355,8 +357,18 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
         return B200_OK;
     };
+    auto launch3 = [&](auto kern) -> int {        // 16 softmax warps (attn3_sm100.cuh)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+        kern<<<grid, ATT3_THREADS, ATT3_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        return B200_OK;
+    };
     int rc;
     switch (variant) {
+        // two softmax warpgroups per Q tile (one per 64-key half), packed-fp32 softmax; 203: every 3rd exp2 pair on the FMA pipe
+        case 200: rc = launch3(attn_fwd_d128_w16_kernel<0>); break;
+        case 203: rc = launch3(attn_fwd_d128_w16_kernel<3>); break;
+        case 204: rc = launch3(attn_fwd_d128_w16_kernel<4>); break;
         // measured at L=75600, H=40 (profiles/attn_variants_r01.txt): 0: 100.5 ms, 1: 97.3 ms, 41: 98.6 ms, 21: 109.0 ms --
         // under the 1 kW power cap extra FMA-pipe work for exp2 costs more clock than the MUFU relief buys
         case 0: rc = launch(attn_fwd_d128_kernel<0, false>); break;

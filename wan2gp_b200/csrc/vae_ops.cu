@@ -812,7 +812,7 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
     // Cin = 96 (the full-resolution stage): K per tap is walked as 3 x 32 channels with 64B-swizzled boxes instead of
     // 2 x 64 with a half-empty second box (25% fewer MMAs and smem bytes)
     static const int row_k32 = env_flag("B200_CONV_ROW_K32", 1);
-    const bool k96 = (Cin == 96) && (BN == 96 || BN == 16) && (!row || row_k32);
+    const bool k96 = (Cin == 96) && (BN == 96 || BN == 16 || (BN == 32 && !row)) && (!row || row_k32);
     const uint32_t kbox = k96 ? 32 : 64;
     CUtensorMap ta, tb;
     {
