@@ -714,7 +714,7 @@ def main():
             result["cfg_split"]["note"] = "BASELINE configs[2]: Wan2.2 i2v 14B 720p x 81f, every CFG pair split over 2 GPUs; value = samples in flight x steps/s"
         except Exception as e:                                   # noqa: BLE001
             result["cfg_split"] = {"error": repr(e)[:300]}
-        if world == 4:
+        if world == 4 or os.environ.get("B200_BENCH_FORCE_HY15"):       # the env switch only exists to exercise this branch on 2 GPUs
             try:
                 result["hy15_t2v_720p129"] = measure_hunyuan("hy15_t2v_720p129", 2, 1, rank, world, local_rank, dev, dist, with_vae=False)
                 result["hy15_t2v_720p129"]["note"] = "BASELINE configs[3]: Hunyuan Video 1.5 t2v 720p x 129f on 4 GPUs (one sample per GPU)"

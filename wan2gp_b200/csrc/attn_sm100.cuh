@@ -46,7 +46,13 @@ constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (ATT_QTILES + 2 * ATT_KV_STAGES)
 // then counts PAIRS (every POLY-th pair of a row takes both exponentials through ex2_poly3_x2 on the FMA pipe).  MUFU.EX2 runs at 16
 // results/clk/SM: the 2 x 16 384 exponentials of one K/V step need the same 2048 clocks as its four 128x128x128 MMAs, so with all of
 // them on MUFU the softmax of one Q tile cannot finish inside the MMA time of the other (ncu r01: tensor 68 %, MUFU 68 %).
-template <int POLY, bool SPLIT, bool PACK2 = false>
+// MC (launched as clusters of two CTAs = two adjacent Q blocks of one head): every K/V tile is fetched from L2 ONCE for both CTAs -- CTA r
+// loads the 64-column slab r of the tile and multicasts it into both shared memories; a stage is refilled only after the MMAs of BOTH
+// CTAs released it (their tcgen05.commit arrives on both "empty" barriers).  All MMAs and the whole softmax <-> MMA hand-off stay
+// CTA-local (unlike attn2_sm100.cuh, whose cross-CTA P hand-off cost more than the shared operands saved); only the prefetch ring is
+// coupled.  Why: K/V come from L2 (hit rate 98.4 %) at 64 KB per CTA per 2048-clock step = 4.7 KB/clk over the chip, 75 % of the ~6.3 KB/clk
+// the L2 can deliver.
+template <int POLY, bool SPLIT, bool PACK2 = false, bool MC = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -80,8 +86,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < ATT_KV_STAGES; ++i) {
-            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], MC ? 2 : 1);        // MC: released by the MMAs of both CTAs
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], MC ? 2 : 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); }
         for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], PACK2 ? 4 : 128);     // PACK2: one arrival per softmax warp (lane 0 after __syncwarp)
@@ -89,8 +95,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (MC) cluster_sync_all(); else __syncthreads();                   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
+    const uint32_t cta_rank = MC ? cluster_ctarank() : 0u;
     const uint32_t tmem_base = *tmem_slot;
 
     // softmax threads keep a whole 128-column S row in registers: take registers from the 4 service warps
@@ -112,18 +119,31 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint32_t ph = (j / ATT_KV_STAGES) & 1;
                 mbar_wait(&k_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
-                tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], col, k_row0 + j * ATT_BN);
-                tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_k, &k_full[st], col + 64, k_row0 + j * ATT_BN);
+                if constexpr (MC) {       // this CTA's 64-column slab of the tile, written into both CTAs (the peer sends the other slab)
+                    tma_load_2d_mcast(sK + st * ATT_TILE_BYTES + cta_rank * (ATT_TILE_BYTES / 2), &tmap_k, &k_full[st], col + (int)cta_rank * 64,
+                                      k_row0 + j * ATT_BN, 0b11);
+                } else {
+                    tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], col, k_row0 + j * ATT_BN);
+                    tma_load_2d(sK + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_k, &k_full[st], col + 64, k_row0 + j * ATT_BN);
+                }
                 mbar_wait(&v_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
-                tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], col, k_row0 + j * ATT_BN);
-                tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_v, &v_full[st], col + 64, k_row0 + j * ATT_BN);
+                if constexpr (MC) {
+                    tma_load_2d_mcast(sV + st * ATT_TILE_BYTES + cta_rank * (ATT_TILE_BYTES / 2), &tmap_v, &v_full[st], col + (int)cta_rank * 64,
+                                      k_row0 + j * ATT_BN, 0b11);
+                } else {
+                    tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], col, k_row0 + j * ATT_BN);
+                    tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_v, &v_full[st], col + 64, k_row0 + j * ATT_BN);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         if (elect_one()) {
+            auto release = [&](uint64_t* bar) {       // K/V stage free: in MC mode the arrival goes to both CTAs' barriers
+                if constexpr (MC) umma_commit_mcast(bar, 0b11); else umma_commit(bar);
+            };
             constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN, /*b_mn_major=*/false);
             constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, ATT_D, /*b_mn_major=*/true);
             auto issue_s = [&](int i, int j) {              // S_i = Q_i K_j^T into TMEM cols [128 i, 128 i + 128)
@@ -156,7 +176,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_after();
             issue_s(0, 0);
             issue_s(1, 0);
-            umma_commit(&k_empty[0]);
+            release(&k_empty[0]);
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j % ATT_KV_STAGES;
                 const uint32_t kvph = (j / ATT_KV_STAGES) & 1;
@@ -171,10 +191,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 // ---- Q tile 1
                 issue_pv(1, j);
-                umma_commit(&v_empty[st]);
+                release(&v_empty[st]);
                 if (more) {
                     issue_s(1, j + 1);
-                    umma_commit(&k_empty[(j + 1) % ATT_KV_STAGES]);
+                    release(&k_empty[(j + 1) % ATT_KV_STAGES]);
                 }
             }
         }
@@ -335,7 +355,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (MC) cluster_sync_all(); else __syncthreads();       // the peer may still multicast into this CTA's shared memory / barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);

@@ -363,8 +363,27 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         kern<<<grid, ATT3_THREADS, ATT3_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
         return B200_OK;
     };
+    auto launch_mc = [&](auto kern) -> int {      // clusters of two adjacent Q blocks sharing every K/V tile through TMA multicast
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y, grid.z);      // an odd block count gets one all-out-of-range Q block
+        cfg.blockDim = dim3(ATT_THREADS);
+        cfg.dynamicSmemBytes = ATT_SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention cluster launch: %s", cudaGetErrorString(e));
+        return B200_OK;
+    };
     int rc;
     switch (variant) {
+        // K/V tiles multicast to a cluster of two CTAs (each loads half): 300 = packed softmax, 303 = + every 3rd exp2 pair on the FMA pipe
+        case 300: rc = launch_mc(attn_fwd_d128_kernel<0, true, true, true>); break;
+        case 303: rc = launch_mc(attn_fwd_d128_kernel<3, true, true, true>); break;
         // two softmax warpgroups per Q tile (one per 64-key half), packed-fp32 softmax; 203: every 3rd exp2 pair on the FMA pipe
         case 200: rc = launch3(attn_fwd_d128_w16_kernel<0>); break;
         case 203: rc = launch3(attn_fwd_d128_w16_kernel<3>); break;

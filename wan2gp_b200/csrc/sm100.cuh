@@ -131,6 +131,19 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem, const void* tmap, u
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// TMA load multicast to every CTA of `cta_mask` in this cluster: the box lands at the SAME shared-memory offset in each destination CTA
+// and completes `bytes` on the mbarrier at the same offset there.  Issued by one CTA, consumed by all: L2 -> SM traffic of a tile shared
+// by the cluster's CTAs is paid once.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+// tcgen05.commit of a single-CTA MMA stream whose arrival is delivered to the barrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 // TMEM allocation for a CTA pair: executed by the same warp index in BOTH CTAs (same smem_dst offset).
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
