@@ -257,7 +257,7 @@ def cpu_port_steps_per_sec(cfg, thw, reps=1):
     workload -- ONE transformer block of this architecture, its two cost components timed separately so that each is scaled by its
     own share of the real step (a 1-frame slice has 11 % attention, the real 720p step 72 %):
       * the row-wise part (LN/modulation, q/k/v/o, cross-attention, FFN) on `Ls` tokens (3 latent frames), scaled by L / Ls;
-      * self-attention of `Lq` sampled query rows against ALL L keys / values (heads in chunks), scaled by L / Lq.
+      * self-attention of `Lq` sampled query rows against ALL L keys / values through torch's CPU SDPA (what the reference calls), scaled by L / Lq.
     step time = 2 forwards x num_layers x (t_rows L/Ls + t_attn L/Lq); stated as extrapolated.  Returns (steps/s, info dict)."""
     from oracle import wan_oracle
     from wan2gp_b200 import synth
@@ -267,7 +267,7 @@ def cpu_port_steps_per_sec(cfg, thw, reps=1):
     big = D > 2000
     Ts = min(T, 3) if big else T
     Ls = Ts * (H // 2) * (W // 2)
-    Lq = min(L, 512 if big else L)
+    Lq = min(L, 2048 if big else L)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     shapes = synth.wan_param_shapes(cfg)
@@ -276,24 +276,33 @@ def cpu_port_steps_per_sec(cfg, thw, reps=1):
     e0 = torch.randn(6, D) * 0.1
     ctx = torch.randn(cfg["text_len"], D)
     cos, sin = wan_oracle.rope_tables((Ts, H, W))
-    q = torch.randn(Lq, NH, 128)
-    k = torch.randn(L, NH, 128)
-    v = torch.randn(L, NH, 128)
-    hc = 4                                         # heads per chunk: S = [hc, Lq, L] fp32 (0.6 GB at Lq = 512, L = 75 600)
+    # self-attention sample: the reference's OWN CPU attention call (shared/attention.py:208-225 sdpa_wrapper ->
+    # F.scaled_dot_product_attention on [1, H, L, 128]), not the oracle's materialised softmax(QK^T)V -- the latter spends its time in
+    # strided copies and a 1.5e9-element exp on one socket and understated the CPU by an order of magnitude in the first version
+    q = torch.randn(1, NH, Lq, 128)
+    k = torch.randn(1, NH, L, 128)
+    v = torch.randn(1, NH, L, 128)
     t_rows, t_attn = [], []
-    with torch.no_grad():
-        wan_oracle.block_forward(sd, cfg, 0, x[:256], e0, ctx, cos[:256], sin[:256], False)          # warm-up (thread pool, allocator)
-        for _ in range(reps):
-            t0 = time.time()
-            wan_oracle.block_forward(sd, cfg, 0, x, e0, ctx, cos, sin, False)
-            t1 = time.time()
-            for h0 in range(0, NH, hc):
-                wan_oracle.attention(q[:, h0:h0 + hc], k[:, h0:h0 + hc], v[:, h0:h0 + hc], False)
-            t2 = time.time()
-            # block_forward(x) contains the Ls x Ls self-attention of the sample itself: remove its (small, separately scaled) cost
-            t_self = (t2 - t1) * (Ls * Ls) / (Lq * L)
-            t_rows.append(max(1e-6, (t1 - t0) - t_self))
-            t_attn.append(t2 - t1)
+    # inside the timed block the oracle's attention is evaluated the way the reference evaluates it on a CPU (SDPA), so that the
+    # sample-sized self-attention contained in block_forward and the separately timed full-length one are the same code
+    sdpa = torch.nn.functional.scaled_dot_product_attention
+    oracle_attention = wan_oracle.attention
+    wan_oracle.attention = lambda q_, k_, v_, emulate: sdpa(q_.permute(1, 0, 2)[None], k_.permute(1, 0, 2)[None], v_.permute(1, 0, 2)[None])[0].permute(1, 0, 2)
+    try:
+      with torch.no_grad():
+          wan_oracle.block_forward(sd, cfg, 0, x[:256], e0, ctx, cos[:256], sin[:256], False)          # warm-up (thread pool, allocator)
+          for _ in range(reps):
+              t0 = time.time()
+              wan_oracle.block_forward(sd, cfg, 0, x, e0, ctx, cos, sin, False)
+              t1 = time.time()
+              sdpa(q, k, v)
+              t2 = time.time()
+              # block_forward(x) contains the Ls x Ls self-attention of the sample itself: remove its (small, separately scaled) cost
+              t_self = (t2 - t1) * (Ls * Ls) / (Lq * L)
+              t_rows.append(max(1e-6, (t1 - t0) - t_self))
+              t_attn.append(t2 - t1)
+    finally:
+        wan_oracle.attention = oracle_attention
     tr, ta = min(t_rows), min(t_attn)
     block_s = tr * L / Ls + ta * L / Lq
     step_s = 2.0 * nl * block_s

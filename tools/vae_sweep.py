@@ -85,7 +85,8 @@ def main():
                 else:
                     # whole clip while ~5 full-resolution bf16 activations (top level: 96 / 128 channels) fit in ~150 GB
                     top_c = 96 if name == "wan" else 128
-                    whole_bytes = 5.0 * frames * h * fs * w * fs * top_c * 2
+                    live = {"wan": 5.0, "hyvae15": 3.0, "hyvae10": 4.5}[name]      # measured peaks: 106 / 72.5 / 114 GB at 129 frames x 720p
+                    whole_bytes = live * frames * h * fs * w * fs * top_c * 2
                     if whole_bytes < 150e9:
                         mode = "whole"
                     elif name == "wan":

@@ -345,11 +345,11 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         return B200_OK;
     }
     dim3 grid((Lq + ATT_QTILES * ATT_BM - 1) / (ATT_QTILES * ATT_BM), H, nseq);
-    // tuning variants (B200_ATT_VARIANT = "<poly><split>", e.g. "41"); the default (1 = no poly, split P) is the measured best
+    // tuning variants (B200_ATT_VARIANT); 1 = the round-1 kernel (scalar softmax, all exp2 on MUFU, split P)
     static int variant = -1;
     if (variant < 0) {
         const char* ev = getenv("B200_ATT_VARIANT");
-        variant = ev ? atoi(ev) : 1;
+        variant = ev ? atoi(ev) : 103;      // default: packed-fp32 softmax, every 3rd pair of exponentials on the FMA pipe (profiles/attn_variants_r02_*.json)
     }
     auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
@@ -398,7 +398,8 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         case 104: rc = launch(attn_fwd_d128_kernel<4, true, true>); break;
         case 103: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
         case 102: rc = launch(attn_fwd_d128_kernel<2, true, true>); break;
-        default: rc = launch(attn_fwd_d128_kernel<0, true>); break;
+        case 1: rc = launch(attn_fwd_d128_kernel<0, true>); break;
+        default: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
     }
     if (rc) return rc;
     CHECK_LAUNCH("attn_fwd_d128");
