@@ -40,6 +40,22 @@ def main():
     torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
     torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
     assert float(lo) == float(hi)
+    # CFG-pair split on GPUs (BASELINE configs[2]): rank 2k runs the cond branch, rank 2k+1 the uncond branch, one NCCL all-gather of the
+    # prediction (+ abort flag) per step; the latents of both ranks stay identical and equal to the single-rank joint pass
+    if world % 2 == 0:
+        grp, cfg_rank, sample, _ = wd.make_cfg_pairs()
+        m = WanModel(**cfg, device=dev)
+        m.load_state_dict(sd)
+        gg = torch.Generator().manual_seed(7 + sample)
+        lat0 = torch.randn(1, 16, 3, 8, 12, generator=gg).to(dev)
+        c, cn = ctxs[sample].to(dev), null.to(dev)
+        for solver in ("euler", "unipc"):
+            split = WanDenoiser(m, num_steps=3, shift=5.0, guide_scale=4.0, device=dev, cfg_group=grp, cfg_rank=cfg_rank, sample_solver=solver, cfg_star_switch=True)
+            joint = WanDenoiser(m, num_steps=3, shift=5.0, guide_scale=4.0, device=dev, sample_solver=solver, cfg_star_switch=True)
+            a, b = lat0.clone(), lat0.clone()
+            for i in range(3):
+                assert split.step(a, i, c, cn) is a and joint.step(b, i, c, cn) is b
+            assert torch.equal(a, b), f"cfg split ({solver}) differs from the joint pass: {float((a - b).abs().max())}"
     if rank == 0:
         print("MGPU_OK", world)
     torch.distributed.destroy_process_group()

@@ -176,3 +176,14 @@ def test_attention_batched_equals_separate(ops, nseq, Lq, Lk, H):
     for z in range(nseq):
         one = ops.attention(q[z * Lq:(z + 1) * Lq], k[z * Lk:(z + 1) * Lk], v[z * Lk:(z + 1) * Lk], H)
         assert torch.equal(both[z * Lq:(z + 1) * Lq], one), z
+
+
+def test_cfg_step_rejects_misaligned_views(ops):
+    """The fused CFG + scheduler kernels use 128-bit loads: an operand that is a view at an odd float offset must be refused up front
+    (round 2: a payload[1:] view of the CFG-pair exchange buffer reached the kernel and raised 'misaligned address' on the GPU)."""
+    from wan2gp_b200 import _lib
+    buf = _randn(1 + 4 * 96, seed=1)
+    lat, c = _randn(4 * 96, seed=2), _randn(4 * 96, seed=3)
+    with pytest.raises(_lib.B200Error):
+        ops.cfg_euler_step_(lat, buf[1:], c, 4.0, 0.05)
+    ops.cfg_euler_step_(lat, buf[4:4 + 384], c, 4.0, 0.05)          # a 16-byte aligned view is fine

@@ -188,9 +188,17 @@ def add_vec(a, b):
     return out
 
 
+def _chk_vec4(*tensors):
+    """The step kernels use 128-bit loads: every operand must start on a 16-byte boundary (a view at an odd float offset does not)."""
+    for t in tensors:
+        if t is not None and t.data_ptr() % 16:
+            raise _lib.B200Error("cfg step: operand not 16-byte aligned (a sliced view?); pass an aligned / contiguous tensor")
+
+
 def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None, cfg_star=False):
     """lat -= dt * (u + g (c - u)); cfg_star=True applies the CFG-Zero* rescale of u (any2video.py:1706-1714)."""
     _chk(lat, f32, "lat"), _chk(cond, f32, "cond")
+    _chk_vec4(lat, cond, uncond, pred_out)
     assert lat.is_contiguous() and cond.is_contiguous() and (uncond is None or uncond.is_contiguous())
     dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
     _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
@@ -205,6 +213,7 @@ def cfg_unipc_step_(lat, cond, uncond, guide, x_last, m0, m1, coef, cfg_star=Fal
         _chk(t_, f32, n_)
         assert t_.is_contiguous() and t_.numel() == lat.numel()
     assert uncond is None or (uncond.is_contiguous() and uncond.numel() == lat.numel())
+    _chk_vec4(lat, cond, uncond, x_last, m0, m1)
     dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
     c = (ctypes.c_float * 8)(coef["sigma"], coef["ca"], coef["cb"], coef["cc"], coef["cd"], coef["pp"], coef["pq"], coef["pr"])
     _lib.call("b200_cfg_unipc_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), x_last.data_ptr(), m0.data_ptr(),

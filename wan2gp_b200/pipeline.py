@@ -212,16 +212,18 @@ class WanDenoiser:
             # `_interrupt` is per process: the pair must AGREE on the abort before either rank skips the collective, otherwise the
             # partner blocks in ncclAllGather forever.  The flag rides in front of the prediction (same collective, +1 float).
             shape = tuple(latents.shape)
-            payload = torch.empty(1 + latents.numel(), device=latents.device, dtype=f32)
-            payload[0] = 1.0 if mine is None else 0.0
-            if mine is not None:
-                payload[1:].copy_(mine.reshape(-1))
+            HDR = 4                                   # 16-byte header: the predictions behind it stay aligned for the 128-bit loads of the step kernel
+            payload = torch.zeros(HDR + latents.numel(), device=latents.device, dtype=f32)
+            if mine is None:
+                payload[0] = 1.0
+            else:
+                payload[HDR:].copy_(mine.reshape(-1))
             both = [torch.empty_like(payload), torch.empty_like(payload)]
             dist.all_gather(both, payload, group=self.cfg_group)                  # ncclAllGather inside the 2-rank pair
             if float(both[0][0]) + float(both[1][0]) > 0:
                 self._interrupt = True                                            # both ranks leave the schedule together
                 return None
-            cond, uncond = both[0][1:].reshape(shape), both[1][1:].reshape(shape)
+            cond, uncond = both[0][HDR:].reshape(shape), both[1][HDR:].reshape(shape)
         else:
             # joint pass: same blocks applied to each branch in turn (any2video.py:1634, model.py:2030-2037)
             cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
