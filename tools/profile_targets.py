@@ -24,6 +24,9 @@ if "gemm" in which:
 if "conv" in which:
     x = torch.randn(13, 720, 1280, 96, device="cuda").to(bf16)
     conv = _Conv(torch.randn(96, 96, 3, 3, 3, device="cuda") * 0.02, torch.randn(96, device="cuda"), "cuda")
-    conv(x)
+    if conv.fusable(1280):   # the variant the decoder runs: CTA pair + fused next-layer RMS_norm/SiLU
+        conv.with_norm(x, torch.ones(96, device="cuda"))
+    else:
+        conv(x)
 torch.cuda.synchronize()
 print("done")
