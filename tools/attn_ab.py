@@ -11,7 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 NAMES = {"p0": "single-CTA (r01 kernel)", "p1": "pair, packed-fp32 softmax", "p2": "pair, scalar softmax", "p4": "pair, packed + 1/4 exp2 on FMA pipe",
          "v1": "single-CTA r01 kernel (scalar softmax, all exp2 on MUFU)", "v100": "single-CTA, packed softmax", "v104": "single-CTA, packed + 1/4 of the exp2 pairs on the FMA pipe",
-         "v103": "single-CTA, packed + 1/3 on the FMA pipe", "v102": "single-CTA, packed + 1/2 on the FMA pipe"}
+         "v103": "single-CTA, packed + 1/3 on the FMA pipe", "v102": "single-CTA, packed + 1/2 on the FMA pipe",
+         "v901": "ABLATION of v103: exponentials replaced by a move", "v902": "ABLATION: half of each S row read from TMEM",
+         "v903": "ABLATION: no softmax (MMA / smem / barrier ceiling)", "v904": "ABLATION: S read from TMEM, nothing computed or stored",
+         "v905": "ABLATION: full arithmetic, P never stored"}
 
 
 def leg():
@@ -20,7 +23,10 @@ def leg():
     bf16 = torch.bfloat16
     out = {"variant": os.environ.get("ATT_LEG"), "parity": [], "timing": []}
     g = torch.Generator(device="cuda").manual_seed(0)
-    for Lq, Lk, H in [(1024, 1024, 2), (2000, 1333, 3), (1100, 512, 2), (9000, 9000, 2)]:
+    # v9xx = limiter ablations (csrc/attn_sm100.cuh ABL): wrong output by construction, timing only
+    ablation = out["variant"].startswith("v9")
+    out["ablation"] = ablation
+    for Lq, Lk, H in ([] if ablation else [(1024, 1024, 2), (2000, 1333, 3), (1100, 512, 2), (9000, 9000, 2)]):
         D = H * 128
         q, k, v = (torch.randn(n, D, device="cuda", generator=g).to(bf16) for n in (Lq, Lk, Lk))
         o = ops.attention(q, k, v, H)
@@ -31,14 +37,14 @@ def leg():
         out["parity"].append({"Lq": Lq, "Lk": Lk, "H": H, "rel_l2": rel, "ok": rel < 4e-3})
         print(out["parity"][-1], flush=True)
     if all(p["ok"] for p in out["parity"]):
-        for L, H in [(75600, 40), (32760, 40)]:
+        for L, H in ([(75600, 40)] if ablation else [(75600, 40), (32760, 40)]):
             D = H * 128
             qkv = torch.randn(L, 3 * D, device="cuda").to(bf16)
             o = torch.empty(L, D, device="cuda", dtype=bf16)
             fn = lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, out=o)
             fn(); torch.cuda.synchronize()
             ts = []
-            for _ in range(4):
+            for _ in range(6 if ablation else 4):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); fn(); b.record(); torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
@@ -54,15 +60,16 @@ if __name__ == "__main__":
         leg()
         sys.exit(0)
     res = {}
-    for var in (sys.argv[1:] or ["v1", "v100", "v104", "v103", "v102"]):
+    for i, var in enumerate(sys.argv[1:] or ["v1", "v100", "v104", "v103", "v102"]):
         # "pN": B200_ATT_PAIR=N (pair kernel family); "vN": single-CTA kernel, B200_ATT_VARIANT=N
         env = dict(os.environ, ATT_LEG=var, B200_ATT_PAIR=var[1:] if var[0] == "p" else "0", B200_ATT_VARIANT=var[1:] if var[0] == "v" else "1")
+        key = var if var not in res else f"{var}#{i}"              # a variant listed twice (drift check) keeps both results
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=240)
             line = [l for l in r.stdout.splitlines() if l.startswith("LEG ")]
-            res[var] = dict(json.loads(line[-1][4:]), name=NAMES.get(var, var)) if line else {"name": NAMES.get(var, var), "error": (r.stdout + r.stderr)[-1500:]}
+            res[key] = dict(json.loads(line[-1][4:]), name=NAMES.get(var, var)) if line else {"name": NAMES.get(var, var), "error": (r.stdout + r.stderr)[-1500:]}
         except subprocess.TimeoutExpired:
-            res[var] = {"name": NAMES.get(var, var), "error": "timeout (hang)"}
-        print(var, json.dumps(res[var])[:600], flush=True)
+            res[key] = {"name": NAMES.get(var, var), "error": "timeout (hang)"}
+        print(key, json.dumps(res[key])[:600], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "attn_ab.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("ATT_AB_OUT", "attn_ab.json")), "w"), indent=1)

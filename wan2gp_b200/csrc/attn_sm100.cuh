@@ -52,7 +52,11 @@ constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (ATT_QTILES + 2 * ATT_KV_STAGES)
 // CTA-local (unlike attn2_sm100.cuh, whose cross-CTA P hand-off cost more than the shared operands saved); only the prefetch ring is
 // coupled.  Why: K/V come from L2 (hit rate 98.4 %) at 64 KB per CTA per 2048-clock step = 4.7 KB/clk over the chip, 75 % of the ~6.3 KB/clk
 // the L2 can deliver.
-template <int POLY, bool SPLIT, bool PACK2 = false, bool MC = false>
+// ABL (measurement only, results are WRONG for ABL != 0 -- tools/attn_ab.py "limiter ablation", profiles/attn_ablation_r02.json): which unit
+// bounds the K/V step.  1: exponentials replaced by a move (MUFU + polynomial off); 2: only half of each S row is read from TMEM (the other
+// half is derived in registers); 3: no softmax at all (S "consumed" and P "published" at once: the MMA / shared-memory / barrier ceiling of
+// this issue order); 4: S is read from TMEM but nothing is computed or stored; 5: full arithmetic, P never stored to TMEM.
+template <int POLY, bool SPLIT, bool PACK2 = false, bool MC = false, int ABL = 0>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -216,9 +220,29 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_after();
             const int valid = p.Lk - j * ATT_BN;       // >= 128 except for the last, partial tile
             uint32_t v[128];
+            if constexpr (ABL == 3) {                     // MMA-only ceiling: hand the (garbage) S straight back as P
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&p_full[qi * 2]); mbar_arrive(&p_full[qi * 2 + 1]); }
+                continue;
+            }
+            if constexpr (ABL == 2) {
+                #pragma unroll
+                for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + c * 32, v + c * 32);
+                tmem_ld_wait();
+                #pragma unroll
+                for (int i = 0; i < 64; ++i) v[64 + i] = v[i] ^ (uint32_t)((j & 1) << 12);      // distinct values: nothing is common-subexpression'd away
+            } else {
             #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + c * 32, v + c * 32);
             tmem_ld_wait();
+            }
+            if constexpr (ABL == 4) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&p_full[qi * 2]); mbar_arrive(&p_full[qi * 2 + 1]); }
+                continue;
+            }
             if (valid < ATT_BN) {
                 #pragma unroll
                 for (int i = 0; i < 128; ++i)
@@ -280,7 +304,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     for (int c = 0; c < 32; ++c) {
                         const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[h * 64 + 2 * c]), __uint_as_float(v[h * 64 + 2 * c + 1])), sc2, nm2);
                         float e0, e1;
-                        if (POLY > 0 && c % (POLY > 0 ? POLY : 1) == POLY - 1) {
+                        if constexpr (ABL == 1) {
+                            unpack_f32x2(x2, e0, e1);
+                        } else if (POLY > 0 && c % (POLY > 0 ? POLY : 1) == POLY - 1) {
                             ex2_poly3_x2(x2, e0, e1);
                         } else {
                             float x0, x1;
@@ -291,9 +317,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         acc2[c & 3] = add_f32x2(acc2[c & 3], pack_f32x2(e0, e1));
                         v[h * 64 + c] = pack_bf16x2(e0, e1);
                     }
-                    tmem_st_32x32b_x32(tS + h * 32, v + h * 64);
+                    if constexpr (ABL != 5) tmem_st_32x32b_x32(tS + h * 32, v + h * 64);
                     if (SPLIT || h == 1) {
-                        tmem_st_wait();
+                        if constexpr (ABL != 5) tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {                                  // 4 instead of 128 shared-memory barrier updates per hand-off

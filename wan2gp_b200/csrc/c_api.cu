@@ -399,6 +399,12 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         case 103: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
         case 102: rc = launch(attn_fwd_d128_kernel<2, true, true>); break;
         case 1: rc = launch(attn_fwd_d128_kernel<0, true>); break;
+        // limiter ablations of the default kernel: timing only, the output is wrong by construction (attn_sm100.cuh "ABL")
+        case 901: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 1>); break;
+        case 902: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 2>); break;
+        case 903: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 3>); break;
+        case 904: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 4>); break;
+        case 905: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 5>); break;
         default: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
     }
     if (rc) return rc;

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "conv_sm100.cuh"
+#include "conv2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -737,6 +738,52 @@ static int launch_conv_row_inst(const CUtensorMap& ta, const CUtensorMap& tb, co
     CHECK_LAUNCH("conv_row_tcgen05");
     return B200_OK;
 }
+// ---- second-generation pair kernel (conv2_sm100.cuh): unrolled taps, grouped weight stages, two epilogue warpgroups
+template <int BN, int ROWS, int BKC, bool NORM, int KHW, int GROUP>
+static int launch_conv_row2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = conv_row2_tcgen05_kernel<BN, ROWS, BKC, NORM, KHW, GROUP>;
+    using S = ConvRow2Smem<BN, ROWS, BKC, KHW, GROUP>;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (b200_first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row2 smem attr: %s", cudaGetErrorString(e));
+        b200_mark_used_on_device(attr_done);
+    }
+    const int pairs = (p.m_tiles + 1) / 2;
+    const int clusters = pairs < b200_num_sms() / 2 ? pairs : b200_num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(CONV2_THREADS);
+    cfg.dynamicSmemBytes = S::kBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "conv_row2 launch: %s", cudaGetErrorString(e));
+    CHECK_LAUNCH("conv_row2_tcgen05");
+    return B200_OK;
+}
+// B200_CONV_V2=0 keeps every pair conv on the first-generation kernel (A/B measurements).  -> 1: no instance for this layer
+static int launch_conv_row2(int BN, bool k32, bool norm, int khw, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    static const int on = env_flag("B200_CONV_V2", 1);
+    if (!on) return 1;
+#define B200_CONV2(BN_, ROWS_, BKC_, KHW_, G_)                                                                   \
+    if (BN == BN_ && k32 == (BKC_ == 32) && khw == KHW_)                                                         \
+        return norm ? launch_conv_row2_inst<BN_, ROWS_, BKC_, true, KHW_, G_>(ta, tb, p, st)                      \
+                    : launch_conv_row2_inst<BN_, ROWS_, BKC_, false, KHW_, G_>(ta, tb, p, st);
+    B200_CONV2(96, 2, 32, 3, 9)        // Wan decoder, full-resolution stage (Cin = 96 as 3 x 32 channels): one weight stage per (dt, chunk)
+    B200_CONV2(96, 2, 64, 2, 4)        // folded 2x up-sampling 192 -> 96 (four 2x2 parity convs)
+    B200_CONV2(192, 1, 64, 3, 3)       // 192-channel stage: one kh row of taps per weight stage
+    B200_CONV2(192, 1, 64, 2, 4)       // folded 2x up-sampling 384 -> 192
+#undef B200_CONV2
+    if (!norm && !k32 && khw == 3) {   // Hunyuan VAE decoders (GroupNorm: no fused norm)
+        if (BN == 128) return launch_conv_row2_inst<128, 2, 64, false, 3, 3>(ta, tb, p, st);
+        if (BN == 256) return launch_conv_row2_inst<256, 1, 64, false, 3, 3>(ta, tb, p, st);
+    }
+    return 1;
+}
 static int conv_row_rows(int BN) { return BN <= 128 ? 2 : 1; }
 // instances with the fused next-layer norm epilogue: the single-N-tile layers of the Wan decoder's 96- and 192-channel stages
 static bool conv_norm_instance(int BN, int Cout) { return Cout == BN && (BN == 96 || BN == 192); }
@@ -889,11 +936,19 @@ static int conv_cl_impl(const void* x, const void* w, const float* bias, const v
         if (!out) p.out = p.norm_out;
         static const int base_off_n = env_flag("B200_CONV_ROW_BASEOFF", 0);
         p.conv_base_offset = base_off_n;
+        if (pair && kh == kw) {
+            const int r2 = launch_conv_row2(BN, k96, true, kh, ta, tb, p, (cudaStream_t)stream);
+            if (r2 != 1) return r2;
+        }
         return launch_conv_row_norm(BN, k96, pair, ta, tb, p, (cudaStream_t)stream);
     }
     if (row) {
         static const int base_off = env_flag("B200_CONV_ROW_BASEOFF", 0);
         p.conv_base_offset = base_off;
+        if (pair && kh == kw && !p.csplit && !p.planar) {
+            const int r2 = launch_conv_row2(BN, k96, false, kh, ta, tb, p, (cudaStream_t)stream);
+            if (r2 != 1) return r2;
+        }
         if (pair) return launch_conv_row_pair(BN, k96, ta, tb, p, (cudaStream_t)stream);
         return launch_conv_row(BN, k96, ta, tb, p, (cudaStream_t)stream);
     }
