@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 NAMES = {"p0": "single-CTA (r01 kernel)", "p1": "pair, packed-fp32 softmax", "p2": "pair, scalar softmax", "p4": "pair, packed + 1/4 exp2 on FMA pipe",
          "v1": "single-CTA r01 kernel (scalar softmax, all exp2 on MUFU)", "v100": "single-CTA, packed softmax", "v104": "single-CTA, packed + 1/4 of the exp2 pairs on the FMA pipe",
          "v103": "single-CTA, packed + 1/3 on the FMA pipe", "v102": "single-CTA, packed + 1/2 on the FMA pipe",
+         "v500": "one Q tile per CTA, double-buffered scores, K/V multicast over a 2-CTA cluster, 8 softmax warps (16x256b)",
+         "v503": "same + 1/3 of the exp2 pairs on the FMA pipe", "v504": "same + 1/4", "v502": "same + 1/2",
          "v901": "ABLATION of v103: exponentials replaced by a move", "v902": "ABLATION: half of each S row read from TMEM",
          "v903": "ABLATION: no softmax (MMA / smem / barrier ceiling)", "v904": "ABLATION: S read from TMEM, nothing computed or stored",
          "v905": "ABLATION: full arithmetic, P never stored"}

@@ -15,7 +15,7 @@
 
 using namespace b200;
 
-template <int MODE>       // 0: ld x32, 1: ld x16, 2: st x32, 3: ld x32 with the wait after every instruction
+template <int MODE>       // 0: ld x32, 1: ld x16, 2: st x32, 3: ld x32 with the wait after every instruction, 4: ld 16x256b.x8, 5: st 16x128b.x8, 6: st 32x32b.x16
 __global__ void __launch_bounds__(256, 1) tmem_bw_kernel(int iters, int nwarps, long long* clocks, uint32_t* sink) {
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
@@ -50,13 +50,25 @@ __global__ void __launch_bounds__(256, 1) tmem_bw_kernel(int iters, int nwarps, 
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_st_32x32b_x32(base + c * 32, v + c * 32);
                 tmem_st_wait();
-            } else {
+            } else if constexpr (MODE == 3) {
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) { tmem_ld_32x32b_x32(base + c * 32, v + c * 32); tmem_ld_wait(); }
+            } else if constexpr (MODE == 4) {       // the same 32 lanes x 128 columns as four 16-lane x 64-column fragment loads
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_16x256b_x8(base + ((uint32_t)((c >> 1) * 16) << 16) + (c & 1) * 64, v + c * 32);
+                tmem_ld_wait();
+            } else if constexpr (MODE == 5) {       // 32 lanes x 128 columns as eight 16-lane x 32-column stores
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) tmem_st_16x128b_x8(base + ((uint32_t)((c >> 2) * 16) << 16) + (c & 3) * 32, v + c * 16);
+                tmem_st_wait();
+            } else {
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) tmem_st_32x32b_x16(base + c * 16, v + c * 16);
+                tmem_st_wait();
             }
             #pragma unroll
             for (int i = 0; i < 128; i += 32) acc ^= v[i];
-            if constexpr (MODE == 2) v[it & 127] += acc;
+            if constexpr (MODE == 2 || MODE >= 5) v[0] += acc;        // constant index: the array stays in registers
         }
     }
     long long t1 = clock64();
@@ -88,12 +100,15 @@ int main() {
     cudaMalloc(&d_clk, 148 * 8 * sizeof(long long));
     cudaMalloc(&d_sink, 4);
     const int iters = 4096;
-    for (int grid : {1, 148}) {
+    for (int grid : {148}) {
         for (int nw : {1, 4, 8}) {
             run<0>("tcgen05.ld.32x32b.x32 (4 per wait)", grid, nw, iters, d_clk, d_sink);
             run<1>("tcgen05.ld.32x32b.x16 (8 per wait)", grid, nw, iters, d_clk, d_sink);
             run<3>("tcgen05.ld.32x32b.x32 (wait each)", grid, nw, iters, d_clk, d_sink);
             run<2>("tcgen05.st.32x32b.x32 (4 per wait)", grid, nw, iters, d_clk, d_sink);
+            run<6>("tcgen05.st.32x32b.x16 (8 per wait)", grid, nw, iters, d_clk, d_sink);
+            run<4>("tcgen05.ld.16x256b.x8 (4 per wait)", grid, nw, iters, d_clk, d_sink);
+            run<5>("tcgen05.st.16x128b.x8 (8 per wait)", grid, nw, iters, d_clk, d_sink);
         }
     }
     return 0;

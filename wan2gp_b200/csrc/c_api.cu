@@ -16,6 +16,7 @@
 #include "../../include/wan2gp_b200.h"
 #include "attn2_sm100.cuh"
 #include "attn3_sm100.cuh"
+#include "attn5_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
@@ -379,8 +380,30 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention cluster launch: %s", cudaGetErrorString(e));
         return B200_OK;
     };
+    auto launch5 = [&](auto kern) -> int {        // attn5_sm100.cuh: one Q tile per CTA, double-buffered scores, clusters of two sharing K/V
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT5_SMEM_BYTES);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+        const unsigned q_tiles = (unsigned)((Lq + ATT_BM - 1) / ATT_BM);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((q_tiles + 1) & ~1u, grid.y, grid.z);     // an odd tile count gets one all-out-of-range Q tile
+        cfg.blockDim = dim3(ATT5_THREADS);
+        cfg.dynamicSmemBytes = ATT5_SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention cluster launch: %s", cudaGetErrorString(e));
+        return B200_OK;
+    };
     int rc;
     switch (variant) {
+        // one Q tile per CTA with double-buffered scores (S_{j+1} runs under the softmax of tile j); 50x: every x-th exp2 pair on the FMA pipe
+        case 500: rc = launch5(attn_s2_fwd_d128_kernel<0>); break;
+        case 503: rc = launch5(attn_s2_fwd_d128_kernel<3>); break;
+        case 504: rc = launch5(attn_s2_fwd_d128_kernel<4>); break;
+        case 502: rc = launch5(attn_s2_fwd_d128_kernel<2>); break;
         // K/V tiles multicast to a cluster of two CTAs (each loads half): 300 = packed softmax, 303 = + every 3rd exp2 pair on the FMA pipe
         case 300: rc = launch_mc(attn_fwd_d128_kernel<0, true, true, true>); break;
         case 303: rc = launch_mc(attn_fwd_d128_kernel<3, true, true, true>); break;
