@@ -17,6 +17,7 @@
 #include "attn2_sm100.cuh"
 #include "attn3_sm100.cuh"
 #include "attn5_sm100.cuh"
+#include "attn6_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
@@ -380,14 +381,15 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention cluster launch: %s", cudaGetErrorString(e));
         return B200_OK;
     };
-    auto launch5 = [&](auto kern) -> int {        // attn5_sm100.cuh: one Q tile per CTA, double-buffered scores, clusters of two sharing K/V
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT5_SMEM_BYTES);
+    int att5_smem = ATT5_SMEM_BYTES;
+    auto launch5 = [&](auto kern) -> int {        // attn5 / attn6_sm100.cuh: one Q tile per CTA, clusters of two sharing K/V
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, att5_smem);
         if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
         const unsigned q_tiles = (unsigned)((Lq + ATT_BM - 1) / ATT_BM);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((q_tiles + 1) & ~1u, grid.y, grid.z);     // an odd tile count gets one all-out-of-range Q tile
         cfg.blockDim = dim3(ATT5_THREADS);
-        cfg.dynamicSmemBytes = ATT5_SMEM_BYTES;
+        cfg.dynamicSmemBytes = att5_smem;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -400,6 +402,10 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
     int rc;
     switch (variant) {
         // one Q tile per CTA with double-buffered scores (S_{j+1} runs under the softmax of tile j); 50x: every x-th exp2 pair on the FMA pipe
+        // three score buffers, two softmax warpgroups alternating over the K/V tiles, fixed reference maximum (attn6_sm100.cuh)
+        case 600: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<0>); break;
+        case 603: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3>); break;
+        case 604: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4>); break;
         case 500: rc = launch5(attn_s2_fwd_d128_kernel<0>); break;
         case 503: rc = launch5(attn_s2_fwd_d128_kernel<3>); break;
         case 504: rc = launch5(attn_s2_fwd_d128_kernel<4>); break;
