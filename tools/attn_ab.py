@@ -16,6 +16,7 @@ NAMES = {"p0": "single-CTA (r01 kernel)", "p1": "pair, packed-fp32 softmax", "p2
          "v503": "same + 1/3 of the exp2 pairs on the FMA pipe", "v504": "same + 1/4", "v502": "same + 1/2",
          "v600": "one Q tile per CTA, three score buffers, two softmax warpgroups alternating over the K/V tiles, fixed reference maximum",
          "v603": "same + 1/3 of the exp2 pairs on the FMA pipe", "v604": "same + 1/4",
+         "v613": "three score buffers, no per-tile max pass, 1/3 poly, both P halves published after one wait", "v614": "same, 1/4 poly", "v612": "same, 1/2 poly",
          "v901": "ABLATION of v103: exponentials replaced by a move", "v902": "ABLATION: half of each S row read from TMEM",
          "v903": "ABLATION: no softmax (MMA / smem / barrier ceiling)", "v904": "ABLATION: S read from TMEM, nothing computed or stored",
          "v905": "ABLATION: full arithmetic, P never stored"}
@@ -33,11 +34,13 @@ def leg():
     # boost > 1: keys beyond the first 200 are scaled up so that later scores outrun the first tile's row maximum by far more than 2^60
     # (the repeat pass of attn6_sm100.cuh; the lazy rescale of the other kernels)
     for Lq, Lk, H, boost in ([] if ablation else [(1024, 1024, 2, 1), (2000, 1333, 3, 1), (1100, 512, 2, 1), (9000, 9000, 2, 1), (100, 100, 1, 1),
-                                                   (300, 256, 1, 1), (129, 384, 2, 1), (700, 1500, 2, 60)]):
+                                                   (300, 256, 1, 1), (129, 384, 2, 1), (700, 1500, 2, 60), (700, 1500, 2, -132), (640, 900, 1, -133)]):
         D = H * 128
         q, k, v = (torch.randn(n, D, device="cuda", generator=g).to(bf16) for n in (Lq, Lk, Lk))
-        if boost != 1:
+        if boost > 1:
             k[200:] *= boost
+        elif boost < 0:                  # ONE key (at a position whose exponential runs on the FMA pipe, resp. on MUFU) far above everything
+            k[-boost] *= 80
         o = ops.attention(q, k, v, H)
         torch.cuda.synchronize()
         qh, kh, vh = (t.double().reshape(-1, H, 128).permute(1, 0, 2) for t in (q, k, v))

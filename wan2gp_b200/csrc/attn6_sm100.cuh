@@ -18,9 +18,11 @@
 //
 //  TMEM: 3 x 128 score columns + 128 O columns = 512.  ONE O accumulator for both warpgroups means one reference maximum per row for the
 //  whole pass: m_ref = the row maximum of K/V tile 0, never changed -- P = exp2(s - m_ref) may exceed 1 (bf16 / fp32 hold 2^127; relative
-//  precision does not depend on the magnitude) and there is no O rescale at all.  A row whose later scores exceed m_ref by more than 2^60
-//  (never seen in practice) sets a flag; if any row of the cluster did, BOTH CTAs repeat the whole pass with m_ref = the true row maxima
-//  recorded in the first pass, so the result is exact for any input.
+//  precision does not depend on the magnitude), there is no O rescale at all and, after tile 0, NO ROW-MAXIMUM PASS (104 of the 618
+//  instructions per warp and tile: the softmax instruction stream, not the chain latency, is what bounds this structure -- 1305 clocks
+//  per tile measured with the max pass).  A row whose partial sum exceeds 2^64 or is not finite, or whose FMA-pipe exponentials saw an
+//  argument above 100, sets a flag (never seen in practice); if any row of the cluster did, BOTH CTAs run two more passes over K/V:
+//  one that only records the true row maxima, one with those as the reference (every P <= 1) -- the result is exact for any input.
 //
 //   warp 0      TMA producer K : K_j tiles through a 3-deep ring, each CTA loads one 64-column slab and multicasts it to both
 //   warp 3      TMA producer V : V_j tiles through a 2-deep ring, same multicast
@@ -39,7 +41,6 @@ constexpr int ATT6_THREADS = 384;
 constexpr int ATT6_K_STAGES = 3, ATT6_V_STAGES = 2;
 constexpr int ATT6_SMEM_BYTES = ATT_TILE_BYTES * (1 + ATT6_K_STAGES + ATT6_V_STAGES) + 1024 + 256 + 5 * 128 * 4;
 static_assert(ATT6_SMEM_BYTES <= 227 * 1024, "shared memory");
-constexpr float ATT6_GUARD = 60.0f;          // log2 units a later row maximum may exceed the reference before the pass is repeated
 
 __device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t cluster_addr) {
     uint32_t v;
@@ -47,7 +48,30 @@ __device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t cluster_addr)
     return v;
 }
 
-template <int POLY>
+// ex2_poly3_x2 (sm100.cuh) that also tracks the largest rounded argument it saw: t = x + 1.5 * 2^23 holds round(x) in its low mantissa
+// bits, so max(t) - 1.5 * 2^23 is the largest exponent added to a polynomial value -- beyond 127 the result is garbage, not +inf.
+__device__ __forceinline__ void ex2_poly3_x2_guard(uint64_t x2, float& e0, float& e1, float& tmax) {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x2 = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+    const uint64_t t2 = add_f32x2(x2, magic);
+    const uint64_t r2 = add_f32x2(t2, nmagic);
+    const uint64_t f2 = fma_f32x2(r2, pack_f32x2(-1.0f, -1.0f), x2);
+    uint64_t p2 = fma_f32x2(pack_f32x2(0.05517105758190155f, 0.05517105758190155f), f2, pack_f32x2(0.2426096349954605f, 0.2426096349954605f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999281764030457f, 0.9999281764030457f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    tmax = fmax3(tmax, t0, t1);
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+// SPLITW: wait for the TMEM store of each 64-key half of P and publish it at once (P V_j can start on the first half) -- or store both
+// halves, wait once and publish both (one blocking wait per tile: the structure is bound by the softmax instruction stream, not by latency)
+template <int POLY, bool SPLITW>
 __global__ void __launch_bounds__(ATT6_THREADS, 1)
 attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -98,19 +122,21 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t peer_flag = mapa_cluster(smem_u32(bad_flag), cta_rank ^ 1u);
 
-    // end of a pass: every thread of both CTAs decides the same thing -- repeat (once) if any row of the cluster outran its reference
-    auto pass_again = [&](int pass) -> bool {
+    // end of a pass: every thread of both CTAs sees the same flags -> did any row of the cluster outrun its reference?
+    auto pass_sync = [&]() -> bool {
         tc_fence_before();
         cluster_sync_all();
         tc_fence_after();
-        return pass == 0 && ((*reinterpret_cast<volatile uint32_t*>(bad_flag) | ld_shared_cluster_u32(peer_flag)) != 0u);
+        return (*reinterpret_cast<volatile uint32_t*>(bad_flag) | ld_shared_cluster_u32(peer_flag)) != 0u;
     };
+    // mode 0: fast pass (reference = row maximum of tile 0).  Only if a row was flagged: mode 1 = record the true row maxima (P is not
+    // computed, the MMAs run on whatever the score buffers hold), mode 2 = the pass again with the true maxima as the reference.
 
     // g = g0 + j numbers the tiles across passes: rings and barrier phases just continue.  The service warps and the softmax warps run the
     // same pass loop in two copies so that the softmax code is dominated by its own setmaxnreg (216 registers: a whole S row per thread).
     if (warp < 4) {
     setmaxnreg_dec<72>();
-    int pass = 0, g0 = 0;
+    int mode = 0, pass = 0, g0 = 0;
     for (;;) {
         if (warp == 0) {
             // ============================ TMA producer: Q (once), K ============================
@@ -187,9 +213,10 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
             __syncwarp();
         }
-        if (!pass_again(pass)) break;
+        const bool flagged = pass_sync();
+        if (mode == 0) { if (!flagged) break; mode = 1; } else if (mode == 1) { mode = 2; } else break;
         g0 += n_kv;
-        pass = 1;
+        ++pass;
         cluster_sync_all();                  // matches the softmax warps' second barrier (exchange arrays read before they are rewritten)
     }
     } else {
@@ -199,14 +226,13 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float m_ref = 0.f, l = 0.f;
-    int pass = 0, g0 = 0;
+    int mode = 0, pass = 0, g0 = 0;
     for (;;) {
         {
             // ============================ softmax (warpgroup gi takes tiles j % 2 == gi) ============================
-            float run_max = -INFINITY;
-            bool bad = false;
+            float run_max = -INFINITY, tmax = 0.f;
             l = 0.f;
-            if (pass == 0 && gi == 1) {                   // group B: wait for the reference maxima of tile 0 (group A)
+            if (mode == 0 && gi == 1) {                   // group B: wait for the reference maxima of tile 0 (group A)
                 named_bar_sync(2, 256);
                 m_ref = x_mref[row];
             }
@@ -225,22 +251,28 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     for (int i = 0; i < 128; ++i)
                         if (i >= valid) v[i] = 0xff800000u;   // -inf: keys beyond Lk
                 }
-                // row maximum of this tile: the reference of the pass (tile 0 of pass 0), else only the guard and the record for a repeat
-                float mx4[4];
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) mx4[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-                #pragma unroll
-                for (int i = 12; i < 124; i += 2) mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                mx4[0] = fmax3(mx4[0], __uint_as_float(v[124]), __uint_as_float(v[125]));
-                mx4[1] = fmax3(mx4[1], __uint_as_float(v[126]), __uint_as_float(v[127]));
-                const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]) * p.scale_log2;      // scale > 0: max commutes with the scaling
-                if (pass == 0 && j == 0) {                // group A, first tile: fix the reference maxima of this pass
-                    m_ref = mx;
-                    x_mref[row] = mx;
-                    named_bar_sync(2, 256);
+                if (mode == 1 || (mode == 0 && j == 0)) {
+                    // row maximum of this tile: the reference of the fast pass (its tile 0), or the record of the scan pass
+                    float mx4[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) mx4[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+                    #pragma unroll
+                    for (int i = 12; i < 124; i += 2) mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                    mx4[0] = fmax3(mx4[0], __uint_as_float(v[124]), __uint_as_float(v[125]));
+                    mx4[1] = fmax3(mx4[1], __uint_as_float(v[126]), __uint_as_float(v[127]));
+                    const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]) * p.scale_log2;  // scale > 0: max commutes with the scaling
+                    if (mode == 0) {                      // group A, first tile: fix the reference maxima of this pass
+                        m_ref = mx;
+                        x_mref[row] = mx;
+                        named_bar_sync(2, 256);
+                    } else {                              // scan pass: hand the score buffer back untouched
+                        run_max = fmaxf(run_max, mx);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(&p_full[buf * 2]); mbar_arrive(&p_full[buf * 2 + 1]); }
+                        continue;
+                    }
                 }
-                run_max = fmaxf(run_max, mx);
-                bad = bad || (mx > m_ref + ATT6_GUARD);
                 // ---- P = exp2(s * scale - m_ref) -> bf16, two keys per 32-bit column, written over S columns [0,64) of the same buffer
                 const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_ref, -m_ref);
                 uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};          // four independent packed accumulators (+0.0f bit pattern)
@@ -251,7 +283,7 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[h * 64 + 2 * c]), __uint_as_float(v[h * 64 + 2 * c + 1])), sc2, nm2);
                         float e0, e1;
                         if (POLY > 0 && c % (POLY > 0 ? POLY : 1) == POLY - 1) {
-                            ex2_poly3_x2(x2, e0, e1);
+                            ex2_poly3_x2_guard(x2, e0, e1, tmax);
                         } else {
                             float x0, x1;
                             unpack_f32x2(x2, x0, x1);
@@ -262,10 +294,15 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         v[h * 64 + c] = pack_bf16x2(e0, e1);
                     }
                     tmem_st_32x32b_x32(tS + h * 32, v + h * 64);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[buf * 2 + h]);
+                    if (SPLITW || h == 1) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (SPLITW) mbar_arrive(&p_full[buf * 2 + h]);
+                            else { mbar_arrive(&p_full[buf * 2]); mbar_arrive(&p_full[buf * 2 + 1]); }
+                        }
+                    }
                 }
                 float a0, a1;
                 unpack_f32x2(add_f32x2(add_f32x2(acc2[0], acc2[1]), add_f32x2(acc2[2], acc2[3])), a0, a1);
@@ -273,14 +310,23 @@ attn_s3_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
             x_rmax[gi * 128 + row] = run_max;
             x_lsum[gi * 128 + row] = l;
-            if (bad) *reinterpret_cast<volatile uint32_t*>(bad_flag) = 1u;
+            // fast pass only: 2^64 bounds every P of the row, so O cannot overflow either; the comparison is false for NaN as well
+            if (mode == 0 && (!(l <= 1.8e19f) || tmax > 12582912.0f + 100.0f)) *reinterpret_cast<volatile uint32_t*>(bad_flag) = 1u;
         }
-        if (!pass_again(pass)) break;
-        // repeat with the true row maxima as the reference: no score can exceed it.  The exchange arrays are rewritten at the end of the
-        // next pass; one more cluster barrier (all threads have read them) keeps that simple -- this path is never taken with real data
-        m_ref = fmaxf(x_rmax[row], x_rmax[128 + row]);
+        const bool flagged = pass_sync();
+        if (mode == 0) {
+            if (!flagged) break;
+            mode = 1;
+        } else if (mode == 1) {
+            m_ref = fmaxf(x_rmax[row], x_rmax[128 + row]);    // the true row maxima: no score can exceed the reference now
+            mode = 2;
+        } else {
+            break;
+        }
+        // the exchange arrays are rewritten at the end of the next pass; one more cluster barrier (all threads have read them) keeps that
+        // simple -- this path is never taken with real data
         g0 += n_kv;
-        pass = 1;
+        ++pass;
         cluster_sync_all();
     }
     {

@@ -403,9 +403,13 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
     switch (variant) {
         // one Q tile per CTA with double-buffered scores (S_{j+1} runs under the softmax of tile j); 50x: every x-th exp2 pair on the FMA pipe
         // three score buffers, two softmax warpgroups alternating over the K/V tiles, fixed reference maximum (attn6_sm100.cuh)
-        case 600: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<0>); break;
-        case 603: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3>); break;
-        case 604: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4>); break;
+        // 60x: P published per 64-key half; 61x: both halves after one wait
+        case 600: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<0, true>); break;
+        case 603: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3, true>); break;
+        case 604: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, true>); break;
+        case 613: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3, false>); break;
+        case 614: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, false>); break;
+        case 612: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<2, false>); break;
         case 500: rc = launch5(attn_s2_fwd_d128_kernel<0>); break;
         case 503: rc = launch5(attn_s2_fwd_d128_kernel<3>); break;
         case 504: rc = launch5(attn_s2_fwd_d128_kernel<4>); break;
