@@ -136,7 +136,7 @@ def measure_hunyuan(workload, steps, warmup, rank, world, local_rank, dev, dist,
            "gpu_launches": launches, "finite": bool(torch.isfinite(latents).all()),
            "model_tflops": fl / (ms / args.steps * 1e-3) / 1e12,
            "model_tensor_frac": fl / (ms / args.steps * 1e-3) / 1e12 / pk["tensor_sustained"],
-           "roofline": {"kernel": "attn_fwd_d128_kernel (joint img+txt attention)", "bound": "tensor", "achieved": att_tf,
+           "roofline": {"kernel": attention_kernel_name() + " (joint img+txt attention)", "bound": "tensor", "achieved": att_tf,
                         "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": None if att_tf is None else att_tf / pk["tensor_sustained"],
                         "peak_source": pk["source"] + ", sustained figure", "launches_timed": len(att), "avg_launch_ms": att_ms,
                         "share_of_step": (sum(a for a, _ in att) / ms) if att else None, "traffic": None},
@@ -364,6 +364,12 @@ def wan_vae_work(Tl, h, w):
     return acc["ref"], acc["ex"], acc["by"], T
 
 
+def attention_kernel_name():
+    """The self-attention kernel behind ops.attention: csrc/c_api.cu picks it from B200_ATT_VARIANT (default 614 = attn6_sm100.cuh)."""
+    v = int(os.environ.get("B200_ATT_VARIANT", "614"))
+    return "attn_s3_fwd_d128_kernel" if 600 <= v < 700 else "attn_s2_fwd_d128_kernel" if 500 <= v < 600 else "attn_fwd_d128_kernel"
+
+
 def dram_traffic(kernel, shape_key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at `shape_key`, from the ncu --set full capture summarised
     in profiles/ncu_dram_traffic.json (written from the .ncu-rep by tools/ncu_summary.py; a profiler number, never measured inside a
@@ -521,7 +527,8 @@ def measure_wan(workload, steps, warmup, rank, world, local_rank, dev, dist, cfg
     flops_step = 2.0 * wan_flops_forward(cfg, L, cfg["text_len"]) * (n_samples / world)      # per GPU
     att_avg = sum(att_ms) / max(1, len(att_ms))
     att_tf = att_work / (att_avg * 1e-3) / 1e12 if att_ms else None
-    traffic, traffic_src = dram_traffic("attn_fwd_d128_kernel", f"L{L}_H{cfg['num_heads']}")
+    att_kernel = attention_kernel_name()
+    traffic, traffic_src = dram_traffic(att_kernel, f"L{L}_H{cfg['num_heads']}")
     gemm_tf = (sum(w for _, w in gm) / (sum(t for t, _ in gm) * 1e-3) / 1e12) if gm else None
     result = {
         "metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": steps,
@@ -535,7 +542,7 @@ def measure_wan(workload, steps, warmup, rank, world, local_rank, dev, dist, cfg
         "finite": ok,
         "model_tflops": flops_step / (ms / steps * 1e-3) / 1e12,
         "model_tensor_frac": flops_step / (ms / steps * 1e-3) / 1e12 / pk["tensor_sustained"],
-        "roofline": {"kernel": "attn_fwd_d128_kernel (self-attention, 72% of step FLOPs)", "bound": "tensor", "achieved": att_tf,
+        "roofline": {"kernel": att_kernel + " (self-attention, 72% of step FLOPs)", "bound": "tensor", "achieved": att_tf,
                      "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": None if att_tf is None else att_tf / pk["tensor_sustained"],
                      "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                      "launches_timed": len(att_ms), "avg_launch_ms": att_avg,

@@ -134,6 +134,25 @@ def test_attention_strided_and_peaky(ops):
     assert rel_l2(out, ref.permute(1, 0, 2).reshape(L, D)) < TOL_BF16
 
 
+@pytest.mark.parametrize("Lq,Lk,H,boost", [(700, 1500, 2, 60), (700, 1500, 2, -132), (640, 900, 1, -133), (130, 257, 1, 60)])
+def test_attention_scores_outrun_first_tile(ops, Lq, Lk, H, boost):
+    """The default kernel (csrc/attn6_sm100.cuh) fixes each row's reference maximum on K/V tile 0 and never rescales; rows whose later
+    scores exceed it by far more than fp32 can hold must take the exact three-pass path.  boost > 1: every key beyond the first 200 is
+    scaled up (row sums overflow); boost < 0: ONE key, at a position whose exponential runs on the FMA pipe (132) or on MUFU (133), is 80x
+    larger than the rest (a polynomial exp2 argument beyond 127 is garbage, not +inf -- the guard must catch it)."""
+    D = H * 128
+    q, k, v = (_randn(L, D, seed=s, dtype=bf16) for L, s in ((Lq, 1), (Lk, 2), (Lk, 3)))
+    if boost > 1:
+        k[200:] *= boost
+    else:
+        k[-boost] *= 80
+    out = ops.attention(q, k, v, H)
+    qh, kh, vh = (t.double().reshape(-1, H, 128).permute(1, 0, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128), -1) @ vh
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref.permute(1, 0, 2).reshape(Lq, D)) < TOL_BF16
+
+
 def test_patch_embed_unpatchify_gemv(ops):
     from oracle import wan_oracle
     C0, C1, T, H, W, D = 16, 20, 3, 8, 12, 256

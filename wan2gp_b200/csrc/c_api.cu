@@ -351,7 +351,9 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
     static int variant = -1;
     if (variant < 0) {
         const char* ev = getenv("B200_ATT_VARIANT");
-        variant = ev ? atoi(ev) : 103;      // default: packed-fp32 softmax, every 3rd pair of exponentials on the FMA pipe (profiles/attn_variants_r02_*.json)
+        // default 614 = attn6_sm100.cuh: one Q tile per CTA, three score buffers, alternating softmax warpgroups, 1/4 of the exp2 pairs on the
+        // FMA pipe, one P-store wait per tile (profiles/attn_variants_r02_call11.json: 80.2 ms against 88.5 ms for 103, the two-Q-tile kernel)
+        variant = ev ? atoi(ev) : 614;
     }
     auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
@@ -408,7 +410,6 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         case 603: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3, true>); break;
         case 604: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, true>); break;
         case 613: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3, false>); break;
-        case 614: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, false>); break;
         case 612: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<2, false>); break;
         case 500: rc = launch5(attn_s2_fwd_d128_kernel<0>); break;
         case 503: rc = launch5(attn_s2_fwd_d128_kernel<3>); break;
@@ -438,7 +439,8 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         case 903: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 3>); break;
         case 904: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 4>); break;
         case 905: rc = launch(attn_fwd_d128_kernel<3, true, true, false, 5>); break;
-        default: rc = launch(attn_fwd_d128_kernel<3, true, true>); break;
+        case 614:
+        default: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, false>); break;
     }
     if (rc) return rc;
     CHECK_LAUNCH("attn_fwd_d128");
