@@ -27,10 +27,6 @@ namespace b200 {
 
 constexpr int CONV2_THREADS = 384;
 
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-
 template <int BN, int ROWS, int BKC, int KHW, int GROUP>
 struct ConvRow2Smem {
     static_assert(ROWS * BN <= 256, "ROWS accumulators of BN columns per TMEM buffer");

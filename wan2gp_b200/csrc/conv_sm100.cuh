@@ -364,7 +364,7 @@ conv_row_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             tc_fence_before();
             if constexpr (PAIR) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
             } else {
                 mbar_arrive(&tempty_bar[acc]);
             }

@@ -278,7 +278,7 @@ gemm_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // this CTA's accumulator rows have been read: one arrival per epilogue warp on the LEADER's barrier
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

@@ -114,6 +114,12 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint3
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed form for "this warp has drained its TMEM accumulator rows": the arrival only has to follow the thread's own tcgen05.ld
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order those); nothing in global / shared memory is published through it.  The
+// .release.cluster form above costs MEMBAR.ALL.GPU + ERRBAR per arrival (12 % of the epilogue warps' samples in profiles/ncu_r02_conv_v1.txt).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair into ITS OWN shared memory; the transaction bytes are credited to the mbarrier at
 // `bar_cluster_addr`, which may live in the peer CTA (the leader's "stage full" barrier).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
