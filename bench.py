@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (config, latent (T,H,W), two experts?, description)
     "wan22_t2v_14b_720p81": ("t2v_2_2", (21, 90, 160), True, "Wan2.2 t2v 14B, latent [1,16,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 12"),
+    # the same model at 480p (832 x 480 x 81f): L = 32 760
+    "wan22_t2v_14b_480p81": ("t2v_2_2", (21, 60, 104), True, "Wan2.2 t2v 14B, latent [1,16,21,60,104] (480p x 81f), CFG pair, 50-step Euler schedule shift 12"),
     # BASELINE configs[2]: Wan2.2 i2v 14B (in_dim 36: 16 latent + 4 mask + 16 image-latent channels), CFG pair
     "wan22_i2v_14b_720p81": ("i2v_2_2", (21, 90, 160), True, "Wan2.2 i2v 14B, latent [1,16,21,90,160] + y [20,21,90,160] (720p x 81f), CFG pair, 50-step Euler schedule shift 5"),
     "wan21_t2v_1.3b_p": ("t2v_1.3B", (9, 30, 52), False, "Wan2.1 t2v 1.3B, latent [1,16,9,30,52] (BASELINE config 0), CFG pair"),
