@@ -225,7 +225,10 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
         p.num_k_iters = (K + GEMM_BK - 1) / GEMM_BK;
         p.m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
         p.n_tiles = N / GEMM2_BN;
-        p.n_group = 16;
+        // N tiles walked in groups so that a slab of weights is reused from L2 while A streams (B200_GEMM_NGROUP: A/B measurements)
+        static int pair_ngroup = -1;
+        if (pair_ngroup < 0) { const char* ev = getenv("B200_GEMM_NGROUP"); pair_ngroup = ev && atoi(ev) > 0 ? atoi(ev) : 16; }
+        p.n_group = pair_ngroup;
         p.out = out; p.out_fp32 = out_fp32; p.accumulate = accumulate; p.ldc = ldc;
         p.bias = bias; p.gate = gate; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16); p.act = act;
         static int pair_tma_reduce = -1;
@@ -411,6 +414,9 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
         case 604: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<4, true>); break;
         case 613: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<3, false>); break;
         case 612: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<2, false>); break;
+        case 615: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<5, false>); break;
+        case 616: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<6, false>); break;
+        case 610: att5_smem = ATT6_SMEM_BYTES; rc = launch5(attn_s3_fwd_d128_kernel<0, false>); break;
         case 500: rc = launch5(attn_s2_fwd_d128_kernel<0>); break;
         case 503: rc = launch5(attn_s2_fwd_d128_kernel<3>); break;
         case 504: rc = launch5(attn_s2_fwd_d128_kernel<4>); break;
