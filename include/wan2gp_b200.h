@@ -248,6 +248,20 @@ int b200_space_to_depth_cl(const void* x, void* y, int T, int H, int W, int C, v
  * The reference has no multi-GPU path; this replaces frames_to_u8 + ncclAllGather. */
 int b200_frames_to_u8_allgather(const float* x, const uint64_t* peer_bufs, int n_peers, int rank, long long n, void* stream);
 
+/* ---- umT5 text encoder, the step in front of the denoise path (models/wan/modules/t5.py).  Its linear
+ * layers go through b200_gemm_bf16; these are the rest ---- */
+/* out fp32 [L,dim] = table[ids] (T5Encoder.token_embedding, t5.py:283); table bf16 or fp32 [vocab,dim], ids int64 on the device */
+int b200_embed_rows(const long long* ids, const void* table, int table_is_bf16, float* out, int L, int dim, void* stream);
+/* T5LayerNorm (t5.py:56-70): out = w * x * rsqrt(mean(x^2) + eps); x fp32 [L,dim]; out bf16 (GEMM operand) or fp32 (final norm) */
+int b200_t5_rmsnorm(const float* x, const float* w, void* out, int out_fp32, int L, int dim, float eps, void* stream);
+/* out = bf16(a * b), bf16 operands: T5FeedForward's fc1(x) * gelu(gate(x)) (t5.py:145) */
+int b200_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+/* T5Attention (t5.py:91-128), one sequence of L <= 512 tokens, head dim 64, no score scaling: out[:, h] = softmax(q_h k_h^T +
+ * bias_rel[h][j - i + L - 1], keys >= n_valid masked) v_h.  q/k/v bf16 with row stride ld (elements), head h at columns [64h, 64h+64);
+ * bias_rel fp32 [heads, 2L-1] = T5RelativeEmbedding (t5.py:219-265) evaluated per offset; out bf16 row stride ldo */
+int b200_t5_attention(const void* q, const void* k, const void* v, long long ld, const float* bias_rel, void* out, long long ldo,
+                      int L, int heads, int n_valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

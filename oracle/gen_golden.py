@@ -331,9 +331,27 @@ def run_unipc(name):
     print(f"dpm++: {steps} steps, final absmean {np.abs(traj[-1]).mean():.6f}")
 
 
+def run_t5(name):
+    """Reference T5Encoder (umT5 layout: per-layer relative position embedding) on seeded ids with a padded tail, fp32, eval mode."""
+    from oracle.refshim import load_reference_t5
+    from wan2gp_b200 import synth
+    cfg = synth.T5_CONFIGS[name]
+    R = load_reference_t5()
+    enc = R.T5Encoder(cfg["vocab_size"], cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_layers"], cfg["num_buckets"],
+                      shared_pos=False, dropout=0.1).eval().float()
+    sd = synth.make_t5_state_dict(cfg, seed=0)
+    missing, unexpected = enc.load_state_dict(sd, strict=True), None
+    length, n_valid = 40, 29
+    ids, mask = synth.make_t5_inputs(cfg, length, n_valid, seed=0)
+    with torch.no_grad():
+        out = enc(ids[None], mask[None])[0]
+    print(f"{name}: reference T5Encoder out {tuple(out.shape)} absmean {out.abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), length=length, n_valid=n_valid, seed=0)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)
+        (run_t5 if n.startswith("t5_") else run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)

@@ -372,3 +372,42 @@ def load_reference_unipc():
                                           FlowDPMSolverMultistepScheduler=m2.FlowDPMSolverMultistepScheduler,
                                           get_sampling_sigmas=m2.get_sampling_sigmas, retrieve_timesteps=m2.retrieve_timesteps)
     return _loaded_unipc
+
+
+_loaded_t5 = None
+
+
+def load_reference_t5():
+    """The reference's T5Encoder (models/wan/modules/t5.py), loaded from its file without importing the `models.wan` package (which pulls
+    the whole model zoo).  Stubs: `shared.utils.gguf_mapping` (checkpoint-name remapping only) and the sibling `tokenizers` module (ftfy is
+    not installed; the encoder takes token ids).  No arithmetic is replaced."""
+    global _loaded_t5
+    if _loaded_t5 is not None:
+        return _loaded_t5
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, "models/wan/modules/t5.py")):
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import importlib.util
+
+    for name in ("shared", "shared.utils"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    gm = types.ModuleType("shared.utils.gguf_mapping")
+    gm.has_standard_gguf_tensor_names = lambda sd: False
+    gm.remap_state_dict_triplet = lambda *a, **k: a[:3]
+    sys.modules["shared.utils.gguf_mapping"] = gm
+    pkg = types.ModuleType("_ref_t5pkg")
+    pkg.__path__ = []
+    tok = types.ModuleType("_ref_t5pkg.tokenizers")
+    tok.HuggingfaceTokenizer = type("HuggingfaceTokenizer", (), {})
+    sys.modules.update({"_ref_t5pkg": pkg, "_ref_t5pkg.tokenizers": tok})
+    spec = importlib.util.spec_from_file_location("_ref_t5pkg.t5", os.path.join(REFERENCE_ROOT, "models/wan/modules/t5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_ref_t5pkg.t5"] = mod
+    import torch
+    cur = torch.cuda.current_device           # t5.py:640 evaluates torch.cuda.current_device() as a default argument at import time
+    torch.cuda.current_device = lambda: 0
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        torch.cuda.current_device = cur
+    _loaded_t5 = mod
+    return mod

@@ -7,7 +7,7 @@ shared/utils/plugins.py:266-271, 671-698; wgp.py:2649-2657, 2717-2735) -- the sa
 
 `load_model` returns `(pipeline_obj, pipe_dict)` like wan_handler.py:1117-1158: `pipeline_obj` is `wan2gp_b200.wan.WanAny2V`
 (level 2: `generate(**kwargs)`, `_interrupt`, `.model`, `.model2`, `.vae`), `pipe_dict` maps the mmgp component names to
-`nn.Module`s (`transformer`, `transformer2`, `vae`, `text_encoder`).  The text encoder is WanGP's own umT5 (`T5EncoderModel`), it
+`nn.Module`s (`transformer`, `transformer2`, `vae`, `text_encoder`).  The text encoder is the umT5 of `wan2gp_b200/wan/t5.py` (WanGP's own `T5EncoderModel` for quantised encoder files), it
 sits in front of the hot path; the transformer(s) and the VAE are the sm_100a implementations.  There is no CPU / eager fallback:
 loading on a machine without the CUDA library or an sm_100 device raises."""
 import os
@@ -130,11 +130,18 @@ class family_handler:
         vae = WanVAE(device=device, state_dict=vae_state_dict, cfg=vae_cfg)
         te_module = None
         if text_encoder is None:
-            # WanGP's umT5 encoder (models/wan/modules/t5.py:270 T5EncoderModel), constructed as any2video.py:119-126 does
-            from models.wan.modules.t5 import T5EncoderModel
+            # the umT5 encoder on the B200 kernels (wan2gp_b200/wan/t5.py), constructed the way any2video.py:119-126 constructs WanGP's own
+            # T5EncoderModel -- same checkpoint (Wan or Hugging Face umT5 names), same tokenizer folder.  Quantised encoder files
+            # (text_encoder_quantization) keep WanGP's encoder: they are not bf16 weights.
             tok = os.path.dirname(text_encoder_filename)
-            text_encoder = T5EncoderModel(text_len=cfg["text_len"], dtype=torch.bfloat16, device=torch.device("cpu"),
-                                          checkpoint_path=text_encoder_filename, tokenizer_path=tok)
+            if text_encoder_quantization in (None, "", "bf16"):
+                from wan2gp_b200.wan.t5 import T5EncoderModel
+                text_encoder = T5EncoderModel(text_len=cfg["text_len"], dtype=torch.bfloat16, device=device,
+                                              checkpoint_path=text_encoder_filename, tokenizer_path=tok)
+            else:
+                from models.wan.modules.t5 import T5EncoderModel
+                text_encoder = T5EncoderModel(text_len=cfg["text_len"], dtype=torch.bfloat16, device=torch.device("cpu"),
+                                              checkpoint_path=text_encoder_filename, tokenizer_path=tok)
             te_module = text_encoder.model
         pipe_obj = WanAny2V(models[0], models[1] if two else None, vae, text_encoder, model_def=dict(model_def or {}, i2v_2_2=cfg["in_dim"] > 16),
                             base_model_type=base_model_type, device=device, dtype=dtype, VAE_dtype=VAE_dtype)

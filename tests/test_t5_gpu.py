@@ -1,0 +1,73 @@
+"""umT5 text encoder on the GPU (wan2gp_b200/wan/t5.py through the C ABI) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import t5_oracle
+from wan2gp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _encoder(cfg, sd):
+    from wan2gp_b200.wan.t5 import T5Encoder
+    enc = T5Encoder(cfg["vocab_size"], cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_layers"], cfg["num_buckets"],
+                    shared_pos=False, device="cuda")
+    enc.load_state_dict(sd)
+    return enc
+
+
+def test_t5_small_matches_oracle_and_reference_fixture():
+    g = np.load(os.path.join(GOLDEN, "t5_small.npz"))
+    cfg = synth.T5_CONFIGS["t5_small"]
+    sd = synth.make_t5_state_dict(cfg, 0)
+    L, nv = int(g["length"]), int(g["n_valid"])
+    ids, mask = synth.make_t5_inputs(cfg, L, nv, 0)
+    out = _encoder(cfg, sd)(ids[None], mask[None])[0]
+    emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
+    assert rel_l2(out, emu) < 4e-3                                      # same roundings
+    ref = torch.from_numpy(g["out"])                                     # the unmodified reference in fp32
+    assert rel_l2(out[:nv], ref[:nv]) < 2e-2                             # rows the pipeline keeps (t5.py:690)
+
+
+@pytest.mark.parametrize("L,nv", [(512, 377), (512, 512), (96, 5)])
+def test_t5_xxl_layer_shape(L, nv):
+    """One block at the umT5-XXL widths (4096 / 64 heads / 10240) on the reference's text_len: pair GEMMs at M = 512, 16 query blocks x 64
+    heads of the position-biased attention, padding mask."""
+    cfg = synth.T5_CONFIGS["t5_1layer_xxl"]
+    sd = synth.make_t5_state_dict(cfg, 1)
+    ids, mask = synth.make_t5_inputs(cfg, L, nv, 1)
+    out = _encoder(cfg, sd)(ids[None], mask[None])[0]
+    emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
+    assert torch.isfinite(out).all()
+    assert rel_l2(out[:nv], emu[:nv]) < 4e-3
+
+
+def test_t5_encoder_model_wrapper_is_the_pipeline_callable():
+    """T5EncoderModel(texts, device) -> list of [n_tokens, dim] tensors: what WanAny2V._encode_prompt consumes (any2video.py:588-595)."""
+    from wan2gp_b200.wan.t5 import T5EncoderModel
+    cfg = synth.T5_CONFIGS["t5_small"]
+    sd = synth.make_t5_state_dict(cfg, 0)
+
+    def tok(texts):                                                      # stand-in tokenizer: bytes -> ids, padded to text_len
+        ids = torch.zeros(len(texts), 64, dtype=torch.long)
+        mask = torch.zeros(len(texts), 64, dtype=torch.long)
+        for i, t in enumerate(texts):
+            b = [1 + (c % 900) for c in t.encode()][:64]
+            ids[i, :len(b)] = torch.tensor(b)
+            mask[i, :len(b)] = 1
+        return ids, mask
+    te = T5EncoderModel(text_len=64, device="cuda", state_dict=sd, tokenizer=tok, encoder=_encoder(cfg, sd))
+    outs = te(["a red fox", "two words"], "cuda")
+    assert [tuple(o.shape) for o in outs] == [(9, 256), (9, 256)]
+    ids, mask = tok(["a red fox"])
+    emu = t5_oracle.t5_encode(sd, cfg, ids[0], mask[0], emulate_bf16=True)
+    assert rel_l2(outs[0], emu[:9]) < 4e-3

@@ -19,6 +19,7 @@
 #include "attn5_sm100.cuh"
 #include "attn6_sm100.cuh"
 #include "attn_sm100.cuh"
+#include "t5_ops.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
@@ -576,5 +577,51 @@ extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* u
     }
     cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, pred_out, star_dots, n4);
     CHECK_LAUNCH("cfg_euler_step");
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ umT5 text encoder (t5_ops.cuh)
+extern "C" int b200_embed_rows(const long long* ids, const void* table, int table_is_bf16, float* out, int L, int dim, void* stream) {
+    if (!ids || !table || !out || L <= 0 || dim <= 0 || dim % 2) return b200_set_error(B200_ERR_ARG, "embed_rows: bad argument");
+    if (table_is_bf16) embed_rows_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(ids, table, out, dim);
+    else embed_rows_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(ids, table, out, dim);
+    CHECK_LAUNCH("embed_rows");
+    return B200_OK;
+}
+
+extern "C" int b200_t5_rmsnorm(const float* x, const float* w, void* out, int out_fp32, int L, int dim, float eps, void* stream) {
+    if (!x || !w || !out || L <= 0 || dim <= 0) return b200_set_error(B200_ERR_ARG, "t5_rmsnorm: bad argument");
+    if (out_fp32) t5_rmsnorm_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(x, w, out, dim, eps);
+    else t5_rmsnorm_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(x, w, out, dim, eps);
+    CHECK_LAUNCH("t5_rmsnorm");
+    return B200_OK;
+}
+
+extern "C" int b200_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+    if (!a || !b || !out || n <= 0 || n % 2) return b200_set_error(B200_ERR_ARG, "mul_bf16: bad argument");
+    const long long n2 = n / 2;
+    mul_bf16_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat162*>(a), reinterpret_cast<const __nv_bfloat162*>(b), reinterpret_cast<__nv_bfloat162*>(out), n2);
+    CHECK_LAUNCH("mul_bf16");
+    return B200_OK;
+}
+
+extern "C" int b200_t5_attention(const void* q, const void* k, const void* v, long long ld, const float* bias_rel, void* out, long long ldo,
+                                 int L, int heads, int n_valid, void* stream) {
+    if (!q || !k || !v || !bias_rel || !out || L <= 0 || heads <= 0) return b200_set_error(B200_ERR_ARG, "t5_attention: null/empty argument");
+    if (L > 512) return b200_set_error(B200_ERR_ARG, "t5_attention: at most 512 tokens (the reference's text_len)");
+    if (ld % 8 || ldo % 2 || n_valid < 1 || n_valid > L) return b200_set_error(B200_ERR_ARG, "t5_attention: strides / n_valid");
+    const int Lp = (L + 31) / 32 * 32;
+    const size_t smem = (size_t)Lp * T5_ATT_D * 2 * 2 + (size_t)((2 * L - 1 + 3) & ~3) * 4 + (size_t)8 * Lp * 4;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (b200_first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return b200_set_error(B200_ERR_CUDA, "t5_attention smem attr: %s", cudaGetErrorString(e));
+        b200_mark_used_on_device(attr_done);
+    }
+    dim3 grid((L + T5_ATT_ROWS - 1) / T5_ATT_ROWS, heads);
+    t5_attention_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+        reinterpret_cast<const __nv_bfloat16*>(v), ld, bias_rel, reinterpret_cast<__nv_bfloat16*>(out), ldo, L, Lp, n_valid);
+    CHECK_LAUNCH("t5_attention");
     return B200_OK;
 }

@@ -619,3 +619,58 @@ def make_hyvae10_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, enco
         else:
             out[n] = make_vae_tensor(n, s, seed, device).to(dtype)
     return out
+
+
+# ---------------------------------------------------------------- umT5 text encoder (models/wan/modules/t5.py:459-472 umt5_xxl, encoder only)
+T5_CONFIGS = {
+    "umt5_xxl": dict(vocab_size=256384, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=24, num_buckets=32),
+    # reduced configs for parity tests (head dim stays 64 as in umT5-XXL)
+    "t5_small": dict(vocab_size=1000, dim=256, dim_attn=256, dim_ffn=512, num_heads=4, num_layers=2, num_buckets=32),
+    "t5_1layer_xxl": dict(vocab_size=2048, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=1, num_buckets=32),
+}
+
+
+def t5_param_shapes(cfg):
+    """Names and shapes of T5Encoder(shared_pos=False) (t5.py:268-281, 165-182, 75-90, 133-142)."""
+    d, da, df, h, nb = cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_buckets"]
+    shapes = {"token_embedding.weight": (cfg["vocab_size"], d), "norm.weight": (d,)}
+    for i in range(cfg["num_layers"]):
+        b = f"blocks.{i}."
+        shapes.update({b + "norm1.weight": (d,), b + "attn.q.weight": (da, d), b + "attn.k.weight": (da, d), b + "attn.v.weight": (da, d),
+                       b + "attn.o.weight": (d, da), b + "norm2.weight": (d,), b + "ffn.gate.0.weight": (df, d), b + "ffn.fc1.weight": (df, d),
+                       b + "ffn.fc2.weight": (d, df), b + "pos_embedding.embedding.weight": (nb, h)})
+    return shapes
+
+
+def make_t5_tensor(name, shape, cfg, seed=0, device="cpu"):
+    """The reference's init_weights (t5.py:29-47) tempered so that a bf16-vs-fp32 comparison sees a realistic softmax: with the stock
+    q std (dim * dim_attn)^-0.5 every logit is ~0 and the attention is uniform whatever the kernel does."""
+    d, df = cfg["dim"], cfg["dim_ffn"]
+    if name.endswith(("norm1.weight", "norm2.weight", "norm.weight")):
+        return _normal(shape, 0.1, seed, name, device, mean=1.0)
+    if name == "token_embedding.weight":
+        return _normal(shape, 1.0, seed, name, device)
+    if name.endswith("pos_embedding.embedding.weight"):
+        return _normal(shape, 0.5, seed, name, device)
+    if name.endswith("attn.q.weight"):
+        return _normal(shape, 0.35 * d ** -0.5, seed, name, device)
+    if name.endswith(("attn.k.weight", "attn.v.weight", "ffn.gate.0.weight", "ffn.fc1.weight")):
+        return _normal(shape, d ** -0.5, seed, name, device)
+    if name.endswith("attn.o.weight"):
+        return _normal(shape, cfg["dim_attn"] ** -0.5, seed, name, device)
+    if name.endswith("ffn.fc2.weight"):
+        return _normal(shape, df ** -0.5, seed, name, device)
+    raise KeyError(name)
+
+
+def make_t5_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    return {k: make_t5_tensor(k, s, cfg, seed, device).to(dtype) for k, s in t5_param_shapes(cfg).items()}
+
+
+def make_t5_inputs(cfg, length, n_valid, seed=0):
+    """ids [length] (padding id 0 after n_valid tokens, as the reference tokenizer pads, tokenizers.py), mask [length]."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    ids = torch.randint(1, cfg["vocab_size"], (length,), generator=g)
+    ids[n_valid:] = 0
+    mask = (torch.arange(length) < n_valid).long()
+    return ids, mask
