@@ -33,7 +33,9 @@ def test_t5_small_matches_oracle_and_reference_fixture():
     ids, mask = synth.make_t5_inputs(cfg, L, nv, 0)
     out = _encoder(cfg, sd)(ids[None], mask[None])[0]
     emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
-    assert rel_l2(out, emu) < 4e-3                                      # same roundings
+    # same rounding points, different transcendental approximations (tanh.approx GELU in the GEMM epilogue, __expf): two bf16 pipelines
+    # agree to about the size of one bf16 rounding per layer (the emulation itself is 7.8e-3 away from the fp32 reference)
+    assert rel_l2(out, emu) < 6e-3
     ref = torch.from_numpy(g["out"])                                     # the unmodified reference in fp32
     assert rel_l2(out[:nv], ref[:nv]) < 2e-2                             # rows the pipeline keeps (t5.py:690)
 
@@ -48,7 +50,7 @@ def test_t5_xxl_layer_shape(L, nv):
     out = _encoder(cfg, sd)(ids[None], mask[None])[0]
     emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
     assert torch.isfinite(out).all()
-    assert rel_l2(out[:nv], emu[:nv]) < 4e-3
+    assert rel_l2(out[:nv], emu[:nv]) < 6e-3
 
 
 def test_t5_encoder_model_wrapper_is_the_pipeline_callable():
@@ -70,4 +72,4 @@ def test_t5_encoder_model_wrapper_is_the_pipeline_callable():
     assert [tuple(o.shape) for o in outs] == [(9, 256), (9, 256)]
     ids, mask = tok(["a red fox"])
     emu = t5_oracle.t5_encode(sd, cfg, ids[0], mask[0], emulate_bf16=True)
-    assert rel_l2(outs[0], emu[:9]) < 4e-3
+    assert rel_l2(outs[0], emu[:9]) < 6e-3
