@@ -459,6 +459,9 @@ def measure_wan(workload, steps, warmup, rank, world, local_rank, dev, dist, cfg
         config["parallelism"] = f"{n_samples} samples, each CFG pair split over 2 GPUs (per-step 2-rank all-gather of the prediction)"
     den = WanDenoiser(model, model2, num_steps=50, shift=5.0 if i2v else 12.0, guide_scale=3.5 if i2v else 4.0,
                       guide2_scale=3.5 if i2v else 3.0, switch_threshold=900 if i2v else 875, device=dev, **cfg_kw)
+    if L <= 16384 and not cfg_kw and os.environ.get("B200_STEP_GRAPH", "1") != "0":
+        den.use_step_graph = True          # launch-bound configs: one captured graph per step (pipeline.WanDenoiser._graph_step)
+        config["cuda_graph"] = "whole step (both CFG forwards + combine + Euler update), timestep / guidance / dt read from device memory"
     freqs = get_rotary_pos_embed(thw)
     g = torch.Generator().manual_seed(1000 + sample_id)
     y_dev = None

@@ -98,6 +98,8 @@ int b200_gemv_f32(const float* x, const float* w, const float* b, float* out, in
                   void* stream);
 /* sinusoidal_embedding_1d (model.py:32-42) */
 int b200_sinusoid(float t, float* out, int dim, void* stream);
+/* same, the timestep read from device memory: a captured whole-step CUDA graph is replayed with a new t */
+int b200_sinusoid_dev(const float* t_dev, float* out, int dim, void* stream);
 /* out[c] = mean_r x[r, c], fp32 [rows, cols] (masked text mean, hyvideo/modules/token_refiner.py:221-226) */
 int b200_col_mean_f32(const float* x, float* out, int rows, int cols, void* stream);
 /* out[i] = a[i] + b[i % bmod] */
@@ -108,6 +110,9 @@ int b200_add_vec(const float* a, const float* b, float* out, int n, int bmod, vo
  * alpha = <c,u> / (||u||^2 + 1e-8) computed over the whole sample (any2video.py:1706-1714, steps > cfg_zero_step). */
 int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt, float* pred_out,
                         float* star_dots, long long n, void* stream);
+/* same, {guide, dt} read from device memory (float[2]) so that the launch can live in a whole-step CUDA graph */
+int b200_cfg_euler_step_dev(float* lat, const float* cond, const float* uncond, const float* guide_dt_dev, float* pred_out,
+                            float* star_dots, long long n, void* stream);
 
 /* One FlowUniPCMultistepScheduler.step (shared/utils/fm_solvers_unipc.py:655-740: solver_order 2, bh2, predict_x0,
  * flow_prediction -- WanGP's default sample_solver, any2video.py:518-522) fused with the CFG combine (any2video.py:1701-1722).

@@ -137,3 +137,28 @@ def test_dpmpp_through_fused_kernel():
         hist = [hist[0], hist[2], hist[1]]
         assert rel_l2(xg.cpu(), xc) < 2e-5, i
     assert WanDenoiser(None, num_steps=4, shift=5.0, sample_solver="dpm++").timesteps[:4] == [float(t) for t in DPMppSchedule(4, 5.0).timesteps]
+
+
+@pytest.mark.parametrize("star", [False, True])
+def test_whole_step_graph_equals_eager_steps(star):
+    """both CFG forwards + combine + Euler update of a step as ONE captured CUDA graph, replayed with the
+    timestep / guidance / dt read from device memory -- bit-identical to the launch-by-launch step over a whole schedule with an expert
+    switch (two graphs) and, with star, the CFG-Zero* rescale switching on after the first step (a second capture per expert)."""
+    from wan2gp_b200.pipeline import WanDenoiser
+    from wan2gp_b200.wan import WanModel
+    cfg, thw, sd, x, t, ctx, _ = wan_case("tiny")
+    m1, m2 = WanModel(**cfg), WanModel(**cfg)
+    m1.load_state_dict(sd), m2.load_state_dict(synth.make_wan_state_dict(cfg, seed=5))
+    ctx, ctx_null = ctx.cuda(), torch.zeros_like(ctx).cuda()
+    kw = dict(num_steps=6, shift=5.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=600, cfg_star_switch=star, cfg_zero_step=0)
+    eager, graph = WanDenoiser(m1, m2, **kw), WanDenoiser(m1, m2, **kw)
+    graph.use_step_graph = True
+    lat0 = torch.randn(1, 16, *thw, generator=torch.Generator().manual_seed(3)).cuda()
+    a, b = lat0.clone(), lat0.clone()
+    for i in range(6):
+        assert eager.step(a, i, ctx, ctx_null) is a
+        assert graph.step(b, i, ctx, ctx_null) is b
+        assert torch.equal(a, b), i
+    assert 2 <= len(graph._step_graphs) <= 4                           # one capture per (expert, CFG-Zero* phase) actually visited
+    graph._interrupt = True                                            # the poll lives at the step boundary
+    assert graph.step(b, 0, ctx, ctx_null) is None

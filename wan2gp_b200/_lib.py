@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200_unpatchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "b200_gemv_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "b200_sinusoid": [c_float, c_void_p, c_int, c_void_p],
+    "b200_sinusoid_dev": [c_void_p, c_void_p, c_int, c_void_p],
     "b200_col_mean_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_add_vec": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "b200_embed_rows": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
@@ -35,6 +36,7 @@ SIGNATURES = {
     "b200_mul_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200_t5_attention": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "b200_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_ll, c_void_p],
+    "b200_cfg_euler_step_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200_cfg_unipc_step": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p],
     "b200_conv3d_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_int, c_int, c_int, c_int, c_void_p],

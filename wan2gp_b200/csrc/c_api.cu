@@ -526,8 +526,14 @@ extern "C" int b200_gemv_f32(const float* x, const float* w, const float* b, flo
 
 extern "C" int b200_sinusoid(float t, float* out, int dim, void* stream) {
     if (!out || dim % 2) return b200_set_error(B200_ERR_ARG, "sinusoid: bad argument");
-    sinusoid_kernel<<<(dim / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, dim);
+    sinusoid_kernel<<<(dim / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, nullptr, out, dim);
     CHECK_LAUNCH("sinusoid");
+    return B200_OK;
+}
+extern "C" int b200_sinusoid_dev(const float* t_dev, float* out, int dim, void* stream) {
+    if (!t_dev || !out || dim % 2) return b200_set_error(B200_ERR_ARG, "sinusoid_dev: bad argument");
+    sinusoid_kernel<<<(dim / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(0.f, t_dev, out, dim);
+    CHECK_LAUNCH("sinusoid_dev");
     return B200_OK;
 }
 
@@ -564,8 +570,19 @@ extern "C" int b200_cfg_unipc_step(float* lat, const float* cond, const float* u
     return B200_OK;
 }
 
+static int cfg_euler_impl(float* lat, const float* cond, const float* uncond, float guide, float dt, const float* gdt_dev,
+                          float* pred_out, float* star_dots, long long n, void* stream);
 extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* uncond, float guide, float dt,
                                    float* pred_out, float* star_dots, long long n, void* stream) {
+    return cfg_euler_impl(lat, cond, uncond, guide, dt, nullptr, pred_out, star_dots, n, stream);
+}
+extern "C" int b200_cfg_euler_step_dev(float* lat, const float* cond, const float* uncond, const float* guide_dt_dev,
+                                       float* pred_out, float* star_dots, long long n, void* stream) {
+    if (!guide_dt_dev) return b200_set_error(B200_ERR_ARG, "cfg_euler_step_dev: null parameter buffer");
+    return cfg_euler_impl(lat, cond, uncond, 0.f, 0.f, guide_dt_dev, pred_out, star_dots, n, stream);
+}
+static int cfg_euler_impl(float* lat, const float* cond, const float* uncond, float guide, float dt, const float* gdt_dev,
+                          float* pred_out, float* star_dots, long long n, void* stream) {
     if (!lat || !cond || n <= 0 || n % 4 || (star_dots && !uncond)) return b200_set_error(B200_ERR_ARG, "cfg_euler_step: bad argument");
     const long long n4 = n / 4;
     if (star_dots) {
@@ -575,7 +592,7 @@ extern "C" int b200_cfg_euler_step(float* lat, const float* cond, const float* u
         cfg_dots_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond, uncond, star_dots, n4);
         CHECK_LAUNCH("cfg_dots");
     }
-    cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, pred_out, star_dots, n4);
+    cfg_euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, dt, gdt_dev, pred_out, star_dots, n4);
     CHECK_LAUNCH("cfg_euler_step");
     return B200_OK;
 }

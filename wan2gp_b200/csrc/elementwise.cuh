@@ -256,10 +256,12 @@ __global__ void gemv_f32_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 // sinusoidal_embedding_1d (model.py:32-42): out[0:half] = cos(t * 10000^(-i/half)), out[half:] = sin(...)
-__global__ void sinusoid_kernel(float t, float* __restrict__ out, int dim) {
+// t_dev != null: the timestep is read from device memory (whole-step CUDA graph: the captured launch must not bake the value in)
+__global__ void sinusoid_kernel(float t, const float* __restrict__ t_dev, float* __restrict__ out, int dim) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim >> 1;
     if (i >= half) return;
+    if (t_dev) t = __ldg(t_dev);
     const float a = t * powf(10000.f, -(float)i / (float)half);
     out[i] = cosf(a);
     out[half + i] = sinf(a);
@@ -324,10 +326,13 @@ cfg_dots_kernel(const float* __restrict__ cond, const float* __restrict__ uncond
     }
 }
 
+// gdt_dev != null: {guide, dt} are read from device memory (whole-step CUDA graph)
 __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond,
-                                 float g, float dt, float* __restrict__ pred_out, const float* __restrict__ star_dots, long long n4) {
+                                 float g, float dt, const float* __restrict__ gdt_dev, float* __restrict__ pred_out,
+                                 const float* __restrict__ star_dots, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (gdt_dev) { g = __ldg(gdt_dev); dt = __ldg(gdt_dev + 1); }
     const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
     float4 u = uncond ? __ldg(reinterpret_cast<const float4*>(uncond) + i) : c;
     if (star_dots) {

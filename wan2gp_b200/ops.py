@@ -168,8 +168,13 @@ def gemv(x, w, b, silu_in=False, silu_out=False):
 
 
 def sinusoid(t, dim, device):
+    """t: a number, or a 1-element fp32 CUDA tensor (read on the device: nothing is baked into a captured graph)."""
     out = torch.empty(dim, device=device, dtype=f32)
-    _lib.call("b200_sinusoid", float(t), out.data_ptr(), dim, _stream())
+    if torch.is_tensor(t) and t.is_cuda:
+        _chk(t, f32, "t")
+        _lib.call("b200_sinusoid_dev", t.data_ptr(), out.data_ptr(), dim, _stream())
+    else:
+        _lib.call("b200_sinusoid", float(t), out.data_ptr(), dim, _stream())
     return out
 
 
@@ -201,6 +206,11 @@ def cfg_euler_step_(lat, cond, uncond, guide, dt, pred_out=None, cfg_star=False)
     _chk_vec4(lat, cond, uncond, pred_out)
     assert lat.is_contiguous() and cond.is_contiguous() and (uncond is None or uncond.is_contiguous())
     dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
+    if torch.is_tensor(dt):              # fp32 CUDA tensor [guide, dt]: read on the device (whole-step CUDA graph); `guide` is ignored
+        _chk(dt, f32, "guide_dt")
+        assert dt.numel() == 2 and dt.is_contiguous()
+        _lib.call("b200_cfg_euler_step_dev", lat.data_ptr(), cond.data_ptr(), _p(uncond), dt.data_ptr(), _p(pred_out), _p(dots), lat.numel(), _stream())
+        return lat
     _lib.call("b200_cfg_euler_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), float(dt), _p(pred_out),
               _p(dots), lat.numel(), _stream())
     return lat

@@ -187,6 +187,14 @@ class WanDenoiser:
         self._interrupt = False                      # written from the UI thread in the reference (wgp.py:1628)
         self.interrupt_source = None                 # pipeline object that owns `_interrupt` when this denoiser is driven by WanAny2V
         self._pred, self._hist = None, None
+        # whole-step CUDA graph: both CFG forwards, the combine and the Euler update of one step captured
+        # once per (expert, latent buffer, prompt, CFG-Zero* phase) and replayed with the timestep / guidance / dt read from device
+        # memory.  For launch-bound configurations (the 1.3B model: ~400 launches of 10-100 us per step); the reference's per-block
+        # interrupt poll becomes a per-step poll.  Single-step solvers on one GPU only; multi-step solvers and the CFG-pair split
+        # take the ordinary path.
+        self.use_step_graph = False
+        self._step_graphs = {}
+        self._staging = {}
 
     def expert(self, t):
         """(model, guidance scale) for timestep t (any2video.py:1437-1443: switch when t <= switch_threshold)."""
@@ -200,6 +208,9 @@ class WanDenoiser:
         t = self.timesteps[i]
         dt = (t - self.timesteps[i + 1]) / 1000.0
         model, g = self.expert(t)
+        if self.use_step_graph and self.unipc is None and self.cfg_group is None and context_null is not None:
+            star = self.cfg_star_switch and i > self.cfg_zero_step
+            return self._graph_step(model, g, latents, t, dt, context, context_null, y, freqs, star)
         tt = torch.tensor([t], dtype=f32)
         # the model polls `pipeline._interrupt` once per block: the object the UI thread writes to (WanAny2V) when one is attached
         kw = dict(y=y, freqs=freqs, pipeline=self.interrupt_source or self, current_step_no=i, max_steps=self.num_steps, callback=callback)
@@ -242,6 +253,46 @@ class WanDenoiser:
             self._hist = [x_last, m1, m0]                                           # the kernel stored x0_i into m1
         return latents
 
+    def _graph_step(self, model, g, latents, t, dt, context, context_null, y, freqs, star):
+        if (self.interrupt_source or self)._interrupt:
+            return None
+        # operands are identified like the model's prompt cache does (address, version, shape): a captured graph replays the text
+        # projections cached at capture time, so a prompt tensor that was written to since must not hit; the entry keeps the
+        # tensors alive so that their addresses cannot be recycled
+        ident = lambda x: None if x is None else (x.data_ptr(), x._version, tuple(x.shape))
+        key = (id(model), latents.data_ptr(), tuple(latents.shape), ident(context), ident(context_null), ident(y), bool(star))
+        ent = self._step_graphs.get(key)
+        if ent is None:
+            tdev = torch.zeros(1, device=latents.device, dtype=f32)
+            gdt = torch.zeros(2, device=latents.device, dtype=f32)
+
+            class _Quiet:                                   # nothing can interrupt a capture; the poll moves to the step boundary
+                _interrupt = False
+            prev = getattr(model, "use_cuda_graphs", False)
+            model.use_cuda_graphs = False                   # per-block graphs cannot be replayed inside a capture
+
+            def body(lat):
+                cond, uncond = model([lat, lat], tdev, [context, context_null], y=y, freqs=freqs, pipeline=_Quiet(), current_step_no=0,
+                                     max_steps=self.num_steps, callback=None)
+                ops.cfg_euler_step_(lat, cond, uncond, 0.0, gdt, cfg_star=star)
+            # one eager step on a scratch copy fills every cache (RoPE tables, text projections, cross K/V, kernel attributes) with the
+            # real values of this step: host-to-device copies and first-use attribute calls are not capturable
+            tdev.fill_(float(t)); gdt[0] = float(g); gdt[1] = float(dt)
+            body(latents.clone())
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body(latents)
+            model.use_cuda_graphs = prev
+            ent = self._step_graphs[key] = (graph, tdev, gdt, (latents, context, context_null, y))
+            if len(self._step_graphs) > 8:                  # each entry pins a memory pool: keep the table small
+                self._step_graphs.pop(next(iter(self._step_graphs)))
+        graph, tdev, gdt = ent[:3]
+        tdev.fill_(float(t))                                # two scalar fills + one graph launch per step
+        gdt.copy_(torch.tensor([float(g), float(dt)], dtype=f32), non_blocking=False)
+        graph.replay()
+        return latents
+
     @staticmethod
     def _combine_step(latents, cond, uncond, g, dt, cfg_star):
         ops.cfg_euler_step_(latents, cond, uncond, g, dt, cfg_star=cfg_star)
@@ -249,10 +300,20 @@ class WanDenoiser:
     @torch.no_grad()
     def step_host(self, latents_host, i, context_host, context_null_host=None, y=None, freqs=None):
         """End-to-end step with HOST buffers (pinned): H2D of the step's inputs, the step, D2H of the new latents."""
-        lat = latents_host.to(self.device, non_blocking=True)
-        ctx = context_host.to(self.device, non_blocking=True)
-        ctxn = None if context_null_host is None else context_null_host.to(self.device, non_blocking=True)
-        out = self.step(lat, i, ctx, ctxn, y=y, freqs=freqs)
+        def stage(name, host):                       # stable device staging buffers: same addresses every step (whole-step graph key)
+            if host is None:
+                return None
+            buf = self._staging.get(name)
+            if buf is None or buf.shape != host.shape:
+                buf = self._staging[name] = torch.empty(host.shape, device=self.device, dtype=host.dtype)
+            buf.copy_(host, non_blocking=True)
+            return buf
+        lat, ctx, ctxn = stage("lat", latents_host), stage("ctx", context_host), stage("ctxn", context_null_host)
+        graph_mode, self.use_step_graph = self.use_step_graph, False      # the prompt is re-uploaded every call here: nothing step-invariant to replay
+        try:
+            out = self.step(lat, i, ctx, ctxn, y=y, freqs=freqs)
+        finally:
+            self.use_step_graph = graph_mode
         if out is None:
             return None
         latents_host.copy_(out, non_blocking=True)

@@ -205,7 +205,10 @@ class WanModel(torch.nn.Module):
     def _time(self, t):
         """e [D], e0 [6D]  (model.py:1815-1818)."""
         g = self._g
-        tval = float(t.flatten()[0]) if torch.is_tensor(t) else float(t)
+        if torch.is_tensor(t) and t.is_cuda:                  # whole-step graph (pipeline.WanDenoiser): the timestep stays on the device
+            tval = t.reshape(-1)[:1].to(f32)
+        else:
+            tval = float(t.flatten()[0]) if torch.is_tensor(t) else float(t)
         s = ops.sinusoid(tval, self.freq_dim, self.device)
         h = ops.gemv(s, g["time_w0"], g["time_b0"], silu_out=True)
         e = ops.gemv(h, g["time_w2"], g["time_b2"])
