@@ -489,7 +489,7 @@ def measure_wan(workload, steps, warmup, rank, world, local_rank, dev, dist, cfg
     for k in range(warmup):
         den.step(latents, step_idx(k), ctx, ctxn, y=y_dev, freqs=freqs)
     barrier()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + den.graph_launches
     ops.TIMED["attention"] = []
     ops.TIMED["gemm"] = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -505,7 +505,7 @@ def measure_wan(workload, steps, warmup, rank, world, local_rank, dev, dist, cfg
     if prof_range:
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + den.graph_launches - launches0      # kernels inside replayed whole-step graphs included
     att = ops.TIMED.pop("attention")
     att_ms = [a.elapsed_time(b) for a, b, _ in att]
     att_work = att[0][2] if att else 0.0

@@ -12,7 +12,7 @@ The reference's UniPC solver, CFG-Zero*, sliding windows etc. stay in the refere
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 f32 = torch.float32
 
@@ -193,6 +193,7 @@ class WanDenoiser:
         # interrupt poll becomes a per-step poll.  Single-step solvers on one GPU only; multi-step solvers and the CFG-pair split
         # take the ordinary path.
         self.use_step_graph = False
+        self.graph_launches = 0
         self._step_graphs = {}
         self._staging = {}
 
@@ -281,16 +282,19 @@ class WanDenoiser:
             body(latents.clone())
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
                 body(latents)
+            n_kernels = _lib.launch_count() - n0            # kernels of ours recorded in the graph (the C ABI counts at launch = capture time)
             model.use_cuda_graphs = prev
-            ent = self._step_graphs[key] = (graph, tdev, gdt, (latents, context, context_null, y))
+            ent = self._step_graphs[key] = (graph, tdev, gdt, (latents, context, context_null, y), n_kernels)
             if len(self._step_graphs) > 8:                  # each entry pins a memory pool: keep the table small
                 self._step_graphs.pop(next(iter(self._step_graphs)))
         graph, tdev, gdt = ent[:3]
         tdev.fill_(float(t))                                # two scalar fills + one graph launch per step
         gdt.copy_(torch.tensor([float(g), float(dt)], dtype=f32), non_blocking=False)
         graph.replay()
+        self.graph_launches += ent[4]                       # kernels launched through graph replays (b200_launch_count does not see them)
         return latents
 
     @staticmethod
