@@ -261,7 +261,8 @@ class WanDenoiser:
         # projections cached at capture time, so a prompt tensor that was written to since must not hit; the entry keeps the
         # tensors alive so that their addresses cannot be recycled
         ident = lambda x: None if x is None else (x.data_ptr(), x._version, tuple(x.shape))
-        key = (id(model), latents.data_ptr(), tuple(latents.shape), ident(context), ident(context_null), ident(y), bool(star))
+        key = (id(model), getattr(model, "weights_version", 0), latents.data_ptr(), tuple(latents.shape), ident(context), ident(context_null),
+               ident(y), bool(star))
         ent = self._step_graphs.get(key)
         if ent is None:
             tdev = torch.zeros(1, device=latents.device, dtype=f32)

@@ -160,6 +160,7 @@ class WanModel(torch.nn.Module):
         self._pack_globals(sd)
         self.blocks = [self._pack_block(sd, f"blocks.{i}.") for i in range(self.num_layers)]
         self._ready = True
+        self.weights_version = getattr(self, "weights_version", 0) + 1        # whole-step graphs of pipeline.WanDenoiser are keyed on it
         self._graphs = {}                                                     # captured graphs / cached projections used the old weights
         self._prompts.clear()
         self._stacked_ckv = {}
@@ -180,6 +181,7 @@ class WanModel(torch.nn.Module):
             self.blocks.append(self._pack_block({n: synth.make_wan_tensor(n, s, cfg, seed, self.device)
                                                  for n, s in shapes.items() if n.startswith(p)}, p))
         self._ready = True
+        self.weights_version = getattr(self, "weights_version", 0) + 1
         self._graphs = {}                                                     # as load_state_dict: nothing captured / cached may
         self._prompts.clear()                                                 # keep pointing at the previous weights
         self._stacked_ckv = {}
