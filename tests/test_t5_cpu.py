@@ -72,3 +72,9 @@ def test_hf_names_map_to_reference_names():
     back = hf_to_wan_names(hf)
     assert set(back) == set(sd) and all(back[k] is sd[k] for k in sd)
     assert hf_to_wan_names(sd) is sd
+
+
+def test_clean_prompt_is_the_reference_whitespace_clean():
+    from wan2gp_b200.wan.t5 import clean_prompt
+    assert clean_prompt("  a &amp;amp; b \n\t c  ") == "a & b c"
+    assert clean_prompt("plain prompt") == "plain prompt"

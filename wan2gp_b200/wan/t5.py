@@ -150,6 +150,7 @@ class T5EncoderModel:
             tok = AutoTokenizer.from_pretrained(tokenizer_path)
 
             def _tok(texts):
+                texts = [clean_prompt(t) for t in ([texts] if isinstance(texts, str) else texts)]     # HuggingfaceTokenizer(clean='whitespace')
                 enc = tok(texts, return_tensors="pt", padding="max_length", truncation=True, max_length=self.text_len, add_special_tokens=True)
                 return enc.input_ids, enc.attention_mask
             self.tokenizer = _tok
@@ -161,6 +162,20 @@ class T5EncoderModel:
         ctx = self.model(ids, mask)
         seq_lens = mask.gt(0).sum(dim=1).long()
         return [u[:int(v)] for u, v in zip(ctx, seq_lens)]
+
+
+def clean_prompt(text):
+    """HuggingfaceTokenizer._clean with clean='whitespace' (tokenizers.py:12-23, :77-79): ftfy.fix_text when ftfy is installed (WanGP
+    requires it), two rounds of html.unescape, runs of whitespace collapsed to one space."""
+    import html
+    import re
+    try:
+        import ftfy
+        text = ftfy.fix_text(text)
+    except ImportError:
+        pass
+    text = html.unescape(html.unescape(text)).strip()
+    return re.sub(r"\s+", " ", text).strip()
 
 
 def hf_to_wan_names(sd):
