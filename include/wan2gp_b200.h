@@ -121,6 +121,10 @@ int b200_cfg_euler_step_dev(float* lat, const float* cond, const float* uncond, 
  * stores lat <- xn, x_last <- xc, m1 <- x0 (the caller swaps the roles of m0 and m1).  All fp32, n % 4 == 0; star_dots as above. */
 int b200_cfg_unipc_step(float* lat, const float* cond, const float* uncond, float guide, float* x_last, const float* m0, float* m1,
                         const float* coef_host8, int use_corrector, float* star_dots, long long n, void* stream);
+/* same, {guide, sigma, ca, cb, cc, cd, pp, pq, pr, use_corrector} read from device memory (float[10]): whole-step CUDA graph with the
+ * multi-step solvers (UniPC, dpm++) */
+int b200_cfg_unipc_step_dev(float* lat, const float* cond, const float* uncond, float* x_last, const float* m0, float* m1,
+                            const float* params_dev10, float* star_dots, long long n, void* stream);
 
 /* ---- WanVAE decode (channels-last bf16 activations [T,H,W,C]) ---- */
 

@@ -139,18 +139,22 @@ def test_dpmpp_through_fused_kernel():
     assert WanDenoiser(None, num_steps=4, shift=5.0, sample_solver="dpm++").timesteps[:4] == [float(t) for t in DPMppSchedule(4, 5.0).timesteps]
 
 
+@pytest.mark.parametrize("solver", ["euler", "unipc", "dpm++"])
 @pytest.mark.parametrize("star", [False, True])
-def test_whole_step_graph_equals_eager_steps(star):
+def test_whole_step_graph_equals_eager_steps(star, solver):
     """both CFG forwards + combine + Euler update of a step as ONE captured CUDA graph, replayed with the
     timestep / guidance / dt read from device memory -- bit-identical to the launch-by-launch step over a whole schedule with an expert
-    switch (two graphs) and, with star, the CFG-Zero* rescale switching on after the first step (a second capture per expert)."""
+    switch (two graphs) and, with star, the CFG-Zero* rescale switching on after the first step (a second capture per expert).  The
+    multi-step solvers (UniPC with its corrector, dpm++) read their ten coefficients from device memory and capture once per step parity
+    (the two x0 history buffers swap roles every step)."""
     from wan2gp_b200.pipeline import WanDenoiser
     from wan2gp_b200.wan import WanModel
     cfg, thw, sd, x, t, ctx, _ = wan_case("tiny")
     m1, m2 = WanModel(**cfg), WanModel(**cfg)
     m1.load_state_dict(sd), m2.load_state_dict(synth.make_wan_state_dict(cfg, seed=5))
     ctx, ctx_null = ctx.cuda(), torch.zeros_like(ctx).cuda()
-    kw = dict(num_steps=6, shift=5.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=600, cfg_star_switch=star, cfg_zero_step=0)
+    kw = dict(num_steps=6, shift=5.0, guide_scale=4.0, guide2_scale=3.0, switch_threshold=600, cfg_star_switch=star, cfg_zero_step=0,
+              sample_solver=solver)
     eager, graph = WanDenoiser(m1, m2, **kw), WanDenoiser(m1, m2, **kw)
     graph.use_step_graph = True
     lat0 = torch.randn(1, 16, *thw, generator=torch.Generator().manual_seed(3)).cuda()
@@ -159,6 +163,10 @@ def test_whole_step_graph_equals_eager_steps(star):
         assert eager.step(a, i, ctx, ctx_null) is a
         assert graph.step(b, i, ctx, ctx_null) is b
         assert torch.equal(a, b), i
-    assert 2 <= len(graph._step_graphs) <= 4                           # one capture per (expert, CFG-Zero* phase) actually visited
+    assert 2 <= len(graph._step_graphs) <= 8                           # one capture per (expert, CFG-Zero* phase[, step parity]) actually visited
+    a2, b2 = lat0.clone(), lat0.clone()                                # a second schedule on new latents: the solver history restarts
+    for i in range(3):
+        eager.step(a2, i, ctx, ctx_null), graph.step(b2, i, ctx, ctx_null)
+        assert torch.equal(a2, b2), i
     graph._interrupt = True                                            # the poll lives at the step boundary
     assert graph.step(b, 0, ctx, ctx_null) is None

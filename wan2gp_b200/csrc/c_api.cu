@@ -551,9 +551,9 @@ extern "C" int b200_col_mean_f32(const float* x, float* out, int rows, int cols,
     return B200_OK;
 }
 
-extern "C" int b200_cfg_unipc_step(float* lat, const float* cond, const float* uncond, float guide, float* x_last, const float* m0,
-                                   float* m1, const float* coef_host8, int use_corrector, float* star_dots, long long n, void* stream) {
-    if (!lat || !cond || !x_last || !m0 || !m1 || !coef_host8 || n <= 0 || n % 4 || (star_dots && !uncond))
+static int cfg_unipc_impl(float* lat, const float* cond, const float* uncond, float guide, float* x_last, const float* m0, float* m1,
+                          const float* coef_host8, int use_corrector, const float* params_dev, float* star_dots, long long n, void* stream) {
+    if (!lat || !cond || !x_last || !m0 || !m1 || (!coef_host8 && !params_dev) || n <= 0 || n % 4 || (star_dots && !uncond))
         return b200_set_error(B200_ERR_ARG, "cfg_unipc_step: bad argument");
     const long long n4 = n / 4;
     if (star_dots) {
@@ -563,11 +563,22 @@ extern "C" int b200_cfg_unipc_step(float* lat, const float* cond, const float* u
         cfg_dots_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond, uncond, star_dots, n4);
         CHECK_LAUNCH("cfg_dots");
     }
-    UniPCCoef k{coef_host8[0], coef_host8[1], coef_host8[2], coef_host8[3], coef_host8[4], coef_host8[5], coef_host8[6], coef_host8[7]};
+    UniPCCoef k{};
+    if (coef_host8) k = UniPCCoef{coef_host8[0], coef_host8[1], coef_host8[2], coef_host8[3], coef_host8[4], coef_host8[5], coef_host8[6], coef_host8[7]};
     cfg_unipc_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lat, cond, uncond, guide, x_last, m0, m1, k, use_corrector,
-                                                                                 star_dots, n4);
+                                                                                 params_dev, star_dots, n4);
     CHECK_LAUNCH("cfg_unipc_step");
     return B200_OK;
+}
+extern "C" int b200_cfg_unipc_step(float* lat, const float* cond, const float* uncond, float guide, float* x_last, const float* m0,
+                                   float* m1, const float* coef_host8, int use_corrector, float* star_dots, long long n, void* stream) {
+    if (!coef_host8) return b200_set_error(B200_ERR_ARG, "cfg_unipc_step: null coefficients");
+    return cfg_unipc_impl(lat, cond, uncond, guide, x_last, m0, m1, coef_host8, use_corrector, nullptr, star_dots, n, stream);
+}
+extern "C" int b200_cfg_unipc_step_dev(float* lat, const float* cond, const float* uncond, float* x_last, const float* m0, float* m1,
+                                       const float* params_dev10, float* star_dots, long long n, void* stream) {
+    if (!params_dev10) return b200_set_error(B200_ERR_ARG, "cfg_unipc_step_dev: null parameter buffer");
+    return cfg_unipc_impl(lat, cond, uncond, 0.f, x_last, m0, m1, nullptr, 0, params_dev10, star_dots, n, stream);
 }
 
 static int cfg_euler_impl(float* lat, const float* cond, const float* uncond, float guide, float dt, const float* gdt_dev,

@@ -349,11 +349,17 @@ __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restric
 // One FlowUniPCMultistepScheduler.step (order <= 2, bh2, predict_x0, flow prediction) fused with the CFG combine; the scalar
 // coefficients come from the host (pipeline.py::UniPCSchedule).  Everything fp32, one pass: 5 reads + 3 writes per element.
 struct UniPCCoef { float sigma, ca, cb, cc, cd, pp, pq, pr; };
+// pdev != null: {guide, sigma, ca, cb, cc, cd, pp, pq, pr, use_corrector} are read from device memory (whole-step CUDA graph)
 __global__ void cfg_unipc_kernel(float* __restrict__ lat, const float* __restrict__ cond, const float* __restrict__ uncond, float g,
                                  float* __restrict__ x_last, const float* __restrict__ m0, float* __restrict__ m1, UniPCCoef k,
-                                 int use_corrector, const float* __restrict__ star_dots, long long n4) {
+                                 int use_corrector, const float* __restrict__ pdev, const float* __restrict__ star_dots, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (pdev) {
+        g = __ldg(pdev);
+        k = UniPCCoef{__ldg(pdev + 1), __ldg(pdev + 2), __ldg(pdev + 3), __ldg(pdev + 4), __ldg(pdev + 5), __ldg(pdev + 6), __ldg(pdev + 7), __ldg(pdev + 8)};
+        use_corrector = __ldg(pdev + 9) != 0.f;
+    }
     const float4 c = __ldg(reinterpret_cast<const float4*>(cond) + i);
     float4 u = uncond ? __ldg(reinterpret_cast<const float4*>(uncond) + i) : c;
     if (star_dots) {

@@ -225,6 +225,12 @@ def cfg_unipc_step_(lat, cond, uncond, guide, x_last, m0, m1, coef, cfg_star=Fal
     assert uncond is None or (uncond.is_contiguous() and uncond.numel() == lat.numel())
     _chk_vec4(lat, cond, uncond, x_last, m0, m1)
     dots = torch.empty(CFG_DOTS_FLOATS, device=lat.device, dtype=f32) if cfg_star else None
+    if torch.is_tensor(coef):            # fp32 CUDA tensor [guide, sigma, ca, cb, cc, cd, pp, pq, pr, use_corrector]: read on the device
+        _chk(coef, f32, "coef")
+        assert coef.numel() == 10 and coef.is_contiguous()
+        _lib.call("b200_cfg_unipc_step_dev", lat.data_ptr(), cond.data_ptr(), _p(uncond), x_last.data_ptr(), m0.data_ptr(), m1.data_ptr(),
+                  coef.data_ptr(), _p(dots), lat.numel(), _stream())
+        return lat
     c = (ctypes.c_float * 8)(coef["sigma"], coef["ca"], coef["cb"], coef["cc"], coef["cd"], coef["pp"], coef["pq"], coef["pr"])
     _lib.call("b200_cfg_unipc_step", lat.data_ptr(), cond.data_ptr(), _p(uncond), float(guide), x_last.data_ptr(), m0.data_ptr(),
               m1.data_ptr(), ctypes.addressof(c), int(coef["use_corrector"]), _p(dots), lat.numel(), _stream())

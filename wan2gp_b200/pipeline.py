@@ -190,11 +190,11 @@ class WanDenoiser:
         # whole-step CUDA graph: both CFG forwards, the combine and the Euler update of one step captured
         # once per (expert, latent buffer, prompt, CFG-Zero* phase) and replayed with the timestep / guidance / dt read from device
         # memory.  For launch-bound configurations (the 1.3B model: ~400 launches of 10-100 us per step); the reference's per-block
-        # interrupt poll becomes a per-step poll.  Single-step solvers on one GPU only; multi-step solvers and the CFG-pair split
-        # take the ordinary path.
+        # interrupt poll becomes a per-step poll.  Every solver (Euler-type and the multi-step UniPC / dpm++: one capture per step
+        # parity, the history buffers swap roles); the CFG-pair split over two GPUs takes the ordinary path.
         self.use_step_graph = False
         self.graph_launches = 0
-        self._step_graphs = {}
+        self._step_graphs, self._ghist = {}, None
         self._staging = {}
 
     def expert(self, t):
@@ -209,9 +209,9 @@ class WanDenoiser:
         t = self.timesteps[i]
         dt = (t - self.timesteps[i + 1]) / 1000.0
         model, g = self.expert(t)
-        if self.use_step_graph and self.unipc is None and self.cfg_group is None and context_null is not None:
+        if self.use_step_graph and self.cfg_group is None and context_null is not None:
             star = self.cfg_star_switch and i > self.cfg_zero_step
-            return self._graph_step(model, g, latents, t, dt, context, context_null, y, freqs, star)
+            return self._graph_step(model, g, latents, i, t, dt, context, context_null, y, freqs, star)
         tt = torch.tensor([t], dtype=f32)
         # the model polls `pipeline._interrupt` once per block: the object the UI thread writes to (WanAny2V) when one is attached
         kw = dict(y=y, freqs=freqs, pipeline=self.interrupt_source or self, current_step_no=i, max_steps=self.num_steps, callback=callback)
@@ -254,46 +254,68 @@ class WanDenoiser:
             self._hist = [x_last, m1, m0]                                           # the kernel stored x0_i into m1
         return latents
 
-    def _graph_step(self, model, g, latents, t, dt, context, context_null, y, freqs, star):
+    def _graph_step(self, model, g, latents, i, t, dt, context, context_null, y, freqs, star):
         if (self.interrupt_source or self)._interrupt:
             return None
+        multistep = self.unipc is not None
+        hist = None
+        if multistep:
+            # UniPC / dpm++: host coefficients of step i (stateful, call in order) -> 10 floats in device memory; the history buffers
+            # have fixed addresses and swap roles every step, so there is one capture per step parity
+            if i == 0 or self._ghist is None or self._ghist[0].shape != latents.shape:
+                self.unipc.reset()
+                if self._ghist is None or self._ghist[0].shape != latents.shape:
+                    self._ghist = [torch.zeros_like(latents) for _ in range(3)]            # last_sample, x0 of the two previous steps
+                else:
+                    for h in self._ghist:
+                        h.zero_()
+            c = self.unipc.coefficients(i)
+            params = [float(g)] + [float(c[k]) for k in ("sigma", "ca", "cb", "cc", "cd", "pp", "pq", "pr")] + [float(bool(c["use_corrector"]))]
+            hist = (self._ghist[0],) + ((self._ghist[1], self._ghist[2]) if i % 2 == 0 else (self._ghist[2], self._ghist[1]))
+        else:
+            params = [float(g), float(dt)]
         # operands are identified like the model's prompt cache does (address, version, shape): a captured graph replays the text
         # projections cached at capture time, so a prompt tensor that was written to since must not hit; the entry keeps the
         # tensors alive so that their addresses cannot be recycled
         ident = lambda x: None if x is None else (x.data_ptr(), x._version, tuple(x.shape))
         key = (id(model), getattr(model, "weights_version", 0), latents.data_ptr(), tuple(latents.shape), ident(context), ident(context_null),
-               ident(y), bool(star))
+               ident(y), bool(star), multistep, (i & 1) if multistep else 0)
         ent = self._step_graphs.get(key)
         if ent is None:
             tdev = torch.zeros(1, device=latents.device, dtype=f32)
-            gdt = torch.zeros(2, device=latents.device, dtype=f32)
+            pdev = torch.zeros(len(params), device=latents.device, dtype=f32)
 
             class _Quiet:                                   # nothing can interrupt a capture; the poll moves to the step boundary
                 _interrupt = False
             prev = getattr(model, "use_cuda_graphs", False)
             model.use_cuda_graphs = False                   # per-block graphs cannot be replayed inside a capture
 
-            def body(lat):
+            def body(lat, hs):
                 cond, uncond = model([lat, lat], tdev, [context, context_null], y=y, freqs=freqs, pipeline=_Quiet(), current_step_no=0,
                                      max_steps=self.num_steps, callback=None)
-                ops.cfg_euler_step_(lat, cond, uncond, 0.0, gdt, cfg_star=star)
-            # one eager step on a scratch copy fills every cache (RoPE tables, text projections, cross K/V, kernel attributes) with the
-            # real values of this step: host-to-device copies and first-use attribute calls are not capturable
-            tdev.fill_(float(t)); gdt[0] = float(g); gdt[1] = float(dt)
-            body(latents.clone())
+                if multistep:
+                    ops.cfg_unipc_step_(lat, cond, uncond, 0.0, hs[0], hs[1], hs[2], pdev, cfg_star=star)
+                else:
+                    ops.cfg_euler_step_(lat, cond, uncond, 0.0, pdev, cfg_star=star)
+            # one eager step on SCRATCH copies of the latents (and of the solver history) fills every cache (RoPE tables, text
+            # projections, cross K/V, kernel attributes) with the real values of this step: host-to-device copies and first-use
+            # attribute calls are not capturable
+            tdev.fill_(float(t))
+            pdev.copy_(torch.tensor(params, dtype=f32))
+            body(latents.clone(), None if hist is None else tuple(h.clone() for h in hist))
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
-                body(latents)
+                body(latents, hist)
             n_kernels = _lib.launch_count() - n0            # kernels of ours recorded in the graph (the C ABI counts at launch = capture time)
             model.use_cuda_graphs = prev
-            ent = self._step_graphs[key] = (graph, tdev, gdt, (latents, context, context_null, y), n_kernels)
-            if len(self._step_graphs) > 8:                  # each entry pins a memory pool: keep the table small
+            ent = self._step_graphs[key] = (graph, tdev, pdev, (latents, context, context_null, y, hist), n_kernels)
+            if len(self._step_graphs) > 12:                 # each entry pins a memory pool: keep the table small
                 self._step_graphs.pop(next(iter(self._step_graphs)))
-        graph, tdev, gdt = ent[:3]
-        tdev.fill_(float(t))                                # two scalar fills + one graph launch per step
-        gdt.copy_(torch.tensor([float(g), float(dt)], dtype=f32), non_blocking=False)
+        graph, tdev, pdev = ent[:3]
+        tdev.fill_(float(t))                                # one scalar fill, one small copy and one graph launch per step
+        pdev.copy_(torch.tensor(params, dtype=f32))
         graph.replay()
         self.graph_launches += ent[4]                       # kernels launched through graph replays (b200_launch_count does not see them)
         return latents
