@@ -379,23 +379,44 @@ class HunyuanDenoiser:
 
     @torch.no_grad()
     def step(self, latents, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=None, byt5_mask=None, freqs=None,
-             text_states_2=None, guidance=None):
+             text_states_2=None, guidance=None, byt5_null=None, byt5_null_mask=None, text_states_2_null=None, cfg_star=False,
+             joint_pass=False, callback=None, pipeline=None):
         """latents fp32 [1,C,T,H,W] (updated in place); cond_latents fp32 [1,C2,T,H,W] (Hunyuan 1.5 concat mask/cond channels) or
-        None; text_null=None => no CFG (guidance-distilled HunyuanVideo 1.0: one forward with the guidance embedding)."""
+        None; text_null=None => no CFG (guidance-distilled HunyuanVideo 1.0: one forward with the guidance embedding).
+        `byt5_null*` / `text_states_2_null`: the negative branch's glyph / pooled states (default: the positive ones);
+        cfg_star = the CFG-Zero* rescale of the unconditional prediction (pipeline_hunyuan_video.py:1721-1731); joint_pass = both
+        branches in ONE forward of batch 2 (:1687-1715) instead of two forwards (:1655-1685) -- same arithmetic per sample;
+        `pipeline` = the object whose `_interrupt` the model polls once per block (default: this denoiser)."""
         t = self.timesteps[i]
         dt = (t - self.timesteps[i + 1]) / 1000.0
         x = latents if cond_latents is None else torch.cat([latents, cond_latents], 1)
         tt = torch.tensor([t], dtype=f32)
-        kw = dict(freqs_cos=None if freqs is None else freqs[0], freqs_sin=None if freqs is None else freqs[1], pipeline=self,
-                  step_no=i, byt5_text_states=byt5, byt5_text_mask=byt5_mask, text_states_2=text_states_2, guidance=guidance)
-        cond = self.model(x, tt, text_states=text, text_mask=text_mask, **kw)
-        if cond is None:
-            return None
+        fr = dict(freqs_cos=None if freqs is None else freqs[0], freqs_sin=None if freqs is None else freqs[1],
+                  pipeline=self if pipeline is None else pipeline, step_no=i, guidance=guidance, callback=callback)
+        pos = dict(text_states=text, text_mask=text_mask, byt5_text_states=byt5, byt5_text_mask=byt5_mask, text_states_2=text_states_2)
         uncond = None
-        if text_null is not None:
-            uncond = self.model(x, tt, text_states=text_null, text_mask=text_null_mask, **kw)
-            if uncond is None:
+        if text_null is None:
+            cond = self.model(x, tt, **pos, **fr)
+            if cond is None:
                 return None
-            uncond = uncond.contiguous()
-        ops.cfg_euler_step_(latents, cond.contiguous(), uncond, self.guide_scale, dt)
+        else:
+            neg = dict(text_states=text_null, text_mask=text_null_mask, byt5_text_states=byt5 if byt5_null is None else byt5_null,
+                       byt5_text_mask=byt5_mask if byt5_null is None else byt5_null_mask,
+                       text_states_2=text_states_2 if text_states_2_null is None else text_states_2_null)
+            if joint_pass:                                   # [uncond, cond] stacked along the batch, as the reference stacks them (:1445-1452)
+                both = {k: (None if pos[k] is None else torch.cat([neg[k].to(pos[k].device), pos[k]], 0)) for k in pos}
+                g2 = None if guidance is None else guidance.reshape(-1)[:1].repeat(2)
+                ret = self.model(torch.cat([x, x], 0), tt.repeat(2), **both, **dict(fr, guidance=g2))
+                if ret is None:
+                    return None
+                uncond, cond = ret[0:1].contiguous(), ret[1:2].contiguous()
+            else:
+                uncond = self.model(x, tt, x_id=0, **neg, **fr)          # the reference runs the unconditional branch first (j = 0)
+                if uncond is None:
+                    return None
+                cond = self.model(x, tt, x_id=1, **pos, **fr)
+                if cond is None:
+                    return None
+                uncond = uncond.contiguous()
+        ops.cfg_euler_step_(latents, cond.contiguous(), uncond, self.guide_scale, dt, cfg_star=bool(cfg_star) and uncond is not None)
         return latents
