@@ -349,9 +349,44 @@ def run_t5(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), length=length, n_valid=n_valid, seed=0)
 
 
+def run_byt5(name):
+    """The byT5 glyph encoder of Hunyuan Video 1.5 (classic T5 v1.1: ONE relative position embedding shared by all blocks), two ways:
+    (a) the reference's own T5Encoder(shared_pos=True) (models/wan/modules/t5.py:268-292) and (b) transformers' T5Stack obtained exactly as
+    the reference obtains its byT5 model -- `T5ForConditionalGeneration(config).get_encoder()`, called as `model(ids, attention_mask=
+    mask.float())[0]` (models/hyvideo/text_encoder/byT5/__init__.py:184-188, pipeline_hunyuan_video.py:1037) -- on the same weights.
+    transformers is third-party arithmetic (requirements.txt:5 pins transformers==4.54.0; the T5 encoder arithmetic is unchanged in the
+    version installed here): the fixture stores both outputs."""
+    import transformers
+    from oracle.refshim import load_reference_t5
+    from wan2gp_b200 import synth
+    cfg = synth.T5_CONFIGS[name]
+    R = load_reference_t5()
+    enc = R.T5Encoder(cfg["vocab_size"], cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_layers"], cfg["num_buckets"],
+                      shared_pos=True, dropout=0.1).eval().float()
+    sd = synth.make_t5_state_dict(cfg, seed=0)
+    enc.load_state_dict(sd, strict=True)
+    length, n_valid = 48, 31
+    ids, mask = synth.make_t5_inputs(cfg, length, n_valid, seed=0)
+    with torch.no_grad():
+        out = enc(ids[None], mask[None])[0]
+    hf_cfg = transformers.T5Config(vocab_size=cfg["vocab_size"], d_model=cfg["dim"], d_kv=cfg["dim_attn"] // cfg["num_heads"], d_ff=cfg["dim_ffn"],
+                                   num_layers=cfg["num_layers"], num_decoder_layers=1, num_heads=cfg["num_heads"],
+                                   relative_attention_num_buckets=cfg["num_buckets"], relative_attention_max_distance=128, dropout_rate=0.0,
+                                   layer_norm_epsilon=1e-6, feed_forward_proj="gated-gelu", tie_word_embeddings=False)
+    hf = transformers.T5ForConditionalGeneration(hf_cfg).get_encoder().eval().float()
+    missing, unexpected = hf.load_state_dict(synth.t5_to_hf_t5stack_names(sd, cfg["num_layers"]), strict=True)
+    with torch.no_grad():
+        out_hf = hf(ids[None], attention_mask=mask[None].float())[0][0]
+    d = float((out_hf[:n_valid] - out[:n_valid]).norm() / out[:n_valid].norm())
+    print(f"{name}: reference T5Encoder(shared_pos=True) out {tuple(out.shape)} absmean {out.abs().mean():.6f}; transformers {transformers.__version__} "
+          f"T5Stack vs it on the valid rows: rel-L2 {d:.3e}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=out.numpy().astype(np.float32), out_hf=out_hf.numpy().astype(np.float32),
+                        length=length, n_valid=n_valid, seed=0, transformers_version=transformers.__version__)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_t5 if n.startswith("t5_") else run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)
+        (run_byt5 if n.startswith("byt5_") else run_t5 if n.startswith("t5_") else run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)

@@ -150,6 +150,9 @@ class family_handler:
                                                            multilingual_prompt_format_color_path=font, multilingual_prompt_format_font_path=color,
                                                            byt5_max_length=256), device=device)
             fmt = MultilingualPromptFormat(font_path=font, color_path=color)
+            # the glyph encoder itself runs on the B200 kernels: same weights (the T5Stack WanGP just loaded), same call surface
+            from wan2gp_b200.hyvideo.byt5 import ByT5Encoder
+            byt5_model = ByT5Encoder.from_state_dict(byt5_model.state_dict(), device=device)
         else:
             from models.hyvideo.text_encoder import TextEncoder
             te2 = TextEncoder(text_encoder_type="clipL", max_length=77, text_encoder_precision="fp16", tokenizer_type="clipL", reproduce=True,

@@ -86,3 +86,38 @@ def test_generate_hunyuan_1_0_matches_oracle_loop(monkeypatch):
     r, p = rel_l2(out, ref), psnr(out.clamp(-1, 1), ref.clamp(-1, 1), 2.0)
     print(f"HunyuanVideoSampler.generate (1.0, embedded guidance, 3 steps + decode) vs oracle loop: rel-L2 {r:.3e}, PSNR {p:.1f} dB")
     assert r < 8e-2 and p > 30.0
+
+
+def test_glyph_prompt_runs_the_byt5_encoder(monkeypatch):
+    """A prompt that quotes text takes the glyph branch of _process_single_byt5_prompt (pipeline_hunyuan_video.py:1009-1041): format ->
+    tokenise (padding to byt5_max_length) -> ByT5Encoder on the B200 kernels -> states + mask into every forward."""
+    import types
+
+    from oracle import t5_oracle
+    from wan2gp_b200.hyvideo.byt5 import ByT5Encoder
+    pipe_obj, pipe, cfg, sd, vsd = make_pipeline("b200_hunyuan_1_5_t2v", device="cuda", monkeypatch=monkeypatch, vae_tiling=False)
+    tcfg = dict(synth.T5_CONFIGS["byt5_2layer"], vocab_size=400)                                  # byT5-small widths: the mapper expects 1472
+    tsd = synth.make_t5_state_dict(tcfg, 4)
+    pipe_obj.byt5_model = ByT5Encoder.from_state_dict(synth.t5_to_hf_t5stack_names(tsd, tcfg["num_layers"]), device="cuda")
+    pipe_obj.byt5_max_length = 32
+    seen = {}
+
+    def tokenizer(text, padding=None, max_length=None, truncation=None, add_special_tokens=None, return_tensors=None):
+        b = [3 + c % 380 for c in text.encode()][:max_length - 1] + [1]
+        ids = torch.zeros(1, max_length, dtype=torch.long)
+        ids[0, :len(b)] = torch.tensor(b)
+        mask = (torch.arange(max_length) < len(b)).long()[None]
+        seen["text"], seen["ids"], seen["mask"] = text, ids, mask
+        return types.SimpleNamespace(input_ids=ids, attention_mask=mask)
+    pipe_obj.byt5_tokenizer = tokenizer
+    pipe_obj.prompt_format = types.SimpleNamespace(format_prompt=lambda texts, styles: "".join(f'Text "{t}". ' for t in texts))
+    emb, mask = pipe_obj._byt5_one('a sign that says "OPEN" and “24h”')
+    assert seen["text"] == 'Text "OPEN". Text "24h". ' and tuple(emb.shape) == (1, 32, 1472) and int(mask.sum()) == int(seen["mask"].sum())
+    nv = int(mask.sum())
+    emu = t5_oracle.t5_encode(tsd, tcfg, seen["ids"][0], seen["mask"][0], emulate_bf16=True)
+    assert rel_l2(emb[0, :nv], emu[:nv]) < 6e-3
+    e0, m0 = pipe_obj._byt5_one("no glyph text here")
+    assert float(e0.abs().max()) == 0.0 and int(m0.sum()) == 0 and tuple(e0.shape) == (1, 32, 1472)
+    out = pipe_obj.generate(**hy_kwargs(input_prompt='a sign that says "OPEN"', sampling_steps=2, seed=2))
+    plain = pipe_obj.generate(**hy_kwargs(input_prompt="a sign that says OPEN", sampling_steps=2, seed=2))
+    assert tuple(out.shape) == (3, 5, 32, 48) and torch.isfinite(out).all() and not torch.equal(out, plain)

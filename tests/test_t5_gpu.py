@@ -73,3 +73,38 @@ def test_t5_encoder_model_wrapper_is_the_pipeline_callable():
     ids, mask = tok(["a red fox"])
     emu = t5_oracle.t5_encode(sd, cfg, ids[0], mask[0], emulate_bf16=True)
     assert rel_l2(outs[0], emu[:9]) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------- byT5 glyph encoder (shared position bias)
+def _byt5(cfg, sd):
+    from wan2gp_b200.hyvideo.byt5 import ByT5Encoder
+    return ByT5Encoder.from_state_dict(synth.t5_to_hf_t5stack_names(sd, cfg["num_layers"]), device="cuda")
+
+
+def test_byt5_tiny_matches_oracle_reference_and_transformers_fixture():
+    """ByT5Encoder (T5Encoder(shared_pos=True) behind the Hugging Face call surface) against the bf16-emulating oracle and the fixture that
+    holds the reference T5Encoder(shared_pos=True) and transformers' T5Stack outputs."""
+    g = np.load(os.path.join(GOLDEN, "byt5_tiny.npz"))
+    cfg = synth.T5_CONFIGS["byt5_tiny"]
+    sd = synth.make_t5_state_dict(cfg, 0)
+    L, nv = int(g["length"]), int(g["n_valid"])
+    ids, mask = synth.make_t5_inputs(cfg, L, nv, 0)
+    out = _byt5(cfg, sd)(ids[None].cuda(), attention_mask=mask[None].float().cuda())[0][0]
+    emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
+    r_emu = rel_l2(out[:nv], emu[:nv])
+    r_ref, r_hf = rel_l2(out[:nv], torch.from_numpy(g["out"])[:nv]), rel_l2(out[:nv], torch.from_numpy(g["out_hf"])[:nv])
+    print(f"byt5_tiny: vs bf16-emulating oracle {r_emu:.3e}; vs reference T5Encoder(shared_pos) {r_ref:.3e}; vs transformers T5Stack {r_hf:.3e}")
+    assert r_emu < 6e-3 and r_ref < 2e-2 and r_hf < 2e-2
+
+
+@pytest.mark.parametrize("L,nv", [(256, 57), (256, 256)])
+def test_byt5_small_widths(L, nv):
+    """Two blocks at the google/byt5-small widths (1472 / 6 heads x 64 / 3584; the GEMM N and K are not multiples of 256: tail tiles) on the
+    reference's byt5_max_length of 256 tokens."""
+    cfg = synth.T5_CONFIGS["byt5_2layer"]
+    sd = synth.make_t5_state_dict(cfg, 2)
+    ids, mask = synth.make_t5_inputs(cfg, L, nv, 2)
+    out = _byt5(cfg, sd)(ids[None].cuda(), attention_mask=mask[None].float().cuda())[0][0]
+    emu = t5_oracle.t5_encode(sd, cfg, ids, mask, emulate_bf16=True)
+    assert tuple(out.shape) == (L, 1472) and torch.isfinite(out).all()
+    assert rel_l2(out[:nv], emu[:nv]) < 6e-3

@@ -627,6 +627,11 @@ T5_CONFIGS = {
     # reduced configs for parity tests (head dim stays 64 as in umT5-XXL)
     "t5_small": dict(vocab_size=1000, dim=256, dim_attn=256, dim_ffn=512, num_heads=4, num_layers=2, num_buckets=32),
     "t5_1layer_xxl": dict(vocab_size=2048, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=1, num_buckets=32),
+    # classic T5 v1.1 layout (shared relative position embedding): google/byt5-small, the glyph encoder of Hunyuan Video 1.5
+    # (d_model 1472, 6 heads x 64, d_ff 3584, 12 layers; vocab 384 + the glyph colour / font tokens)
+    "byt5_small": dict(vocab_size=1510, dim=1472, dim_attn=384, dim_ffn=3584, num_heads=6, num_layers=12, num_buckets=32, shared_pos=True),
+    "byt5_tiny": dict(vocab_size=400, dim=192, dim_attn=128, dim_ffn=320, num_heads=2, num_layers=3, num_buckets=32, shared_pos=True),
+    "byt5_2layer": dict(vocab_size=1510, dim=1472, dim_attn=384, dim_ffn=3584, num_heads=6, num_layers=2, num_buckets=32, shared_pos=True),
 }
 
 
@@ -634,11 +639,15 @@ def t5_param_shapes(cfg):
     """Names and shapes of T5Encoder(shared_pos=False) (t5.py:268-281, 165-182, 75-90, 133-142)."""
     d, da, df, h, nb = cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_buckets"]
     shapes = {"token_embedding.weight": (cfg["vocab_size"], d), "norm.weight": (d,)}
+    if cfg.get("shared_pos"):
+        shapes["pos_embedding.embedding.weight"] = (nb, h)
     for i in range(cfg["num_layers"]):
         b = f"blocks.{i}."
         shapes.update({b + "norm1.weight": (d,), b + "attn.q.weight": (da, d), b + "attn.k.weight": (da, d), b + "attn.v.weight": (da, d),
                        b + "attn.o.weight": (d, da), b + "norm2.weight": (d,), b + "ffn.gate.0.weight": (df, d), b + "ffn.fc1.weight": (df, d),
-                       b + "ffn.fc2.weight": (d, df), b + "pos_embedding.embedding.weight": (nb, h)})
+                       b + "ffn.fc2.weight": (d, df)})
+        if not cfg.get("shared_pos"):
+            shapes[b + "pos_embedding.embedding.weight"] = (nb, h)
     return shapes
 
 
@@ -674,3 +683,18 @@ def make_t5_inputs(cfg, length, n_valid, seed=0):
     ids[n_valid:] = 0
     mask = (torch.arange(length) < n_valid).long()
     return ids, mask
+
+
+def t5_to_hf_t5stack_names(sd, num_layers):
+    """Reference T5Encoder names -> transformers T5Stack names (the inverse of wan2gp_b200/wan/t5.py::hf_to_wan_names for the classic,
+    shared-position layout: the bias lives in block 0)."""
+    out = {"embed_tokens.weight": sd["token_embedding.weight"], "final_layer_norm.weight": sd["norm.weight"],
+           "block.0.layer.0.SelfAttention.relative_attention_bias.weight": sd["pos_embedding.embedding.weight"]}
+    for i in range(num_layers):
+        b, h = f"blocks.{i}.", f"block.{i}.layer."
+        out[h + "0.layer_norm.weight"], out[h + "1.layer_norm.weight"] = sd[b + "norm1.weight"], sd[b + "norm2.weight"]
+        for n in "qkvo":
+            out[h + f"0.SelfAttention.{n}.weight"] = sd[b + f"attn.{n}.weight"]
+        out[h + "1.DenseReluDense.wi_0.weight"], out[h + "1.DenseReluDense.wi_1.weight"] = sd[b + "ffn.gate.0.weight"], sd[b + "ffn.fc1.weight"]
+        out[h + "1.DenseReluDense.wo.weight"] = sd[b + "ffn.fc2.weight"]
+    return out

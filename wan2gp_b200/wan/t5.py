@@ -1,7 +1,8 @@
 """umT5 text encoder on the B200 kernels -- the step in front of the denoise path.
 
-Mirrors /root/reference/models/wan/modules/t5.py: `T5Encoder` (:268-292, the umT5 layout `shared_pos=False`: every block owns its
-relative position embedding, :165-188) with the reference's state-dict names, and `T5EncoderModel` (:632-690), the object
+Mirrors /root/reference/models/wan/modules/t5.py: `T5Encoder` (:268-292; the umT5 layout `shared_pos=False`: every block owns its
+relative position embedding, :165-188, and the classic T5 / byT5 layout `shared_pos=True`: one embedding for all blocks, :275-276, 286-287)
+with the reference's state-dict names, and `T5EncoderModel` (:632-690), the object
 `WanAny2V` holds as `self.text_encoder` and calls as `text_encoder([prompt], device) -> [ctx [n_tokens, 4096]]` (any2video.py:125, :588-589).
 
 One prompt = one sequence of text_len (512) token ids.  Per block: T5LayerNorm -> fused q|k|v GEMM -> 64-wide attention with the block's
@@ -41,12 +42,12 @@ def relative_bias_table(emb_weight, L, num_buckets):
 
 
 class T5Encoder(torch.nn.Module):
-    """Same constructor arguments and state-dict names as the reference class; `shared_pos=False` (umT5) only."""
+    """Same constructor arguments and state-dict names as the reference class.  `shared_pos=False` = umT5 (Wan, t5.py:469);
+    `shared_pos=True` = classic T5 v1.1 / byT5 (the glyph encoder of Hunyuan Video 1.5): `pos_embedding.embedding.weight` serves every block."""
 
     def __init__(self, vocab, dim, dim_attn, dim_ffn, num_heads, num_layers, num_buckets, shared_pos=False, dropout=0.1, device="cuda"):
         super().__init__()
-        if shared_pos:
-            raise NotImplementedError("T5Encoder: shared_pos=True (classic T5) is not on the Wan path (umt5_xxl, t5.py:469)")
+        self.shared_pos = bool(shared_pos)
         if dim_attn // num_heads != 64:
             raise NotImplementedError("T5Encoder: head dim 64 only (umT5-XXL: 4096 / 64)")
         self.vocab_size, self.dim, self.dim_attn, self.dim_ffn = int(vocab), dim, dim_attn, dim_ffn
@@ -60,6 +61,7 @@ class T5Encoder(torch.nn.Module):
         g = lambda k: sd[k].detach()
         self.table = g("token_embedding.weight").to(dev, bf16).contiguous()
         self.norm_w = g("norm.weight").to(dev, f32).contiguous()
+        shared = g("pos_embedding.embedding.weight").to(dev, f32).contiguous() if self.shared_pos else None
         self.blocks = []
         for i in range(self.num_layers):
             b = f"blocks.{i}."
@@ -69,13 +71,13 @@ class T5Encoder(torch.nn.Module):
                 wo=g(b + "attn.o.weight").to(dev, bf16).contiguous(),
                 wg=g(b + "ffn.gate.0.weight").to(dev, bf16).contiguous(), w1=g(b + "ffn.fc1.weight").to(dev, bf16).contiguous(),
                 w2=g(b + "ffn.fc2.weight").to(dev, bf16).contiguous(),
-                pos=g(b + "pos_embedding.embedding.weight").to(dev, f32).contiguous()))
+                pos=shared if self.shared_pos else g(b + "pos_embedding.embedding.weight").to(dev, f32).contiguous()))
         self._bias_cache = {}
         self._ready = True
         return torch.nn.modules.module._IncompatibleKeys([], [])
 
     def _bias(self, i, L):
-        key = (i, L)
+        key = (0 if self.shared_pos else i, L)
         if key not in self._bias_cache:
             self._bias_cache[key] = relative_bias_table(self.blocks[i]["pos"], L, self.num_buckets)
         return self._bias_cache[key]
@@ -184,6 +186,10 @@ def hf_to_wan_names(sd):
     if "token_embedding.weight" in sd:
         return sd
     import re
+    if not any(k.startswith("encoder.") for k in sd):          # a bare T5Stack (`T5ForConditionalGeneration.get_encoder()`, byT5): no prefix
+        sd = {"encoder." + k: v for k, v in sd.items()}
+    bias_blocks = [k for k in sd if k.endswith("SelfAttention.relative_attention_bias.weight")]
+    shared = len(bias_blocks) == 1 and sum(1 for k in sd if k.endswith("layer.0.SelfAttention.q.weight")) > 1
     out = {}
     rules = [(r"^encoder\.final_layer_norm\.weight$", "norm.weight"),
              (r"^encoder\.block\.(\d+)\.layer\.0\.layer_norm\.weight$", "blocks.{}.norm1.weight"),
@@ -196,6 +202,9 @@ def hf_to_wan_names(sd):
     for k, v in sd.items():
         if k in ("shared.weight", "encoder.embed_tokens.weight"):
             out.setdefault("token_embedding.weight", v)
+            continue
+        if shared and k == bias_blocks[0]:                       # classic T5: block 0's bias is every block's (T5Stack passes position_bias on)
+            out["pos_embedding.embedding.weight"] = v
             continue
         for pat, repl in rules:
             m = re.match(pat, k)
