@@ -48,7 +48,7 @@ def hy_flops_forward(cfg, L, Lt):
     return (nl + ns) * (4.0 * n * n * D + 8.0 * n * D * D + 16.0 * n * D * D)
 
 
-def measure_hunyuan(workload, steps, warmup, rank, world, local_rank, dev, dist, with_vae=True):
+def measure_hunyuan(workload, steps, warmup, rank, world, local_rank, dev, dist, with_vae=True, cfg_split=False):
     """Hunyuan Video denoise-step measurement (same JSON contract, steps of cond+uncond forwards + CFG + Euler) -> result dict."""
     import types
     from wan2gp_b200 import _lib, ops, synth
@@ -71,8 +71,14 @@ def measure_hunyuan(workload, steps, warmup, rank, world, local_rank, dev, dist,
                                         out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
                                         mm_double_blocks_depth=cfg["mm_double_blocks_depth"], text_states_dim=cfg["text_states_dim"],
                                         device=dev, **kw).init_synthetic(seed=1)
-    den = HunyuanDenoiser(model, num_steps=30, shift=9.0 if not v10 else 7.0, guide_scale=6.0, device=dev)
-    g = torch.Generator().manual_seed(1000 + rank)
+    # cfg_split (BASELINE configs[3] as 2 samples x 2 CFG branches on 4 GPUs): ranks (2k, 2k+1) hold the same sample, each runs ONE
+    # forward per step and the pair exchanges the fp32 prediction (one 2-rank all-gather per step), as `--cfg-split` does for Wan
+    group, cfg_rank, sample, n_samples = None, 0, rank, world
+    if cfg_split and dist is not None and world % 2 == 0 and not v10:
+        from wan2gp_b200 import dist as wd
+        group, cfg_rank, sample, n_samples = wd.make_cfg_pairs()
+    den = HunyuanDenoiser(model, num_steps=30, shift=9.0 if not v10 else 7.0, guide_scale=6.0, device=dev, cfg_group=group, cfg_rank=cfg_rank)
+    g = torch.Generator().manual_seed(1000 + sample)
     lat_host = torch.randn(1, cfg["out_channels"], T, H, W, generator=g).pin_memory()
     latents = lat_host.to(dev)
     cond = torch.zeros(1, cfg["in_channels"] - cfg["out_channels"], T, H, W, device=dev) if cfg["in_channels"] > cfg["out_channels"] else None
@@ -124,16 +130,18 @@ def measure_hunyuan(workload, steps, warmup, rank, world, local_rank, dev, dist,
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
     pk = peaks()
-    fl = (1.0 if v10 else 2.0) * hy_flops_forward(cfg, L, Lt + Lb)
+    fl = (1.0 if v10 or group is not None else 2.0) * hy_flops_forward(cfg, L, Lt + Lb)      # per GPU and step
     att_ms = sum(a for a, _ in att) / max(1, len(att))
     att_tf = (att[0][1] / (att_ms * 1e-3) / 1e12) if att else None
-    res = {"metric": "denoise_steps_per_sec", "value": world * args.steps / (ms / 1e3), "unit": "steps/s", "n_gpus": world,
+    par = (f"{n_samples} samples in flight, every CFG pair split over 2 GPUs (one forward per GPU and step, one 2-rank all-gather of the "
+           f"fp32 prediction per step)") if group is not None else f"{world} independent samples (batch split), 1 per GPU"
+    res = {"metric": "denoise_steps_per_sec", "value": n_samples * args.steps / (ms / 1e3), "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "latent": [1, cfg["out_channels"], T, H, W], "tokens": L,
-                      "text_tokens": Lt + Lb, "cfg_pair": not v10, "parallelism": f"{world} independent samples (batch split), 1 per GPU",
+                      "text_tokens": Lt + Lb, "cfg_pair": not v10, "parallelism": par,
                       "l2_policy": "inputs larger than L2; no flush needed"},
-           "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "steps/s", "steps": n_e2e,
+           "e2e": {"value": n_samples * n_e2e / (e2e_ms / 1e3), "unit": "steps/s", "steps": n_e2e,
                    "h2d_bytes_per_step": lat_host.numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 4},
            "gpu_launches": launches, "finite": bool(torch.isfinite(latents).all()),
            "model_tflops": fl / (ms / args.steps * 1e-3) / 1e12,
@@ -690,7 +698,8 @@ def main():
         if world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=dev)
-        res = measure_hunyuan(args.workload, args.steps, args.warmup, rank, world, local_rank, dev, dist, with_vae=not args.no_vae)
+        res = measure_hunyuan(args.workload, args.steps, args.warmup, rank, world, local_rank, dev, dist, with_vae=not args.no_vae and not args.cfg_split,
+                              cfg_split=args.cfg_split)
         if rank == 0:
             print(json.dumps(res))
         if dist is not None:
@@ -741,6 +750,15 @@ def main():
                 result["hy15_t2v_720p129"]["note"] = "BASELINE configs[3]: Hunyuan Video 1.5 t2v 720p x 129f on 4 GPUs (one sample per GPU)"
             except Exception as e:                               # noqa: BLE001
                 result["hy15_t2v_720p129"] = {"error": repr(e)[:300]}
+            if os.environ.get("B200_BENCH_HY15_SPLIT", "1") != "0":
+                try:                                             # the same configuration as 2 samples x 2 CFG branches: half the step latency
+                    sub = measure_hunyuan("hy15_t2v_720p129", 2, 1, rank, world, local_rank, dev, dist, with_vae=False, cfg_split=True)
+                    result["hy15_t2v_720p129_cfg_split"] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config",
+                                                                                 "gpu_launches", "finite", "model_tflops", "e2e", "clocks") if k in sub}
+                    result["hy15_t2v_720p129_cfg_split"]["note"] = ("BASELINE configs[3] with every CFG pair split over 2 GPUs; value = samples in flight x "
+                                                                    "steps/s; the step latency of one sample is ms_per_step")
+                except Exception as e:                           # noqa: BLE001
+                    result["hy15_t2v_720p129_cfg_split"] = {"error": repr(e)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, info = cpu_port_steps_per_sec(cfg, thw)

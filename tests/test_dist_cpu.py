@@ -139,3 +139,62 @@ def test_interrupt_is_agreed_collectively_gloo():
     for rank, outcomes, batch_none in res:
         assert outcomes == [False, True, True], (rank, outcomes)      # step 0 completes on both, step 1 aborts on BOTH
         assert batch_none
+
+
+class _FakeHYModel:
+    """Stands in for HYVideoDiffusionTransformer on CPU: a deterministic function of (x, text states); `fail_from` makes the forward
+    return None (the reference's abort contract, models.py:1146-1149) from that call on."""
+    out_channels = 8
+
+    def __init__(self, fail_from=None):
+        self.calls, self.fail_from = 0, fail_from
+
+    def __call__(self, x, t, text_states=None, text_mask=None, **kw):
+        self.calls += 1
+        if self.fail_from is not None and self.calls >= self.fail_from:
+            return None
+        return x[:, :8] * 0.5 + text_states.float().mean() * 0.1 + float(t[0]) * 1e-4
+
+
+def _hy_cfg_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import wan2gp_b200.pipeline as pl
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    wd.init(backend="gloo")
+    group, cfg_rank, sample, n_pairs = wd.make_cfg_pairs()
+    pl.ops.cfg_euler_step_ = lambda lat, c, u, g, dt, cfg_star=False: lat.sub_(dt * (c if u is None else u + g * (c - u)))   # CPU stand-in of the fused kernel
+    g = torch.Generator().manual_seed(200 + sample)
+    lat = torch.randn(1, 8, 2, 4, 4, generator=g)
+    cond_lat = torch.zeros(1, 9, 2, 4, 4)
+    txt, txtn = torch.randn(1, 6, 16, generator=g), torch.randn(1, 6, 16, generator=g)
+    tm = torch.ones(1, 6, dtype=torch.long)
+    den = pl.HunyuanDenoiser(_FakeHYModel(), num_steps=4, shift=9.0, guide_scale=6.0, device="cpu", cfg_group=group, cfg_rank=cfg_rank)
+    ref = pl.HunyuanDenoiser(_FakeHYModel(), num_steps=4, shift=9.0, guide_scale=6.0, device="cpu")
+    a, b = lat.clone(), lat.clone()
+    for i in range(4):
+        assert den.step(a, cond_lat, i, txt, tm, txtn, tm) is a
+        assert ref.step(b, cond_lat, i, txt, tm, txtn, tm) is b
+    same, calls = bool(torch.allclose(a, b, atol=1e-6)), den.model.calls
+    # abort on ONE rank of pair 0 only: its partner leaves the step with it, the other pair finishes
+    den2 = pl.HunyuanDenoiser(_FakeHYModel(fail_from=2 if rank == 1 else None), num_steps=4, shift=9.0, guide_scale=6.0, device="cpu",
+                              cfg_group=group, cfg_rank=cfg_rank)
+    c = lat.clone()
+    outcomes = [den2.step(c, cond_lat, i, txt, tm, txtn, tm) is None for i in range(2)]
+    q.put((rank, sample, n_pairs, same, calls, float(a.sum()), outcomes))
+    dist.destroy_process_group()
+
+
+def test_hunyuan_cfg_pair_split_gloo():
+    """BASELINE configs[3] (Hunyuan 1.5 on 4 GPUs) as 2 samples x 2 CFG branches: each rank runs ONE forward per step, the pair exchanges the
+    prediction, latents stay replicated and equal the single-process two-forward result; an abort on one rank is agreed inside its pair."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hy_cfg_worker, args=(r, 4, 29671, q)) for r in range(4)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert [r[1] for r in res] == [0, 0, 1, 1] and all(r[2] == 2 and r[3] for r in res)
+    assert all(r[4] == 4 for r in res)                                   # one forward per step and rank (the unsplit denoiser runs two)
+    assert res[0][5] == res[1][5] and res[2][5] == res[3][5] and res[0][5] != res[2][5]
+    assert res[0][6] == [False, True] and res[1][6] == [False, True]     # pair 0 (ranks 0, 1): step 0 completes, step 1 aborts on BOTH
+    assert res[2][6] == [False, False] and res[3][6] == [False, False]   # pair 1 is unaffected

@@ -28,5 +28,15 @@ if "conv" in which:
         conv.with_norm(x, torch.ones(96, device="cuda"))
     else:
         conv(x)
+if "rows" in which:          # the HBM-bound row kernels of a 14B block: LayerNorm + modulation, q|k RMSNorm + RoPE (one launch)
+    x = torch.randn(L, D, device="cuda")
+    y = torch.empty(L, D, device="cuda", dtype=bf16)
+    ops.ln_modulate(x, torch.randn(D, device="cuda"), torch.randn(D, device="cuda"), out=y)
+    del x, y
+    qkv = torch.randn(L, 3 * D, device="cuda").to(bf16)
+    w = torch.ones(D, device="cuda")
+    cos, sin = torch.randn(L, 128, device="cuda"), torch.randn(L, 128, device="cuda")
+    ops.qk_rmsnorm_rope_(qkv[:, :D], qkv[:, D:2 * D], w, w, 1e-6, cos, sin)
+    del qkv
 torch.cuda.synchronize()
 print("done")

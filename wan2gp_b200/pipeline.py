@@ -156,6 +156,27 @@ class DPMppSchedule:
         return c
 
 
+def exchange_cfg_pair(mine, like, group):
+    """The one per-step exchange of a CFG pair split over two ranks: every rank contributes its branch's fp32
+    prediction (`mine`, or None if its forward was interrupted) and gets (prediction of pair rank 0, prediction of pair rank 1), or None
+    if EITHER rank was interrupted.  `_interrupt` is per process: the pair must agree on the abort before either rank skips the
+    collective, otherwise the partner blocks in ncclAllGather forever -- the flag rides in front of the prediction (same collective,
+    16 bytes: the predictions behind the header stay aligned for the 128-bit loads of the step kernels)."""
+    import torch.distributed as dist
+    HDR = 4
+    shape = tuple(like.shape)
+    payload = torch.zeros(HDR + like.numel(), device=like.device, dtype=f32)
+    if mine is None:
+        payload[0] = 1.0
+    else:
+        payload[HDR:].copy_(mine.reshape(-1))
+    both = [torch.empty_like(payload), torch.empty_like(payload)]
+    dist.all_gather(both, payload, group=group)                                   # ncclAllGather inside the 2-rank pair
+    if float(both[0][0]) + float(both[1][0]) > 0:
+        return None
+    return both[0][HDR:].reshape(shape), both[1][HDR:].reshape(shape)
+
+
 class WanDenoiser:
     """Holds the expert(s) and the schedule; `step()` is one denoise step on device-resident latents."""
 
@@ -219,23 +240,12 @@ class WanDenoiser:
             cond = model([latents], tt, [context], **kw)[0]
             uncond = None
         elif self.cfg_group is not None:
-            import torch.distributed as dist
             mine = model([latents], tt, [context if self.cfg_rank == 0 else context_null], **kw)[0]
-            # `_interrupt` is per process: the pair must AGREE on the abort before either rank skips the collective, otherwise the
-            # partner blocks in ncclAllGather forever.  The flag rides in front of the prediction (same collective, +1 float).
-            shape = tuple(latents.shape)
-            HDR = 4                                   # 16-byte header: the predictions behind it stay aligned for the 128-bit loads of the step kernel
-            payload = torch.zeros(HDR + latents.numel(), device=latents.device, dtype=f32)
-            if mine is None:
-                payload[0] = 1.0
-            else:
-                payload[HDR:].copy_(mine.reshape(-1))
-            both = [torch.empty_like(payload), torch.empty_like(payload)]
-            dist.all_gather(both, payload, group=self.cfg_group)                  # ncclAllGather inside the 2-rank pair
-            if float(both[0][0]) + float(both[1][0]) > 0:
+            pair = exchange_cfg_pair(mine, latents, self.cfg_group)
+            if pair is None:
                 self._interrupt = True                                            # both ranks leave the schedule together
                 return None
-            cond, uncond = both[0][HDR:].reshape(shape), both[1][HDR:].reshape(shape)
+            cond, uncond = pair
         else:
             # joint pass: same blocks applied to each branch in turn (any2video.py:1634, model.py:2030-2037)
             cond, uncond = model([latents, latents], tt, [context, context_null], **kw)
@@ -371,8 +381,12 @@ class HunyuanDenoiser:
     (:1655/:1687), CFG combine (:1719-1743) and the flow-matching scheduler step (:1755; FlowMatchDiscreteScheduler, reverse=True, euler), here the
     Euler update fused with the combine.  guidance 6.0 / shift 9 are defaults/hunyuan_1_5_t2v.json."""
 
-    def __init__(self, model, num_steps=30, shift=9.0, guide_scale=6.0, device="cuda"):
+    def __init__(self, model, num_steps=30, shift=9.0, guide_scale=6.0, device="cuda", cfg_group=None, cfg_rank=0):
         self.model, self.device, self.guide_scale = model, torch.device(device), guide_scale
+        # CFG-pair split (SURVEY.md section 8e; BASELINE configs[3]: Hunyuan 1.5 on 4 GPUs = 2 samples x 2 branches): rank 0 of the pair
+        # runs the conditional forward, rank 1 the unconditional one, one 2-rank all-gather of the fp32 prediction per step, then both
+        # apply the same fused combine + Euler update (deterministic: the latents stay replicated) -- as WanDenoiser does.
+        self.cfg_group, self.cfg_rank = cfg_group, cfg_rank
         self.timesteps = flow_match_timesteps(num_steps, shift)              # scheduler.step = x + v (sigma_next - sigma) (:237-240)
         self.num_steps = num_steps
         self._interrupt = False
@@ -403,7 +417,14 @@ class HunyuanDenoiser:
             neg = dict(text_states=text_null, text_mask=text_null_mask, byt5_text_states=byt5 if byt5_null is None else byt5_null,
                        byt5_text_mask=byt5_mask if byt5_null is None else byt5_null_mask,
                        text_states_2=text_states_2 if text_states_2_null is None else text_states_2_null)
-            if joint_pass:                                   # [uncond, cond] stacked along the batch, as the reference stacks them (:1445-1452)
+            if self.cfg_group is not None:
+                mine = self.model(x, tt, x_id=1 - self.cfg_rank, **(pos if self.cfg_rank == 0 else neg), **fr)
+                pair = exchange_cfg_pair(mine, latents, self.cfg_group)
+                if pair is None:
+                    self._interrupt = True
+                    return None
+                cond, uncond = pair
+            elif joint_pass:                                 # [uncond, cond] stacked along the batch, as the reference stacks them (:1445-1452)
                 both = {k: (None if pos[k] is None else torch.cat([neg[k].to(pos[k].device), pos[k]], 0)) for k in pos}
                 g2 = None if guidance is None else guidance.reshape(-1)[:1].repeat(2)
                 ret = self.model(torch.cat([x, x], 0), tt.repeat(2), **both, **dict(fr, guidance=g2))
