@@ -82,6 +82,41 @@ if "rows" in which:
     qkv = torch.randn(L, 3 * D, device="cuda").to(bf16); w = torch.ones(D, device="cuda")
     cos = torch.randn(L, 128, device="cuda"); sin = torch.randn(L, 128, device="cuda")
     rec("rmsnorm_rope L x D (strided in qkv)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6, cos, sin)), bytes_=L * D * 4 + L * 128 * 8)
+if "libattn" in which:
+    # ---- the attention half of the library bar again, with the DEFAULT attention kernel (attn6 since round 2, call 12): cuDNN SDPA -- what
+    # the unmodified reference runs on a B200 (shared/attention.py:208-225) -- next to ours in the same process, ours timed before AND after
+    # the library kernel (boxes and the power cap drift within a process), self- and cross-attention shapes of the 14B model.
+    import torch.nn.functional as Fn
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    la = []
+    for Lq, Lk, tag in [(L, L, "self-attention L=75600 H=40 d=128"), (32760, 32760, "self-attention L=32760 (480p) H=40 d=128"),
+                        (L, 512, "cross-attention Lq=75600 Lk=512 H=40 d=128")]:
+        qkv = torch.randn(max(Lq, Lk), 3 * D, device="cuda").to(bf16)
+        out = torch.empty(Lq, D, device="cuda", dtype=bf16)
+        q, k, v = qkv[:Lq, :D], qkv[:Lk, D:2 * D], qkv[:Lk, 2 * D:]
+        ours_fn = lambda: ops.attention(q, k, v, H, out=out)
+        q4 = q.reshape(1, Lq, H, 128).transpose(1, 2)
+        k4, v4 = (t.reshape(1, Lk, H, 128).transpose(1, 2) for t in (k, v))
+
+        def lib_fn():
+            with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                return Fn.scaled_dot_product_attention(q4, k4, v4)
+        fl = 4.0 * Lq * Lk * D
+        r = {"shape": tag, "flops": fl}
+        try:
+            r["ours_ms_before"] = timeit(ours_fn, iters=3, warm=1)
+            r["cudnn_ms"] = timeit(lib_fn, iters=3, warm=1)
+            r["ours_ms_after"] = timeit(ours_fn, iters=3, warm=1)
+            r["max_abs_diff"] = float((lib_fn().transpose(1, 2).reshape(Lq, D).float() - out.float()).abs().max())
+            ours = min(r["ours_ms_before"], r["ours_ms_after"])
+            r.update(ours_tflops=fl / ours / 1e9, cudnn_tflops=fl / r["cudnn_ms"] / 1e9, ours_over_cudnn=r["cudnn_ms"] / ours)
+        except Exception as e:   # noqa: BLE001
+            r["error"] = repr(e)[:200]
+        la.append(r); print(json.dumps(r), flush=True)
+        del qkv, out, q4, k4, v4
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"what": "default attention kernel vs cuDNN SDPA, same process (tools/kernel_bench.py libattn)", "variant_env": os.environ.get("B200_ATT_VARIANT", "default"),
+               "rows": la}, open("gpurun_out/lib_bar_attn.json", "w"), indent=1)
 if "lib" in which:
     # ---- the library bar: what the UNMODIFIED reference would run on this GPU for the same shapes --
     # F.scaled_dot_product_attention (shared/attention.py:208-225; cuDNN / flash backends), torch.matmul -> cuBLASLt
