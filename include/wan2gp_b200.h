@@ -271,6 +271,18 @@ int b200_mul_bf16(const void* a, const void* b, void* out, long long n, void* st
 int b200_t5_attention(const void* q, const void* k, const void* v, long long ld, const float* bias_rel, void* out, long long ldo,
                       int L, int heads, int n_valid, void* stream);
 
+/* ---- decoder-only LLM text towers in front of the Hunyuan denoise path (transformers' Qwen2.5-VL / Llama language models as
+ * models/hyvideo/text_encoder/text_encoder_1_5.py:86-117, 439-505 and text_encoder/__init__.py run them).  The
+ * linear layers go through b200_gemm_bf16, the RMS norm / embedding / gated product through the T5 entries above. ---- */
+/* rotate-half RoPE in place (transformers apply_rotary_pos_emb): for every row and each of the first `nheads` 128-wide heads of x bf16
+ * [L, ld]: (x1, x2) <- (x1 cos - x2 sin, x2 cos + x1 sin), halves of 64; cos_t / sin_t fp32 [L, 64] */
+int b200_rope_half(void* x, long long ld, const float* cos_t, const float* sin_t, int L, int nheads, void* stream);
+/* causal grouped-query attention, head dim 128: out[i, h] = softmax_{j <= i}(scale q[i, h] . k[j, h / (q_heads / kv_heads)]) v[j, ...];
+ * q bf16 [L, q_heads * 128] row stride ldq, k / v bf16 [L, kv_heads * 128] row stride ldkv (views into one fused q|k|v buffer), out bf16
+ * row stride ldo (Qwen2_5_VLAttention / LlamaAttention with a causal mask; right padding never reaches a valid row) */
+int b200_causal_gqa_attention(const void* q, const void* k, const void* v, long long ldq, long long ldkv, void* out, long long ldo,
+                              int L, int q_heads, int kv_heads, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,9 +384,41 @@ def run_byt5(name):
                         length=length, n_valid=n_valid, seed=0, transformers_version=transformers.__version__)
 
 
+def run_llm(name):
+    """transformers' own language-model classes on seeded synthetic weights, called the way the reference's TextEncoder.encode calls its
+    model (input_ids + right-padded attention_mask, output_hidden_states=True; text_encoder_1_5.py:470-476): `Qwen2_5_VLTextModel` (the
+    language tower of Qwen2_5_VLForConditionalGeneration, multimodal RoPE sections [16, 24, 24]) for qwen_*, `LlamaModel` for llama_*.
+    Eager attention, fp32.  Stores every hidden state on the VALID rows (padded rows are don't-care: the mask crops them downstream)."""
+    import transformers
+    from wan2gp_b200 import synth
+    cfg = synth.LLM_CONFIGS[name]
+    common = dict(vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                  num_hidden_layers=cfg["num_layers"], num_attention_heads=cfg["num_heads"], num_key_value_heads=cfg["num_kv_heads"],
+                  rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"], max_position_embeddings=4096, attn_implementation="eager",
+                  tie_word_embeddings=False)
+    if name.startswith("qwen"):
+        from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLTextConfig
+        from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLTextModel
+        model = Qwen2_5_VLTextModel(Qwen2_5_VLTextConfig(rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]}, **common))
+    else:
+        model = transformers.LlamaModel(transformers.LlamaConfig(attention_bias=False, mlp_bias=False, head_dim=128, **common))
+    model = model.eval().float()
+    sd = synth.make_llm_state_dict(cfg, seed=0)
+    model.load_state_dict(sd, strict=True)
+    length, n_valid = 40, 27
+    ids, mask = synth.make_llm_inputs(cfg, length, n_valid, seed=0)
+    with torch.no_grad():
+        out = model(input_ids=ids[None], attention_mask=mask[None], output_hidden_states=True)
+    hs = torch.stack([h[0, :n_valid] for h in out.hidden_states])                 # [layers + 1, n_valid, D]
+    assert hs.shape[0] == cfg["num_layers"] + 1 and torch.equal(out.last_hidden_state[0, :n_valid], hs[-1])
+    print(f"{name}: transformers {transformers.__version__} {type(model).__name__} hidden states {tuple(hs.shape)}, absmean of [-3] {hs[-3].abs().mean():.6f}")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), hidden_states=hs.numpy().astype(np.float32), length=length, n_valid=n_valid, seed=0,
+                        transformers_version=transformers.__version__)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or ["tiny", "tiny_i2v", "small", "vae_tiny", "vae_small"]
     for n in names:
-        (run_byt5 if n.startswith("byt5_") else run_t5 if n.startswith("t5_") else run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)
+        (run_llm if n in ("qwen_tiny", "llama_tiny") else run_byt5 if n.startswith("byt5_") else run_t5 if n.startswith("t5_") else run_wan if n in WAN_CASES else run_hy if n in HY_CASES else run_hyvae if n in HYVAE_CASES else run_hyvae10 if n in HYVAE10_CASES else run_vae_enc if n in VAE_ENC_CASES else run_unipc if n == "unipc" else run_vae_tiled if n in TILED_CASES else run_hyvae_enc if n in HYVAE_ENC_CASES else run_hyvae10_enc if n in HYVAE10_ENC_CASES else run_hy_tiled if n in HY_TILED_CASES else run_vae)(n)

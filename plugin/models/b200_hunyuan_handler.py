@@ -8,8 +8,9 @@ contract as the built-in `models/hyvideo/hunyuan_handler.py` (:8-357), restricte
 `load_model` returns `(pipeline_obj, pipe_dict)` like hunyuan_handler.py:239-278: `pipeline_obj` is
 `wan2gp_b200.hyvideo.hunyuan.HunyuanVideoSampler` (level 2: `generate(**kwargs)`, `_interrupt`, `.model`, `.vae`), `pipe_dict` maps the
 mmgp component names to `nn.Module`s.  The text encoders (Qwen2.5-VL / llava-llama-3, CLIP-L, glyph-byT5) sit in front of the hot path
-and are WanGP's own objects, built exactly as hunyuan.py:283-305, 372-446 builds them; the transformer and the VAE are the sm_100a
-implementations.  There is no CPU / eager fallback: loading without the CUDA library or an sm_100 device raises."""
+and are WanGP's own `TextEncoder` objects, built exactly as hunyuan.py:283-305, 372-446 builds them -- with the language model and the byT5
+model inside them moved onto the B200 kernels (`wan2gp_b200.hyvideo.llm.LlamaLikeTextModel`, `.byt5.ByT5Encoder`) for bf16 encoder files;
+the transformer and the VAE are the sm_100a implementations.  There is no CPU / eager fallback: loading without the CUDA library or an sm_100 device raises."""
 import json
 import os
 
@@ -117,9 +118,12 @@ class family_handler:
                              ["hunyuan_video_VAE_fp32.safetensors", "hunyuan_video_VAE_config.json"]]}
 
     @staticmethod
-    def _reference_text_encoders(v15, model_def, text_encoder_filename, device):
+    def _reference_text_encoders(v15, model_def, text_encoder_filename, device, text_encoder_quantization=None):
         """The encoders in front of the path, built as hunyuan.py:283-305 (glyph-byT5) and :372-446 (LLM, CLIP-L) build them.
-        Needs WanGP's own packages (`models.hyvideo`, `shared`): this runs inside WanGP."""
+        Needs WanGP's own packages (`models.hyvideo`, `shared`): this runs inside WanGP.  WanGP's `TextEncoder` objects keep their
+        tokenizer, prompt templates and crop logic; for bf16 encoder files the language model inside (`te.model`: transformers'
+        Qwen2.5-VL / llava-llama-3) is replaced by `LlamaLikeTextModel` on the B200 kernels (same weights, same call surface), as the glyph
+        byT5 model is replaced by `ByT5Encoder`.  Quantised encoder files keep WanGP's own modules; CLIP-L (HunyuanVideo 1.0) stays WanGP's."""
         from models.hyvideo.constants import PROMPT_TEMPLATE
         from shared.utils import files_locator as fl
         text_len = 512                                                               # hunyuan.py:179 (256 only for the avatar variant)
@@ -139,6 +143,11 @@ class family_handler:
                             tokenizer_path=tok_path, i2v_mode=False, prompt_template=PROMPT_TEMPLATE[image_tpl],
                             prompt_template_video=PROMPT_TEMPLATE[video_tpl], hidden_state_skip_layer=2, apply_final_norm=False,
                             reproduce=True, device="cpu", image_embed_interleave=1, text_encoder_path=text_encoder_filename)
+        if text_encoder_quantization in (None, "", "bf16"):
+            from wan2gp_b200.hyvideo.llm import LLAMA3_8B, QWEN25_VL_7B, LlamaLikeTextModel
+            preset = QWEN25_VL_7B if v15 else LLAMA3_8B
+            te.model = LlamaLikeTextModel.from_state_dict(te.model.state_dict(), preset["num_heads"], preset["num_kv_heads"], preset["rms_eps"],
+                                                          preset["rope_theta"], device=device)
         te2 = byt5_model = byt5_tok = fmt = None
         if v15:
             from models.hyvideo.text_encoder.byT5 import load_glyph_byT5_v2
@@ -198,7 +207,7 @@ class family_handler:
         vae._model_dtype = torch.float32 if VAE_dtype == torch.float32 else torch.bfloat16
         if text_encoder is None:
             text_encoder, text_encoder_2, byt5_model, byt5_tokenizer, prompt_format = family_handler._reference_text_encoders(
-                v15, model_def, text_encoder_filename, device)
+                v15, model_def, text_encoder_filename, device, text_encoder_quantization)
         pipe_obj = HunyuanVideoSampler(model, vae, text_encoder=text_encoder, text_encoder_2=text_encoder_2, byt5_model=byt5_model,
                                        byt5_tokenizer=byt5_tokenizer, prompt_format=prompt_format, hunyuan_1_5=v15, enable_cfg=v15,
                                        device=device, model_def=model_def, vae_tiling=vae_tiling)

@@ -35,6 +35,8 @@ SIGNATURES = {
     "b200_t5_rmsnorm": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
     "b200_mul_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200_t5_attention": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    "b200_rope_half": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "b200_causal_gqa_attention": [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
     "b200_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_ll, c_void_p],
     "b200_cfg_euler_step_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200_cfg_unipc_step": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p],

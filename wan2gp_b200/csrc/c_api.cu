@@ -20,6 +20,7 @@
 #include "attn6_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "t5_ops.cuh"
+#include "llm_ops.cuh"
 #include "elementwise.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
@@ -651,5 +652,29 @@ extern "C" int b200_t5_attention(const void* q, const void* k, const void* v, lo
     t5_attention_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
         reinterpret_cast<const __nv_bfloat16*>(v), ld, bias_rel, reinterpret_cast<__nv_bfloat16*>(out), ldo, L, Lp, n_valid);
     CHECK_LAUNCH("t5_attention");
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ decoder-only LLM text towers (llm_ops.cuh)
+extern "C" int b200_rope_half(void* x, long long ld, const float* cos_t, const float* sin_t, int L, int nheads, void* stream) {
+    if (!x || !cos_t || !sin_t || L <= 0 || nheads <= 0) return b200_set_error(B200_ERR_ARG, "rope_half: null/empty argument");
+    if (ld < (long long)nheads * LLM_HD) return b200_set_error(B200_ERR_ARG, "rope_half: row stride %lld < %d heads x 128", ld, nheads);
+    rope_half_kernel<<<L, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, cos_t, sin_t, nheads);
+    CHECK_LAUNCH("rope_half");
+    return B200_OK;
+}
+
+extern "C" int b200_causal_gqa_attention(const void* q, const void* k, const void* v, long long ldq, long long ldkv, void* out, long long ldo,
+                                         int L, int q_heads, int kv_heads, float scale, void* stream) {
+    if (!q || !k || !v || !out || L <= 0 || q_heads <= 0 || kv_heads <= 0) return b200_set_error(B200_ERR_ARG, "causal_gqa_attention: null/empty argument");
+    if (q_heads % kv_heads) return b200_set_error(B200_ERR_ARG, "causal_gqa_attention: %d q heads not a multiple of %d kv heads", q_heads, kv_heads);
+    if (ldq % 4 || ldkv % 8 || ldo % 4) return b200_set_error(B200_ERR_ARG, "causal_gqa_attention: strides must keep rows 8 / 16 / 8-byte aligned");
+    if (((uintptr_t)q & 7) || ((uintptr_t)k & 15) || ((uintptr_t)v & 7) || ((uintptr_t)out & 7))
+        return b200_set_error(B200_ERR_ARG, "causal_gqa_attention: operand alignment (q, v, out 8 bytes; k 16 bytes)");
+    dim3 grid((L + 7) / 8, q_heads);
+    causal_gqa_attention_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+        reinterpret_cast<const __nv_bfloat16*>(v), ldq, ldkv, reinterpret_cast<__nv_bfloat16*>(out), ldo, L, q_heads / kv_heads,
+        scale * 1.4426950408889634f);
+    CHECK_LAUNCH("causal_gqa_attention");
     return B200_OK;
 }

@@ -698,3 +698,61 @@ def t5_to_hf_t5stack_names(sd, num_layers):
         out[h + "1.DenseReluDense.wi_0.weight"], out[h + "1.DenseReluDense.wi_1.weight"] = sd[b + "ffn.gate.0.weight"], sd[b + "ffn.fc1.weight"]
         out[h + "1.DenseReluDense.wo.weight"] = sd[b + "ffn.fc2.weight"]
     return out
+
+
+# --------------------------------------------------------------------------- decoder-only LLM text towers (Hunyuan text encoders)
+
+LLM_CONFIGS = {
+    # Qwen2.5-VL-7B-Instruct language model (config.json of the checkpoint the reference downloads: hunyuan_handler.py:47-53)
+    "qwen25_vl_7b": dict(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28, num_heads=28, num_kv_heads=4,
+                         rms_eps=1e-6, rope_theta=1e6, qkv_bias=True),
+    # llava-llama-3-8b language tower (Llama-3-8B + the llava tokens; hunyuan_handler.py:55-60)
+    "llama3_8b": dict(vocab_size=128320, hidden_size=4096, intermediate_size=14336, num_layers=32, num_heads=32, num_kv_heads=8,
+                      rms_eps=1e-5, rope_theta=5e5, qkv_bias=False),
+    # reduced configs for parity tests (head dim stays 128)
+    "qwen_tiny": dict(vocab_size=300, hidden_size=256, intermediate_size=512, num_layers=4, num_heads=2, num_kv_heads=1, rms_eps=1e-6,
+                      rope_theta=1e6, qkv_bias=True),
+    "llama_tiny": dict(vocab_size=300, hidden_size=512, intermediate_size=768, num_layers=3, num_heads=4, num_kv_heads=2, rms_eps=1e-5,
+                       rope_theta=5e5, qkv_bias=False),
+    "qwen_2layer_7b": dict(vocab_size=1024, hidden_size=3584, intermediate_size=18944, num_layers=2, num_heads=28, num_kv_heads=4,
+                           rms_eps=1e-6, rope_theta=1e6, qkv_bias=True),
+}
+
+
+def llm_param_shapes(cfg):
+    """transformers names (without the `model.` / `model.language_model.` prefix) and shapes of Qwen2_5_VLTextModel / LlamaModel."""
+    D, Fi, H, Hk = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_heads"], cfg["num_kv_heads"]
+    s = {"embed_tokens.weight": (cfg["vocab_size"], D), "norm.weight": (D,)}
+    for i in range(cfg["num_layers"]):
+        p = f"layers.{i}."
+        s.update({p + "input_layernorm.weight": (D,), p + "post_attention_layernorm.weight": (D,),
+                  p + "self_attn.q_proj.weight": (H * 128, D), p + "self_attn.k_proj.weight": (Hk * 128, D),
+                  p + "self_attn.v_proj.weight": (Hk * 128, D), p + "self_attn.o_proj.weight": (D, H * 128),
+                  p + "mlp.gate_proj.weight": (Fi, D), p + "mlp.up_proj.weight": (Fi, D), p + "mlp.down_proj.weight": (D, Fi)})
+        if cfg["qkv_bias"]:
+            s.update({p + "self_attn.q_proj.bias": (H * 128,), p + "self_attn.k_proj.bias": (Hk * 128,), p + "self_attn.v_proj.bias": (Hk * 128,)})
+    return s
+
+
+def make_llm_tensor(name, shape, cfg, seed=0, device="cpu"):
+    """Unit-variance activations everywhere (q . k / sqrt(128) ~ N(0, 1): a real softmax, not a uniform one)."""
+    if name.endswith("layernorm.weight") or name == "norm.weight":
+        return _normal(shape, 0.1, seed, name, device, mean=1.0)
+    if name == "embed_tokens.weight":
+        return _normal(shape, 1.0, seed, name, device)
+    if name.endswith(".bias"):
+        return _normal(shape, 0.1, seed, name, device)
+    return _normal(shape, shape[1] ** -0.5, seed, name, device)
+
+
+def make_llm_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32):
+    return {k: make_llm_tensor(k, s, cfg, seed, device).to(dtype) for k, s in llm_param_shapes(cfg).items()}
+
+
+def make_llm_inputs(cfg, length, n_valid, seed=0):
+    """ids [length] (right padded with id 0, as the reference tokenizers pad: padding_side="right"), mask [length]."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    ids = torch.randint(1, cfg["vocab_size"], (length,), generator=g)
+    ids[n_valid:] = 0
+    return ids, (torch.arange(length) < n_valid).long()
+
