@@ -33,7 +33,8 @@ def test_rope_half_and_causal_gqa_attention_kernels(L, H, Hk):
     ref = qkv.double().cpu().clone()
     qk = ref[:, :(H + Hk) * 128].reshape(L, H + Hk, 128)
     ref[:, :(H + Hk) * 128] = llm_oracle.apply_rope(qk, cos.double(), sin.double()).reshape(L, -1)
-    _lib.call("b200_rope_half", qkv.data_ptr(), qkv.stride(0), cos.cuda().data_ptr(), sin.cuda().data_ptr(), L, H + Hk, _s())
+    cos_d, sin_d = cos.cuda(), sin.cuda()                 # named: a temporary would be freed before the kernel reads it
+    _lib.call("b200_rope_half", qkv.data_ptr(), qkv.stride(0), cos_d.data_ptr(), sin_d.data_ptr(), L, H + Hk, _s())
     torch.cuda.synchronize()
     assert rel_l2(qkv[:, :(H + Hk) * 128], ref[:, :(H + Hk) * 128]) < 4e-3 and torch.equal(qkv[:, (H + Hk) * 128:].double().cpu(), ref[:, (H + Hk) * 128:])
     # attention on the roped buffer

@@ -28,6 +28,23 @@ def _randn(*shape, seed=0, scale=1.0, dtype=f32):
     return (torch.randn(*shape, generator=g, device="cuda", dtype=f32) * scale).to(dtype)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 1472, 384), (300, 1472, 3584), (130, 800, 128), (640, 1184, 256)])
+def test_gemm_accumulate_with_n_tail(ops, M, N, K):
+    """fp32 residual-stream accumulate (`x += gate * (a @ b^T + bias)`) when N is not a multiple of the 256-wide tile (byT5: 1472): the
+    TMA reduce-add epilogue must not let the chunks beyond N touch its staging buffers (round 2, call 26: the last 32 valid columns raced with
+    the reduce-store still reading them).  Repeated launches, every column checked."""
+    a, b = _randn(M, K, seed=1, dtype=bf16), _randn(N, K, seed=2, scale=K ** -0.5, dtype=bf16)
+    bias, gate = _randn(N, seed=3), _randn(N, seed=4)
+    lin = (a.double() @ b.double().t() + bias.double()) * gate.double()
+    x0 = _randn(M, N, seed=5)
+    for rep in range(4):
+        x = x0.clone()
+        ops.gemm(a, b, out=x, bias=bias, gate=gate, accumulate=True)
+        err = (x.double() - (x0.double() + lin)).abs()
+        assert float(err.max()) < 1e-3 * float(lin.abs().max()), (rep, int(err.argmax()) % N)
+    assert rel_l2(x[:, N - 32:], (x0.double() + lin)[:, N - 32:]) < TOL_F32
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (300, 512, 320), (1000, 768, 1536),
                                    (130, 64, 128), (4096, 1536, 1536), (77, 96, 72), (257, 192, 200), (64, 1560, 384)])
 def test_gemm_bf16_out(ops, M, N, K):

@@ -256,10 +256,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const bool leader = (warp == 4 && lane == 0);
                 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
+                    const int n0 = n_blk * BN + c * 32;
+                    // N tail (N % BN != 0): the remaining chunks lie beyond N.  They must not touch the staging buffers: a chunk that
+                    // stages without committing a store breaks the "buffer (c & 1) was committed two chunks ago" accounting of
+                    // bulk_wait_group_read<1> below and overwrites a tile the TMA engine may still be reading (found with the byT5
+                    // widths, N = 1472: the last 32 valid columns raced).  n0 is uniform over the 128 epilogue threads.
+                    if (n0 >= p.N) break;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
-                    const int n0 = n_blk * BN + c * 32;
                     float f[32];
                     #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
