@@ -7,6 +7,7 @@ echo "== smoke =="; timeout 300 python -c "import __graft_entry__ as g; g.smoke(
 echo "== libattn =="; timeout 300 python tools/kernel_bench.py libattn > gpurun_out/call28_libattn.log 2>&1; echo "rc=$?"; cat gpurun_out/call28_libattn.log | cut -c1-400
 echo "== ncu rows =="; timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ln_modulate|rmsnorm_rope" -c 2 -o gpurun_out/prof_r02_rows -f python tools/profile_targets.py rows > gpurun_out/call28_ncu.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/call28_ncu.log
 python tools/ncu_summary.py gpurun_out/prof_r02_rows.ncu-rep > gpurun_out/ncu_r02_rows.txt 2>&1; grep -E "kernel:|gpu__time_duration|dram__bytes|dram_throughput" gpurun_out/ncu_r02_rows.txt | head -12
+echo "== llm bench =="; timeout 200 python tools/llm_bench.py > gpurun_out/llm_bench_r02.jsonl 2> gpurun_out/llm_bench.err; echo "rc=$?"; cat gpurun_out/llm_bench_r02.jsonl; tail -2 gpurun_out/llm_bench.err
 echo "== bench default shape =="; timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_r02_final.json 2> gpurun_out/bench_r02_final.err; echo "rc=$?"
 python - <<'PY'
 import json
