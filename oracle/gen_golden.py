@@ -115,7 +115,8 @@ def run_vae_enc(name):
     np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), out=mu.numpy().astype(np.float32))
 
 
-HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0), "hy10_tiny": ("hy10_tiny", (2, 8, 12), 1)}
+HY_CASES = {"hy_tiny": ("hy_tiny", (3, 6, 10), 0), "hy10_tiny": ("hy10_tiny", (2, 8, 12), 1),
+            "hy_tiny_i2v": ("hy_tiny_i2v", (3, 6, 10), 2)}          # hunyuan_1_5_i2v: latent_concat + projected image-encoder tokens
 
 
 def run_hy(name):
@@ -128,7 +129,11 @@ def run_hy(name):
     kw.update({k: cfg[k] for k in ("hidden_size", "heads_num", "mlp_width_ratio", "mm_double_blocks_depth", "text_states_dim")})
     if v10:
         kw.update(mm_single_blocks_depth=cfg["mm_single_blocks_depth"], text_states_dim_2=cfg["text_states_dim_2"])
-    model = hy.HYVideoDiffusionTransformer(i2v_condition_type=None, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], **kw)
+    i2v = "vision_states_dim" in cfg
+    if i2v:
+        kw.update(vision_states_dim=cfg["vision_states_dim"])
+    model = hy.HYVideoDiffusionTransformer(i2v_condition_type="latent_concat" if i2v else None, in_channels=cfg["in_channels"],
+                                           out_channels=cfg["out_channels"], **kw)
     model = model.eval().requires_grad_(False)
     sd = synth.make_hy_state_dict(cfg, seed)
     missing, unexpected = model.load_state_dict(sd, strict=False)
@@ -150,6 +155,8 @@ def run_hy(name):
                      guidance=torch.tensor([6000.0]))
     else:
         extra = dict(byt5_text_states=b5, byt5_text_mask=bm)
+        if i2v:
+            extra["vision_states"] = synth.make_hy_vision_states(cfg, seed=seed)
     with torch.no_grad():
         out = model(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=Pipe(), **extra)
     print(f"{name}: reference HY forward out {tuple(out.shape)} {out.dtype} absmean {out.float().abs().mean():.6f}")

@@ -167,8 +167,17 @@ def single_block(sd, cfg, i, img, txt, vec, cos, sin, n_txt_valid, ref_casts, em
     return x[:L], x[L:]
 
 
+def vision_projection(sd, vs, em):
+    """VisionProjection (embed_layers.py:62-77): LayerNorm -> Linear -> GELU -> Linear -> LayerNorm (eps 1e-5, affine)."""
+    Dv, D = vs.shape[-1], sd["vision_in.proj.3.weight"].shape[0]
+    h = _q(F.layer_norm(vs, (Dv,), sd["vision_in.proj.0.weight"].float(), sd["vision_in.proj.0.bias"].float(), 1e-5), em)
+    h = _q(F.gelu(lin(sd, "vision_in.proj.1", h, em)), em)
+    h = lin(sd, "vision_in.proj.3", h, em)
+    return _q(F.layer_norm(h, (D,), sd["vision_in.proj.4.weight"].float(), sd["vision_in.proj.4.bias"].float(), 1e-5), em)
+
+
 def hy_forward(sd, cfg, x, t, text_states, text_mask, byt5_states=None, byt5_mask=None, freqs=None, ref_casts=True,
-               emulate_bf16=False, num_blocks=None, text_states_2=None, guidance=None):
+               emulate_bf16=False, num_blocks=None, text_states_2=None, guidance=None, vision_states=None):
     """x [1,Cin,T,H,W] -> [1,Cout,T,H,W]; masks must mark a valid PREFIX (as the reference's encoders produce)."""
     em = emulate_bf16
     D = cfg["hidden_size"]
@@ -194,6 +203,10 @@ def hy_forward(sd, cfg, x, t, text_states, text_mask, byt5_states=None, byt5_mas
         b5 = byt5_mapper(sd, byt5_states[0, :nb].float(), em) + sd["cond_type_embedding.weight"][1].float()
         txt = torch.cat([b5, txt], 0)                           # reorder_txt_token(zero_feat=True), models.py:910-935
         n_valid, n_pad = n_valid + nb, n_pad + byt5_states.shape[1] - nb
+    if vision_states is not None:                              # models.py:1063-1071: projected image-encoder tokens in front, cond type 2
+        vis = vision_projection(sd, vision_states[0].float(), em) + sd["cond_type_embedding.weight"][2].float()
+        txt = torch.cat([vis, txt], 0)
+        n_valid += vis.shape[0]
     txt = torch.cat([txt, txt.new_zeros(n_pad, D)], 0)
     nblk = cfg["mm_double_blocks_depth"] if num_blocks is None else num_blocks
     for i in range(nblk):

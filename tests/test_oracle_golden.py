@@ -105,3 +105,18 @@ def test_hyvae_oracle_matches_reference(name, zshape, seed):
     sd = synth.make_hyvae_state_dict(cfg, seed)
     z = synth._normal((1,) + zshape, 1.0, seed, "input.z", "cpu")[0]
     assert rel_l2(hyvae_oracle.hyvae_decode(sd, cfg, z), load_golden(name)["out"][0]) < 1e-5
+
+
+def test_hy_i2v_oracle_matches_reference_fixture():
+    """hunyuan_1_5_i2v: the reference HYVideoDiffusionTransformer with vision_projection='linear' and 200 image-encoder tokens
+    (tests/golden/hy_tiny_i2v.npz, oracle/gen_golden.py) -- VisionProjection, cond-type embedding 2, tokens in front of the text stream."""
+    from oracle import hy_oracle
+    from tests.helpers import load_golden, rel_l2
+    from wan2gp_b200 import synth
+    cfg = synth.HY_CONFIGS["hy_tiny_i2v"]
+    sd = synth.make_hy_state_dict(cfg, 2)
+    x, t, txt, tm, b5, bm = synth.make_hy_inputs(cfg, (3, 6, 10), seed=2)
+    vs = synth.make_hy_vision_states(cfg, seed=2)
+    g = load_golden("hy_tiny_i2v")["out"]
+    assert rel_l2(hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, vision_states=vs), g) < 5e-5
+    assert rel_l2(hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm), g) > 1e-2           # the vision tokens matter in this fixture

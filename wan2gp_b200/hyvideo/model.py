@@ -50,10 +50,12 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
                  mm_single_blocks_depth=40, rope_dim_list=(16, 56, 56), qkv_bias=True, qk_norm=True, qk_norm_type="rms",
                  guidance_embed=False, text_projection="single_refiner", use_attention_mask=True, text_states_dim=4096,
                  text_states_dim_2=768, text_pool_type=True, glyph_byT5_v2=False, use_cond_type_embedding=False,
-                 use_meanflow=False, vision_projection=False, pre_split_qkv=False, device="cuda", **unused):
+                 use_meanflow=False, vision_projection=False, vision_states_dim=1280, pre_split_qkv=False, device="cuda", **unused):
         super().__init__()
-        if use_meanflow or i2v_condition_type:
-            raise NotImplementedError("meanflow / token-replace (i2v) conditioning is outside the t2v hot path")
+        if use_meanflow or i2v_condition_type not in (None, "latent_concat"):   # "latent_concat" acts outside the model (extra input channels)
+            raise NotImplementedError("meanflow / token-replace (i2v) conditioning is outside the hot path")
+        if vision_projection not in (False, None, "linear"):
+            raise NotImplementedError(f"vision_projection {vision_projection!r}")
         if hidden_size // heads_num != 128 or not qk_norm or qk_norm_type != "rms" or text_projection != "single_refiner":
             raise NotImplementedError("HY hot path requires head_dim 128, RMS qk-norm and the single_refiner text projection")
         if tuple(patch_size) not in ((1, 1, 1), (1, 2, 2)):
@@ -66,6 +68,7 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         self.rope_dim_list, self.text_states_dim = list(rope_dim_list), text_states_dim
         self.glyph_byT5_v2, self.use_cond = glyph_byT5_v2, use_cond_type_embedding
         self.i2v_condition_type, self.guidance_embed = i2v_condition_type, guidance_embed
+        self.vision_projection, self.vision_states_dim = vision_projection or None, vision_states_dim
         self.device = torch.device(device)
         self.cache = None
         self.double_blocks, self.single_blocks = [], []
@@ -116,6 +119,11 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
                 g["byt5_" + n] = self._lin(sd, "byt5_in." + n)
         if self.use_cond:
             g["cond"] = self._d(sd["cond_type_embedding.weight"], f32)
+        g.pop("vision", None)
+        if self.vision_projection == "linear" and "vision_in.proj.1.weight" in sd:       # t2v checkpoints may omit it (only used with vision_states)
+            g["vision"] = {"ln0": (self._d(sd["vision_in.proj.0.weight"], f32), self._d(sd["vision_in.proj.0.bias"], f32)),
+                           "fc1": self._lin(sd, "vision_in.proj.1"), "fc2": self._lin(sd, "vision_in.proj.3"),
+                           "ln1": (self._d(sd["vision_in.proj.4.weight"], f32), self._d(sd["vision_in.proj.4.bias"], f32))}
         if self.text_pool_type is not None:
             g["vector_in.in_layer"] = self._lin(sd, "vector_in.in_layer", f32)
             g["vector_in.out_layer"] = self._lin(sd, "vector_in.out_layer", f32)
@@ -177,9 +185,18 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
         h = ops.gemm(h, g["byt5_fc2"][0], bias=g["byt5_fc2"][1], act=ACT_GELU_ERF)
         return ops.gemm(h, g["byt5_fc3"][0], bias=g["byt5_fc3"][1], out_dtype=f32)
 
-    def _text(self, text_states, text_mask, byt5_states, byt5_mask, t):
-        """txt_in + cond-type embedding + byT5 + reorder_txt_token(zero_feat=True) (models.py:1036-1071, 910-935):
-        returns the fp32 text stream [Lt, D] ordered [byT5 valid | LLM valid | zero padding] and the valid length."""
+    def _vision(self, vs):
+        """VisionProjection (embed_layers.py:62-77): LayerNorm -> Linear -> GELU(erf) -> Linear -> LayerNorm, vs fp32 [n, vision_dim] -> fp32 [n, D]."""
+        v = self._g["vision"]
+        h = ops.ln_modulate(vs, v["ln0"][1], v["ln0"][0], affine=True, eps=1e-5)
+        h = ops.gemm(h, v["fc1"][0], bias=v["fc1"][1], act=ACT_GELU_ERF)
+        h = ops.gemm(h, v["fc2"][0], bias=v["fc2"][1], out_dtype=f32)
+        return ops.ln_modulate(h, v["ln1"][1], v["ln1"][0], affine=True, eps=1e-5).float()       # bf16 tokens, as the reference's (bf16) stream holds them
+
+    def _text(self, text_states, text_mask, byt5_states, byt5_mask, t, vision_states=None):
+        """txt_in + cond-type embedding + byT5 + reorder_txt_token(zero_feat=True) (+ the projected image-encoder tokens in front,
+        models.py:1036-1071, 910-935): returns the fp32 text stream [Lt, D] ordered [vision | byT5 valid | LLM valid | zero padding] and the
+        valid length."""
         D = self.hidden_size
         tm = text_mask.bool().cpu() if text_mask is not None else torch.ones(text_states.shape[0], dtype=torch.bool)
         valid = self._refiner(text_states.to(self.device, f32)[tm.to(self.device)].contiguous(), t)
@@ -194,6 +211,12 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
                 if self.use_cond:
                     b = ops.add_vec(b.reshape(-1), self._g["cond"][1]).reshape(-1, D)
                 parts.insert(0, b)
+        if vision_states is not None:                        # models.py:1063-1071: all vision tokens are valid, cond type 2, in front
+            v = self._vision(vision_states.to(self.device, f32).contiguous())
+            if self.use_cond:
+                v = ops.add_vec(v.reshape(-1), self._g["cond"][2]).reshape(-1, D)
+            n_total += v.shape[0]
+            parts.insert(0, v)
         n_valid = sum(p.shape[0] for p in parts)
         txt = torch.zeros(n_total, D, device=self.device, dtype=f32)
         txt[:n_valid] = torch.cat(parts, 0)
@@ -249,9 +272,11 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
             raise ValueError("Didn't get guidance strength for guidance distilled model.")       # models.py:1023-1026
         for name, v in (("ref_latents", ref_latents), ("audio_prompts", audio_prompts),
                         ("motion_exp", motion_exp), ("motion_pose", motion_pose), ("fps", fps), ("bg_latents", bg_latents),
-                        ("vision_states", vision_states), ("timesteps_r", timesteps_r)):
+                        ("timesteps_r", timesteps_r)):
             if v is not None:
-                raise NotImplementedError(f"HYVideoDiffusionTransformer.forward: `{name}` is outside the t2v hot path")
+                raise NotImplementedError(f"HYVideoDiffusionTransformer.forward: `{name}` is outside the hot path")
+        if vision_states is not None and "vision" not in self._g:
+            raise ValueError("vision_states given but the model has no vision_in projection (vision_projection='linear' + its weights)")
         B, Cin, T, H, W = x.shape
         P, D = self.patch_size[1], self.hidden_size
         L = T * (H // P) * (W // P)
@@ -273,7 +298,8 @@ class HYVideoDiffusionTransformer(torch.nn.Module):
             img = ops.patch_embed(x[i].to(self.device, f32).contiguous(), None, self._g["img_w"], self._g["img_b"], D, patch=P)
             txt, n_valid = self._text(text_states[i], None if text_mask is None else text_mask[i],
                                       None if byt5_text_states is None else byt5_text_states[i],
-                                      None if byt5_text_mask is None else byt5_text_mask[i], ti)
+                                      None if byt5_text_mask is None else byt5_text_mask[i], ti,
+                                      None if vision_states is None else vision_states[0])        # the reference repeats ONE image's tokens over the batch (:1064)
             Lt = txt.shape[0]
             cat = torch.zeros(L + Lt, D + self.mlp_hidden, device=self.device, dtype=bf16) if self.single_blocks else None
             streams.append((img, txt, vec, n_valid, torch.empty(L + Lt, 3 * D, device=self.device, dtype=bf16),

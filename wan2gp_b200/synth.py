@@ -289,6 +289,7 @@ HY_CONFIGS["HYVideo-T/2-cfgdistill"] = dict(hidden_size=3072, heads_num=24, mlp_
                                             mm_single_blocks_depth=40, in_channels=16, out_channels=16, text_states_dim=4096,
                                             text_states_dim_2=768, patch_size=[1, 2, 2], rope_dim_list=[16, 56, 56],
                                             guidance_embed=True, family="1.0")
+HY_CONFIGS["hy_tiny_i2v"] = dict(HY_CONFIGS["hy_tiny"], vision_states_dim=64)      # + the image-encoder token projection of hunyuan_1_5_i2v
 HY_BYT5_DIMS = (1472, 2048, 2048)      # ByT5Mapper(in_dim, hidden_dim, out_dim) constants, models.py:647-653
 
 
@@ -341,11 +342,17 @@ def hy_param_shapes(cfg):
     lin("final_layer.linear", pp * Co, D), lin("final_layer.adaLN_modulation.1", 2 * D, D)
     if not v10:
         s["cond_type_embedding.weight"] = (3, D)
+    if cfg.get("vision_states_dim"):                            # VisionProjection (embed_layers.py:62-77), Hunyuan 1.5 i2v
+        Dv = cfg["vision_states_dim"]
+        s["vision_in.proj.0.weight"] = s["vision_in.proj.0.bias"] = (Dv,)
+        lin("vision_in.proj.1", Dv, Dv), lin("vision_in.proj.3", D, Dv)
+        s["vision_in.proj.4.weight"] = s["vision_in.proj.4.bias"] = (D,)
     return s
 
 
 def make_hy_tensor(name, shape, seed=0, device="cpu"):
-    if name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight"):
+    if name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight") \
+            or name in ("vision_in.proj.0.weight", "vision_in.proj.4.weight"):
         return 1.0 + _normal(shape, 0.1, seed, name, device)
     if name.endswith("bias"):
         return _normal(shape, 0.02, seed, name, device)
@@ -370,6 +377,11 @@ def make_hy_inputs(cfg, latent_thw, n_txt=24, n_txt_valid=17, n_byt5=12, n_byt5_
     bm = torch.zeros(1, n_byt5, dtype=torch.long)
     bm[:, :n_byt5_valid] = 1
     return x, torch.tensor([500.0]), txt, tm, byt5, bm
+
+
+def make_hy_vision_states(cfg, n_tokens=200, seed=0):
+    """SigLIP-like image-encoder states [1, n_tokens, vision_states_dim] (729 x 1152 in production: hunyuan.py:305-307)."""
+    return _normal((1, n_tokens, cfg["vision_states_dim"]), 1.0, seed, "hy.vision", "cpu")
 
 
 # --------------------------------------------------------------------------- Hunyuan Video 1.5 VAE decoder (AutoencoderKLConv3D)
