@@ -3,6 +3,7 @@ Video 1.5 / HunyuanVideo 1.0 text-to-video path with WanGP's model registry thro
 contract as the built-in `models/hyvideo/hunyuan_handler.py` (:8-357), restricted to the model types of the hot path:
 
     b200_hunyuan_1_5_t2v  ('HYVideo-1_5': 54 double-stream blocks, 65 -> 32 channels, CFG pair, Hunyuan 1.5 VAE 16x / 4x)
+    b200_hunyuan_1_5_i2v  (the same architecture; start image as latent-concat condition + image-encoder tokens, hunyuan.py:211-215)
     b200_hunyuan          ('HYVideo-T/2-cfgdistill': 20 double + 40 single blocks, embedded guidance, HunyuanVideo 1.0 VAE 8x / 4x)
 
 `load_model` returns `(pipeline_obj, pipe_dict)` like hunyuan_handler.py:239-278: `pipeline_obj` is
@@ -18,8 +19,10 @@ import torch
 
 ARCHS = {   # plugin architecture name -> (wan2gp_b200.synth.HY_CONFIGS key, Hunyuan 1.5?)
     "b200_hunyuan_1_5_t2v": ("HYVideo-1_5", True),
+    "b200_hunyuan_1_5_i2v": ("HYVideo-1_5", True),
     "b200_hunyuan": ("HYVideo-T/2-cfgdistill", False),
 }
+I2V = {"b200_hunyuan_1_5_i2v"}          # latent-concat start image + SigLIP tokens through the model's vision_in projection
 
 
 def _read_state_dict(path):
@@ -33,16 +36,17 @@ def _is_1_5(base_model_type):
     return ARCHS[base_model_type][1]
 
 
-def build_transformer(cfg, v15, device="cuda"):
+def build_transformer(cfg, v15, device="cuda", i2v=False):
     """HYVideoDiffusionTransformer with the constructor arguments hunyuan.py:227-253 / models.py:1280-1363 give the two families."""
     from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer
-    common = dict(i2v_condition_type=None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
+    common = dict(i2v_condition_type="latent_concat" if i2v else None, patch_size=cfg["patch_size"], in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
                   hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"], mlp_width_ratio=cfg["mlp_width_ratio"],
                   mm_double_blocks_depth=cfg["mm_double_blocks_depth"], rope_dim_list=cfg["rope_dim_list"],
                   text_states_dim=cfg["text_states_dim"], device=device)
     if v15:
         return HYVideoDiffusionTransformer(mm_single_blocks_depth=0, text_pool_type=None, text_states_dim_2=None, glyph_byT5_v2=True,
-                                           use_cond_type_embedding=True, pre_split_qkv=True, vision_projection="linear", **common)
+                                           use_cond_type_embedding=True, pre_split_qkv=True, vision_projection="linear",
+                                           vision_states_dim=cfg.get("vision_states_dim", 1152), **common)
     return HYVideoDiffusionTransformer(mm_single_blocks_depth=cfg["mm_single_blocks_depth"], text_states_dim_2=cfg["text_states_dim_2"],
                                        guidance_embed=bool(cfg.get("guidance_embed", False)), **common)
 
@@ -87,6 +91,8 @@ class family_handler:
                  "text_encoder_URLs": model_def.get("text_encoder_URLs", urls), "fps": 24, "frames_minimum": 5, "frames_steps": 4,
                  "sliding_window": False, "flow_shift": True, "cfg_star": v15, "tea_cache": False, "mag_cache": False,
                  "no_steps_skipping": True, "group": "hunyuan_b200", "profiles_dir": []}
+        if base_model_type in I2V:
+            extra.update({"i2v_class": True, "image_prompt_types_allowed": "S"})
         if v15:
             extra["guidance_max_phases"] = 1
         else:
@@ -105,12 +111,13 @@ class family_handler:
     def query_model_files(computeList, base_model_type, model_def=None):
         """The downloads hunyuan_handler.py:208-236 lists for the family, minus the files of the conditioning variants."""
         if _is_1_5(base_model_type):
+            siglip = [["siglip_vision_model"], [["model.safetensors", "config.json", "preprocessor_config.json"]]] if base_model_type in I2V else [[], []]
             return [{"repoId": "DeepBeepMeep/Qwen_image", "sourceFolderList": ["Qwen2.5-VL-7B-Instruct"],
                      "fileList": [["merges.txt", "tokenizer_config.json", "config.json", "vocab.json", "video_preprocessor_config.json",
                                    "preprocessor_config.json", "chat_template.json"]]},
-                    {"repoId": "DeepBeepMeep/HunyuanVideo1.5", "sourceFolderList": ["Glyph-SDXL-v2", "Glyph-SDXL-v2/byt5-small", ""],
+                    {"repoId": "DeepBeepMeep/HunyuanVideo1.5", "sourceFolderList": ["Glyph-SDXL-v2", "Glyph-SDXL-v2/byt5-small", ""] + siglip[0],
                      "fileList": [["color_idx.json", "multilingual_10-lang_idx.json"], ["config.json", "model.safetensors", "byt5_model.safetensors"],
-                                  ["hunyuan_video_1_5_VAE_fp32.safetensors", "hunyuan_video_1_5_VAE.json"]]}]
+                                  ["hunyuan_video_1_5_VAE_fp32.safetensors", "hunyuan_video_1_5_VAE.json"]] + siglip[1]}]
         return {"repoId": "DeepBeepMeep/HunyuanVideo", "sourceFolderList": ["llava-llama-3-8b", "clip_vit_large_patch14", ""],
                 "fileList": [["config.json", "special_tokens_map.json", "tokenizer.json", "tokenizer_config.json", "preprocessor_config.json"],
                              ["config.json", "merges.txt", "model.safetensors", "preprocessor_config.json", "special_tokens_map.json",
@@ -173,7 +180,7 @@ class family_handler:
                    text_encoder_quantization=None, dtype=torch.bfloat16, VAE_dtype=torch.float32, mixed_precision_transformer=False,
                    save_quantized=False, submodel_no_list=None, text_encoder_filename=None, text_encoder=None, text_encoder_2=None,
                    byt5_model=None, byt5_tokenizer=None, prompt_format=None, state_dict=None, vae_state_dict=None, vae_cfg=None,
-                   vae_tiling=True, device="cuda", **kwargs):
+                   vae_tiling=True, vision_encoder=None, device="cuda", **kwargs):
         """-> (pipeline_obj, pipe_dict).  Extra keyword-only hooks for tests / embedders: `state_dict` (already loaded transformer
         weights), `vae_state_dict` + `vae_cfg` (reduced VAE), `text_encoder` / `text_encoder_2` / `byt5_*` / `prompt_format` (injected
         conditioning models with the reference's protocol), `vae_tiling` (False = the one-pass B200 decode instead of the reference's tiles)."""
@@ -191,8 +198,11 @@ class family_handler:
             if not files:
                 raise ValueError(f"{base_model_type}: no transformer checkpoint given")
             state_dict = _read_state_dict(files[0])
-        model = build_transformer(cfg, v15, device)
+        i2v = base_model_type in I2V
+        model = build_transformer(cfg, v15, device, i2v=i2v)
         model.load_state_dict(state_dict)
+        if i2v and "vision" not in model._g:
+            raise ValueError(f"{base_model_type}: the checkpoint has no `vision_in.*` weights (a text-to-video checkpoint?)")
         model.mixed_precision = bool(mixed_precision_transformer)                  # hunyuan.py:256; selects the latent / noise dtype
         if vae_state_dict is None:
             from shared.utils import files_locator as fl                          # WanGP's checkpoint locator (hunyuan.py:326-349)
@@ -208,11 +218,19 @@ class family_handler:
         if text_encoder is None:
             text_encoder, text_encoder_2, byt5_model, byt5_tokenizer, prompt_format = family_handler._reference_text_encoders(
                 v15, model_def, text_encoder_filename, device, text_encoder_quantization)
+            if i2v and vision_encoder is None:                                   # hunyuan.py:305-309: WanGP's SigLIP encoder, in front of the path
+                from models.hyvideo.vision_encoder import VisionEncoder
+                from shared.utils import files_locator as fl
+                vision_encoder = VisionEncoder(vision_encoder_type="siglip", vision_encoder_precision="fp16",
+                                               vision_encoder_path=fl.locate_folder("siglip_vision_model"), processor_type=None, processor_path=None,
+                                               output_key=None, logger=None, device=device)
+                vision_encoder.vision_num_semantic_tokens, vision_encoder.vision_states_dim = 729, 1152
         pipe_obj = HunyuanVideoSampler(model, vae, text_encoder=text_encoder, text_encoder_2=text_encoder_2, byt5_model=byt5_model,
-                                       byt5_tokenizer=byt5_tokenizer, prompt_format=prompt_format, hunyuan_1_5=v15, enable_cfg=v15,
-                                       device=device, model_def=model_def, vae_tiling=vae_tiling)
+                                       byt5_tokenizer=byt5_tokenizer, prompt_format=prompt_format, hunyuan_1_5=v15, enable_cfg=v15, i2v=i2v,
+                                       device=device, model_def=model_def, vae_tiling=vae_tiling, vision_encoder=vision_encoder)
         pipe = {"transformer": model, "vae": vae}
-        for name, m in (("text_encoder", text_encoder), ("text_encoder_2", text_encoder_2), ("byt5_model", byt5_model)):
+        for name, m in (("text_encoder", text_encoder), ("text_encoder_2", text_encoder_2), ("byt5_model", byt5_model),
+                        ("vision_encoder", vision_encoder)):
             mod = getattr(m, "model", m)
             if isinstance(mod, torch.nn.Module):
                 pipe[name] = mod
@@ -227,6 +245,8 @@ class family_handler:
         ui_defaults["embedded_guidance_scale"] = 6.0                                 # hunyuan_handler.py:302
         if base_model_type == "b200_hunyuan":
             ui_defaults.update({"guidance_scale": 7.0})                              # :304-307
+        if base_model_type in I2V:
+            ui_defaults.update({"image_prompt_type": "S", "sliding_window_overlap": 1})   # :342-346
 
     @staticmethod
     def validate_generative_settings(base_model_type, model_def, inputs):
@@ -235,6 +255,6 @@ class family_handler:
             return "Step skipping (TeaCache / MagCache) is not available with the B200-native Hunyuan path"
         if inputs.get("activated_loras"):
             return "LoRAs are not available with the B200-native Hunyuan path"
-        if inputs.get("image_prompt_type", "") not in ("", None) and any(c in inputs.get("image_prompt_type", "") for c in "SVLE"):
+        if base_model_type not in I2V and inputs.get("image_prompt_type", "") not in ("", None) and any(c in inputs.get("image_prompt_type", "") for c in "SVLE"):
             return "Image / video conditioning is not available with the B200-native Hunyuan text-to-video path"
         return None

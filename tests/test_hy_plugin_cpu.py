@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # reduced architectures whose latent channels match the reduced VAEs (synth.HYVAE_CONFIGS / HYVAE10_CONFIGS)
 HY15_CFG = dict(synth.HY_CONFIGS["hy_tiny"], in_channels=17, out_channels=8)          # 8 latent + 8 condition + 1 mask channels
 HY10_CFG = dict(synth.HY_CONFIGS["hy10_tiny"], in_channels=8, out_channels=8)
+HY15_I2V_CFG = dict(HY15_CFG, vision_states_dim=64)                                      # + the vision_in projection of hunyuan_1_5_i2v
 VAE15_KW = dict(latent_channels=8, block_out_channels=[32, 64, 64], layers_per_block=1, ffactor_spatial=4, ffactor_temporal=2, sample_size=16,
                 sample_tsize=8, scaling_factor=1.03, shift_factor=0.1)
 
@@ -58,6 +59,20 @@ class FakeLLM:
         return types.SimpleNamespace(hidden_state=torch.stack(hs), attention_mask=None if self.pooled else torch.stack(ms))
 
 
+class FakeVision:
+    """WanGP's SigLIP `VisionEncoder` surface (vision_encoder/__init__.py:185-209): encode_images(uint8 HWC array) -> .last_hidden_state."""
+
+    def __init__(self, dim, n_tokens=40):
+        self.dim, self.n_tokens, self.seen = dim, n_tokens, []
+
+    def encode_images(self, images):
+        import numpy as np
+        assert isinstance(images, np.ndarray) and images.dtype == np.uint8 and images.ndim == 3 and images.shape[2] == 3
+        self.seen.append(images)
+        g = torch.Generator().manual_seed(int(images.astype(np.int64).sum()) % 100003)
+        return types.SimpleNamespace(last_hidden_state=torch.randn(1, self.n_tokens, self.dim, generator=g))
+
+
 def hy_kwargs(**over):
     """The keyword set wgp.py passes to a Hunyuan pipeline object (the common generate(**kwargs) call, wgp.py:7762-7880): the named
     arguments of hunyuan.py:728-757 plus the ones that land in **kwargs."""
@@ -73,8 +88,8 @@ def hy_kwargs(**over):
 
 def make_pipeline(arch, device="cpu", monkeypatch=None, **extra):
     h = load_hy_handler()
-    v15 = arch == "b200_hunyuan_1_5_t2v"
-    cfg = HY15_CFG if v15 else HY10_CFG
+    v15, i2v = arch.startswith("b200_hunyuan_1_5"), arch.endswith("i2v")
+    cfg = (HY15_I2V_CFG if i2v else HY15_CFG) if v15 else HY10_CFG
     monkeypatch.setitem(synth.HY_CONFIGS, h.ARCHS[arch][0], cfg)          # reduced architecture behind the production name
     sd = synth.make_hy_state_dict(cfg, 0)
     if v15:
@@ -82,6 +97,9 @@ def make_pipeline(arch, device="cpu", monkeypatch=None, **extra):
         vsd = {"decoder." + k: v for k, v in synth.make_hyvae_state_dict(vcfg, 0).items()}
         vae_cfg = VAE15_KW
         te = dict(text_encoder=FakeLLM(cfg["text_states_dim"]))
+        if i2v:
+            vsd.update({"encoder." + k: v for k, v in synth.make_hyvae_state_dict(vcfg, 0, encoder=True).items()})
+            te["vision_encoder"] = FakeVision(cfg["vision_states_dim"])
     else:
         vae_cfg = dict(synth.HYVAE10_CONFIGS["hyvae10_tiny"], sample_size=32, sample_tsize=16, scaling_factor=0.476986)
         vsd = synth.make_hyvae10_state_dict(synth.HYVAE10_CONFIGS["hyvae10_tiny"], 0)
@@ -100,7 +118,7 @@ def test_hunyuan_family_handler_contract():
                  "set_cache_parameters", "get_lora_dir", "register_lora_cli_args", "get_rgb_factors"):
         assert callable(getattr(fh, name)), name                    # hunyuan_handler.py:8-357 / wgp.py:2717-2735
     types_ = fh.query_supported_types()
-    assert set(types_) == {"b200_hunyuan_1_5_t2v", "b200_hunyuan"}
+    assert set(types_) == {"b200_hunyuan_1_5_t2v", "b200_hunyuan_1_5_i2v", "b200_hunyuan"}
     for t in types_:
         d = json.load(open(os.path.join(ROOT, "plugin", "defaults", t + ".json")))
         assert d["model"]["architecture"] == t and all("quanto" not in u for u in d["model"]["URLs"])
@@ -114,6 +132,8 @@ def test_hunyuan_family_handler_contract():
     assert ui == {"embedded_guidance_scale": 6.0, "guidance_scale": 7.0}
     assert fh.validate_generative_settings("b200_hunyuan", {}, {"activated_loras": ["x"]}) is not None
     assert fh.validate_generative_settings("b200_hunyuan", {}, {"image_prompt_type": "S"}) is not None
+    assert fh.validate_generative_settings("b200_hunyuan_1_5_i2v", {}, {"image_prompt_type": "S"}) is None
+    assert fh.query_model_def("b200_hunyuan_1_5_i2v", {})["i2v_class"] and "siglip_vision_model" in fh.query_model_files([], "b200_hunyuan_1_5_i2v")[1]["sourceFolderList"]
     assert fh.validate_generative_settings("b200_hunyuan_1_5_t2v", {}, {}) is None
     with pytest.raises(NotImplementedError):
         fh.set_cache_parameters("tea", "b200_hunyuan", {}, {}, None)
@@ -176,4 +196,38 @@ def test_generate_hunyuan_1_0_contract_and_interrupt(stub_abi, monkeypatch):  # 
     assert pipe_obj.generate(**hy_kwargs(model_type="b200_hunyuan", callback=callback)) is None
     pipe_obj._interrupt = False
     assert pipe_obj.generate(**hy_kwargs(model_type="b200_hunyuan")) is not None
+
+
+def test_generate_hunyuan_1_5_i2v_contract(stub_abi, monkeypatch):  # noqa: F811
+    """hunyuan_1_5_i2v: the start frame is VAE-encoded into frame 0 of the concat condition (mask 1 there), the image encoder sees the uint8
+    frame (convert_tensor_to_image), its tokens go into every forward; geometry follows the image (hunyuan.py:879-893, pipeline :1513-1531)."""
+    import wan2gp_b200.pipeline as pl
+    pipe_obj, pipe, cfg, _, _ = make_pipeline("b200_hunyuan_1_5_i2v", monkeypatch=monkeypatch)
+    assert pipe_obj.i2v_mode and pipe_obj.default_negative_prompt.startswith("deformation") and "vision_encoder" not in pipe   # not an nn.Module here
+    seen = []
+    real_step = pl.HunyuanDenoiser.step
+
+    def spy(self, latents, cond_latents, i, *a, **k):
+        seen.append((cond_latents.clone(), k.get("vision_states")))
+        return real_step(self, latents, cond_latents, i, *a, **k)
+    monkeypatch.setattr(pl.HunyuanDenoiser, "step", spy)
+    img = torch.rand(3, 32, 48, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    out = pipe_obj.generate(**hy_kwargs(model_type="b200_hunyuan_1_5_i2v", image_start=img, height=64, width=64, shift=7.0))
+    assert tuple(out.shape) == (3, 5, 32, 48)                                       # the image's size wins over height / width
+    cond, vis = seen[0]
+    assert tuple(cond.shape) == (1, 9, 3, 8, 12) and float(cond[:, 8, 0].min()) == 1.0 and float(cond[:, 8, 1:].abs().max()) == 0.0
+    assert float(cond[:, :8, 1:].abs().max()) == 0.0 and tuple(vis.shape) == (1, 40, 64) and vis.dtype == torch.bfloat16
+    ve = pipe_obj.vision_encoder
+    want = img.clone().add_(1.).mul_(127.5).permute(1, 2, 0).to(torch.uint8).numpy()
+    assert len(ve.seen) == 1 and (ve.seen[0] == want).all()
+    assert {"b200_hy_downsample_cl", "b200_group_mean_cl"} <= set(stub_abi)          # the VAE encoder ran
+    # the first frame of a video works the same way; without either the call is an error; t2v objects still reject images
+    out = pipe_obj.generate(**hy_kwargs(model_type="b200_hunyuan_1_5_i2v", input_video=torch.rand(3, 2, 32, 48) * 2 - 1, joint_pass=True))
+    assert tuple(out.shape) == (3, 5, 32, 48)
+    with pytest.raises(ValueError):
+        pipe_obj.generate(**hy_kwargs(model_type="b200_hunyuan_1_5_i2v"))
+    with pytest.raises(NotImplementedError):
+        load_hy_handler()  # noqa: B018
+        from wan2gp_b200.hyvideo.hunyuan import HunyuanVideoSampler
+        HunyuanVideoSampler(pipe_obj.model, pipe_obj.vae, hunyuan_1_5=False, i2v=True, device="cpu")
 

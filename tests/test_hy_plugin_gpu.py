@@ -121,3 +121,77 @@ def test_glyph_prompt_runs_the_byt5_encoder(monkeypatch):
     out = pipe_obj.generate(**hy_kwargs(input_prompt='a sign that says "OPEN"', sampling_steps=2, seed=2))
     plain = pipe_obj.generate(**hy_kwargs(input_prompt="a sign that says OPEN", sampling_steps=2, seed=2))
     assert tuple(out.shape) == (3, 5, 32, 48) and torch.isfinite(out).all() and not torch.equal(out, plain)
+
+
+def test_hy_i2v_forward_and_generate(monkeypatch):
+    """hunyuan_1_5_i2v on the GPU: (a) the transformer forward with image-encoder tokens against the reference fixture (hy_tiny_i2v) and the
+    bf16-emulating oracle; (b) generate() with a start image against the oracle loop -- single-frame VAE encode (latent_dist.mode() *
+    scaling_factor) into frame 0 of the concat condition, vision tokens in both CFG branches."""
+    from oracle import hy_oracle, hyvae_oracle, wan_oracle
+    from tests.helpers import load_golden
+    from tests.test_hy_plugin_cpu import HY15_I2V_CFG
+    from wan2gp_b200.hyvideo import HYVideoDiffusionTransformer
+    from wan2gp_b200.pipeline import flow_match_timesteps
+    # (a)
+    cfg = synth.HY_CONFIGS["hy_tiny_i2v"]
+    sd = synth.make_hy_state_dict(cfg, 2)
+    x, t, txt, tm, b5, bm = synth.make_hy_inputs(cfg, (3, 6, 10), seed=2)
+    vs = synth.make_hy_vision_states(cfg, seed=2)
+    m = HYVideoDiffusionTransformer(i2v_condition_type="latent_concat", patch_size=cfg["patch_size"], in_channels=cfg["in_channels"],
+                                    out_channels=cfg["out_channels"], hidden_size=cfg["hidden_size"], heads_num=cfg["heads_num"],
+                                    mlp_width_ratio=cfg["mlp_width_ratio"], mm_double_blocks_depth=cfg["mm_double_blocks_depth"],
+                                    mm_single_blocks_depth=0, text_states_dim=cfg["text_states_dim"], text_pool_type=None, glyph_byT5_v2=True,
+                                    use_cond_type_embedding=True, pre_split_qkv=True, vision_projection="linear", vision_states_dim=cfg["vision_states_dim"])
+    m.load_state_dict(sd)
+    cos, sin = hy_oracle.rope_tables_hy((3, 6, 10))
+
+    class P:
+        _interrupt = False
+    got = m(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=P(), byt5_text_states=b5, byt5_text_mask=bm, vision_states=vs).cpu()
+    emu = hy_oracle.hy_forward(sd, cfg, x, t, txt, tm, b5, bm, emulate_bf16=True, vision_states=vs)
+    g = load_golden("hy_tiny_i2v")["out"]
+    novis = m(x, t, text_states=txt, text_mask=tm, freqs_cos=cos, freqs_sin=sin, pipeline=P(), byt5_text_states=b5, byt5_text_mask=bm).cpu()
+    print(f"hy_tiny_i2v: vs bf16-emulating oracle {rel_l2(got, emu):.3e}; vs reference {rel_l2(got, g):.3e}; without the vision tokens {rel_l2(novis, g):.3e}")
+    assert rel_l2(got, emu) < 6e-3 and rel_l2(got, g) < 6e-3 and rel_l2(novis, g) > 1e-2
+    vis_tok = m._vision(vs[0].cuda()).cpu()
+    assert rel_l2(vis_tok, hy_oracle.vision_projection(sd, vs[0], True)) < 4e-3
+    # (b)
+    pipe_obj, pipe, cfg2, sd2, vsd = make_pipeline("b200_hunyuan_1_5_i2v", device="cuda", monkeypatch=monkeypatch, vae_tiling=False)
+    assert cfg2 == HY15_I2V_CFG
+    steps, shift, gsc, seed = 2, 7.0, 6.0, 9
+    img = torch.rand(3, 32, 48, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    kw = hy_kwargs(model_type="b200_hunyuan_1_5_i2v", image_start=img, sampling_steps=steps, shift=shift, guide_scale=gsc, seed=seed, frame_num=5)
+    out = pipe_obj.generate(**kw)
+    assert tuple(out.shape) == (3, 5, 32, 48)
+    thw = (3, 8, 12)
+    vcfg = synth.HYVAE_CONFIGS["hyvae_tiny"]
+    esd = {k[len("encoder."):]: v for k, v in vsd.items() if k.startswith("encoder.")}
+    dsd = {k[len("decoder."):]: v for k, v in vsd.items() if k.startswith("decoder.")}
+    vc = pipe_obj.vae.config
+    mom = hyvae_oracle.hyvae_encode(esd, vcfg, img[:, None], emulate_bf16=True)               # [2 z, 1, h, w]
+    img_lat = mom[:8] * vc.scaling_factor
+    enc_gpu = pipe_obj.vae.encode(img[None, :, None].cuda()).latent_dist.mode()[0].cpu()
+    print(f"single-frame Hunyuan 1.5 VAE encode vs bf16-emulating oracle: {rel_l2(enc_gpu, mom[:8]):.3e}")
+    assert rel_l2(enc_gpu, mom[:8]) < 2.5e-2
+    cond_lat = torch.zeros(1, 9, *thw)
+    cond_lat[0, :8, 0], cond_lat[0, 8, 0] = img_lat[:, 0], 1.0
+    lat = torch.randn((1, 8) + thw, generator=torch.Generator("cuda").manual_seed(seed), device="cuda", dtype=torch.bfloat16).float().cpu()
+    te, ve = pipe_obj.text_encoder, pipe_obj.vision_encoder
+    txt, tm = _states(te, kw["input_prompt"])
+    txtn, tmn = _states(te, pipe_obj.default_negative_prompt, True)
+    vis = ve.encode_images(ve.seen[0]).last_hidden_state.to(torch.bfloat16).float()
+    b5, bm = torch.zeros(1, 256, 1472), torch.zeros(1, 256, dtype=torch.long)
+    ts = flow_match_timesteps(steps, shift)
+    freqs = hy_oracle.rope_tables_hy(thw)
+    for i in range(steps):
+        xin = torch.cat([lat, cond_lat], 1)
+        tt = torch.tensor([ts[i]])
+        c = hy_oracle.hy_forward(sd2, cfg2, xin, tt, txt, tm, b5, bm, freqs=freqs, emulate_bf16=True, vision_states=vis)
+        u = hy_oracle.hy_forward(sd2, cfg2, xin, tt, txtn, tmn, b5, bm, freqs=freqs, emulate_bf16=True, vision_states=vis)
+        lat = wan_oracle.euler_step(lat, wan_oracle.cfg_combine(c, u, gsc), ts[i] / 1000.0, ts[i + 1] / 1000.0)
+    ref = hyvae_oracle.hyvae_decode(dsd, vcfg, (lat / vc.scaling_factor + vc.shift_factor)[0], emulate_bf16=True)
+    r, p = rel_l2(out, ref), psnr(out.clamp(-1, 1), ref.clamp(-1, 1), 2.0)
+    print(f"HunyuanVideoSampler.generate (1.5 i2v, start image + vision tokens, 2 steps + decode) vs oracle loop: rel-L2 {r:.3e}, PSNR {p:.1f} dB")
+    assert r < 4e-2 and p > 35.0
+    other = pipe_obj.generate(**dict(kw, image_start=-img))
+    assert not torch.equal(other, out)

@@ -20,7 +20,11 @@ What runs where:
      `HunyuanDenoiser.step` (both CFG branches + CFG / CFG-Zero* combine + Euler update in one fused kernel)
   -> latents / scaling_factor (+ shift_factor) -> VAE decode (the reference always decodes tiled: `enable_tiling=True`, :1068).
 
-Conditioning variants of the model zoo (i2v token-replace / latent-concat with a start image, custom, custom-audio / -edit, avatar,
+Hunyuan 1.5 image-to-video (`i2v=True`: hunyuan_1_5_i2v) is built as well: the start frame is VAE-encoded (`latent_dist.mode() *
+scaling_factor`, hunyuan.py:886-891), its latent becomes frame 0 of the 32 concat channels with mask 1 (pipeline :1513-1521) and WanGP's
+SigLIP encoder's tokens enter every forward through the model's `vision_in` projection (:1528-1531, models.py:1063-1071).
+
+Other conditioning variants of the model zoo (the token-replace i2v of HunyuanVideo 1.0, custom, custom-audio / -edit, avatar,
 the 1.5 upsampler, IP / reference images, masks) are outside the hot path: asking for one raises NotImplementedError naming the
 argument, which WanGP reports like any other generation error."""
 import random
@@ -35,6 +39,7 @@ f32 = torch.float32
 
 NEGATIVE_PROMPT = ("Aerial view, aerial view, overexposed, low quality, deformation, a poor composition, bad hands, bad teeth, bad eyes, "
                    "bad limbs, distortion")                                                       # models/hyvideo/constants.py:72
+NEGATIVE_PROMPT_I2V = "deformation, a poor composition and deformed video, bad teeth, bad eyes, bad limbs"                        # :73
 
 
 def align_to(value, alignment):
@@ -56,18 +61,21 @@ class HunyuanVideoSampler:
     """`pipeline_obj` returned by the plugin's `family_handler.load_model` for b200_hunyuan_1_5_t2v / b200_hunyuan (level 1)."""
 
     def __init__(self, model, vae, text_encoder=None, text_encoder_2=None, byt5_model=None, byt5_tokenizer=None, byt5_max_length=256,
-                 prompt_format=None, hunyuan_1_5=True, enable_cfg=None, i2v=False, device="cuda", model_def=None, vae_tiling=True):
-        if i2v:
-            raise NotImplementedError("HunyuanVideoSampler: image-to-video conditioning is outside the t2v hot path")
+                 prompt_format=None, hunyuan_1_5=True, enable_cfg=None, i2v=False, device="cuda", model_def=None, vae_tiling=True,
+                 vision_encoder=None):
+        if i2v and not hunyuan_1_5:
+            raise NotImplementedError("HunyuanVideoSampler: the token-replace image-to-video of HunyuanVideo 1.0 is outside the hot path "
+                                      "(Hunyuan 1.5 i2v = latent concat + image-encoder tokens is built)")
         self.model, self.vae = model, vae
         self.text_encoder, self.text_encoder_2 = text_encoder, text_encoder_2
         self.byt5_model, self.byt5_tokenizer, self.byt5_max_length, self.prompt_format = byt5_model, byt5_tokenizer, byt5_max_length, prompt_format
         self.hunyuan_1_5 = bool(hunyuan_1_5)
         self.enable_cfg = self.hunyuan_1_5 if enable_cfg is None else bool(enable_cfg)          # hunyuan.py:391, 413: 1.5 / custom / avatar only
-        self.i2v_mode, self.custom, self.avatar, self.upsampler, self.vision_encoder = False, False, False, None, None
+        self.i2v_mode, self.custom, self.avatar, self.upsampler = bool(i2v), False, False, None
+        self.vision_encoder = vision_encoder   # WanGP's SigLIP `VisionEncoder` (hunyuan.py:305-309): `.encode_images(np_uint8).last_hidden_state`
         self.device = torch.device(device)
         self.model_def = dict(model_def or {})
-        self.default_negative_prompt = NEGATIVE_PROMPT
+        self.default_negative_prompt = NEGATIVE_PROMPT_I2V if self.i2v_mode else NEGATIVE_PROMPT      # hunyuan.py:541-544
         self.vae_tiling = vae_tiling           # the reference pipeline always enables tiling before the decode (:1068, :1790-1795)
         self._interrupt = False                # written from the UI thread (wgp.py:1628); hunyuan.py:580-586 forwards it to the pipeline
         self.pipeline = self                   # `.pipeline._interrupt` is what the reference's property reads
@@ -131,8 +139,18 @@ class HunyuanVideoSampler:
                      input_video=input_video, image_start=image_start)
         for k in self._UNSUPPORTED:
             v = given[k]
+            if self.i2v_mode and k in ("input_video", "image_start"):
+                continue
             if v is not None and not (isinstance(v, (list, tuple, str)) and len(v) == 0):
-                raise NotImplementedError(f"HunyuanVideoSampler.generate: `{k}` belongs to a conditioning variant outside the t2v hot path")
+                raise NotImplementedError(f"HunyuanVideoSampler.generate: `{k}` belongs to a conditioning variant outside the t2v / i2v hot path")
+        first_frame = None
+        if self.i2v_mode:                      # hunyuan.py:879 (`first_frame = input_video[:, 0]`); a bare start image is accepted as well
+            if input_video is not None:
+                first_frame = input_video[:, 0]
+            elif image_start is not None:
+                first_frame = image_start if image_start.dim() == 3 else image_start[:, 0]
+            else:
+                raise ValueError("HunyuanVideoSampler.generate: image-to-video needs `input_video` (its first frame) or `image_start`")
         if VAE_tile_size is not None:                                                          # :759-772
             if self.hunyuan_1_5:
                 self.vae.set_tile_sample_min_size(VAE_tile_size["tile_sample_min_size"],
@@ -183,6 +201,14 @@ class HunyuanVideoSampler:
         negative = [n_prompt.strip()]
         do_cfg = guide_scale > 1                                                                # pipeline :951-953
         comp, tcomp = self._compression()
+        img_latents = vision_states = None
+        if self.i2v_mode:                                                                       # hunyuan.py:886-893, pipeline :1528-1531
+            ff = first_frame.to(self.device, f32)
+            semantic = ff.clone().add_(1.).mul_(127.5).permute(1, 2, 0).to(torch.uint8).cpu().numpy()     # np.array(convert_tensor_to_image(frame))
+            img_latents = self.vae.encode(ff[None, :, None].contiguous()).latent_dist.mode() * self.vae.config.scaling_factor   # [1, C, 1, h, w]
+            target_height, target_width = int(ff.shape[1]), int(ff.shape[2])                   # `target_width, target_height = semantic_images.size`
+            if self.vision_encoder is not None:
+                vision_states = self.vision_encoder.encode_images(semantic).last_hidden_state.to(self.device, torch.bfloat16)
         freqs = self.get_rotary_pos_embed(frame_num, target_height, target_width, enable_RIFLEx, spatial_compression=comp,
                                           temporal_compression=tcomp)
         callback = kwargs.pop("callback", None)
@@ -221,6 +247,11 @@ class HunyuanVideoSampler:
         cond_latents = None
         if self.hunyuan_1_5:       # i2v_condition_type "latent_concat" without an image: zero condition + zero mask channel (:1523-1525)
             cond_latents = torch.zeros(1, C + 1, *shape[2:], device=self.device, dtype=f32)
+            if img_latents is not None:                                                         # :1513-1521: frame 0 = the image latent, mask 1 there
+                if tuple(img_latents.shape[3:]) != tuple(shape[3:]) or img_latents.shape[1] != C:
+                    raise ValueError(f"start-image latent {tuple(img_latents.shape)} does not match the latent geometry {shape}")
+                cond_latents[:, :C, 0] = img_latents[:, :, 0].to(f32)
+                cond_latents[:, C, 0] = 1.0
         guidance = None
         if embedded_guidance_scale is not None and getattr(self.model, "guidance_embed", False):
             guidance = (torch.tensor([embedded_guidance_scale], dtype=f32).to(latent_dtype) * 1000.0).to(f32)   # :1661-1670
@@ -238,7 +269,7 @@ class HunyuanVideoSampler:
                 if den.step(lat, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=byt5, byt5_mask=byt5_mask, freqs=freqs,
                             text_states_2=pooled, guidance=guidance, byt5_null=byt5_null, byt5_null_mask=byt5_null_mask,
                             text_states_2_null=pooled_null, cfg_star=bool(cfg_star_switch), joint_pass=bool(joint_pass), callback=callback,
-                            pipeline=self) is None or self._interrupt:
+                            pipeline=self, vision_states=vision_states) is None or self._interrupt:
                     return None
             if callback is not None:
                 callback(i, latents.squeeze(0), False)                                          # :1762-1763

@@ -394,19 +394,22 @@ class HunyuanDenoiser:
     @torch.no_grad()
     def step(self, latents, cond_latents, i, text, text_mask, text_null, text_null_mask, byt5=None, byt5_mask=None, freqs=None,
              text_states_2=None, guidance=None, byt5_null=None, byt5_null_mask=None, text_states_2_null=None, cfg_star=False,
-             joint_pass=False, callback=None, pipeline=None):
+             joint_pass=False, callback=None, pipeline=None, vision_states=None):
         """latents fp32 [1,C,T,H,W] (updated in place); cond_latents fp32 [1,C2,T,H,W] (Hunyuan 1.5 concat mask/cond channels) or
         None; text_null=None => no CFG (guidance-distilled HunyuanVideo 1.0: one forward with the guidance embedding).
         `byt5_null*` / `text_states_2_null`: the negative branch's glyph / pooled states (default: the positive ones);
         cfg_star = the CFG-Zero* rescale of the unconditional prediction (pipeline_hunyuan_video.py:1721-1731); joint_pass = both
         branches in ONE forward of batch 2 (:1687-1715) instead of two forwards (:1655-1685) -- same arithmetic per sample;
-        `pipeline` = the object whose `_interrupt` the model polls once per block (default: this denoiser)."""
+        `pipeline` = the object whose `_interrupt` the model polls once per block (default: this denoiser); `vision_states` = the
+        image-encoder tokens of Hunyuan 1.5 i2v, the same for both branches (:1681)."""
         t = self.timesteps[i]
         dt = (t - self.timesteps[i + 1]) / 1000.0
         x = latents if cond_latents is None else torch.cat([latents, cond_latents], 1)
         tt = torch.tensor([t], dtype=f32)
         fr = dict(freqs_cos=None if freqs is None else freqs[0], freqs_sin=None if freqs is None else freqs[1],
                   pipeline=self if pipeline is None else pipeline, step_no=i, guidance=guidance, callback=callback)
+        if vision_states is not None:
+            fr["vision_states"] = vision_states
         pos = dict(text_states=text, text_mask=text_mask, byt5_text_states=byt5, byt5_text_mask=byt5_mask, text_states_2=text_states_2)
         uncond = None
         if text_null is None:
