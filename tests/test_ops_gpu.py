@@ -126,6 +126,42 @@ def test_rmsnorm_rope(ops):
         assert rel_l2(y.cpu(), wan_oracle.rms_norm_full(keep[:, :D].float().cpu(), w.cpu(), 1e-6)) < TOL_BF16
 
 
+@pytest.mark.parametrize("L,heads", [(4099, 40), (2048, 12), (2051, 1)])
+def test_rmsnorm_rope_pipelined_kernel_equals_row_kernel(ops, L, heads):
+    """L >= 2048 full-width rows take the cp.async-pipelined kernel (8 (row, segment) items per CTA through a 3-stage shared-memory ring;
+    4099 rows x 2 segments leaves a last CTA with 6 items): bit-identical to the one-CTA-per-row kernel (which chunks below 2048 rows still
+    take) -- same fp32 operations in the same order -- for the single-segment call, the fused q|k call and the call without RoPE; the v
+    columns of the fused buffer stay untouched."""
+    D = heads * 128
+    g = torch.Generator(device="cuda").manual_seed(L)
+    cos, sin = torch.randn(L, 128, device="cuda", generator=g), torch.randn(L, 128, device="cuda", generator=g)
+    buf = _randn(L, 3 * D, seed=1, dtype=bf16)
+    wq, wk = 0.3 * (1 + _randn(D, seed=2, scale=0.1)), 0.3 * (1 + _randn(D, seed=9, scale=0.1))
+    want = buf.clone()
+    for r0 in range(0, L, 1500):                             # chunks below the threshold: the row kernel
+        r1 = min(L, r0 + 1500)
+        ops.qk_rmsnorm_rope_(want[r0:r1, :D], want[r0:r1, D:2 * D], wq, wk, 1e-6, cos[r0:r1].contiguous(), sin[r0:r1].contiguous())
+    got = buf.clone()
+    ops.qk_rmsnorm_rope_(got[:, :D], got[:, D:2 * D], wq, wk, 1e-6, cos, sin)
+    assert torch.equal(got, want) and torch.equal(got[:, 2 * D:], buf[:, 2 * D:]) and not torch.equal(got[:, :D], buf[:, :D])
+    one = buf.clone()
+    ops.rmsnorm_rope_(one[:, D:2 * D], wk, 1e-6, cos, sin)
+    assert torch.equal(one[:, D:2 * D], want[:, D:2 * D]) and torch.equal(one[:, :D], buf[:, :D])
+    nr, nr_want = buf[:, :D].contiguous(), buf[:, :D].contiguous()
+    ops.rmsnorm_rope_(nr, wq, 1e-6)
+    for r0 in range(0, L, 1500):
+        ops.rmsnorm_rope_(nr_want[r0:min(L, r0 + 1500)], wq, 1e-6)
+    assert torch.equal(nr, nr_want)
+    # and against fp64 on a sample of rows
+    rows = torch.tensor([0, 1, 7, 8, L // 2, L - 7, L - 1], device="cuda")
+    x = buf[rows, :D].double()
+    y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * wq.double()
+    y = y.reshape(len(rows), heads, 64, 2)
+    c, s_ = cos[rows].double().reshape(len(rows), 1, 64, 2), sin[rows].double().reshape(len(rows), 1, 64, 2)
+    ref = torch.stack([y[..., 0] * c[..., 0] - y[..., 1] * s_[..., 0], y[..., 1] * c[..., 1] + y[..., 0] * s_[..., 1]], -1).reshape(len(rows), D)
+    assert rel_l2(got[rows, :D], ref) < TOL_BF16
+
+
 # Lq >= 1024 takes the CTA-pair kernel (attn2_sm100.cuh: 512 query rows per cluster): full / ragged pair blocks, a second CTA that is
 # entirely out of range (1100 = 2 x 512 + 76), partial last K/V tile, cross-attention length 512
 @pytest.mark.parametrize("Lq,Lk,H", [(128, 128, 1), (128, 256, 2), (200, 333, 3), (1000, 1000, 2), (300, 512, 4), (64, 80, 1),

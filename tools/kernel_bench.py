@@ -82,6 +82,9 @@ if "rows" in which:
     qkv = torch.randn(L, 3 * D, device="cuda").to(bf16); w = torch.ones(D, device="cuda")
     cos = torch.randn(L, 128, device="cuda"); sin = torch.randn(L, 128, device="cuda")
     rec("rmsnorm_rope L x D (strided in qkv)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6, cos, sin)), bytes_=L * D * 4 + L * 128 * 8)
+    rec("qk_rmsnorm_rope L x 2D (q and k of the fused buffer, one launch; B200_RMSROPE_PIPE=%s)" % os.environ.get("B200_RMSROPE_PIPE", "default"),
+        timeit(lambda: ops.qk_rmsnorm_rope_(qkv[:, :D], qkv[:, D:2 * D], w, w, 1e-6, cos, sin)), bytes_=L * D * 8 + L * 128 * 8)
+    rec("rmsnorm L x D, no RoPE (cross-attention q)", timeit(lambda: ops.rmsnorm_rope_(qkv[:, :D], w, 1e-6)), bytes_=L * D * 4)
 if "libattn" in which:
     # ---- the attention half of the library bar again, with the DEFAULT attention kernel (attn6 since round 2, call 12): cuDNN SDPA -- what
     # the unmodified reference runs on a B200 (shared/attention.py:208-225) -- next to ours in the same process, ours timed before AND after

@@ -465,12 +465,33 @@ extern "C" int b200_ln_modulate(const float* x, const float* shift, const float*
     return B200_OK;
 }
 
+// B200_RMSROPE_PIPE (default 1): full-width rows through the cp.async-pipelined kernel; 0 = one CTA per row (A/B runs).  Per-head norms
+// (Hunyuan) and short inputs keep the one-CTA-per-row kernel.
+static bool rmsrope_pipe_wanted(int L, int per_head, const void* a, const void* b) {
+    static int use = -1;
+    if (use < 0) { const char* ev = getenv("B200_RMSROPE_PIPE"); use = ev ? atoi(ev) : 1; }
+    return use && !per_head && L >= 2048 && !(((uintptr_t)a | (uintptr_t)b) & 15);
+}
+static int launch_rmsrope_pipe(__nv_bfloat16* a, __nv_bfloat16* b, long long ld, const float* wa, const float* wb, int L, int D, float eps,
+                               const float* cos_t, const float* sin_t, int nseg, void* stream) {
+    const long long n_items = (long long)L * nseg;
+    const size_t smem = (size_t)RP_STAGES * (D >> 3) * sizeof(uint4);           // 3 rows: 30 KB at D = 5120 (below the 48 KB default limit)
+    if (smem > 48 * 1024) return -1;                                             // caller falls back to the one-CTA-per-row kernel
+    rmsnorm_rope_pipe_kernel<<<(unsigned)((n_items + RP_ITEMS - 1) / RP_ITEMS), 256, smem, (cudaStream_t)stream>>>(a, b, ld, wa, wb, D, eps, cos_t, sin_t,
+                                                                                                                 n_items, nseg);
+    return 0;
+}
+
 extern "C" int b200_rmsnorm_rope(void* x, long long ld, const float* w, int L, int D, float eps, const float* cos_t,
                                  const float* sin_t, int per_head, void* stream) {
     if (!x || !w || L <= 0) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: null/empty argument");
     if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
     if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "rmsnorm_rope: cos/sin must both be given");
     auto xb = reinterpret_cast<__nv_bfloat16*>(x);
+    if (rmsrope_pipe_wanted(L, per_head, x, x) && launch_rmsrope_pipe(xb, xb, ld, w, w, L, D, eps, cos_t, sin_t, 1, stream) == 0) {
+        CHECK_LAUNCH("rmsnorm_rope_pipe");
+        return B200_OK;
+    }
     if (per_head) rmsnorm_rope_kernel<true><<<L, 256, 0, (cudaStream_t)stream>>>(xb, xb, ld, w, w, D, eps, cos_t, sin_t);
     else rmsnorm_rope_kernel<false><<<L, 256, 0, (cudaStream_t)stream>>>(xb, xb, ld, w, w, D, eps, cos_t, sin_t);
     CHECK_LAUNCH("rmsnorm_rope");
@@ -483,6 +504,10 @@ extern "C" int b200_qk_rmsnorm_rope(void* q, void* k, long long ld, const float*
     if (D % 128 || D > 256 * 8 * RN_MAXV || ld % 8) return b200_set_error(B200_ERR_ARG, "qk_rmsnorm_rope: D=%d ld=%lld unsupported", D, ld);
     if ((cos_t == nullptr) != (sin_t == nullptr)) return b200_set_error(B200_ERR_ARG, "qk_rmsnorm_rope: cos/sin must both be given");
     auto qb = reinterpret_cast<__nv_bfloat16*>(q), kb = reinterpret_cast<__nv_bfloat16*>(k);
+    if (rmsrope_pipe_wanted(L, per_head, q, k) && launch_rmsrope_pipe(qb, kb, ld, wq, wk, L, D, eps, cos_t, sin_t, 2, stream) == 0) {
+        CHECK_LAUNCH("qk_rmsnorm_rope_pipe");
+        return B200_OK;
+    }
     const dim3 grid(L, 2);
     if (per_head) rmsnorm_rope_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(qb, kb, ld, wq, wk, D, eps, cos_t, sin_t);
     else rmsnorm_rope_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(qb, kb, ld, wq, wk, D, eps, cos_t, sin_t);

@@ -146,6 +146,112 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same arithmetic (full-width RMSNorm + interleaved-pair RoPE, in place), software-pipelined.  ncu of the kernel above at the 14B
+// shape (profiles/ncu_r02_rows.txt): 967 us for 3.19 GB = 3.3 TB/s, half of the HBM rate, with the long-scoreboard stall at 15 issue
+// slots per instruction -- a CTA loads its 10 KB row, waits, reduces, stores, and only then does the next CTA's load start: at 4 CTAs per
+// SM there are never more than 40 KB in flight per SM and nothing at all during the reduce / store phase.  Here a CTA walks RP_ITEMS
+// consecutive (row, segment) items with a ring of RP_STAGES shared-memory rows filled by cp.async (LDGSTS): the loads of the next two
+// rows are in flight while the current row is reduced, rotated and stored.  Every thread copies exactly the 16-byte chunks it later reads
+// itself, so cp.async.wait_group is the only synchronisation the ring needs (no mbarrier, no __syncthreads beyond the block reduction).
+constexpr int RP_STAGES = 3, RP_ITEMS = 8;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_pipe_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ x2, long long ld, const float* __restrict__ w,
+                         const float* __restrict__ w2, int D, float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                         long long n_items, int nseg) {
+    extern __shared__ uint4 rp_smem[];                 // [RP_STAGES][nv]
+    __shared__ float red[8];
+    const int nv = D >> 3;
+    const long long item0 = (long long)blockIdx.x * RP_ITEMS;
+    const int n_my = (int)((n_items - item0) < RP_ITEMS ? (n_items - item0) : RP_ITEMS);
+    auto row_ptr = [&](long long item) -> uint4* {
+        const long long row = item / nseg;
+        return reinterpret_cast<uint4*>(((item - row * nseg) ? x2 : x) + row * ld);
+    };
+    auto issue = [&](int it) {
+        const uint4* g = row_ptr(item0 + it);
+        uint4* sdst = rp_smem + (it % RP_STAGES) * nv;
+        for (int idx = threadIdx.x; idx < nv; idx += 256) cp_async_16(sdst + idx, g + idx);
+    };
+    #pragma unroll
+    for (int it = 0; it < RP_STAGES - 1; ++it) {
+        if (it < n_my) issue(it);
+        cp_async_commit();
+    }
+    for (int it = 0; it < n_my; ++it) {
+        if (it + RP_STAGES - 1 < n_my) issue(it + RP_STAGES - 1);   // into the stage this thread finished reading one iteration ago
+        cp_async_commit();
+        cp_async_wait<RP_STAGES - 1>();                             // this thread's chunks of item `it` have landed
+        const long long item = item0 + it;
+        const long long row = item / nseg;
+        const bool second = (item - row * nseg) != 0;
+        const float* wr = second ? w2 : w;
+        uint4* xr = row_ptr(item);
+        const uint4* sr = rp_smem + (it % RP_STAGES) * nv;
+        uint4 v[RN_MAXV];
+        float s = 0.f;
+        #pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * 256;
+            float si = 0.f;
+            if (idx < nv) {
+                v[i] = sr[idx];
+                const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = __uint_as_float(u[k] << 16), b = __uint_as_float(u[k] & 0xffff0000u);
+                    si += a * a + b * b;
+                }
+            }
+            s += si;
+        }
+        const float r = rsqrtf(block_sum_256(s, red) / D + eps);
+        float cv[8], sv[8];
+        if (cos_t) {
+            const int d = (threadIdx.x << 3) & 127;
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(cos_t + row * 128 + d + 4));
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sin_t + row * 128 + d + 4));
+            cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+            sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+        }
+        #pragma unroll
+        for (int i = 0; i < RN_MAXV; ++i) {
+            const int idx = threadIdx.x + i * 256;
+            if (idx < nv) {
+                const int col = idx << 3;
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + col));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + col + 4));
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                float f[8];
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    f[2 * k] = __uint_as_float(u[k] << 16) * r * wv[2 * k];
+                    f[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u) * r * wv[2 * k + 1];
+                }
+                if (cos_t) {
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float x0 = f[2 * k], x1 = f[2 * k + 1];
+                        f[2 * k] = x0 * cv[2 * k] - x1 * sv[2 * k];
+                        f[2 * k + 1] = x1 * cv[2 * k + 1] + x0 * sv[2 * k + 1];
+                    }
+                }
+                xr[idx] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp32 -> bf16 cast (context / misc), n % 4 == 0
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
