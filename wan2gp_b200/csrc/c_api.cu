@@ -476,7 +476,7 @@ static int launch_rmsrope_pipe(__nv_bfloat16* a, __nv_bfloat16* b, long long ld,
                                const float* cos_t, const float* sin_t, int nseg, void* stream) {
     const long long n_items = (long long)L * nseg;
     const size_t smem = (size_t)RP_STAGES * (D >> 3) * sizeof(uint4);           // 3 rows: 30 KB at D = 5120 (below the 48 KB default limit)
-    if (smem > 48 * 1024) return -1;                                             // caller falls back to the one-CTA-per-row kernel
+    if (smem > 40 * 1024) return -1;     // D > 6826: the ring + the reduction scratch would pass the 48 KB default limit -> one-CTA-per-row kernel
     rmsnorm_rope_pipe_kernel<<<(unsigned)((n_items + RP_ITEMS - 1) / RP_ITEMS), 256, smem, (cudaStream_t)stream>>>(a, b, ld, wa, wb, D, eps, cos_t, sin_t,
                                                                                                                  n_items, nseg);
     return 0;
