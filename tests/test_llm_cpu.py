@@ -108,3 +108,33 @@ def test_text_model_host_path(stub_abi, monkeypatch, name):  # noqa: F811
         m(input_ids=ids, attention_mask=mask.flip(1), output_hidden_states=True)
     with pytest.raises(ValueError):
         llm.LlamaLikeTextModel.from_state_dict(sd, cfg["num_heads"] * 2, cfg["num_kv_heads"], device="cpu")
+
+
+@pytest.mark.parametrize("name", ["qwen_tiny", "llama_tiny"])
+def test_oracle_matches_transformers_live(name):
+    """The same pin as the fixture, live: transformers' own classes (installed in this image; on a box without them the test skips) on another
+    seed, length and padding -- every hidden state on the valid rows."""
+    transformers = pytest.importorskip("transformers")
+    cfg = synth.LLM_CONFIGS[name]
+    common = dict(vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                  num_hidden_layers=cfg["num_layers"], num_attention_heads=cfg["num_heads"], num_key_value_heads=cfg["num_kv_heads"],
+                  rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"], max_position_embeddings=4096, attn_implementation="eager",
+                  tie_word_embeddings=False)
+    try:
+        if name.startswith("qwen"):
+            from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLTextConfig
+            from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLTextModel
+            model = Qwen2_5_VLTextModel(Qwen2_5_VLTextConfig(rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]}, **common))
+        else:
+            model = transformers.LlamaModel(transformers.LlamaConfig(attention_bias=False, mlp_bias=False, head_dim=128, **common))
+    except (ImportError, TypeError) as e:                       # another transformers version without these classes / arguments
+        pytest.skip(f"transformers {transformers.__version__}: {e}")
+    model = model.eval().float()
+    sd = synth.make_llm_state_dict(cfg, seed=5)
+    model.load_state_dict(sd, strict=True)
+    ids, mask = synth.make_llm_inputs(cfg, 33, 19, seed=5)
+    with torch.no_grad():
+        out = model(input_ids=ids[None], attention_mask=mask[None], output_hidden_states=True)
+    hs = llm_oracle.llm_hidden_states(sd, cfg, ids, 19)
+    for i, (h, r) in enumerate(zip(hs, out.hidden_states)):
+        assert float((h[:19] - r[0, :19]).norm() / r[0, :19].norm()) < 1e-6, i

@@ -148,3 +148,22 @@ def test_byt5_encoder_host_path(stub_abi, monkeypatch):  # noqa: F811
     out = m(ids[None], attention_mask=mask[None].float())
     assert isinstance(out, tuple) and tuple(out[0].shape) == (1, 24, 192)
     assert len(e._bias_cache) == 1 and stub_abi.count("b200_t5_attention") == 3
+
+
+def test_byt5_oracle_matches_transformers_t5stack_live():
+    """Live pin against transformers' T5Stack, built and called as the reference builds / calls its byT5 glyph encoder
+    (text_encoder/byT5/__init__.py:184-188, pipeline_hunyuan_video.py:1037); skips where transformers is not installed."""
+    transformers = pytest.importorskip("transformers")
+    cfg = synth.T5_CONFIGS["byt5_tiny"]
+    sd = synth.make_t5_state_dict(cfg, 7)
+    hf_cfg = transformers.T5Config(vocab_size=cfg["vocab_size"], d_model=cfg["dim"], d_kv=64, d_ff=cfg["dim_ffn"], num_layers=cfg["num_layers"],
+                                   num_decoder_layers=1, num_heads=cfg["num_heads"], relative_attention_num_buckets=cfg["num_buckets"],
+                                   relative_attention_max_distance=128, dropout_rate=0.0, layer_norm_epsilon=1e-6, feed_forward_proj="gated-gelu",
+                                   tie_word_embeddings=False)
+    hf = transformers.T5ForConditionalGeneration(hf_cfg).get_encoder().eval().float()
+    hf.load_state_dict(synth.t5_to_hf_t5stack_names(sd, cfg["num_layers"]), strict=True)
+    ids, mask = synth.make_t5_inputs(cfg, 41, 23, 7)
+    with torch.no_grad():
+        ref = hf(ids[None], attention_mask=mask[None].float())[0][0]
+    out = t5_oracle.t5_encode(sd, cfg, ids, mask)
+    assert float((out[:23] - ref[:23]).norm() / ref[:23].norm()) < 1e-6
