@@ -289,7 +289,7 @@ class WanDenoiser:
         # tensors alive so that their addresses cannot be recycled
         ident = lambda x: None if x is None else (x.data_ptr(), x._version, tuple(x.shape))
         key = (id(model), getattr(model, "weights_version", 0), latents.data_ptr(), tuple(latents.shape), ident(context), ident(context_null),
-               ident(y), bool(star), multistep, (i & 1) if multistep else 0)
+               ident(y), None if freqs is None else (ident(freqs[0]), ident(freqs[1])), bool(star), multistep, (i & 1) if multistep else 0)
         ent = self._step_graphs.get(key)
         if ent is None:
             tdev = torch.zeros(1, device=latents.device, dtype=f32)
@@ -320,7 +320,7 @@ class WanDenoiser:
                 body(latents, hist)
             n_kernels = _lib.launch_count() - n0            # kernels of ours recorded in the graph (the C ABI counts at launch = capture time)
             model.use_cuda_graphs = prev
-            ent = self._step_graphs[key] = (graph, tdev, pdev, (latents, context, context_null, y, hist), n_kernels)
+            ent = self._step_graphs[key] = (graph, tdev, pdev, (latents, context, context_null, y, hist, freqs), n_kernels)   # freqs: RIFLEx tables differ at equal shapes
             if len(self._step_graphs) > 12:                 # each entry pins a memory pool: keep the table small
                 self._step_graphs.pop(next(iter(self._step_graphs)))
         graph, tdev, pdev = ent[:3]
